@@ -1,0 +1,248 @@
+"""Test-side helpers: ctypes bindings to the CPU checkers under oracle/, synthetic input generators
+and a restatement of the reference's sparse packing. TEST INFRASTRUCTURE -- the product package never
+imports this module nor anything under oracle/.
+
+Reference citations are relative to /root/reference/tensorflow_ctc_ext_beam_search_decoder/.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libctcx_ref.so")
+ORACLE_SO = os.path.join(ORACLE_DIR, "libctcx_oracle.so")
+
+_c_int_p = ctypes.POINTER(ctypes.c_int)
+_c_float_p = ctypes.POINTER(ctypes.c_float)
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+
+
+class OracleError(Exception):
+    """Raised with the reference's Status message (kernels.cc:111-138, decoder.h:237-243)."""
+
+
+def build_oracles(force=False):
+    """Compile oracle/libctcx_oracle.so and (where /root/reference exists) oracle/_ref."""
+    if force or not os.path.exists(ORACLE_SO) or (
+            os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(ORACLE_DIR, "ctcx_oracle.c"))):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
+    if os.path.isdir("/root/reference/tensorflow_ctc_ext_beam_search_decoder") and (
+            force or not os.path.exists(REF_SO)
+            or os.path.getmtime(REF_SO) < os.path.getmtime(os.path.join(ORACLE_DIR, "ref_driver.cc"))):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref"])
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+_libs = {}
+
+
+def _load(path):
+    if path not in _libs:
+        _libs[path] = ctypes.CDLL(path)
+    return _libs[path]
+
+
+def _ptr(a, typ):
+    return a.ctypes.data_as(typ)
+
+
+def _dense_out(B, P, T, dtype):
+    n = max(B * P, 1)
+    return (np.zeros(n, np.int32), np.full(n * max(T, 1), -7, np.int32), np.zeros(n, np.int32),
+            np.full(n * max(T, 1), -7, np.int32), np.zeros(n, dtype))
+
+
+class DenseResult:
+    """Dense rows per (b, p): decoded labels, alignment, log-prob (float32 or float64)."""
+
+    def __init__(self, B, P, T, dec_len, dec, ali_len, ali, logp):
+        self.B, self.P, self.T = B, P, T
+        Ts = max(T, 1)
+        self.dec_len = dec_len[:B * P].reshape(B, P)
+        self.ali_len = ali_len[:B * P].reshape(B, P)
+        self.dec = dec[:B * P * Ts].reshape(B, P, Ts)
+        self.ali = ali[:B * P * Ts].reshape(B, P, Ts)
+        self.logp = logp[:B * P].reshape(B, P)
+
+    def decoded(self, b, p):
+        return self.dec[b, p, :self.dec_len[b, p]].tolist()
+
+    def alignment(self, b, p):
+        return self.ali[b, p, :self.ali_len[b, p]].tolist()
+
+
+def _check_inputs(logits, seq_len):
+    logits = np.ascontiguousarray(logits)
+    if logits.ndim != 3:
+        raise OracleError("inputs is not a 3-Tensor")  # kernels.cc:111-113
+    seq_len = np.ascontiguousarray(seq_len, dtype=np.int32)
+    if seq_len.ndim != 1:
+        raise OracleError("sequence_length is not a vector")  # kernels.cc:122-124
+    T, B, C = logits.shape
+    if T == 0:
+        raise OracleError("max_time is 0")  # kernels.cc:118-120
+    if seq_len.shape[0] != B:
+        raise OracleError("len(sequence_length) != batch_size.  len(sequence_length):  %d batch_size: %d"
+                          % (seq_len.shape[0], B))  # kernels.cc:126-130
+    return logits, seq_len
+
+
+def ref_decode(logits, seq_len, beam_width, top_paths, merge_repeated=False, blank_index=0,
+               blank_label=-1, b_range=None):
+    """The reference's own decoder (compiled from /root/reference into oracle/_ref)."""
+    lib = _load(REF_SO)
+    logits, seq_len = _check_inputs(logits, seq_len)
+    T, B, C = logits.shape
+    if logits.dtype == np.float64:
+        fn, fp, dt = lib.ctcx_ref_decode_f64, _c_double_p, np.float64
+    else:
+        logits = logits.astype(np.float32, copy=False)
+        fn, fp, dt = lib.ctcx_ref_decode_f32, _c_float_p, np.float32
+    b0, b1 = b_range if b_range is not None else (0, B)
+    dec_len, dec, ali_len, ali, logp = _dense_out(B, top_paths, T, dt)
+    err = ctypes.create_string_buffer(256)
+    rc = fn(_ptr(logits, fp), T, B, C, _ptr(seq_len, _c_int_p), b0, b1, beam_width, top_paths,
+            int(bool(merge_repeated)), blank_index, blank_label, _ptr(dec_len, _c_int_p),
+            _ptr(dec, _c_int_p), _ptr(ali_len, _c_int_p), _ptr(ali, _c_int_p), _ptr(logp, fp), err, 256)
+    if rc != 0:
+        raise OracleError(err.value.decode())
+    return DenseResult(B, top_paths, T, dec_len, dec, ali_len, ali, logp)
+
+
+def ref_trace(logits_tc, beam_width, merge_repeated=False, blank_index=0, blank_label=-1):
+    """Per-frame beam (best first) of one utterance from the compiled reference: list over t of
+    [(logp, prefix, alignment), ...]."""
+    lib = _load(REF_SO)
+    x = np.ascontiguousarray(logits_tc, dtype=np.float32)
+    T, C = x.shape
+    W = beam_width
+    n = np.zeros(T, np.int32)
+    logp = np.zeros(T * W, np.float32)
+    dec_len = np.zeros(T * W, np.int32)
+    dec = np.zeros(T * W * T, np.int32)
+    ali = np.zeros(T * W * T, np.int32)
+    lib.ctcx_ref_trace_f32(_ptr(x, _c_float_p), T, C, W, int(bool(merge_repeated)), blank_index,
+                           blank_label, _ptr(n, _c_int_p), _ptr(logp, _c_float_p),
+                           _ptr(dec_len, _c_int_p), _ptr(dec, _c_int_p), _ptr(ali, _c_int_p))
+    out = []
+    for t in range(T):
+        row = []
+        for p in range(n[t]):
+            r = t * W + p
+            row.append((float(logp[r]), dec[r * T:r * T + dec_len[r]].tolist(),
+                        ali[r * T:r * T + t + 1].tolist()))
+        out.append(row)
+    return out
+
+
+N_MARGINS = 5  # CTCX_MARGIN_{ACCEPT,BOTTOM,ORDER,ALIGN,FINAL} in oracle/ctcx_oracle.c
+MARGIN_NAMES = ("accept", "bottom", "order", "align", "final")
+
+
+class OracleStats(ctypes.Structure):
+    """Mirror of ctcx_oracle_stats in oracle/ctcx_oracle.c."""
+    _fields_ = [
+        ("frames", ctypes.c_longlong),
+        ("turns_passed_gate", ctypes.c_longlong),
+        ("child_evals", ctypes.c_longlong),
+        ("accepted", ctypes.c_longlong),
+        ("wipes", ctypes.c_longlong),
+        ("wipes_before_turn", ctypes.c_longlong),
+        ("frames_with_effective_wipe", ctypes.c_longlong),
+        ("relevant_children", ctypes.c_longlong),
+        ("surviving_children", ctypes.c_longlong),
+        ("revisit_accepts", ctypes.c_longlong),
+        ("max_relevant_children", ctypes.c_longlong),
+        ("effective_wipes", ctypes.c_longlong),
+    ]
+
+
+def oracle_decode(logits, seq_len, beam_width, top_paths, merge_repeated=False, blank_index=0,
+                  blank_label=-1, want_margin=False, want_stats=False):
+    """This repo's plain-C restatement (oracle/ctcx_oracle.c). Returns DenseResult; with
+    want_margin also a float64 [B,5] array with each utterance's minimum decision margins."""
+    lib = _load(ORACLE_SO)
+    logits, seq_len = _check_inputs(logits, seq_len)
+    T, B, C = logits.shape
+    if logits.dtype == np.float64:
+        fn, fp, dt = lib.ctcx_oracle_decode_f64, _c_double_p, np.float64
+    else:
+        logits = logits.astype(np.float32, copy=False)
+        fn, fp, dt = lib.ctcx_oracle_decode_f32, _c_float_p, np.float32
+    dec_len, dec, ali_len, ali, logp = _dense_out(B, top_paths, T, dt)
+    margin = np.full((max(B, 1), N_MARGINS), np.inf, np.float64)
+    stats = OracleStats()
+    err = ctypes.create_string_buffer(256)
+    rc = fn(_ptr(logits, fp), T, B, C, _ptr(seq_len, _c_int_p), beam_width, top_paths,
+            int(bool(merge_repeated)), blank_index, blank_label, _ptr(dec_len, _c_int_p),
+            _ptr(dec, _c_int_p), _ptr(ali_len, _c_int_p), _ptr(ali, _c_int_p), _ptr(logp, fp),
+            _ptr(margin, _c_double_p), ctypes.byref(stats), err, 256)
+    if rc != 0:
+        raise OracleError(err.value.decode())
+    res = DenseResult(B, top_paths, T, dec_len, dec, ali_len, ali, logp)
+    out = [res]
+    if want_margin:
+        out.append(margin[:B])
+    if want_stats:
+        out.append(stats)
+    return out[0] if len(out) == 1 else tuple(out)
+
+
+def pack_sparse(res, P=None):
+    """Restates StoreAllDecodedSequences (kernels.cc:163-257): per path p, row-major over b then
+    position: indices [N_p,2] = [b, pos], values [N_p], shape [B, max length over batch] -- returned
+    in the raw op's output order (ops.cc:17-23): 6 lists of P arrays + log_probability."""
+    P = res.P if P is None else P
+    B = res.B
+    out = ([], [], [], [], [], [])
+    for lens, rows, (o_idx, o_val, o_shape) in ((res.dec_len, res.dec, out[0:3]),
+                                               (res.ali_len, res.ali, out[3:6])):
+        for p in range(P):
+            idx, val, mx = [], [], 0
+            for b in range(B):
+                n = int(lens[b, p])
+                mx = max(mx, n)
+                val.extend(rows[b, p, :n].tolist())
+                idx.extend([b, i] for i in range(n))
+            o_idx.append(np.asarray(idx, np.int64).reshape(-1, 2))
+            o_val.append(np.asarray(val, np.int64))
+            o_shape.append(np.asarray([B, mx], np.int64))
+    return out + (res.logp.copy(),)
+
+
+# ----------------------------------------------------------------------------------------------
+# Synthetic inputs: identical tensors for the CPU checkers and the GPU path.
+def make_logits(kind, T, B, C, blank_index, seed, sigma=1.0, spike=8.0):
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal((T, B, C)) * sigma).astype(np.float32)
+    if kind == "gauss":
+        return x
+    if kind == "peaky":
+        nonblank = np.array([c for c in range(C) if c != blank_index], np.int64)
+        is_spike = rng.random((T, B)) < 0.25
+        lab = nonblank[rng.integers(0, C - 1, (T, B))]
+        cls = np.where(is_spike, lab, blank_index)
+        tt, bb = np.meshgrid(np.arange(T), np.arange(B), indexing="ij")
+        x[tt, bb, cls] += np.float32(spike)
+        return x
+    raise ValueError(kind)
+
+
+def ragged_lengths(T, B, seed):
+    rng = np.random.default_rng(seed + 1000003)
+    return rng.integers(T // 2, T + 1, B).astype(np.int32)
+
+
+PAPER_PROBS = [[0.3, 0.5, 0.2], [0.25, 0.6, 0.15], [0.6, 0.2, 0.2], [0.4, 0.35, 0.25],
+               [0.5, 0.4, 0.1], [0.3, 0.3, 0.4], [0.1, 0.2, 0.7], [0.2, 0.3, 0.5]]
+
+
+def paper_logits(dtype=np.float64):
+    """python/ops/ctc_ext_beam_search_decoder_ops_test.py:25-33 (np.log of the table, float64)."""
+    return np.log(np.asarray(PAPER_PROBS, np.float64))[:, None, :].astype(dtype)
