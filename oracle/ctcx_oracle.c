@@ -44,6 +44,7 @@ typedef struct {
   long long revisit_accepts;            /* evicted member re-accepted on revisit (rounding case) */
   long long max_relevant_children;
   long long effective_wipes;
+  long long revisit_above_former;       /* re-scored evicted member scoring above its former total */
 } ctcx_oracle_stats;
 
 #define CTCX_CAT_(a, b) a##b

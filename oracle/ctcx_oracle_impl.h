@@ -43,6 +43,7 @@ typedef struct {
   int turn;       /* its index in `branches` in that frame */
   int shadow_valid;
   REAL shadow_total, shadow_blank;
+  REAL evicted_total; /* n_total at the moment of eviction (instrumentation) */
 } SUF(Node);
 
 typedef struct {
@@ -216,14 +217,19 @@ static void SUF(dec_reset)(SUF(Dec)* d) {
   d->frame = 0;
 }
 
-/* index within leaves of the first minimum of n_total; *second = the runner-up's value. */
+/* index within leaves of the beam bottom; *second = the runner-up's value.
+ * TIE POLICY (this repo's, documented in DESIGN.md): `leaves` is kept in arrival order (members in
+ * `branches` order, then accepted children in visiting order). Among exactly equal totals the LAST
+ * arrival is the bottom, and sorting is stable, i.e. the beam is totally ordered by
+ * (total descending, arrival ascending). The reference's order among equal keys is whatever
+ * libstdc++'s heap leaves (unspecified); the CTCX_MARGIN_* records tell where that can matter. */
 static int SUF(bottom)(const SUF(Dec)* d, REAL* second) {
   int bi = 0;
   REAL sec = (REAL)INFINITY;
   for (int i = 1; i < d->n_leaves; ++i) {
     REAL v = d->nodes[d->leaves[i]].n_total;
     REAL bv = d->nodes[d->leaves[bi]].n_total;
-    if (v < bv) {
+    if (v <= bv) {
       sec = bv;
       bi = i;
     } else if (v < sec) {
@@ -391,15 +397,18 @@ static void SUF(step)(SUF(Dec)* d, const REAL* x) {
       c->n_total = c->n_label; /* :187 */
       if (st) st->child_evals += 1;
       const int revisit = (c->stamp == d->frame); /* was a member at the start of this frame */
+      if (st && revisit && c->n_total > c->evicted_total) st->revisit_above_former += 1;
       if (SUF(is_candidate)(d, c->n_total, 1)) { /* :189 */
         if (d->n_leaves == d->W) {               /* :192-198 evict the bottom */
           REAL second;
           int k = SUF(bottom)(d, &second);
           SUF(Node)* bot = &d->nodes[d->leaves[k]];
           SUF(note)(d, CTCX_MARGIN_BOTTOM, (double)second - (double)bot->n_total);
+          bot->evicted_total = bot->n_total;
           SUF(reset_prob_new)(bot);
           SUF(reset_cands_new)(bot);
-          d->leaves[k] = d->leaves[--d->n_leaves];
+          for (int q = k + 1; q < d->n_leaves; ++q) d->leaves[q - 1] = d->leaves[q];
+          --d->n_leaves;
         }
         d->leaves[d->n_leaves++] = ci; /* :199 */
         SUF(note)(d, CTCX_MARGIN_ALIGN, (double)c->n_an.prob - (double)c->n_an.second);

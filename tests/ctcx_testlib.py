@@ -160,6 +160,7 @@ class OracleStats(ctypes.Structure):
         ("revisit_accepts", ctypes.c_longlong),
         ("max_relevant_children", ctypes.c_longlong),
         ("effective_wipes", ctypes.c_longlong),
+        ("revisit_above_former", ctypes.c_longlong),
     ]
 
 
