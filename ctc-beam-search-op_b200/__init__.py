@@ -1,0 +1,17 @@
+"""ctcx: B200-native (sm_100a) CTC "extended" beam-search decode -- a drop-in for
+prouast/ctc-beam-search-op's `ctc_ext_beam_search_decoder` (CTC beam search that also returns the
+best alignment of every returned path). See DESIGN.md / INTEGRATION.md at the repository root.
+
+    from ctc_beam_search_op_b200 import ctc_ext_beam_search_decoder
+    decoded, alignment, log_probability = ctc_ext_beam_search_decoder(
+        inputs, sequence_length, beam_width=100, top_paths=1, merge_repeated=True,
+        blank_index=28, blank_label=-1)
+"""
+from .decoder import (CTCExtBeamSearchDecoder, CtcxError, FailedPreconditionError,  # noqa: F401
+                      InvalidArgumentError, SparseTensor, UnsupportedError,
+                      ctc_ext_beam_search_decoder, ctc_ext_beam_search_decoder_raw,
+                      decode_host_cabi)
+
+__all__ = ["ctc_ext_beam_search_decoder", "ctc_ext_beam_search_decoder_raw", "decode_host_cabi",
+           "SparseTensor", "CTCExtBeamSearchDecoder", "CtcxError", "InvalidArgumentError",
+           "FailedPreconditionError", "UnsupportedError"]

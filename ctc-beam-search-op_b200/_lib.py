@@ -1,0 +1,74 @@
+"""ctypes binding of include/ctcx.h. There is no CPU fallback: if the CUDA library is missing and
+cannot be built, or no CUDA device is present, the op raises."""
+import ctypes
+import os
+
+from . import build as _build
+
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_i64pp = ctypes.POINTER(_i64p)
+_vp = ctypes.c_void_p
+
+
+class CtcxSizes(ctypes.Structure):
+    _fields_ = [("n_decoded", _i64p), ("max_decoded", _i64p), ("n_alignment", _i64p),
+                ("max_alignment", _i64p)]
+
+
+class CtcxLimits(ctypes.Structure):
+    _fields_ = [("max_beam_width", ctypes.c_int), ("max_classes", ctypes.c_int),
+                ("max_top_paths", ctypes.c_int)]
+
+
+class CtcxHostResult(ctypes.Structure):
+    _fields_ = [("top_paths", ctypes.c_int), ("n_decoded", _i64p), ("n_alignment", _i64p),
+                ("decoded_indices", _i64pp), ("decoded_values", _i64pp), ("decoded_shape", _i64pp),
+                ("alignment_indices", _i64pp), ("alignment_values", _i64pp),
+                ("alignment_shape", _i64pp), ("log_probability", ctypes.POINTER(ctypes.c_float)),
+                ("flags", ctypes.c_int32)]
+
+
+# every symbol include/ctcx.h declares (tests check that the library exports all of them)
+EXPORTS = ("ctcx_strerror", "ctcx_last_cuda_error", "ctcx_get_limits", "ctcx_workspace_bytes",
+           "ctcx_decode_f32", "ctcx_pack_f32", "ctcx_decode_host_f32", "ctcx_free_host",
+           "ctcx_workspace_views")
+
+_lib = None
+
+
+def load():
+    """Load (building first if the sources are newer) lib/libctcx.so. Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if _build.is_stale():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on this box and no prebuilt library
+            if not os.path.exists(path):
+                raise RuntimeError(
+                    "ctcx: the CUDA library %s is missing and could not be built (%s). "
+                    "There is no CPU fallback." % (path, e))
+    lib = ctypes.CDLL(path)
+    lib.ctcx_strerror.restype = ctypes.c_char_p
+    lib.ctcx_strerror.argtypes = [ctypes.c_int]
+    lib.ctcx_last_cuda_error.restype = ctypes.c_char_p
+    lib.ctcx_get_limits.argtypes = [ctypes.POINTER(CtcxLimits)]
+    lib.ctcx_workspace_bytes.restype = ctypes.c_size_t
+    lib.ctcx_workspace_bytes.argtypes = [ctypes.c_int] * 5
+    lib.ctcx_decode_f32.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int,
+                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
+                                    ctypes.c_size_t, _vp, ctypes.POINTER(CtcxSizes),
+                                    ctypes.POINTER(ctypes.c_int32)]
+    lib.ctcx_pack_f32.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [_vp] * 6 + [_vp, _vp]
+    lib.ctcx_decode_host_f32.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_int,
+                                         ctypes.POINTER(ctypes.POINTER(CtcxHostResult))]
+    lib.ctcx_free_host.argtypes = [ctypes.POINTER(CtcxHostResult)]
+    lib.ctcx_free_host.restype = None
+    lib.ctcx_workspace_views.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [_vp] * 5
+    lib.ctcx_debug_math_f32.argtypes = [ctypes.c_int, _vp, _vp, ctypes.c_int, _vp]
+    _lib = lib
+    return lib

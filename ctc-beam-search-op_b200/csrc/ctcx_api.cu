@@ -1,0 +1,467 @@
+// C-ABI shim (include/ctcx.h) over the kernels in ctcx_kernels.cuh: validation, workspace carve-up,
+// launches and the host-buffer convenience entry. No global state; no CPU fallback.
+//
+// Reference counterparts (tensorflow_ctc_ext_beam_search_decoder/cc/kernels/
+// ctc_ext_beam_search_decoder_kernels.cc): ValidateInputsGenerateOutputs :97-160, Compute :20-95,
+// StoreAllDecodedSequences :163-257.
+#include "../../include/ctcx.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "ctcx_kernels.cuh"
+
+namespace {
+
+thread_local char g_cuda_err[256] = "";
+
+bool Check(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  std::snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+  return false;
+}
+#define CTCX_CUDA(call)                                 \
+  do {                                                  \
+    if (!Check((call), #call)) return CTCX_ERR_CUDA;    \
+  } while (0)
+
+constexpr int kMaxBeamWidth = 1024;
+constexpr int kMaxClasses = 65535;
+constexpr int kListCapMax = 4608;  // candidate-list entries kept in shared memory (8 B each)
+constexpr uint32_t kMagic = 0x43544358u;  // "CTCX"
+
+size_t Align256(size_t v) { return (v + 255) / 256 * 256; }
+
+// Everything a decode leaves behind for pack, at fixed offsets inside the caller's workspace.
+struct Workspace {
+  struct Header {
+    uint32_t magic;
+    int T, B, C, W, P;
+  };
+  size_t header, off, bp, fin_total, fin_kind, fin_n, flags, dec_len, ali_len, dec, ali, dec_off,
+      ali_off, sizes, ptrs, stats, bytes;
+  void Init(int T, int B, int C, int W, int P) {
+    size_t o = 0;
+    const size_t b = (size_t)B, t = (size_t)T, w = (size_t)W, pp = (size_t)P;
+    (void)C;
+    header = o; o += Align256(sizeof(Header));
+    off = o; o += Align256(t * b * 4);
+    bp = o; o += Align256(b * t * w * 8);
+    fin_total = o; o += Align256(b * pp * 4);
+    fin_kind = o; o += Align256(b * pp * 4);
+    fin_n = o; o += Align256(b * 4);
+    flags = o; o += Align256(b * 4);
+    dec_len = o; o += Align256(b * pp * 4);
+    ali_len = o; o += Align256(b * pp * 4);
+    dec = o; o += Align256(b * pp * t * 4);
+    ali = o; o += Align256(b * pp * t * 4);
+    dec_off = o; o += Align256(pp * b * 8);
+    ali_off = o; o += Align256(pp * b * 8);
+    sizes = o; o += Align256(4 * pp * 8);
+    ptrs = o; o += Align256(6 * pp * 8);
+    stats = o; o += Align256(16 * 4);
+    bytes = o;
+  }
+};
+
+struct Tier {
+  int wmax, nt;
+};
+Tier PickTier(int W) {
+  if (W <= 32) return {32, 128};
+  if (W <= 128) return {128, 256};
+  if (W <= 256) return {256, 256};
+  return {1024, 1024};
+}
+
+template <int WMAX, int NT>
+cudaError_t LaunchBeam(const ctcx::BeamParams& p, size_t smem, cudaStream_t stream) {
+  auto kern = ctcx::BeamKernel<WMAX, NT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<p.B, NT, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// Reduces the per-utterance flags to {anomaly, too_few_leaves, first bad utterance}.
+__global__ void FlagsKernel(const int* flags, const int* seq_len, int B, int T, int* out) {
+  // out[0] = OR of anomaly bits, out[1] = first b with too few leaves (or B), out[2] = first b with
+  // sequence_length out of range (or B), out[3] = first b with negative sequence_length (or B)
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    const int f = flags ? flags[b] : 0;
+    if (f & 1) atomicOr(&out[0], 1);
+    if (f & 2) atomicMin(&out[1], b);
+    if (seq_len[b] > T) atomicMin(&out[2], b);
+    if (seq_len[b] < 0) atomicMin(&out[3], b);
+  }
+}
+
+thread_local int g_err_batch = -1;
+thread_local int g_err_max_time = 0;
+thread_local char g_msg[160];
+
+}  // namespace
+
+extern "C" {
+
+const char* ctcx_strerror(int code) {
+  switch (code) {
+    case CTCX_OK: return "ok";
+    case CTCX_ERR_INPUTS_NOT_3D: return "inputs is not a 3-Tensor";
+    case CTCX_ERR_MAX_TIME_ZERO: return "max_time is 0";
+    case CTCX_ERR_SEQ_LEN_NOT_VECTOR: return "sequence_length is not a vector";
+    case CTCX_ERR_SEQ_LEN_BATCH: return "len(sequence_length) != batch_size.  ";
+    case CTCX_ERR_SEQ_LEN_RANGE:
+      std::snprintf(g_msg, sizeof(g_msg), "sequence_length(%d) <= %d", g_err_batch, g_err_max_time);
+      return g_msg;
+    case CTCX_ERR_TOO_MANY_PATHS: return "requested more paths than the beam width.";
+    case CTCX_ERR_TOO_FEW_LEAVES: return "Less leaves in the beam search than requested.";
+    case CTCX_ERR_BAD_ARGUMENT: return "bad argument (blank_index outside [0, num_classes), negative sequence_length, or beam_width/top_paths < 1)";
+    case CTCX_ERR_UNSUPPORTED: return "shape not supported by this build (see ctcx_get_limits)";
+    case CTCX_ERR_WORKSPACE: return "workspace missing, misaligned, too small or not produced by ctcx_decode_f32";
+    case CTCX_ERR_CUDA: return g_cuda_err;
+    default: return "unknown error";
+  }
+}
+
+const char* ctcx_last_cuda_error(void) { return g_cuda_err; }
+
+int ctcx_get_limits(ctcx_limits* out) {
+  if (out) {
+    out->max_beam_width = kMaxBeamWidth;
+    out->max_classes = kMaxClasses;
+    out->max_top_paths = kMaxBeamWidth;
+  }
+  return 100;
+}
+
+size_t ctcx_workspace_bytes(int T, int B, int C, int W, int P) {
+  if (T <= 0 || B < 0 || C <= 0 || W <= 0 || P <= 0) return 0;
+  Workspace ws;
+  ws.Init(T, B, C, W, P);
+  return ws.bytes;
+}
+
+int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t* seq_len_dev, int W,
+                    int P, int merge_repeated, int blank_index, int blank_label, void* workspace,
+                    size_t workspace_bytes, void* stream_v, ctcx_sizes* sizes, int32_t* flags_out) {
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  // --- validation, in the reference's order (kernels.cc:111-138), then TopPaths' (decoder.h:237) ---
+  if (T == 0) return CTCX_ERR_MAX_TIME_ZERO;
+  if (T < 0 || B < 0 || C <= 0 || W < 1 || P < 1 || blank_index < 0 || blank_index >= C)
+    return CTCX_ERR_BAD_ARGUMENT;
+  if (W > kMaxBeamWidth || C > kMaxClasses) return CTCX_ERR_UNSUPPORTED;
+  if (sizes == nullptr) return CTCX_ERR_BAD_ARGUMENT;
+  Workspace ws;
+  ws.Init(T, B, C, W, P);
+  if (workspace == nullptr || workspace_bytes < ws.bytes || ((uintptr_t)workspace & 255u))
+    return CTCX_ERR_WORKSPACE;
+  unsigned char* base = (unsigned char*)workspace;
+  int* d_stats = (int*)(base + ws.stats);
+
+  // sequence_length range check on the device (the data lives there)
+  {
+    const int init[4] = {0, B, B, B};
+    CTCX_CUDA(cudaMemcpyAsync(d_stats, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+    if (B > 0) {
+      FlagsKernel<<<(B + 255) / 256, 256, 0, stream>>>(nullptr, seq_len_dev, B, T, d_stats);
+      CTCX_CUDA(cudaGetLastError());
+    }
+    int h[4];
+    CTCX_CUDA(cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    CTCX_CUDA(cudaStreamSynchronize(stream));
+    if (h[2] < B) {
+      g_err_batch = h[2];
+      g_err_max_time = T;
+      return CTCX_ERR_SEQ_LEN_RANGE;
+    }
+    if (h[3] < B) return CTCX_ERR_BAD_ARGUMENT;
+  }
+  // TopPaths is reached for utterance 0 only after its frames; for B == 0 it is never reached
+  if (B > 0 && P > W) return CTCX_ERR_TOO_MANY_PATHS;
+
+  Workspace::Header hdr = {kMagic, T, B, C, W, P};
+  CTCX_CUDA(cudaMemcpyAsync(base + ws.header, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, stream));
+
+  if (B > 0) {
+    // kernel 1: normalisers
+    const long long rows = (long long)T * B;
+    int sm_count = 148;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    long long blocks = (rows + 7) / 8;
+    if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
+    ctcx::LogNormKernel<<<(unsigned)blocks, 256, 0, stream>>>(logits_dev, (float*)(base + ws.off), rows, C);
+    CTCX_CUDA(cudaGetLastError());
+
+    // kernel 2: beam search
+    ctcx::BeamParams bp;
+    bp.logits = logits_dev;
+    bp.off = (const float*)(base + ws.off);
+    bp.seq_len = seq_len_dev;
+    bp.T = T; bp.B = B; bp.C = C; bp.W = W; bp.P = P;
+    bp.blank_index = blank_index;
+    bp.kid_words = (C + 31) / 32;
+    const long long full_list = (long long)W * C;
+    bp.cand_cap = (full_list <= kListCapMax) ? (int)full_list : 0;
+    bp.bp = (uint2*)(base + ws.bp);
+    bp.fin_total = (float*)(base + ws.fin_total);
+    bp.fin_kind = (int*)(base + ws.fin_kind);
+    bp.fin_n = (int*)(base + ws.fin_n);
+    bp.flags = (int*)(base + ws.flags);
+    bp.dbg_totals = nullptr;
+    bp.dbg_n = nullptr;
+    const Tier tier = PickTier(W);
+    ctcx::BeamSmem lay;
+    lay.Init(tier.wmax, tier.nt, C, bp.kid_words, bp.cand_cap);
+    if (lay.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
+    cudaError_t e;
+    switch (tier.wmax) {
+      case 32: e = LaunchBeam<32, 128>(bp, lay.bytes, stream); break;
+      case 128: e = LaunchBeam<128, 256>(bp, lay.bytes, stream); break;
+      case 256: e = LaunchBeam<256, 256>(bp, lay.bytes, stream); break;
+      default: e = LaunchBeam<1024, 1024>(bp, lay.bytes, stream); break;
+    }
+    CTCX_CUDA(e);
+
+    // kernel 3: trace-back
+    ctcx::TraceParams tp;
+    tp.bp = bp.bp; tp.seq_len = seq_len_dev; tp.fin_total = bp.fin_total; tp.fin_kind = bp.fin_kind;
+    tp.fin_n = bp.fin_n; tp.T = T; tp.B = B; tp.W = W; tp.P = P;
+    tp.merge_repeated = merge_repeated ? 1 : 0; tp.blank_label = blank_label;
+    tp.dec_len = (int*)(base + ws.dec_len); tp.dec = (int*)(base + ws.dec);
+    tp.ali_len = (int*)(base + ws.ali_len); tp.ali = (int*)(base + ws.ali);
+    const long long walks = (long long)B * P;
+    ctcx::TraceKernel<<<(unsigned)((walks + 127) / 128), 128, 0, stream>>>(tp);
+    CTCX_CUDA(cudaGetLastError());
+
+    // kernel 4: per-path offsets and sizes
+    ctcx::ScanParams sp;
+    sp.dec_len = tp.dec_len; sp.ali_len = tp.ali_len; sp.B = B; sp.P = P;
+    sp.dec_off = (long long*)(base + ws.dec_off); sp.ali_off = (long long*)(base + ws.ali_off);
+    sp.sizes = (long long*)(base + ws.sizes);
+    ctcx::ScanKernel<<<P, 1024, 0, stream>>>(sp);
+    CTCX_CUDA(cudaGetLastError());
+
+    FlagsKernel<<<(B + 255) / 256, 256, 0, stream>>>(bp.flags, seq_len_dev, B, T, d_stats);
+    CTCX_CUDA(cudaGetLastError());
+  } else {
+    CTCX_CUDA(cudaMemsetAsync(base + ws.sizes, 0, 4 * (size_t)P * 8, stream));
+  }
+
+  std::vector<long long> h_sizes(4 * (size_t)P);
+  int h_stats[4];
+  CTCX_CUDA(cudaMemcpyAsync(h_sizes.data(), base + ws.sizes, h_sizes.size() * 8, cudaMemcpyDeviceToHost, stream));
+  CTCX_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
+  CTCX_CUDA(cudaStreamSynchronize(stream));
+  if (h_stats[1] < B) return CTCX_ERR_TOO_FEW_LEAVES;
+  for (int p = 0; p < P; ++p) {
+    if (sizes->n_decoded) sizes->n_decoded[p] = h_sizes[0 * (size_t)P + p];
+    if (sizes->max_decoded) sizes->max_decoded[p] = h_sizes[1 * (size_t)P + p];
+    if (sizes->n_alignment) sizes->n_alignment[p] = h_sizes[2 * (size_t)P + p];
+    if (sizes->max_alignment) sizes->max_alignment[p] = h_sizes[3 * (size_t)P + p];
+  }
+  if (flags_out) *flags_out = h_stats[0];
+  return CTCX_OK;
+}
+
+int ctcx_pack_f32(const void* workspace, int T, int B, int P, int64_t* const* decoded_indices,
+                  int64_t* const* decoded_values, int64_t* const* decoded_shape,
+                  int64_t* const* alignment_indices, int64_t* const* alignment_values,
+                  int64_t* const* alignment_shape, float* log_probability, void* stream_v) {
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  if (workspace == nullptr || T <= 0 || B < 0 || P < 1) return CTCX_ERR_WORKSPACE;
+  const unsigned char* base = (const unsigned char*)workspace;
+  Workspace::Header hdr;
+  CTCX_CUDA(cudaMemcpyAsync(&hdr, base, sizeof(hdr), cudaMemcpyDeviceToHost, stream));
+  CTCX_CUDA(cudaStreamSynchronize(stream));
+  if (hdr.magic != kMagic || hdr.T != T || hdr.B != B || hdr.P != P) return CTCX_ERR_WORKSPACE;
+  Workspace ws;
+  ws.Init(hdr.T, hdr.B, hdr.C, hdr.W, hdr.P);
+  // device copy of the 6*P output pointers
+  std::vector<long long*> table(6 * (size_t)P);
+  for (int p = 0; p < P; ++p) {
+    table[0 * (size_t)P + p] = (long long*)decoded_indices[p];
+    table[1 * (size_t)P + p] = (long long*)decoded_values[p];
+    table[2 * (size_t)P + p] = (long long*)decoded_shape[p];
+    table[3 * (size_t)P + p] = (long long*)alignment_indices[p];
+    table[4 * (size_t)P + p] = (long long*)alignment_values[p];
+    table[5 * (size_t)P + p] = (long long*)alignment_shape[p];
+  }
+  unsigned char* wbase = (unsigned char*)workspace;
+  CTCX_CUDA(cudaMemcpyAsync(wbase + ws.ptrs, table.data(), table.size() * sizeof(void*),
+                            cudaMemcpyHostToDevice, stream));
+  if (B > 0) {
+    ctcx::PackParams pp;
+    pp.dec_len = (const int*)(base + ws.dec_len); pp.dec = (const int*)(base + ws.dec);
+    pp.ali_len = (const int*)(base + ws.ali_len); pp.ali = (const int*)(base + ws.ali);
+    pp.dec_off = (const long long*)(base + ws.dec_off); pp.ali_off = (const long long*)(base + ws.ali_off);
+    pp.sizes = (const long long*)(base + ws.sizes);
+    pp.fin_total = (const float*)(base + ws.fin_total);
+    pp.ptrs = (long long* const*)(base + ws.ptrs);
+    pp.log_prob = log_probability;
+    pp.T = T; pp.B = B; pp.P = P;
+    dim3 grid((unsigned)B, (unsigned)P);
+    ctcx::PackKernel<<<grid, 128, 0, stream>>>(pp);
+    CTCX_CUDA(cudaGetLastError());
+  } else {
+    // empty batch: shapes [0, 0]
+    const long long zeros[2] = {0, 0};
+    for (int p = 0; p < P; ++p) {
+      CTCX_CUDA(cudaMemcpyAsync(decoded_shape[p], zeros, 16, cudaMemcpyHostToDevice, stream));
+      CTCX_CUDA(cudaMemcpyAsync(alignment_shape[p], zeros, 16, cudaMemcpyHostToDevice, stream));
+    }
+  }
+  // the pointer table was staged from a stack/heap vector: make sure the copy has been consumed
+  CTCX_CUDA(cudaStreamSynchronize(stream));
+  return CTCX_OK;
+}
+
+int ctcx_workspace_views(const void* workspace, int T, int B, int P, const int32_t** dec_len,
+                         const int32_t** dec, const int32_t** ali_len, const int32_t** ali,
+                         const float** logp) {
+  if (workspace == nullptr) return CTCX_ERR_WORKSPACE;
+  const unsigned char* base = (const unsigned char*)workspace;
+  Workspace::Header hdr;
+  CTCX_CUDA(cudaMemcpy(&hdr, base, sizeof(hdr), cudaMemcpyDeviceToHost));
+  if (hdr.magic != kMagic || hdr.T != T || hdr.B != B || hdr.P != P) return CTCX_ERR_WORKSPACE;
+  Workspace ws;
+  ws.Init(hdr.T, hdr.B, hdr.C, hdr.W, hdr.P);
+  if (dec_len) *dec_len = (const int32_t*)(base + ws.dec_len);
+  if (dec) *dec = (const int32_t*)(base + ws.dec);
+  if (ali_len) *ali_len = (const int32_t*)(base + ws.ali_len);
+  if (ali) *ali = (const int32_t*)(base + ws.ali);
+  if (logp) *logp = (const float*)(base + ws.fin_total);
+  return CTCX_OK;
+}
+
+void ctcx_free_host(ctcx_host_result* r) {
+  if (!r) return;
+  auto free_list = [&](int64_t** l) {
+    if (!l) return;
+    for (int p = 0; p < r->top_paths; ++p) std::free(l[p]);
+    std::free(l);
+  };
+  free_list(r->decoded_indices);
+  free_list(r->decoded_values);
+  free_list(r->decoded_shape);
+  free_list(r->alignment_indices);
+  free_list(r->alignment_values);
+  free_list(r->alignment_shape);
+  std::free(r->n_decoded);
+  std::free(r->n_alignment);
+  std::free(r->log_probability);
+  std::free(r);
+}
+
+int ctcx_decode_host_f32(const float* logits_host, int T, int B, int C, const int32_t* seq_len_host,
+                         int W, int P, int merge_repeated, int blank_index, int blank_label,
+                         int device, ctcx_host_result** result) {
+  if (result == nullptr) return CTCX_ERR_BAD_ARGUMENT;
+  *result = nullptr;
+  if (T == 0) return CTCX_ERR_MAX_TIME_ZERO;
+  if (T < 0 || B < 0 || C <= 0 || W < 1 || P < 1) return CTCX_ERR_BAD_ARGUMENT;
+  CTCX_CUDA(cudaSetDevice(device));
+  cudaStream_t stream;
+  CTCX_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  const size_t n_logits = (size_t)T * B * C;
+  const size_t ws_bytes = ctcx_workspace_bytes(T, B, C, W, P);
+  float* d_logits = nullptr;
+  int32_t* d_seq = nullptr;
+  void* d_ws = nullptr;
+  unsigned char* d_out = nullptr;
+  int rc = CTCX_OK;
+  std::vector<int64_t> n_dec(P), max_dec(P), n_ali(P), max_ali(P);
+  ctcx_sizes sizes = {n_dec.data(), max_dec.data(), n_ali.data(), max_ali.data()};
+  int32_t flags = 0;
+  ctcx_host_result* r = nullptr;
+  std::vector<int64_t*> p_di(P), p_dv(P), p_ds(P), p_ai(P), p_av(P), p_as(P);
+  size_t out_bytes = 0;
+#define CTCX_TRY(call)                                        \
+  do {                                                        \
+    if (!Check((call), #call)) { rc = CTCX_ERR_CUDA; goto done; } \
+  } while (0)
+  CTCX_TRY(cudaMalloc(&d_logits, n_logits * 4 + 4));
+  CTCX_TRY(cudaMalloc(&d_seq, (size_t)B * 4 + 4));
+  CTCX_TRY(cudaMalloc(&d_ws, ws_bytes));
+  CTCX_TRY(cudaMemcpyAsync(d_logits, logits_host, n_logits * 4, cudaMemcpyHostToDevice, stream));
+  CTCX_TRY(cudaMemcpyAsync(d_seq, seq_len_host, (size_t)B * 4, cudaMemcpyHostToDevice, stream));
+  rc = ctcx_decode_f32(d_logits, T, B, C, d_seq, W, P, merge_repeated, blank_index, blank_label, d_ws,
+                       ws_bytes, stream, &sizes, &flags);
+  if (rc != CTCX_OK) goto done;
+  {
+    // one device block for all outputs, then one D2H copy
+    std::vector<size_t> offs;
+    size_t o = 0;
+    auto take = [&](size_t n64) { size_t at = o; o += Align256(n64 * 8); return at; };
+    std::vector<size_t> o_di(P), o_dv(P), o_ds(P), o_ai(P), o_av(P), o_as(P);
+    for (int p = 0; p < P; ++p) {
+      o_di[p] = take((size_t)n_dec[p] * 2); o_dv[p] = take((size_t)n_dec[p]); o_ds[p] = take(2);
+      o_ai[p] = take((size_t)n_ali[p] * 2); o_av[p] = take((size_t)n_ali[p]); o_as[p] = take(2);
+    }
+    const size_t o_lp = o;
+    o += Align256((size_t)B * P * 4);
+    out_bytes = o;
+    CTCX_TRY(cudaMalloc(&d_out, out_bytes + 256));
+    for (int p = 0; p < P; ++p) {
+      p_di[p] = (int64_t*)(d_out + o_di[p]); p_dv[p] = (int64_t*)(d_out + o_dv[p]); p_ds[p] = (int64_t*)(d_out + o_ds[p]);
+      p_ai[p] = (int64_t*)(d_out + o_ai[p]); p_av[p] = (int64_t*)(d_out + o_av[p]); p_as[p] = (int64_t*)(d_out + o_as[p]);
+    }
+    rc = ctcx_pack_f32(d_ws, T, B, P, p_di.data(), p_dv.data(), p_ds.data(), p_ai.data(), p_av.data(),
+                       p_as.data(), (float*)(d_out + o_lp), stream);
+    if (rc != CTCX_OK) goto done;
+    std::vector<unsigned char> h_out(out_bytes);
+    CTCX_TRY(cudaMemcpyAsync(h_out.data(), d_out, out_bytes, cudaMemcpyDeviceToHost, stream));
+    CTCX_TRY(cudaStreamSynchronize(stream));
+    r = (ctcx_host_result*)std::calloc(1, sizeof(ctcx_host_result));
+    r->top_paths = P;
+    r->flags = flags;
+    r->n_decoded = (int64_t*)std::malloc(sizeof(int64_t) * P);
+    r->n_alignment = (int64_t*)std::malloc(sizeof(int64_t) * P);
+    auto mk = [&]() { return (int64_t**)std::calloc((size_t)P, sizeof(int64_t*)); };
+    r->decoded_indices = mk(); r->decoded_values = mk(); r->decoded_shape = mk();
+    r->alignment_indices = mk(); r->alignment_values = mk(); r->alignment_shape = mk();
+    auto dup = [&](size_t at, size_t n64) {
+      int64_t* m = (int64_t*)std::malloc(n64 * 8 + 8);
+      std::memcpy(m, h_out.data() + at, n64 * 8);
+      return m;
+    };
+    for (int p = 0; p < P; ++p) {
+      r->n_decoded[p] = n_dec[p];
+      r->n_alignment[p] = n_ali[p];
+      r->decoded_indices[p] = dup(o_di[p], (size_t)n_dec[p] * 2);
+      r->decoded_values[p] = dup(o_dv[p], (size_t)n_dec[p]);
+      r->decoded_shape[p] = dup(o_ds[p], 2);
+      r->alignment_indices[p] = dup(o_ai[p], (size_t)n_ali[p] * 2);
+      r->alignment_values[p] = dup(o_av[p], (size_t)n_ali[p]);
+      r->alignment_shape[p] = dup(o_as[p], 2);
+    }
+    r->log_probability = (float*)std::malloc((size_t)B * P * 4 + 4);
+    std::memcpy(r->log_probability, h_out.data() + o_lp, (size_t)B * P * 4);
+    *result = r;
+  }
+done:
+#undef CTCX_TRY
+  cudaFree(d_logits);
+  cudaFree(d_seq);
+  cudaFree(d_ws);
+  cudaFree(d_out);
+  cudaStreamDestroy(stream);
+  return rc;
+}
+
+/* test hook: y = f(x) element-wise with the exact device math; op 0 expf, 1 log1pf, 2 logf */
+int ctcx_debug_math_f32(int op, const float* x_dev, float* y_dev, int n, void* stream_v) {
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  if (n <= 0) return CTCX_OK;
+  ctcx::MathTestKernel<<<(n + 255) / 256, 256, 0, stream>>>(op, x_dev, y_dev, n);
+  CTCX_CUDA(cudaGetLastError());
+  return CTCX_OK;
+}
+
+}  // extern "C"

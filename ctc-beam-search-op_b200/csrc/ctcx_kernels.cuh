@@ -1,0 +1,908 @@
+// Hand-written sm_100a kernels for the CTC "extended" beam-search decode.
+//
+// What each kernel replaces in the reference (paths relative to
+// tensorflow_ctc_ext_beam_search_decoder/cc/):
+//   LogNormKernel   util/ctc_ext_beam_search_decoder.h:71-80   softmax normaliser of Step()
+//   BeamKernel      util/ctc_ext_beam_search_decoder.h:84-209  Step(): extract/sort, member update,
+//                   grow + prune; util/ctc_beam_entry.h (BeamEntry trie, BeamProbability,
+//                   AddAlignmentCandidate); gtl::TopN; util/ctc_loss_util.h LogSumExp
+//   TraceKernel     util/ctc_ext_beam_search_decoder.h:229-261 TopPaths +
+//                   util/ctc_beam_entry.h:123-152 LabelSeq / AlignmentLabelSeq
+//   ScanKernel/PackKernel  kernels/ctc_ext_beam_search_decoder_kernels.cc:163-257
+//                   StoreAllDecodedSequences
+//
+// The beam kernel does NOT translate the reference's sequential trie walk. It implements the
+// parallel formulation derived in DESIGN.md (validated on the CPU by tests/model/ctcx_model.cc):
+// one CTA per utterance, the beam as sorted structure-of-arrays in shared memory, prefix identity by
+// 64-bit hash, fresh children as a filtered candidate list, the reference's order-dependent
+// "revisit-wipe" side effect as a count-based fixed point, the next beam by radix select + rank,
+// and 8-byte back-pointer records per (frame, slot) in HBM for the device trace-back.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "ctcx_math.cuh"
+
+namespace ctcx {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr unsigned long long kRootHash = 0x243F6A8885A308D3ull;
+
+// back-pointer record, word 0: [0,11) prev_self slot | [11,22) an_src slot | [22] ab_kind | [23,25) an_kind
+constexpr unsigned kInvalidSlot = 0x7ffu;
+enum { kAbFromAb = 0, kAbFromAn = 1 };
+enum { kAnSelfAn = 0, kAnParAb = 1, kAnParAn = 2, kAnNone = 3 };
+
+__device__ __forceinline__ unsigned PackRec(unsigned prev_self, unsigned an_src, unsigned ab_kind,
+                                            unsigned an_kind) {
+  return prev_self | (an_src << 11) | (ab_kind << 22) | (an_kind << 23);
+}
+
+__device__ __forceinline__ float NegInf() { return __int_as_float((int)0xff800000); }
+
+// Monotone map float -> uint32 (larger float <=> larger key); -0.0 is canonicalised to +0.0.
+__device__ __forceinline__ unsigned KeyOf(float s) {
+  const unsigned u = __float_as_uint(__fadd_rn(s, 0.0f));
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float UnKey(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+constexpr unsigned kKeyNegInf = 0x007fffffu;  // KeyOf(-inf)
+
+__device__ __forceinline__ unsigned long long HashChild(unsigned long long h, int label) {
+  unsigned long long z = (h ^ (unsigned long long)(unsigned)(label + 1)) * 0x9E3779B97F4A7C15ull;
+  z ^= z >> 29;
+  z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 32;
+  return z;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 1: per-row softmax normaliser off[t,b] = max_j x_j + logf(sum_{j in index order} expf(x_j - max))
+// (decoder.h:71-80). One warp per row; lanes evaluate expf in parallel, the float sum is accumulated
+// in index order (the reference's order) through shuffles so that the result is bit-identical.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) LogNormKernel(const float* __restrict__ logits,
+                                                     float* __restrict__ off, long long rows, int C) {
+  __shared__ unsigned long long s_tab[32];
+  LoadExpTable(s_tab, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp_global; row < rows; row += nwarps) {
+    const float* x = logits + row * C;
+    float mx = NegInf();
+    for (int j = lane; j < C; j += 32) mx = fmaxf(mx, x[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+    float sum = 0.0f;
+    for (int base = 0; base < C; base += 32) {
+      const int j = base + lane;
+      const float e = (j < C) ? ExpfExact(__fsub_rn(x[j], mx), s_tab) : 0.0f;
+      const int m = min(32, C - base);
+      for (int k = 0; k < m; ++k) sum = __fadd_rn(sum, __shfl_sync(kFull, e, k));
+    }
+    if (lane == 0) off[row] = __fadd_rn(mx, LogfExact(sum));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 2: the beam kernel.
+// ---------------------------------------------------------------------------------------------
+struct BeamParams {
+  const float* logits;  // [T,B,C] time-major raw logits
+  const float* off;     // [T,B]   normaliser from LogNormKernel
+  const int* seq_len;   // [B]
+  int T, B, C, W, P;
+  int blank_index;
+  int cand_cap;   // capacity of the shared-memory candidate list; 0 = streaming mode
+  int kid_words;  // ceil(C/32)
+  uint2* bp;      // [B,T,W] back-pointer records {packed, label}
+  float* fin_total;  // [B,P]
+  int* fin_kind;     // [B,P] 1 = best alignment ends in blank
+  int* fin_n;        // [B]   members in the final beam
+  int* flags;        // [B]   bit0 rounding anomaly, bit1 fewer leaves than top_paths
+  float* dbg_totals;  // optional [B,T,W]
+  int* dbg_n;         // optional [B,T]
+};
+
+// Shared-memory carve-up, computed identically on host and device.
+struct BeamSmem {
+  // byte offsets
+  size_t hash, phash;          // u64 [2][WMAX]
+  size_t surv;                 // u64 [WMAX]
+  size_t exptab;               // u64 [32]
+  size_t total, blk, lab, ab, an;  // f32 [2][WMAX]
+  size_t label;                // i32 [2][WMAX]
+  size_t m_nt, m_nb, m_nl, m_nab, m_nan;  // f32 [WMAX]
+  size_t m_key, m_rec;         // u32 [WMAX]
+  size_t m_pslot;              // i32 [WMAX]
+  size_t risk, risk_new;       // i32 [WMAX]
+  size_t wiped;                // u32 [WMAX] (0/1)
+  size_t part;                 // i32 [NT]
+  size_t htab;                 // i32 [2*WMAX]
+  size_t hist;                 // u32 [256]
+  size_t x;                    // f32 [2][Cpad]
+  size_t kid;                  // u32 [WMAX*kid_words]
+  size_t c_key, c_id;          // u32 [cand_cap]
+  size_t scal;                 // i32/u32 [32] scalars
+  size_t bytes;
+
+  __host__ __device__ static size_t Align(size_t v, size_t a) { return (v + a - 1) / a * a; }
+  __host__ __device__ void Init(int wmax, int nt, int C, int kid_words, int cand_cap) {
+    size_t o = 0;
+    const size_t w = (size_t)wmax;
+    hash = o; o += 2 * w * 8;
+    phash = o; o += 2 * w * 8;
+    surv = o; o += w * 8;
+    exptab = o; o += 32 * 8;
+    total = o; o += 2 * w * 4;
+    blk = o; o += 2 * w * 4;
+    lab = o; o += 2 * w * 4;
+    ab = o; o += 2 * w * 4;
+    an = o; o += 2 * w * 4;
+    label = o; o += 2 * w * 4;
+    m_nt = o; o += w * 4;
+    m_nb = o; o += w * 4;
+    m_nl = o; o += w * 4;
+    m_nab = o; o += w * 4;
+    m_nan = o; o += w * 4;
+    m_key = o; o += w * 4;
+    m_rec = o; o += w * 4;
+    m_pslot = o; o += w * 4;
+    risk = o; o += w * 4;
+    risk_new = o; o += w * 4;
+    wiped = o; o += w * 4;
+    part = o; o += (size_t)nt * 4;
+    htab = o; o += 2 * w * 4;
+    hist = o; o += 256 * 4;
+    const size_t cpad = Align((size_t)C, 4);
+    x = o; o += 2 * cpad * 4;
+    kid = o; o += w * (size_t)kid_words * 4;
+    c_key = o; o += (size_t)cand_cap * 4;
+    c_id = o; o += (size_t)cand_cap * 4;
+    scal = o; o += 32 * 4;
+    bytes = Align(o, 16);
+  }
+};
+
+// indices into the scalar block
+enum {
+  kScNCand = 0, kScNRisk, kScMinKey, kScMaxKey, kScChanged, kScPrefix, kScK, kScE, kScNSurv,
+  kScTotalItems, kScOff0, kScOff1, kScAnomaly
+};
+
+template <int WMAX, int NT>
+__global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int NWARP = NT / 32;
+  constexpr int TS = 2 * WMAX;  // hash-table slots (power of two)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const int W = p.W, C = p.C, T = p.T, B = p.B, KW = p.kid_words, blank = p.blank_index;
+  const bool list_mode = p.cand_cap > 0;
+  const int L = p.seq_len[b];
+
+  BeamSmem lay;
+  lay.Init(WMAX, NT, C, KW, p.cand_cap);
+  unsigned long long* s_hash = (unsigned long long*)(smem + lay.hash);
+  unsigned long long* s_phash = (unsigned long long*)(smem + lay.phash);
+  unsigned long long* s_surv = (unsigned long long*)(smem + lay.surv);
+  unsigned long long* s_exptab = (unsigned long long*)(smem + lay.exptab);
+  float* s_total = (float*)(smem + lay.total);
+  float* s_blk = (float*)(smem + lay.blk);
+  float* s_lab = (float*)(smem + lay.lab);
+  float* s_ab = (float*)(smem + lay.ab);
+  float* s_an = (float*)(smem + lay.an);
+  int* s_label = (int*)(smem + lay.label);
+  float* m_nt = (float*)(smem + lay.m_nt);
+  float* m_nb = (float*)(smem + lay.m_nb);
+  float* m_nl = (float*)(smem + lay.m_nl);
+  float* m_nab = (float*)(smem + lay.m_nab);
+  float* m_nan = (float*)(smem + lay.m_nan);
+  unsigned* m_key = (unsigned*)(smem + lay.m_key);
+  unsigned* m_rec = (unsigned*)(smem + lay.m_rec);
+  int* m_pslot = (int*)(smem + lay.m_pslot);
+  int* s_risk = (int*)(smem + lay.risk);
+  int* s_risk_new = (int*)(smem + lay.risk_new);
+  unsigned* s_wiped = (unsigned*)(smem + lay.wiped);
+  int* s_part = (int*)(smem + lay.part);
+  int* s_htab = (int*)(smem + lay.htab);
+  unsigned* s_hist = (unsigned*)(smem + lay.hist);
+  float* s_x = (float*)(smem + lay.x);
+  unsigned* s_kid = (unsigned*)(smem + lay.kid);
+  unsigned* c_key = (unsigned*)(smem + lay.c_key);
+  unsigned* c_id = (unsigned*)(smem + lay.c_id);
+  volatile int* sc = (volatile int*)(smem + lay.scal);
+  int* sci = (int*)(smem + lay.scal);
+  unsigned* scu = (unsigned*)(smem + lay.scal);
+  const int cpad = (int)BeamSmem::Align((size_t)C, 4);
+
+  // ---- initial state: the root (decoder.h:212-227) ----
+  LoadExpTable(s_exptab, tid, NT);
+  for (int i = tid; i < TS; i += NT) s_htab[i] = -1;
+  for (int i = tid; i < WMAX * KW; i += NT) s_kid[i] = 0u;
+  for (int i = tid; i < WMAX; i += NT) s_wiped[i] = 0u;
+  if (tid == 0) {
+    s_total[0] = 0.0f;
+    s_blk[0] = 0.0f;
+    s_lab[0] = NegInf();
+    s_ab[0] = 0.0f;  // empty alignment with probability 1 (entry.h:204-209)
+    s_an[0] = NegInf();
+    s_label[0] = -1;
+    s_hash[0] = kRootHash;
+    s_phash[0] = 0ull;
+    sci[kScAnomaly] = 0;
+  }
+  int n = 1;  // members in the beam (uniform across the CTA)
+  // row 0 of the logits
+  if (L > 0) {
+    const float* g = p.logits + (size_t)b * C;
+    for (int l = tid; l < C; l += NT) s_x[l] = g[l];
+    if (tid == 0) ((float*)sci)[kScOff0] = p.off[b];
+  }
+  __syncthreads();
+  if (tid == 0) s_htab[(unsigned)kRootHash & (TS - 1)] = 0;
+  __syncthreads();
+
+  for (int t = 0; t < L; ++t) {
+    const int cur = t & 1, nxt = cur ^ 1;
+    const float* x = s_x + cur * cpad;
+    const float off = ((const float*)sci)[kScOff0 + cur];
+    const float* o_total = s_total + cur * WMAX;
+    const float* o_blk = s_blk + cur * WMAX;
+    const float* o_lab = s_lab + cur * WMAX;
+    const float* o_ab = s_ab + cur * WMAX;
+    const float* o_an = s_an + cur * WMAX;
+    const int* o_label = s_label + cur * WMAX;
+    const unsigned long long* o_hash = s_hash + cur * WMAX;
+    const unsigned long long* o_phash = s_phash + cur * WMAX;
+
+    // prefetch the next frame's row (consumed after the barrier that ends this frame)
+    if (t + 1 < L) {
+      const float* g = p.logits + ((size_t)(t + 1) * B + b) * C;
+      float* dst = s_x + nxt * cpad;
+      for (int l = tid; l < C; l += NT) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + l);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(g + l));
+      }
+      if (tid == 0) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared((float*)sci + kScOff0 + nxt);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa),
+                     "l"(p.off + (size_t)(t + 1) * B + b));
+      }
+      asm volatile("cp.async.commit_group;\n" ::);
+    }
+    if (tid == 0) {
+      sci[kScNCand] = 0;
+      sci[kScNRisk] = 0;
+      scu[kScMinKey] = 0xffffffffu;
+      scu[kScMaxKey] = 0u;
+      sci[kScNSurv] = 0;
+    }
+    __syncthreads();
+
+    // ---- (A) update the existing members (decoder.h:95-143) ----
+    const float xb = x[blank];
+    const float pb = __fsub_rn(xb, off);
+    unsigned my_key = 0u;
+    if (tid < n) {
+      const int i = tid;
+      const int lbl = o_label[i];
+      int pslot = -1;
+      float v_nl = o_lab[i], v_an = NegInf();
+      unsigned an_kind = kAnNone, an_src = kInvalidSlot;
+      if (lbl >= 0) {
+        const unsigned long long ph = o_phash[i];
+        unsigned h = (unsigned)ph & (TS - 1);
+        for (;;) {  // parent->Active() <=> the parent prefix is in the beam (decoder.h:97)
+          const int s = s_htab[h];
+          if (s < 0) break;
+          if (o_hash[s] == ph) { pslot = s; break; }
+          h = (h + 1) & (TS - 1);
+        }
+        const float xl = x[lbl];
+        const float pl = __fsub_rn(xl, off);
+        const float self_an = __fadd_rn(o_an[i], pl);
+        if (pslot >= 0) {
+          const bool same = (lbl == o_label[pslot]);
+          const float base = same ? o_blk[pslot] : o_total[pslot];
+          v_nl = __fsub_rn(__fadd_rn(LogSumExp(o_lab[i], base, s_exptab), xl), off);  // :102-104,:113-115
+          v_an = __fadd_rn(o_ab[pslot], pl);
+          an_kind = kAnParAb;
+          an_src = (unsigned)pslot;
+          if (!same) {
+            const float c2 = __fadd_rn(o_an[pslot], pl);
+            if (c2 > v_an) { v_an = c2; an_kind = kAnParAn; }
+          }
+          if (self_an > v_an) { v_an = self_an; an_kind = kAnSelfAn; an_src = (unsigned)i; }
+        } else {
+          v_nl = __fadd_rn(o_lab[i], pl);  // :125
+          v_an = self_an;
+          an_kind = kAnSelfAn;
+          an_src = (unsigned)i;
+        }
+      }
+      const float v_nb = __fsub_rn(__fadd_rn(o_total[i], xb), off);  // :132
+      const float c1 = __fadd_rn(o_ab[i], pb), c2 = __fadd_rn(o_an[i], pb);
+      const unsigned ab_kind = (c2 > c1) ? kAbFromAn : kAbFromAb;
+      const float v_nt = LogSumExp(v_nb, v_nl, s_exptab);  // :139
+      m_nt[i] = v_nt;
+      m_nb[i] = v_nb;
+      m_nl[i] = v_nl;
+      m_nab[i] = (c2 > c1) ? c2 : c1;
+      m_nan[i] = v_an;
+      my_key = KeyOf(v_nt);
+      m_key[i] = my_key;
+      m_rec[i] = PackRec((unsigned)i, an_src, ab_kind, an_kind);
+      m_pslot[i] = pslot;
+      if (pslot >= 0) {
+        atomicOr(&s_kid[pslot * KW + (lbl >> 5)], 1u << (lbl & 31));
+        if (pslot < i) {  // the parent's turn comes first: candidate for the revisit-wipe
+          const int q = atomicAdd(&sci[kScNRisk], 1);
+          s_risk[q] = i;
+        }
+      }
+    }
+    // min / max member key
+    {
+      unsigned kmin = (tid < n) ? my_key : 0xffffffffu, kmax = (tid < n) ? my_key : 0u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(kFull, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(kFull, kmax, o));
+      }
+      if (lane == 0 && warp * 32 < n) {
+        atomicMin(&scu[kScMinKey], kmin);
+        atomicMax(&scu[kScMaxKey], kmax);
+      }
+    }
+    __syncthreads();
+    // the hash table has served this frame's look-ups: clear it for the next beam
+    for (int i = tid; i < TS; i += NT) s_htab[i] = -1;
+
+    // weakest a-priori threshold: with a full beam nothing at or below the W-th member total can
+    // ever be admitted (decoder.h:151-155); keys are compared instead of floats from here on
+    const unsigned th0 = (n == W) ? max(scu[kScMinKey], kKeyNegInf) : kKeyNegInf;
+
+    // ---- (C) fresh children above the threshold (decoder.h:161-187) ----
+    // evaluates (row, label) -> score key; used to build the list or, in streaming mode, directly
+    auto eval_child = [&](int row, int l, unsigned& skey) -> bool {
+      if (l == blank) return false;
+      if ((s_kid[row * KW + (l >> 5)] >> (l & 31)) & 1u) return false;  // c.Active(): merged in (A)
+      const float pl = __fsub_rn(x[l], off);
+      const float base = (l == o_label[row]) ? o_blk[row] : o_total[row];
+      skey = KeyOf(__fadd_rn(pl, base));  // :172-182
+      return skey > th0;
+    };
+    {
+      unsigned kmax = 0u, kmin = 0xffffffffu;
+      int cnt_stream = 0;
+      for (int row = warp; row < n; row += NWARP) {
+        for (int l0 = 0; l0 < C; l0 += 32) {
+          const int l = l0 + lane;
+          unsigned skey = 0u;
+          const bool ok = (l < C) && eval_child(row, l, skey);
+          if (ok) { kmax = max(kmax, skey); kmin = min(kmin, skey); }
+          if (list_mode) {
+            const unsigned m = __ballot_sync(kFull, ok);
+            if (m) {
+              int base = 0;
+              if (lane == 0) base = atomicAdd(&sci[kScNCand], __popc(m));
+              base = __shfl_sync(kFull, base, 0);
+              if (ok) {
+                const int pos = base + __popc(m & ((1u << lane) - 1u));
+                c_key[pos] = skey;
+                c_id[pos] = ((unsigned)row << 16) | (unsigned)l;
+              }
+            }
+          } else {
+            cnt_stream += ok ? 1 : 0;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(kFull, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(kFull, kmax, o));
+        cnt_stream += __shfl_xor_sync(kFull, cnt_stream, o);
+      }
+      if (lane == 0) {
+        if (kmax != 0u) {
+          atomicMin(&scu[kScMinKey], kmin);
+          atomicMax(&scu[kScMaxKey], kmax);
+        }
+        if (!list_mode && cnt_stream) atomicAdd(&sci[kScNCand], cnt_stream);
+      }
+    }
+    __syncthreads();
+    const int n_cand = sci[kScNCand];
+    const int n_risk = sci[kScNRisk];
+
+    // ---- (D) revisit-wipe fixed point (DESIGN.md "Parallel formulation") ----
+    bool any_wiped = false;
+    if (n_risk > 0) {
+      for (;;) {
+        if (tid == 0) sci[kScChanged] = 0;
+        for (int q = warp; q < n_risk; q += NWARP) {  // one warp per at-risk member
+          const int m = s_risk[q];
+          const int pb_slot = m_pslot[m];
+          int verdict = 0;
+          if (!s_wiped[pb_slot]) {
+            const unsigned vkey = m_key[m];
+            const unsigned idm = ((unsigned)pb_slot << 16) | (unsigned)o_label[m];
+            int cnt = 0;
+            for (int j = lane; j < n; j += 32) {
+              const unsigned kj = m_key[j];
+              cnt += (kj > vkey || (kj == vkey && j < m)) ? 1 : 0;
+            }
+            if (list_mode) {
+              for (int c = lane; c < n_cand; c += 32) {
+                const unsigned id = c_id[c];
+                cnt += (c_key[c] > vkey && id < idm && !s_wiped[id >> 16]) ? 1 : 0;
+              }
+            } else {
+              for (int row = 0; row <= pb_slot; ++row) {
+                if (s_wiped[row]) continue;
+                const int lend = (row == pb_slot) ? o_label[m] : C;
+                for (int l = lane; l < lend; l += 32) {
+                  unsigned skey;
+                  cnt += (eval_child(row, l, skey) && skey > vkey) ? 1 : 0;
+                }
+              }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
+            verdict = (cnt >= W) ? 1 : 0;
+          }
+          if (lane == 0) s_risk_new[q] = verdict;
+        }
+        __syncthreads();
+        for (int q = tid; q < n_risk; q += NT) {
+          const int m = s_risk[q];
+          const unsigned v = (unsigned)s_risk_new[q];
+          if (s_wiped[m] != v) {
+            s_wiped[m] = v;
+            sci[kScChanged] = 1;
+          }
+        }
+        __syncthreads();
+        const int changed = sc[kScChanged];
+        __syncthreads();  // everyone has read the flag before it is written again
+        if (!changed) break;
+      }
+      // documented rounding anomaly: a wiped member whose re-scored value would beat its own
+      // former total (never observed). Flag the utterance instead of modelling it.
+      for (int q = tid; q < n_risk; q += NT) {
+        const int m = s_risk[q];
+        if (s_wiped[m]) {
+          const int pslot = m_pslot[m];
+          const int lbl = o_label[m];
+          const float pl = __fsub_rn(x[lbl], off);
+          const float base = (lbl == o_label[pslot]) ? o_blk[pslot] : o_total[pslot];
+          if (KeyOf(__fadd_rn(pl, base)) > m_key[m]) sci[kScAnomaly] = 1;
+          sci[kScChanged] = 2;  // "some member is wiped"
+        }
+      }
+      __syncthreads();
+      any_wiped = (sc[kScChanged] == 2);
+    }
+
+    // ---- (E) next beam = first W items in (score desc, members before children, visiting order) ----
+    // Items are the members (key m_key, tie order = slot) and the live candidates (tie order =
+    // (row,label)). Radix select on the score key finds the W-th key; exact ties at that key are cut
+    // by a second select on the tie order.
+    auto live = [&](unsigned id) -> bool { return !any_wiped || !s_wiped[id >> 16]; };
+    // for_each_item(f): f(score_key, order_key) for every item, each handled by exactly one thread
+    auto for_each_item = [&](auto&& f) {
+      for (int i = tid; i < n; i += NT) f(m_key[i], (unsigned)i);
+      if (list_mode) {
+        for (int c = tid; c < n_cand; c += NT) {
+          const unsigned id = c_id[c];
+          if (live(id)) f(c_key[c], 0x80000000u | id);
+        }
+      } else {
+        for (int row = warp; row < n; row += NWARP) {
+          if (any_wiped && s_wiped[row]) continue;
+          for (int l = lane; l < C; l += 32) {
+            unsigned skey;
+            if (eval_child(row, l, skey)) f(skey, 0x80000000u | ((unsigned)row << 16) | (unsigned)l);
+          }
+        }
+      }
+    };
+    // one radix-select level: among items with pred(), find the K-th largest of key(); returns the
+    // selected key in sc[kScPrefix] (+lo), the number still to take at that key in sc[kScK] and the
+    // number of items equal to it in sc[kScE]; sc[kScTotalItems] = number of items seen.
+    auto radix_select = [&](unsigned lo, unsigned range, int K, auto&& keyfn) {
+      const int nbits = (range == 0u) ? 0 : (32 - __clz(range));
+      int npass = (nbits + 7) / 8;
+      if (npass == 0) npass = 1;
+      if (tid == 0) { scu[kScPrefix] = 0u; sci[kScK] = K; }
+      for (int pass = npass - 1; pass >= 0; --pass) {
+        const int shift = pass * 8;
+        for (int i = tid; i < 256; i += NT) s_hist[i] = 0u;
+        __syncthreads();
+        const unsigned prefix = scu[kScPrefix];
+        for_each_item([&](unsigned skey, unsigned okey) {
+          unsigned key;
+          if (!keyfn(skey, okey, key)) return;
+          const unsigned d = key - lo;
+          const unsigned hi = (shift + 8 >= 32) ? 0u : (d >> (shift + 8));
+          if (hi == prefix) atomicAdd(&s_hist[(d >> shift) & 255u], 1u);
+        });
+        __syncthreads();
+        if (warp == 0) {
+          const int k = sci[kScK];
+          unsigned h[8];
+          unsigned loc = 0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { h[q] = s_hist[lane * 8 + q]; loc += h[q]; }
+          unsigned suf = loc;  // inclusive suffix sum over lanes >= lane
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_down_sync(kFull, suf, o);
+            if (lane + o < 32) suf += v;
+          }
+          const unsigned above = suf - loc;  // items in higher lanes' bins
+          if (pass == npass - 1 && lane == 0) sci[kScTotalItems] = (int)suf;
+          if ((int)suf >= k && (int)above < k) {
+            unsigned acc = above;
+#pragma unroll
+            for (int q = 7; q >= 0; --q) {
+              if ((int)(acc + h[q]) >= k && (int)acc < k) {
+                scu[kScPrefix] = (prefix << 8) | (unsigned)(lane * 8 + q);
+                sci[kScK] = k - (int)acc;
+                sci[kScE] = (int)h[q];
+              }
+              acc += h[q];
+            }
+          }
+        }
+        __syncthreads();
+      }
+    };
+
+    const int n_items_upper = n + n_cand;  // before removing wiped rows
+    unsigned cut_d = 0u, cut_o = 0u;       // survivors: d > cut_d || (d == cut_d && ~okey >= cut_o)
+    const unsigned lo = scu[kScMinKey];
+    bool take_all = (!any_wiped && n_items_upper <= W);
+    if (!take_all) {
+      const unsigned range = scu[kScMaxKey] - lo;
+      radix_select(lo, range, W, [&](unsigned skey, unsigned, unsigned& key) { key = skey; return true; });
+      const int total_items = sc[kScTotalItems];
+      if (total_items <= W) {
+        take_all = true;
+      } else {
+        cut_d = scu[kScPrefix];
+        const int k_rem = sc[kScK], e = sc[kScE];
+        __syncthreads();
+        if (e != k_rem) {  // exact ties straddle the beam boundary: cut them by tie order
+          const unsigned want = cut_d + lo;
+          radix_select(0u, 0xffffffffu, k_rem, [&](unsigned skey, unsigned okey, unsigned& key) {
+            key = ~okey;
+            return skey == want;
+          });
+          cut_o = scu[kScPrefix];
+          __syncthreads();
+        }
+      }
+    }
+    // collect survivors as 64-bit composites (score key, ~tie order): larger = earlier in the beam
+    for_each_item([&](unsigned skey, unsigned okey) {
+      const unsigned d = skey - lo;
+      if (take_all || d > cut_d || (d == cut_d && ~okey >= cut_o)) {
+        const int pos = atomicAdd(&sci[kScNSurv], 1);
+        if (pos < WMAX) s_surv[pos] = ((unsigned long long)skey << 32) | (unsigned long long)(~okey);
+      }
+    });
+    __syncthreads();
+    const int n_new = min(sci[kScNSurv], WMAX);
+
+    // ---- (F) rank the survivors and write the next beam + back-pointers ----
+    {
+      static_assert(NT >= WMAX && NT % WMAX == 0, "one thread per beam slot is assumed");
+      constexpr int PARTS = NT / WMAX;
+      const int k = (PARTS > 1) ? (tid % WMAX) : tid;
+      const int part = (PARTS > 1) ? (tid / WMAX) : 0;
+      int cnt = 0;
+      if (k < n_new && part < PARTS) {
+        const unsigned long long mine = s_surv[k];
+        const int j0 = (int)((long long)n_new * part / PARTS), j1 = (int)((long long)n_new * (part + 1) / PARTS);
+        for (int j = j0; j < j1; ++j) cnt += (s_surv[j] > mine) ? 1 : 0;
+      }
+      if (PARTS > 1) {
+        s_part[tid] = cnt;
+        __syncthreads();
+        if (part == 0 && k < n_new) {
+          for (int q = 1; q < PARTS; ++q) cnt += s_part[q * WMAX + k];
+        }
+      }
+      float* w_total = s_total + nxt * WMAX;
+      float* w_blk = s_blk + nxt * WMAX;
+      float* w_lab = s_lab + nxt * WMAX;
+      float* w_ab = s_ab + nxt * WMAX;
+      float* w_an = s_an + nxt * WMAX;
+      int* w_label = s_label + nxt * WMAX;
+      unsigned long long* w_hash = s_hash + nxt * WMAX;
+      unsigned long long* w_phash = s_phash + nxt * WMAX;
+      if (part == 0 && k < n_new) {
+        const int r = cnt;  // new slot
+        const unsigned long long comp = s_surv[k];
+        const unsigned okey = ~(unsigned)(comp & 0xffffffffull);
+        unsigned rec;
+        int lbl;
+        unsigned long long hsh;
+        if (!(okey & 0x80000000u)) {  // surviving member
+          const int i = (int)okey;
+          w_total[r] = m_nt[i];
+          w_blk[r] = m_nb[i];
+          w_lab[r] = m_nl[i];
+          w_ab[r] = m_nab[i];
+          w_an[r] = m_nan[i];
+          lbl = o_label[i];
+          hsh = o_hash[i];
+          w_phash[r] = o_phash[i];
+          rec = m_rec[i];
+        } else {  // fresh child (decoder.h:170-187)
+          const int row = (int)((okey & 0x7fffffffu) >> 16);
+          lbl = (int)(okey & 0xffffu);
+          const float s = UnKey((unsigned)(comp >> 32));
+          const float pl = __fsub_rn(x[lbl], off);
+          float v_an = __fadd_rn(o_ab[row], pl);
+          unsigned an_kind = kAnParAb;
+          if (lbl != o_label[row]) {
+            const float c2 = __fadd_rn(o_an[row], pl);
+            if (c2 > v_an) { v_an = c2; an_kind = kAnParAn; }
+          }
+          w_total[r] = s;
+          w_blk[r] = NegInf();
+          w_lab[r] = s;
+          w_ab[r] = NegInf();
+          w_an[r] = v_an;
+          hsh = HashChild(o_hash[row], lbl);
+          w_phash[r] = o_hash[row];
+          rec = PackRec(kInvalidSlot, (unsigned)row, kAbFromAb, an_kind);
+        }
+        w_label[r] = lbl;
+        w_hash[r] = hsh;
+        p.bp[((size_t)b * T + t) * W + r] = make_uint2(rec, (unsigned)lbl);
+        if (p.dbg_totals) p.dbg_totals[((size_t)b * T + t) * W + r] = w_total[r];
+        // next frame's parent look-up table
+        unsigned h = (unsigned)hsh & (TS - 1);
+        while (atomicCAS(&s_htab[h], -1, r) != -1) h = (h + 1) & (TS - 1);
+      }
+      // un-mark this frame's member children and wipes
+      if (tid < n) {
+        const int ps = m_pslot[tid];
+        if (ps >= 0) s_kid[ps * KW + (o_label[tid] >> 5)] = 0u;
+        s_wiped[tid] = 0u;
+      }
+      if (p.dbg_n && tid == 0) p.dbg_n[(size_t)b * T + t] = n_new;
+    }
+    asm volatile("cp.async.wait_all;\n" ::);
+    __syncthreads();
+    n = n_new;
+  }
+
+  // ---- final beam (decoder.h:229-261): already sorted, the first P slots are the top paths ----
+  {
+    const int cur = L & 1;
+    if (tid < p.P) {
+      if (tid < n) {
+        p.fin_total[(size_t)b * p.P + tid] = s_total[cur * WMAX + tid];
+        p.fin_kind[(size_t)b * p.P + tid] = (s_ab[cur * WMAX + tid] > s_an[cur * WMAX + tid]) ? 1 : 0;
+      } else {
+        p.fin_total[(size_t)b * p.P + tid] = 0.0f;
+        p.fin_kind[(size_t)b * p.P + tid] = 0;
+      }
+    }
+    if (tid == 0) {
+      p.fin_n[b] = n;
+      p.flags[b] = (sci[kScAnomaly] ? 1 : 0) | ((p.P > n) ? 2 : 0);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 3: trace-back. One thread per (utterance, path) walks the back-pointer records from the
+// last frame to the first, emitting the alignment (entry.h:137-152) and the decoded labels
+// (entry.h:123-136, with optional repeat merging).
+// ---------------------------------------------------------------------------------------------
+struct TraceParams {
+  const uint2* bp;
+  const int* seq_len;
+  const float* fin_total;
+  const int* fin_kind;
+  const int* fin_n;
+  int T, B, W, P;
+  int merge_repeated, blank_label;
+  int* dec_len;  // [B,P]
+  int* dec;      // [B,P,T]
+  int* ali_len;  // [B,P]
+  int* ali;      // [B,P,T]
+};
+
+__global__ void __launch_bounds__(128) TraceKernel(TraceParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.B * p.P) return;
+  const int b = idx / p.P, path = idx - b * p.P;
+  const int L = p.seq_len[b];
+  int* ali = p.ali + (size_t)idx * p.T;
+  int* dec = p.dec + (size_t)idx * p.T;
+  if (path >= p.fin_n[b] || L <= 0) {
+    p.dec_len[idx] = 0;
+    p.ali_len[idx] = 0;
+    return;
+  }
+  int slot = path;
+  int kind_ab = p.fin_kind[idx];
+  const uint2* bp = p.bp + (size_t)b * p.T * p.W;
+  for (int t = L - 1; t >= 0; --t) {
+    const uint2 r = bp[(size_t)t * p.W + slot];
+    const unsigned prev_self = r.x & 0x7ffu, an_src = (r.x >> 11) & 0x7ffu;
+    const unsigned ab_kind = (r.x >> 22) & 1u, an_kind = (r.x >> 23) & 3u;
+    if (kind_ab) {
+      ali[t] = p.blank_label;
+      dec[t] = -1;
+      kind_ab = (ab_kind == kAbFromAb) ? 1 : 0;
+      slot = (int)prev_self;
+    } else {
+      ali[t] = (int)r.y;
+      if (an_kind == kAnSelfAn) {
+        dec[t] = -1;
+        slot = (int)prev_self;
+      } else {
+        dec[t] = (int)r.y;  // a new label was emitted at this frame
+        slot = (int)an_src;
+        kind_ab = (an_kind == kAnParAb) ? 1 : 0;
+      }
+    }
+  }
+  int pos = 0, prev = -1;
+  for (int t = 0; t < L; ++t) {
+    const int v = dec[t];
+    if (v >= 0) {
+      if (!p.merge_repeated || v != prev) dec[pos++] = v;
+      prev = v;
+    }
+  }
+  p.dec_len[idx] = pos;
+  p.ali_len[idx] = L;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernels 4/5: sparse packing (kernels.cc:163-257). ScanKernel: per path, exclusive prefix sums of
+// the lengths over the batch + totals + maxima. PackKernel: indices [b,pos], values, shapes.
+// ---------------------------------------------------------------------------------------------
+struct ScanParams {
+  const int* dec_len;  // [B,P]
+  const int* ali_len;  // [B,P]
+  int B, P;
+  long long* dec_off;  // [P,B]
+  long long* ali_off;  // [P,B]
+  long long* sizes;    // [4,P]: n_dec, max_dec, n_ali, max_ali
+};
+
+__global__ void __launch_bounds__(1024) ScanKernel(ScanParams p) {
+  __shared__ long long s_sum[2][32];
+  __shared__ int s_max[2][32];
+  const int path = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (p.B + 1023) / 1024;
+  const int b0 = min(p.B, tid * per), b1 = min(p.B, b0 + per);
+  long long sum[2] = {0, 0};
+  int mx[2] = {0, 0};
+  for (int b = b0; b < b1; ++b) {
+    const int d = p.dec_len[(size_t)b * p.P + path], a = p.ali_len[(size_t)b * p.P + path];
+    sum[0] += d; sum[1] += a;
+    mx[0] = max(mx[0], d); mx[1] = max(mx[1], a);
+  }
+  long long incl[2];
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {
+    long long v = sum[w];
+    int m = mx[w];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long u = __shfl_up_sync(kFull, v, o);
+      if (lane >= o) v += u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(kFull, m, o));
+    incl[w] = v;
+    if (lane == 31) s_sum[w][warp] = v;
+    if (lane == 0) s_max[w][warp] = m;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      long long v = s_sum[w][lane];
+      int m = s_max[w][lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long u = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += u;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(kFull, m, o));
+      s_sum[w][lane] = v;  // inclusive over warps
+      if (lane == 31) p.sizes[(w * 2) * p.P + path] = v;
+      if (lane == 0) p.sizes[(w * 2 + 1) * p.P + path] = m;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {
+    long long base = incl[w] - sum[w] + (warp > 0 ? s_sum[w][warp - 1] : 0);
+    long long* out = (w == 0 ? p.dec_off : p.ali_off) + (size_t)path * p.B;
+    for (int b = b0; b < b1; ++b) {
+      out[b] = base;
+      base += (w == 0) ? p.dec_len[(size_t)b * p.P + path] : p.ali_len[(size_t)b * p.P + path];
+    }
+  }
+}
+
+struct PackParams {
+  const int* dec_len; const int* dec; const int* ali_len; const int* ali;  // dense rows
+  const long long* dec_off; const long long* ali_off;                      // [P,B]
+  const long long* sizes;                                                   // [4,P]
+  const float* fin_total;                                                   // [B,P]
+  long long* const* ptrs;  // device table [6,P]: dec_idx, dec_val, dec_shape, ali_idx, ali_val, ali_shape
+  float* log_prob;         // [B,P]
+  int T, B, P;
+};
+
+__global__ void __launch_bounds__(128) PackKernel(PackParams p) {
+  const int b = blockIdx.x, path = blockIdx.y;
+  const size_t row = (size_t)b * p.P + path;
+  {
+    const int n = p.dec_len[row];
+    const long long o = p.dec_off[(size_t)path * p.B + b];
+    long long* idx = p.ptrs[0 * p.P + path];
+    long long* val = p.ptrs[1 * p.P + path];
+    const int* src = p.dec + row * p.T;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      idx[2 * (o + i)] = b;
+      idx[2 * (o + i) + 1] = i;
+      val[o + i] = src[i];
+    }
+  }
+  {
+    const int n = p.ali_len[row];
+    const long long o = p.ali_off[(size_t)path * p.B + b];
+    long long* idx = p.ptrs[3 * p.P + path];
+    long long* val = p.ptrs[4 * p.P + path];
+    const int* src = p.ali + row * p.T;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      idx[2 * (o + i)] = b;
+      idx[2 * (o + i) + 1] = i;
+      val[o + i] = src[i];
+    }
+  }
+  if (threadIdx.x == 0) {
+    p.log_prob[row] = p.fin_total[row];  // kernels.cc:87-89
+    if (b == 0) {
+      long long* ds = p.ptrs[2 * p.P + path];
+      long long* as = p.ptrs[5 * p.P + path];
+      ds[0] = p.B; ds[1] = p.sizes[1 * p.P + path];  // kernels.cc:236-237
+      as[0] = p.B; as[1] = p.sizes[3 * p.P + path];  // kernels.cc:253-254
+    }
+  }
+}
+
+// Test hook: element-wise evaluation of the exact math functions.
+__global__ void MathTestKernel(int op, const float* x, float* y, int n) {
+  __shared__ unsigned long long s_tab[32];
+  LoadExpTable(s_tab, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  y[i] = (op == 0) ? ExpfExact(v, s_tab) : (op == 1) ? Log1pfExact(v) : LogfExact(v);
+}
+
+}  // namespace ctcx

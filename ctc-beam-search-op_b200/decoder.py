@@ -1,0 +1,219 @@
+"""Host side of the drop-in: `ctc_ext_beam_search_decoder` with the reference's signature.
+
+Mirrors (paths relative to /root/reference/tensorflow_ctc_ext_beam_search_decoder/):
+  * the op contract                      cc/ops/ctc_ext_beam_search_decoder_ops.cc:9-24
+  * the Python surface                   python/ops/ctc_ext_beam_search_decoder_ops.py:10-12
+    (the generated raw wrapper: keyword call, result indexable [0..6] -- see
+    python/ops/ctc_ext_beam_search_decoder_ops_test.py:67-100)
+  * the documented return value          README.md:19-31  `(decoded, alignment, log_probability)`
+  * validation order and messages        cc/kernels/ctc_ext_beam_search_decoder_kernels.cc:97-160
+                                         cc/util/ctc_ext_beam_search_decoder.h:237-243
+
+All compute happens in the CUDA library behind include/ctcx.h; PyTorch is used only for device
+memory and streams. There is no CPU path: without a CUDA device the call raises.
+"""
+import collections
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+SparseTensor = collections.namedtuple("SparseTensor", ["indices", "values", "dense_shape"])
+
+# Same field order as the raw op's outputs (ops.cc:17-23); indexable like the generated TF wrapper.
+CTCExtBeamSearchDecoder = collections.namedtuple(
+    "CTCExtBeamSearchDecoder",
+    ["decoded_indices", "decoded_values", "decoded_shape", "alignment_indices", "alignment_values",
+     "alignment_shape", "log_probability"])
+
+
+class CtcxError(ValueError):
+    """Base class; `.code` is the C-ABI return code (include/ctcx.h)."""
+
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = code
+
+
+class InvalidArgumentError(CtcxError):
+    """tf.errors.InvalidArgumentError counterpart."""
+
+
+class FailedPreconditionError(CtcxError):
+    """tf.errors.FailedPreconditionError counterpart."""
+
+
+class UnsupportedError(CtcxError):
+    """Shape outside the limits of this build (not a reference error)."""
+
+
+_ERR_CLASS = {1: InvalidArgumentError, 2: InvalidArgumentError, 3: InvalidArgumentError,
+              4: FailedPreconditionError, 5: FailedPreconditionError, 6: InvalidArgumentError,
+              7: InvalidArgumentError, 8: InvalidArgumentError, 9: UnsupportedError}
+
+FLAG_ROUNDING_ANOMALY = 1  # see DESIGN.md "Known deviation"
+
+last_flags = 0  # flags of the most recent decode in this process (diagnostics only)
+
+
+def _raise(lib, rc):
+    msg = lib.ctcx_strerror(rc).decode()
+    if rc in _ERR_CLASS:
+        raise _ERR_CLASS[rc](rc, msg)
+    raise RuntimeError("ctcx: %s (code %d)" % (msg, rc))
+
+
+def _as_tensor(a):
+    if isinstance(a, torch.Tensor):
+        return a, False
+    return torch.from_numpy(np.ascontiguousarray(a)), True
+
+
+def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_paths,
+                                    merge_repeated=False, blank_index=0, blank_label=-1,
+                                    name=None, device=None):
+    """The raw op: returns a 7-field namedtuple of (lists of) tensors, exactly the op's outputs.
+
+    inputs            [max_time, batch, num_classes] float32 (float64 is accepted: computed in
+                      float32, log_probability returned as float64), numpy array or torch tensor on
+                      any device
+    sequence_length   [batch] int32
+    beam_width >= 1, top_paths >= 1, merge_repeated=False, blank_index=0, blank_label=-1
+    Outputs live where the inputs live (numpy in -> numpy out).
+    """
+    del name
+    if int(beam_width) < 1:
+        raise ValueError("Attr beam_width has value %d less than minimum 1" % int(beam_width))
+    if int(top_paths) < 1:
+        raise ValueError("Attr top_paths has value %d less than minimum 1" % int(top_paths))
+    lib = _lib.load()
+    x, x_np = _as_tensor(inputs)
+    seq, _ = _as_tensor(np.asarray(sequence_length, dtype=np.int32)
+                        if not isinstance(sequence_length, torch.Tensor) else sequence_length)
+    # kernels.cc:111-130, in order
+    if x.dim() != 3:
+        raise InvalidArgumentError(1, lib.ctcx_strerror(1).decode())
+    T, B, C = (int(s) for s in x.shape)
+    if T == 0:
+        raise InvalidArgumentError(2, lib.ctcx_strerror(2).decode())
+    if seq.dim() != 1:
+        raise InvalidArgumentError(3, lib.ctcx_strerror(3).decode())
+    if int(seq.shape[0]) != B:
+        raise FailedPreconditionError(
+            4, "len(sequence_length) != batch_size.  len(sequence_length):  %d batch_size: %d"
+            % (int(seq.shape[0]), B))
+    if not x.dtype.is_floating_point:
+        raise TypeError("inputs must be float32 or float64, got %s" % x.dtype)
+    if not torch.cuda.is_available():
+        raise RuntimeError("ctcx: no CUDA device available and there is no CPU fallback")
+
+    out_dtype = torch.float64 if x.dtype == torch.float64 else torch.float32
+    if device is None:
+        device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    host_out = not x.is_cuda
+    with torch.cuda.device(device):
+        xd = x.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+        sd = seq.to(device=device, dtype=torch.int32, non_blocking=True).contiguous()
+        stream = torch.cuda.current_stream(device).cuda_stream
+        P = int(top_paths)
+        ws_bytes = lib.ctcx_workspace_bytes(T, B, C, int(beam_width), P)
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=device)
+        arr = ctypes.c_int64 * P
+        n_dec, max_dec, n_ali, max_ali = arr(), arr(), arr(), arr()
+        sizes = _lib.CtcxSizes(n_dec, max_dec, n_ali, max_ali)
+        flags = ctypes.c_int32(0)
+        rc = lib.ctcx_decode_f32(xd.data_ptr(), T, B, C, sd.data_ptr(), int(beam_width), P,
+                                 int(bool(merge_repeated)), int(blank_index), int(blank_label),
+                                 ws.data_ptr(), ws_bytes, stream, ctypes.byref(sizes),
+                                 ctypes.byref(flags))
+        if rc != 0:
+            _raise(lib, rc)
+        global last_flags
+        last_flags = int(flags.value)
+        i64 = dict(dtype=torch.int64, device=device)
+        dec_idx = [torch.empty((int(n_dec[p]), 2), **i64) for p in range(P)]
+        dec_val = [torch.empty((int(n_dec[p]),), **i64) for p in range(P)]
+        dec_shp = [torch.empty((2,), **i64) for p in range(P)]
+        ali_idx = [torch.empty((int(n_ali[p]), 2), **i64) for p in range(P)]
+        ali_val = [torch.empty((int(n_ali[p]),), **i64) for p in range(P)]
+        ali_shp = [torch.empty((2,), **i64) for p in range(P)]
+        logp = torch.empty((B, P), dtype=torch.float32, device=device)
+        ptrs = ctypes.c_void_p * P
+
+        def table(ts):
+            return ptrs(*[t.data_ptr() for t in ts])
+
+        rc = lib.ctcx_pack_f32(ws.data_ptr(), T, B, P, table(dec_idx), table(dec_val), table(dec_shp),
+                               table(ali_idx), table(ali_val), table(ali_shp), logp.data_ptr(), stream)
+        if rc != 0:
+            _raise(lib, rc)
+        logp = logp.to(out_dtype)
+        groups = [dec_idx, dec_val, dec_shp, ali_idx, ali_val, ali_shp]
+        if host_out:
+            groups = [[t.cpu() for t in g] for g in groups]
+            logp = logp.cpu()
+            if x_np:
+                groups = [[t.numpy() for t in g] for g in groups]
+                logp = logp.numpy()
+    return CTCExtBeamSearchDecoder(*groups, logp)
+
+
+def ctc_ext_beam_search_decoder(inputs, sequence_length, beam_width, top_paths,
+                                merge_repeated=False, blank_index=0, blank_label=-1, name=None,
+                                device=None):
+    """`(decoded, alignment, log_probability)` as documented by the reference (README.md:19-31):
+    decoded[j] / alignment[j] are SparseTensor(indices [N,2] rows [batch, position], values [N],
+    dense_shape [batch, max length]) for path j; log_probability is [batch, top_paths]."""
+    raw = ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_paths,
+                                          merge_repeated, blank_index, blank_label, name, device)
+    decoded = [SparseTensor(i, v, s) for i, v, s in zip(raw[0], raw[1], raw[2])]
+    alignment = [SparseTensor(i, v, s) for i, v, s in zip(raw[3], raw[4], raw[5])]
+    return decoded, alignment, raw[6]
+
+
+def decode_host_cabi(inputs, sequence_length, beam_width, top_paths, merge_repeated=False,
+                     blank_index=0, blank_label=-1, device=0):
+    """The host-buffer C-ABI entry (ctcx_decode_host_f32) exactly as a TensorFlow CPU OpKernel
+    would call it: numpy in, numpy out, all copies inside the call."""
+    lib = _lib.load()
+    x = np.ascontiguousarray(inputs, dtype=np.float32)
+    if x.ndim != 3:
+        raise InvalidArgumentError(1, lib.ctcx_strerror(1).decode())
+    seq = np.ascontiguousarray(sequence_length, dtype=np.int32)
+    if seq.ndim != 1:
+        raise InvalidArgumentError(3, lib.ctcx_strerror(3).decode())
+    T, B, C = x.shape
+    if seq.shape[0] != B:
+        raise FailedPreconditionError(
+            4, "len(sequence_length) != batch_size.  len(sequence_length):  %d batch_size: %d"
+            % (seq.shape[0], B))
+    res = ctypes.POINTER(_lib.CtcxHostResult)()
+    rc = lib.ctcx_decode_host_f32(x.ctypes.data, T, B, C, seq.ctypes.data, int(beam_width),
+                                  int(top_paths), int(bool(merge_repeated)), int(blank_index),
+                                  int(blank_label), int(device), ctypes.byref(res))
+    if rc != 0:
+        _raise(lib, rc)
+    try:
+        r = res.contents
+        P = r.top_paths
+
+        def arr(pp, n):
+            return np.ctypeslib.as_array(pp, shape=(n,)).copy() if n else np.zeros((0,), np.int64)
+
+        out = [[], [], [], [], [], []]
+        for p in range(P):
+            nd, na = int(r.n_decoded[p]), int(r.n_alignment[p])
+            out[0].append(arr(r.decoded_indices[p], nd * 2).reshape(nd, 2))
+            out[1].append(arr(r.decoded_values[p], nd))
+            out[2].append(arr(r.decoded_shape[p], 2))
+            out[3].append(arr(r.alignment_indices[p], na * 2).reshape(na, 2))
+            out[4].append(arr(r.alignment_values[p], na))
+            out[5].append(arr(r.alignment_shape[p], 2))
+        logp = (np.ctypeslib.as_array(r.log_probability, shape=(B * P,)).copy().reshape(B, P)
+                if B * P else np.zeros((B, P), np.float32))
+    finally:
+        lib.ctcx_free_host(res)
+    return CTCExtBeamSearchDecoder(*out, logp)

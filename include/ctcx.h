@@ -1,0 +1,138 @@
+/* ctcx -- B200-native CTC "extended" beam-search decode (sm_100a): C-ABI boundary.
+ *
+ * This header is the drop-in boundary for ONE operator of prouast/ctc-beam-search-op: the TensorFlow
+ * custom op `CTCExtBeamSearchDecoder`. Citations are relative to
+ * tensorflow_ctc_ext_beam_search_decoder/cc/ in the reference:
+ *   ops/ctc_ext_beam_search_decoder_ops.cc:9-24          the op signature (inputs, attrs, outputs)
+ *   kernels/ctc_ext_beam_search_decoder_kernels.cc:20-95 CTCExtBeamSearchDecoderOp<T>::Compute
+ *   kernels/...kernels.cc:97-160                         ValidateInputsGenerateOutputs
+ *   kernels/...kernels.cc:163-257                        StoreAllDecodedSequences (sparse packing)
+ *   util/ctc_ext_beam_search_decoder.h:229-261           TopPaths (its two InvalidArgument errors)
+ *
+ * Plain pointers and sizes only; no torch/TF types. Output sizes are data dependent, so a decode is
+ * two calls: ctcx_decode_* runs the kernels and reports, per path, how many sparse entries there are;
+ * the caller allocates and ctcx_pack_* fills the 6*top_paths int64 tensors and log_probability.
+ * The library keeps no global state: everything lives in the caller's workspace, so calls on
+ * different streams/workspaces may run concurrently (the reference's Compute is re-entrant too).
+ *
+ * There is NO CPU fallback: every entry point needs a CUDA device of compute capability 10.x.
+ */
+#ifndef CTCX_H_
+#define CTCX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Return codes. 1-7 map 1:1 to the reference's Status errors (message text in ctcx_strerror). */
+enum {
+  CTCX_OK = 0,
+  CTCX_ERR_INPUTS_NOT_3D = 1,       /* kernels.cc:111-113 "inputs is not a 3-Tensor" (host side) */
+  CTCX_ERR_MAX_TIME_ZERO = 2,       /* kernels.cc:118-120 "max_time is 0" */
+  CTCX_ERR_SEQ_LEN_NOT_VECTOR = 3,  /* kernels.cc:122-124 "sequence_length is not a vector" (host) */
+  CTCX_ERR_SEQ_LEN_BATCH = 4,       /* kernels.cc:126-130 "len(sequence_length) != batch_size. ..." */
+  CTCX_ERR_SEQ_LEN_RANGE = 5,       /* kernels.cc:134-138 "sequence_length(b) <= max_time" */
+  CTCX_ERR_TOO_MANY_PATHS = 6,      /* decoder.h:237-239 "requested more paths than the beam width." */
+  CTCX_ERR_TOO_FEW_LEAVES = 7,      /* decoder.h:240-243 "Less leaves in the beam search than requested." */
+  CTCX_ERR_BAD_ARGUMENT = 8,        /* not validated by the reference (UB there): blank_index outside
+                                       [0,C), negative sequence_length, beam_width/top_paths < 1 */
+  CTCX_ERR_UNSUPPORTED = 9,         /* shape outside what this build supports (see ctcx_limits) */
+  CTCX_ERR_WORKSPACE = 10,          /* workspace too small / NULL */
+  CTCX_ERR_CUDA = 11                /* a CUDA runtime call failed; ctcx_last_cuda_error() has it */
+};
+
+/* Human-readable text of a return code; for 1-7 the reference's own message. `detail` (may be NULL)
+ * receives e.g. the offending batch index for CTCX_ERR_SEQ_LEN_RANGE. */
+const char* ctcx_strerror(int code);
+
+/* Last CUDA error string seen by this thread ("" if none). */
+const char* ctcx_last_cuda_error(void);
+
+/* Library build info: returns the sm arch the kernels were built for (100), fills limits. */
+typedef struct {
+  int max_beam_width;  /* largest supported beam_width */
+  int max_classes;     /* largest supported num_classes */
+  int max_top_paths;   /* bounded by beam_width anyway */
+} ctcx_limits;
+int ctcx_get_limits(ctcx_limits* out);
+
+/* Bytes of device workspace needed by ctcx_decode_f32 for this shape (0 on invalid shape). */
+size_t ctcx_workspace_bytes(int max_time, int batch, int num_classes, int beam_width, int top_paths);
+
+/* Per-path sparse sizes produced by a decode (host memory, caller-allocated, top_paths entries each). */
+typedef struct {
+  int64_t* n_decoded;     /* [P] total decoded entries over the batch   (rows of decoded_indices[p]) */
+  int64_t* max_decoded;   /* [P] longest decoded sequence               (decoded_shape[p][1])        */
+  int64_t* n_alignment;   /* [P] total alignment entries over the batch (rows of alignment_indices[p]) */
+  int64_t* max_alignment; /* [P] longest alignment                      (alignment_shape[p][1])      */
+} ctcx_sizes;
+
+/* Decode: replaces Compute's validation + batch/time loops + TopPaths (kernels.cc:20-90).
+ *   logits_dev   [max_time, batch, num_classes] float32, time-major, raw logits, DEVICE memory
+ *   seq_len_dev  [batch] int32, DEVICE memory
+ *   attrs        as ops.cc:12-16 (merge_repeated / blank_index / blank_label defaults are the host's job)
+ *   workspace    DEVICE memory of at least ctcx_workspace_bytes(...) bytes, 256-byte aligned; it holds
+ *                the decode result until ctcx_pack_f32 has run
+ *   stream       cudaStream_t (as void*), may be NULL for the default stream
+ *   sizes        host output, see ctcx_sizes
+ *   flags_out    optional host int32: bit0 = some utterance hit the documented rounding anomaly
+ * Synchronises `stream` once (sizes must reach the host). */
+int ctcx_decode_f32(const float* logits_dev, int max_time, int batch, int num_classes,
+                    const int32_t* seq_len_dev, int beam_width, int top_paths, int merge_repeated,
+                    int blank_index, int blank_label, void* workspace, size_t workspace_bytes,
+                    void* stream, ctcx_sizes* sizes, int32_t* flags_out);
+
+/* Pack: replaces StoreAllDecodedSequences (kernels.cc:163-257) and the log-prob copy (:87-89).
+ * All pointers are DEVICE memory; arrays of `top_paths` device pointers are HOST arrays.
+ *   decoded_indices[p]   int64 [n_decoded[p], 2]   rows [b, position], row-major over b then position
+ *   decoded_values[p]    int64 [n_decoded[p]]
+ *   decoded_shape[p]     int64 [2] = [batch, max_decoded[p]]
+ *   alignment_*          likewise
+ *   log_probability      float32 [batch, top_paths]
+ * Does not synchronise. */
+int ctcx_pack_f32(const void* workspace, int max_time, int batch, int top_paths,
+                  int64_t* const* decoded_indices, int64_t* const* decoded_values,
+                  int64_t* const* decoded_shape, int64_t* const* alignment_indices,
+                  int64_t* const* alignment_values, int64_t* const* alignment_shape,
+                  float* log_probability, void* stream);
+
+/* Host-buffer entry point: what a TensorFlow CPU OpKernel::Compute (the reference's only
+ * registration, kernels.cc:269-275) would call with its host tensors. Copies the inputs to the
+ * device, decodes, and returns one malloc'd host block per output group which the caller copies into
+ * its framework-allocated tensors and releases with ctcx_free_host. Layout of the result:
+ *   for p in [0,P): dec_indices[p] (n_decoded[p]*2 int64), dec_values[p], dec_shape[p] (2),
+ *                   ali_indices[p], ali_values[p], ali_shape[p]; then log_probability.
+ * device = CUDA device ordinal. */
+typedef struct {
+  int top_paths;
+  int64_t* n_decoded;       /* [P] */
+  int64_t* n_alignment;     /* [P] */
+  int64_t** decoded_indices;   /* [P] -> [n_decoded[p]*2] */
+  int64_t** decoded_values;    /* [P] -> [n_decoded[p]]   */
+  int64_t** decoded_shape;     /* [P] -> [2]              */
+  int64_t** alignment_indices; /* [P] -> [n_alignment[p]*2] */
+  int64_t** alignment_values;  /* [P] -> [n_alignment[p]] */
+  int64_t** alignment_shape;   /* [P] -> [2]              */
+  float* log_probability;      /* [batch*top_paths]       */
+  int32_t flags;
+} ctcx_host_result;
+
+int ctcx_decode_host_f32(const float* logits_host, int max_time, int batch, int num_classes,
+                         const int32_t* seq_len_host, int beam_width, int top_paths,
+                         int merge_repeated, int blank_index, int blank_label, int device,
+                         ctcx_host_result** result);
+void ctcx_free_host(ctcx_host_result* result);
+
+/* Debug/test hook: dense per-(b,p) rows as left in the workspace by ctcx_decode_f32 (device
+ * pointers into the workspace; stride max_time per row). Any output pointer may be NULL. */
+int ctcx_workspace_views(const void* workspace, int max_time, int batch, int top_paths,
+                         const int32_t** dec_len, const int32_t** dec, const int32_t** ali_len,
+                         const int32_t** ali, const float** logp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTCX_H_ */
