@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the CTC extended beam-search decode (BASELINE.json metric: utterance-frames
+decoded per second at beam=100).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--kind gauss|peaky]
+
+One "step" = one decode of one batch of synthetic logits: the LibriSpeech char-CTC shape the metric
+is quoted on (BASELINE.json configs[1]): T=500, B=256 per GPU, C=29 (blank=28), beam_width=100,
+top_paths=1, merge_repeated=true. Multi-GPU: utterances are independent, so every rank decodes its
+own B=256 batch (weak scaling, no collective on the data path); value = frames of all ranks / max
+time over ranks.
+
+Own arm: `value` times the op with logits resident in HBM (CUDA events, decode + pack, outputs left
+on the device); `e2e` times the public call with pinned HOST logits and HOST results (H2D + decode +
+pack + D2H inside the timed region). `roofline` is for the dominant kernel (the beam kernel):
+algorithmic bytes = 4*C per frame (the fp32 logits, read once) over its CUDA-event duration, against
+the measured HBM peak in MEASURED_PEAKS.json. `cpu_baseline` times the reference's own CPU
+implementation (oracle/_ref, compiled from the reference's unmodified headers; falls back to the
+plain-C port in oracle/) on the host cores on a bounded sample of the same workload.
+
+Reference arm (--impl reference): the reference CPU op on all host cores, same config and metric.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CFG = dict(workload="librispeech-char-ctc (BASELINE configs[1])", T=500, B=256, C=29, blank_index=28,
+           beam_width=100, top_paths=1, merge_repeated=True, blank_label=-1)
+L2_BYTES = 126 * 1024 * 1024
+
+
+def make_batch(kind, seed, T, B, C, blank):
+    import ctcx_testlib as L
+    return L.make_logits(kind, T, B, C, blank, seed)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(x, n_utt, threads):
+    """Decode the first n_utt utterances of x with the reference CPU implementation on `threads`
+    host threads (one utterance per task; the library releases the GIL). Returns (seconds, kind)."""
+    import ctcx_testlib as L
+    L.build_oracles()
+    T, B, C = x.shape
+    sl = np.full(B, T, np.int32)
+    kind = "reference" if L.have_ref() else "port"
+
+    def one(b):
+        if kind == "reference":
+            L.ref_decode(x, sl, CFG["beam_width"], CFG["top_paths"], CFG["merge_repeated"],
+                         CFG["blank_index"], CFG["blank_label"], b_range=(b, b + 1))
+        else:
+            L.oracle_decode(x[:, b:b + 1], sl[b:b + 1], CFG["beam_width"], CFG["top_paths"],
+                            CFG["merge_repeated"], CFG["blank_index"], CFG["blank_label"])
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(one, range(n_utt)))
+    return time.perf_counter() - t0, kind
+
+
+def host_threads():
+    """Host threads used for the CPU reference: all cores the process may use, capped at 64 (the
+    reference keeps ~0.5 GB of trie per in-flight utterance)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 64))
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = host_threads()
+    T, B, C = CFG["T"], CFG["B"], CFG["C"]
+    x = make_batch(args.kind, 1, T, B, C, CFG["blank_index"])
+    n_utt = min(B, cores)  # one utterance per core per step: a bounded sample of the workload
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_reference_run(x, min(n_utt, cores), cores)
+    times = []
+    kind = "reference"
+    for _ in range(args.steps):
+        dt, kind = cpu_reference_run(x, n_utt, cores)
+        times.append(dt)
+    total = sum(times)
+    value = n_utt * T * len(times) / total
+    line = {
+        "impl": "reference", "metric": "utterance_frames_per_s_beam100", "value": value,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (%s logits, seed 1)" % args.kind,
+        "config": dict(CFG, n_gpus=args.gpus, kind=args.kind,
+                       note="CPU reference; each step decodes %d utterances (1 per host thread)" % n_utt),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
+                         "sample": "%d utterances of T=%d per step, %d steps" % (n_utt, T, len(times))},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_own_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import ctc_beam_search_op_b200 as op
+    from ctc_beam_search_op_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    T, B, C = CFG["T"], CFG["B"], CFG["C"]
+    W, P = CFG["beam_width"], CFG["top_paths"]
+    kw = dict(beam_width=W, top_paths=P, merge_repeated=CFG["merge_repeated"],
+              blank_index=CFG["blank_index"], blank_label=CFG["blank_label"])
+
+    # inputs rotate over enough distinct batches that consecutive steps never find their logits in
+    # L2 (total > 126 MB); every step also streams ~100 MB of back-pointer records through L2.
+    bytes_per_batch = T * B * C * 4
+    n_rot = L2_BYTES // bytes_per_batch + 2
+    base = make_batch(args.kind, 1 + rank, T, B, C, CFG["blank_index"])
+    host_batches, dev_batches = [], []
+    rng = np.random.default_rng(77 + rank)
+    for r in range(n_rot):
+        xb = base if r == 0 else np.ascontiguousarray(base[:, rng.permutation(B), :])
+        hb = torch.from_numpy(xb).pin_memory()
+        host_batches.append(hb)
+        dev_batches.append(hb.to(dev))
+    seq_host = torch.full((B,), T, dtype=torch.int32).pin_memory()
+    seq_dev = seq_host.to(dev)
+    frames_per_step = T * B
+
+    def step_device(i):
+        return op.ctc_ext_beam_search_decoder_raw(dev_batches[i % n_rot], seq_dev, **kw)
+
+    def step_e2e(i):
+        return op.ctc_ext_beam_search_decoder_raw(host_batches[i % n_rot], seq_host, **kw)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for i in range(max(args.warmup, 3)):
+        step_device(i)
+    step_e2e(0)
+    barrier()
+
+    # ---- device-resident timing (CUDA events per step on the launching stream) ----
+    lib.ctcx_profile_enable(1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    kern_ms = np.zeros((args.steps, 5), np.float32)
+    buf = (ctypes.c_float * 5)()
+    barrier()
+    wall0 = time.perf_counter()
+    for i, (e0, e1) in enumerate(evs):
+        e0.record()
+        step_device(i)
+        e1.record()
+        lib.ctcx_profile_get(buf)
+        kern_ms[i] = list(buf)
+    barrier()
+    wall_dev = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    lib.ctcx_profile_enable(0)
+    dev_ms = float(sum(e0.elapsed_time(e1) for e0, e1 in evs))
+
+    # ---- end-to-end timing: pinned host logits in, host results out ----
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for i in range(args.steps):
+        out = step_e2e(i)
+        d2h = sum(t.numel() * t.element_size() for g in out[:6] for t in g) + out[6].numel() * 4
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+    else:
+        e2e_ms = e2e_s * 1e3
+    if rank != 0:
+        return
+
+    total_frames = frames_per_step * args.steps * world
+    value = total_frames / (dev_ms * 1e-3)
+    e2e_value = total_frames / (e2e_ms * 1e-3)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    beam_ms = float(kern_ms[:, 1].mean())
+    algo_bytes = 4.0 * C * frames_per_step  # per beam-kernel launch
+    achieved = algo_bytes / (beam_ms * 1e-3) / 1e9
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "beam_kernel_traffic.json")
+    if os.path.exists(tr_path):
+        traffic = json.load(open(tr_path)).get("dram_bytes_per_launch")
+
+    line = {
+        "metric": "utterance_frames_per_s_beam100", "value": value, "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (%s logits, seed 1+rank)" % args.kind,
+        "config": dict(CFG, n_gpus=world, kind=args.kind, global_batch=B * world,
+                       l2="inputs rotate over %d distinct batches (%.0f MB > 126 MB L2)"
+                          % (n_rot, n_rot * bytes_per_batch / 1e6)),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": bytes_per_batch + B * 4,
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": 7 * args.steps,
+        "kernel_ms": {"lognorm": float(kern_ms[:, 0].mean()), "beam": beam_ms,
+                      "trace": float(kern_ms[:, 2].mean()), "scan": float(kern_ms[:, 3].mean()),
+                      "wall_ms_per_step": 1e3 * wall_dev / args.steps},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "kernel": "BeamKernel<128,256>",
+                     "peak_source": peak_src,
+                     "note": "algorithmic bytes = 4*C per frame (logits read once); the kernel is "
+                             "bound by the T-long serial recurrence per utterance, not by HBM"},
+    }
+    if not args.no_cpu_baseline:
+        cores = host_threads()
+        n_utt = min(B, cores)
+        dt, kind = cpu_reference_run(base, n_utt, cores)
+        dt1, _ = cpu_reference_run(base, 1, 1)
+        line["cpu_baseline"] = {"value": n_utt * T / dt, "unit": "frames/s", "cores": cores, "kind": kind,
+                                "sample": "%d utterances of this workload, one per host thread (%.1f s); "
+                                          "1 thread alone: %.0f frames/s" % (n_utt, dt, T / dt1)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kind", default="gauss", choices=["gauss", "peaky"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_own_arm(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

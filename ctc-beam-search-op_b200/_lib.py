@@ -69,6 +69,10 @@ def load():
     lib.ctcx_free_host.argtypes = [ctypes.POINTER(CtcxHostResult)]
     lib.ctcx_free_host.restype = None
     lib.ctcx_workspace_views.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [_vp] * 5
+    lib.ctcx_profile_enable.argtypes = [ctypes.c_int]
+    lib.ctcx_profile_enable.restype = None
+    lib.ctcx_profile_get.argtypes = [ctypes.POINTER(ctypes.c_float)]
+    lib.ctcx_profile_get.restype = None
     lib.ctcx_debug_math_f32.argtypes = [ctypes.c_int, _vp, _vp, ctypes.c_int, _vp]
     _lib = lib
     return lib

@@ -100,6 +100,20 @@ __global__ void FlagsKernel(const int* flags, const int* seq_len, int B, int T, 
   }
 }
 
+// optional per-kernel timing (ctcx_profile_enable): CUDA events on the launching stream
+thread_local int g_profile = 0;
+thread_local cudaEvent_t g_ev[6];
+thread_local bool g_ev_ready = false;
+thread_local float g_ms[5] = {0, 0, 0, 0, 0};  // lognorm, beam, trace, scan+flags, total
+void ProfRecord(int i, cudaStream_t s) {
+  if (!g_profile) return;
+  if (!g_ev_ready) {
+    for (int k = 0; k < 6; ++k) cudaEventCreate(&g_ev[k]);
+    g_ev_ready = true;
+  }
+  cudaEventRecord(g_ev[i], s);
+}
+
 thread_local int g_err_batch = -1;
 thread_local int g_err_max_time = 0;
 thread_local char g_msg[160];
@@ -189,6 +203,7 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
 
   if (B > 0) {
     // kernel 1: normalisers
+    ProfRecord(0, stream);
     const long long rows = (long long)T * B;
     int sm_count = 148;
     int dev = 0;
@@ -198,6 +213,7 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
     if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
     ctcx::LogNormKernel<<<(unsigned)blocks, 256, 0, stream>>>(logits_dev, (float*)(base + ws.off), rows, C);
     CTCX_CUDA(cudaGetLastError());
+    ProfRecord(1, stream);
 
     // kernel 2: beam search
     ctcx::BeamParams bp;
@@ -228,6 +244,7 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
       default: e = LaunchBeam<1024, 1024>(bp, lay.bytes, stream); break;
     }
     CTCX_CUDA(e);
+    ProfRecord(2, stream);
 
     // kernel 3: trace-back
     ctcx::TraceParams tp;
@@ -239,6 +256,7 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
     const long long walks = (long long)B * P;
     ctcx::TraceKernel<<<(unsigned)((walks + 127) / 128), 128, 0, stream>>>(tp);
     CTCX_CUDA(cudaGetLastError());
+    ProfRecord(3, stream);
 
     // kernel 4: per-path offsets and sizes
     ctcx::ScanParams sp;
@@ -250,6 +268,7 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
 
     FlagsKernel<<<(B + 255) / 256, 256, 0, stream>>>(bp.flags, seq_len_dev, B, T, d_stats);
     CTCX_CUDA(cudaGetLastError());
+    ProfRecord(4, stream);
   } else {
     CTCX_CUDA(cudaMemsetAsync(base + ws.sizes, 0, 4 * (size_t)P * 8, stream));
   }
@@ -259,6 +278,10 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
   CTCX_CUDA(cudaMemcpyAsync(h_sizes.data(), base + ws.sizes, h_sizes.size() * 8, cudaMemcpyDeviceToHost, stream));
   CTCX_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
   CTCX_CUDA(cudaStreamSynchronize(stream));
+  if (g_profile && B > 0) {
+    for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&g_ms[k], g_ev[k], g_ev[k + 1]);
+    cudaEventElapsedTime(&g_ms[4], g_ev[0], g_ev[4]);
+  }
   if (h_stats[1] < B) return CTCX_ERR_TOO_FEW_LEAVES;
   for (int p = 0; p < P; ++p) {
     if (sizes->n_decoded) sizes->n_decoded[p] = h_sizes[0 * (size_t)P + p];
@@ -453,6 +476,13 @@ done:
   cudaFree(d_out);
   cudaStreamDestroy(stream);
   return rc;
+}
+
+/* measurement hook (bench.py): per-kernel device times of this thread's last ctcx_decode_f32, from
+ * CUDA events recorded on the launching stream. out_ms = {lognorm, beam, trace, scan, total}. */
+void ctcx_profile_enable(int on) { g_profile = on; }
+void ctcx_profile_get(float* out_ms) {
+  for (int k = 0; k < 5; ++k) out_ms[k] = g_ms[k];
 }
 
 /* test hook: y = f(x) element-wise with the exact device math; op 0 expf, 1 log1pf, 2 logf */
