@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "ctcx_kernels.cuh"
+#include "ctcx_beam_v2.cuh"
 
 namespace {
 
@@ -81,6 +82,15 @@ Tier PickTier(int W) {
 template <int WMAX, int NT>
 cudaError_t LaunchBeam(const ctcx::BeamParams& p, size_t smem, cudaStream_t stream) {
   auto kern = ctcx::BeamKernel<WMAX, NT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<p.B, NT, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <int WMAX, int NT>
+cudaError_t LaunchBeamV2(const ctcx::BeamParams& p, size_t smem, cudaStream_t stream) {
+  auto kern = ctcx::BeamKernelV2<WMAX, NT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<p.B, NT, smem, stream>>>(p);
@@ -233,15 +243,30 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
     bp.dbg_totals = nullptr;
     bp.dbg_n = nullptr;
     const Tier tier = PickTier(W);
-    ctcx::BeamSmem lay;
-    lay.Init(tier.wmax, tier.nt, C, bp.kid_words, bp.cand_cap);
-    if (lay.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
+    // fast path: narrow vocabulary with the candidate list in shared memory (ctcx_beam_v2.cuh);
+    // CTCX_BEAM_IMPL=generic forces the generic kernel (A/B tests)
+    const char* impl = std::getenv("CTCX_BEAM_IMPL");
+    const bool want_generic = impl != nullptr && std::strcmp(impl, "generic") == 0;
     cudaError_t e;
-    switch (tier.wmax) {
-      case 32: e = LaunchBeam<32, 128>(bp, lay.bytes, stream); break;
-      case 128: e = LaunchBeam<128, 256>(bp, lay.bytes, stream); break;
-      case 256: e = LaunchBeam<256, 256>(bp, lay.bytes, stream); break;
-      default: e = LaunchBeam<1024, 1024>(bp, lay.bytes, stream); break;
+    if (!want_generic && C <= 32 && bp.cand_cap > 0 && tier.wmax <= 256) {
+      ctcx::BeamSmemV2 lay2;
+      lay2.Init(tier.wmax, bp.cand_cap);
+      if (lay2.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
+      switch (tier.wmax) {
+        case 32: e = LaunchBeamV2<32, 256>(bp, lay2.bytes, stream); break;
+        case 128: e = LaunchBeamV2<128, 256>(bp, lay2.bytes, stream); break;
+        default: e = LaunchBeamV2<256, 256>(bp, lay2.bytes, stream); break;
+      }
+    } else {
+      ctcx::BeamSmem lay;
+      lay.Init(tier.wmax, tier.nt, C, bp.kid_words, bp.cand_cap);
+      if (lay.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
+      switch (tier.wmax) {
+        case 32: e = LaunchBeam<32, 128>(bp, lay.bytes, stream); break;
+        case 128: e = LaunchBeam<128, 256>(bp, lay.bytes, stream); break;
+        case 256: e = LaunchBeam<256, 256>(bp, lay.bytes, stream); break;
+        default: e = LaunchBeam<1024, 1024>(bp, lay.bytes, stream); break;
+      }
     }
     CTCX_CUDA(e);
     ProfRecord(2, stream);

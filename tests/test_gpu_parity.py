@@ -10,13 +10,25 @@ import ctcx_testlib as L
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def op():
+@pytest.fixture(scope="module", params=["fast", "generic"])
+def op(request):
+    """Both beam kernels: the default dispatch (v2 fast path where it applies) and the generic
+    kernel forced through CTCX_BEAM_IMPL=generic."""
+    import os
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import ctc_beam_search_op_b200 as m
-    return m
+    old = os.environ.get("CTCX_BEAM_IMPL")
+    if request.param == "generic":
+        os.environ["CTCX_BEAM_IMPL"] = "generic"
+    else:
+        os.environ.pop("CTCX_BEAM_IMPL", None)
+    yield m
+    if old is None:
+        os.environ.pop("CTCX_BEAM_IMPL", None)
+    else:
+        os.environ["CTCX_BEAM_IMPL"] = old
 
 
 def _dense_from_raw(raw, B, P, T):
@@ -76,6 +88,18 @@ def test_parity_small(op, case):
     x = L.make_logits(kind, T, B, C, blank, seed=11)
     sl = L.ragged_lengths(T, B, 11) if ragged else np.full(B, T, np.int32)
     check_against_oracle(op, x, sl, W, P, merge, blank, blank_label)
+
+
+def test_constant_logits_pathological_ties(op):
+    """All classes equally likely: every child of a row ties exactly; the cut through the tied
+    scores must follow the stable order (members, then (row, label))."""
+    for (T, B, C, W, P) in [(12, 2, 8, 10, 3), (10, 2, 29, 100, 2), (8, 1, 4, 3, 3)]:
+        x = np.zeros((T, B, C), np.float32)
+        check_against_oracle(op, x, np.full(B, T, np.int32), W, P, False, C - 1, -1)
+    # two distinct values only
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, 2, (15, 4, 12)).astype(np.float32)
+    check_against_oracle(op, x, np.full(4, 15, np.int32), 20, 4, True, 0, -1)
 
 
 def test_device_math_is_bit_exact(op):
