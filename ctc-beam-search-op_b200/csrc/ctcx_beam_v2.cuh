@@ -40,6 +40,9 @@ struct BeamSmemV2 {
   size_t wiped;                    // u32 [WMAX]
   size_t htab;                     // i32 [2*WMAX]
   size_t hist, offs, bins2;        // u32 [256] each
+  size_t rowstart;                 // i32 [WMAX+1] list offset of each row's first candidate
+  size_t pl;                       // f32 [32]     x[l] - off of the current frame
+  size_t wsum;                     // i32 [32]     per-warp candidate counts (block scan)
   size_t x;                        // f32 [2][32]
   size_t scal;                     // 32 x 4 B
   size_t bytes;
@@ -74,6 +77,9 @@ struct BeamSmemV2 {
     hist = o; o += kBinsV2 * 4;
     offs = o; o += kBinsV2 * 4;
     bins2 = o; o += kBinsV2 * 4;
+    rowstart = o; o += (w + 1 + 3) / 4 * 4 * 4;
+    pl = o; o += 32 * 4;
+    wsum = o; o += 32 * 4;
     x = o; o += 2 * 32 * 4;
     scal = o; o += 32 * 4;
     bytes = (o + 15) / 16 * 16;
@@ -82,7 +88,8 @@ struct BeamSmemV2 {
 
 enum {
   kV2NCand = 0, kV2NRisk, kV2MinKey, kV2MaxKey, kV2Changed, kV2NBnd, kV2Bstar, kV2KRem, kV2E,
-  kV2NNew, kV2Off0, kV2Off1, kV2Anomaly, kV2MinBase, kV2LpMin, kV2Prefix, kV2PrefixHi, kV2K
+  kV2NNew, kV2Off0, kV2Off1, kV2Anomaly, kV2MinBase, kV2LpMin, kV2Prefix, kV2PrefixHi, kV2K,
+  kV2LpMax, kV2Gap, kV2TopBin
 };
 
 template <int WMAX, int NT>
@@ -126,6 +133,9 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
   unsigned* s_hist = (unsigned*)(smem + lay.hist);
   unsigned* s_offs = (unsigned*)(smem + lay.offs);
   unsigned* s_bins2 = (unsigned*)(smem + lay.bins2);
+  int* s_rowstart = (int*)(smem + lay.rowstart);
+  float* s_pl = (float*)(smem + lay.pl);
+  int* s_wsum = (int*)(smem + lay.wsum);
   float* s_x = (float*)(smem + lay.x);
   volatile int* sc = (volatile int*)(smem + lay.scal);
   int* sci = (int*)(smem + lay.scal);
@@ -155,8 +165,15 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
     scu[kV2MaxKey] = 0u;
     sci[kV2NBnd] = 0;
     scu[kV2MinBase] = 0xffffffffu;
+    scu[kV2Gap] = 0u;
   }
   int n = 1;
+  // thread -> (row, class slice) mapping of the candidate pass
+  constexpr int PARTS = NT / WMAX;  // threads per row
+  constexpr int CP = 32 / PARTS;    // classes per thread
+  static_assert(NT % WMAX == 0 && 32 % PARTS == 0, "row/class tiling");
+  const int prow = tid / PARTS, pbase = (tid % PARTS) * CP;
+  const unsigned class_mask = ((C >= 32) ? 0xffffffffu : ((1u << C) - 1u)) & ~(1u << blank);
   if (L > 0) {
     const float* g = p.logits + (size_t)b * C;
     if (tid < C) s_x[tid] = g[tid];
@@ -196,11 +213,24 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
       asm volatile("cp.async.commit_group;\n" ::);
     }
 
-    // per-lane class constants (lane = class index)
+    // per-class log-probabilities of this frame (lane = class index), their max and min
     const bool lane_ok = (lane < C) && (lane != blank);
     const float pl_lane = lane_ok ? __fsub_rn(x[lane], off) : 0.0f;
     const float xb = x[blank];
     const float pb = __fsub_rn(xb, off);
+    if (warp == 0) {
+      s_pl[lane] = pl_lane;
+      float mx = lane_ok ? pl_lane : NegInf(), mn = lane_ok ? pl_lane : 0.0f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(kFull, mn, o));
+      }
+      if (lane == 0) {
+        ((float*)sci)[kV2LpMax] = mx;
+        ((float*)sci)[kV2LpMin] = mn;
+      }
+    }
 
     // ---- PA: update the existing members (decoder.h:95-143) ----
     unsigned my_key = 0u;
@@ -280,52 +310,100 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
         const float ob = o_blk[tid], ot = o_total[tid];
         if (ot > NegInf()) kb = KeyOf((ob > NegInf()) ? fminf(ot, ob) : ot);
       }
-      float lpm = lane_ok ? pl_lane : 0.0f;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        kb = min(kb, __shfl_xor_sync(kFull, kb, o));
-        lpm = fminf(lpm, __shfl_xor_sync(kFull, lpm, o));
-      }
-      if (lane == 0) {
-        if (warp * 32 < n) atomicMin(&scu[kV2MinBase], kb);
-        if (warp == 0) ((float*)sci)[kV2LpMin] = lpm;
-      }
+      for (int o = 16; o > 0; o >>= 1) kb = min(kb, __shfl_xor_sync(kFull, kb, o));
+      if (lane == 0 && warp * 32 < n) atomicMin(&scu[kV2MinBase], kb);
     }
     __syncthreads();
 
     // ---- PB: fresh children (decoder.h:146-187) + score histogram ----
     const unsigned minkey_m = scu[kV2MinKey];
     const float th0f = (n == W) ? UnKey(minkey_m) : NegInf();
-    unsigned lo_key;
+    const float lp_max = ((const float*)sci)[kV2LpMax];
+    unsigned lo_true;  // no item lies below this key
     if (n == W) {
-      lo_key = minkey_m;
+      lo_true = minkey_m;
     } else {
       const unsigned kb = scu[kV2MinBase];
       unsigned lo_c = minkey_m;
       if (kb != 0xffffffffu) lo_c = KeyOf(__fadd_rn(UnKey(kb), ((const float*)sci)[kV2LpMin]));
-      lo_key = min(minkey_m, lo_c);
-      lo_key = max(lo_key, kKeyNegInf);
+      lo_true = max(min(minkey_m, lo_c), kKeyNegInf);
     }
-    const unsigned hi_key = max(scu[kV2MaxKey], KeyOf(o_total[0]));
+    // every item is <= max(best member, best possible child); old totals are sorted, slot 0 is the max
+    const unsigned hi_key = max(scu[kV2MaxKey], KeyOf(__fadd_rn(lp_max, o_total[0])));
+    // Histogram range. Survivors crowd near the top while the admissible range reaches far below,
+    // so the 256 bins are centred on a PREDICTION of the W-th score: the previous frame's
+    // top-to-threshold gap (x3 + slack). Keys below the range are clamped into bin 0. This only
+    // affects speed: whatever bin the W-th item falls in is cut exactly in PF.
+    unsigned lo_key = lo_true;
+    {
+      const unsigned gap = scu[kV2Gap];
+      if (gap != 0u && n == W) {
+        const unsigned long long reach = 3ull * gap + 64ull;
+        if (reach < (unsigned long long)(hi_key - lo_true)) lo_key = hi_key - (unsigned)reach;
+      }
+    }
+    const bool clamped = (lo_key != lo_true);
     const unsigned span = hi_key - lo_key;
     const int shift = max(0, (32 - __clz(span | 1u)) - 8);  // (key - lo) >> shift < 256
-    if (tid < n) atomicAdd(&s_hist[(my_key - lo_key) >> shift], 1u);
-    for (int row = warp; row < n; row += NWARP) {
-      const uint4 ri = s_row[row];
-      const float base = ((int)ri.z == lane) ? __uint_as_float(ri.y) : __uint_as_float(ri.x);
-      const float s = __fadd_rn(pl_lane, base);  // decoder.h:172-182: (x - off) + old blank/total
-      const bool ok = lane_ok && !((ri.w >> lane) & 1u) && (s > th0f);
-      const unsigned m = __ballot_sync(kFull, ok);
-      if (m) {
-        int basepos = 0;
-        if (lane == 0) basepos = atomicAdd(&sci[kV2NCand], __popc(m));
-        basepos = __shfl_sync(kFull, basepos, 0);
-        if (ok) {
-          const unsigned key = KeyOf(s);
-          c_list[basepos + __popc(m & ((1u << lane) - 1u))] =
-              make_uint2(key, ((unsigned)row << 16) | (unsigned)lane);
-          atomicAdd(&s_hist[(key - lo_key) >> shift], 1u);
+    auto bucket_of = [&](unsigned key) -> int { return (key > lo_key) ? (int)((key - lo_key) >> shift) : 0; };
+    if (tid < n) atomicAdd(&s_hist[bucket_of(my_key)], 1u);
+
+    // pass 1: each thread counts the admissible children in its (row, class slice)
+    unsigned okmask = 0u;
+    float r_ot = 0.0f, r_ob = 0.0f;
+    int r_label = -1;
+    if (prow < n) {
+      const uint4 ri = s_row[prow];
+      r_ot = __uint_as_float(ri.x);
+      r_ob = __uint_as_float(ri.y);
+      r_label = (int)ri.z;
+      const unsigned vm = ((~ri.w) & class_mask) >> pbase;  // not blank, not already a member
+      if ((CP == 32 ? vm : (vm & ((1u << (CP & 31)) - 1u))) && __fadd_rn(lp_max, r_ot) > th0f) {
+#pragma unroll
+        for (int k = 0; k < CP; ++k) {
+          const int l = pbase + k;
+          const float s = __fadd_rn(s_pl[l], (l == r_label) ? r_ob : r_ot);  // :172-182
+          if (((vm >> k) & 1u) && s > th0f) okmask |= 1u << k;
         }
+      }
+    }
+    int pos0;
+    {
+      const int cnt = __popc(okmask);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) s_wsum[warp] = incl;
+      __syncthreads();
+      int before = 0, total = 0;
+#pragma unroll
+      for (int w2 = 0; w2 < NWARP; ++w2) {
+        const int v = s_wsum[w2];
+        total += v;
+        if (w2 < warp) before += v;
+      }
+      pos0 = before + incl - cnt;
+      if (tid == 0) {
+        sci[kV2NCand] = total;
+        s_rowstart[n] = total;
+      }
+      if (prow < n && pbase == 0) s_rowstart[prow] = pos0;
+    }
+    // pass 2: write them in visiting order (row, then class) and count them in the histogram
+    {
+      unsigned m = okmask;
+      int pos = pos0;
+      while (m) {
+        const int k = __ffs(m) - 1;
+        m &= m - 1u;
+        const int l = pbase + k;
+        const unsigned key = KeyOf(__fadd_rn(s_pl[l], (l == r_label) ? r_ob : r_ot));
+        c_list[pos++] = make_uint2(key, ((unsigned)prow << 16) | (unsigned)l);
+        atomicAdd(&s_hist[bucket_of(key)], 1u);
       }
     }
     __syncthreads();
@@ -348,7 +426,8 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
               const unsigned kj = m_key[j];
               cnt += (kj > vkey || (kj == vkey && j < m)) ? 1 : 0;
             }
-            for (int c = lane; c < n_cand; c += 32) {
+            const int c_end = s_rowstart[pslot + 1];  // children visited up to the parent's turn
+            for (int c = lane; c < c_end; c += 32) {
               const uint2 e = c_list[c];
               cnt += (e.x > vkey && e.y < idm && !s_wiped[e.y >> 16]) ? 1 : 0;
             }
@@ -387,7 +466,7 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
         for (int c = tid; c < n_cand; c += NT) {
           const uint2 e = c_list[c];
           if (s_wiped[e.y >> 16]) {
-            atomicSub(&s_hist[(e.x - lo_key) >> shift], 1u);
+            atomicSub(&s_hist[bucket_of(e.x)], 1u);
             c_list[c].x = 0u;
           }
         }
@@ -410,6 +489,12 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
       const unsigned above = suf - loc;
       const int total = (int)__shfl_sync(kFull, suf, 0);
       const int K = min(W, total);
+      int topbin = -1;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (h[q]) topbin = lane * 8 + q;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) topbin = max(topbin, __shfl_xor_sync(kFull, topbin, o));
+      if (lane == 0) sci[kV2TopBin] = topbin;
       unsigned acc = above;
 #pragma unroll
       for (int q = 7; q >= 0; --q) {
@@ -427,10 +512,14 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
     __syncthreads();
     const int bstar = sc[kV2Bstar], k_rem = sc[kV2KRem], e_b = sc[kV2E], n_new = sc[kV2NNew];
     const bool bnd_all = (e_b == k_rem);
+    // next frame's range prediction: measured top-to-threshold gap; if the prediction missed (the
+    // threshold fell into the clamped bin) widen to the whole range just used
+    const unsigned gap_next = (clamped && bstar == 0) ? span
+                                                      : ((unsigned)(sc[kV2TopBin] - bstar + 1) << shift);
 
     // ---- PE: scatter every item at or above the boundary bin into its score group ----
     auto place = [&](unsigned key, unsigned okey) {
-      const int bucket = (int)((key - lo_key) >> shift);
+      const int bucket = bucket_of(key);
       const unsigned long long comp = ((unsigned long long)key << 32) | (unsigned long long)(~okey);
       if (bucket > bstar || (bucket == bstar && bnd_all)) {
         const unsigned pos = s_offs[bucket] + atomicAdd(&s_hist[bucket], 1u);
@@ -463,21 +552,19 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
           if (lane == 0) s_hist[bstar] = (unsigned)k_rem;
         }
       } else {
-        // pathological ties (e.g. constant logits): radix select of the k_rem largest
-        // (key, ~order) composites among the items of the boundary bin
-        const unsigned lo_b = lo_key + ((unsigned)bstar << shift);
+        // many items in the boundary bin (coarse bins after a missed prediction, or pathological
+        // ties such as constant logits): radix select of the k_rem largest (key, ~order) composites
         auto for_each_bnd = [&](auto&& f) {
-          if (tid < n && (int)((my_key - lo_key) >> shift) == bstar)
-            f(((unsigned long long)(my_key - lo_b) << 32) | (unsigned long long)(~(unsigned)tid), my_key,
-              (unsigned)tid);
+          if (tid < n && bucket_of(my_key) == bstar)
+            f(((unsigned long long)my_key << 32) | (unsigned long long)(~(unsigned)tid), my_key, (unsigned)tid);
           for (int c = tid; c < n_cand; c += NT) {
             const uint2 e = c_list[c];
-            if (e.x && (int)((e.x - lo_key) >> shift) == bstar)
-              f(((unsigned long long)(e.x - lo_b) << 32) | (unsigned long long)(~(0x80000000u | e.y)), e.x,
+            if (e.x && bucket_of(e.x) == bstar)
+              f(((unsigned long long)e.x << 32) | (unsigned long long)(~(0x80000000u | e.y)), e.x,
                 0x80000000u | e.y);
           }
         };
-        const int npass = (32 + shift + 7) / 8;
+        const int npass = 8;
         if (tid == 0) { scu[kV2Prefix] = 0u; scu[kV2PrefixHi] = 0u; sci[kV2K] = k_rem; }
         __syncthreads();
         for (int pass = npass - 1; pass >= 0; --pass) {
@@ -549,7 +636,7 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
       int r = -1;
       if (tid < n_new) {
         comp = s_sorted[tid];
-        const int bucket = (int)(((unsigned)(comp >> 32) - lo_key) >> shift);
+        const int bucket = bucket_of((unsigned)(comp >> 32));
         const int g0 = (int)s_offs[bucket], g1 = g0 + (int)s_hist[bucket];
         int rank = 0;
         for (int j = g0; j < g1; ++j) rank += (s_sorted[j] > comp) ? 1 : 0;
@@ -564,6 +651,7 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
         scu[kV2MaxKey] = 0u;
         sci[kV2NBnd] = 0;
         scu[kV2MinBase] = 0xffffffffu;
+        scu[kV2Gap] = gap_next;
       }
       if (tid < n) s_wiped[tid] = 0u;
       if (r >= 0) {
