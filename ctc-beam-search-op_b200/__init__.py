@@ -12,6 +12,8 @@ from .decoder import (CTCExtBeamSearchDecoder, CtcxError, FailedPreconditionErro
                       ctc_ext_beam_search_decoder, ctc_ext_beam_search_decoder_raw,
                       decode_host_cabi)
 
-__all__ = ["ctc_ext_beam_search_decoder", "ctc_ext_beam_search_decoder_raw", "decode_host_cabi",
+from .sharding import decode_distributed, decode_multi_device, merge_raw, shard_bounds  # noqa: F401,E402
+
+__all__ = ["decode_multi_device", "decode_distributed", "shard_bounds", "merge_raw","ctc_ext_beam_search_decoder", "ctc_ext_beam_search_decoder_raw", "decode_host_cabi",
            "SparseTensor", "CTCExtBeamSearchDecoder", "CtcxError", "InvalidArgumentError",
            "FailedPreconditionError", "UnsupportedError"]

@@ -247,3 +247,97 @@ PAPER_PROBS = [[0.3, 0.5, 0.2], [0.25, 0.6, 0.15], [0.6, 0.2, 0.2], [0.4, 0.35, 
 def paper_logits(dtype=np.float64):
     """python/ops/ctc_ext_beam_search_decoder_ops_test.py:25-33 (np.log of the table, float64)."""
     return np.log(np.asarray(PAPER_PROBS, np.float64))[:, None, :].astype(dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU model of the parallel formulation (tests/model/ctcx_model.cc)
+MODEL_SRC = os.path.join(ROOT, "tests", "model", "ctcx_model.cc")
+MODEL_SO = os.path.join(ROOT, "tests", "model", "libctcx_model.so")
+MODEL_STATS = ("frames cands at_risk fp_iters fp_iters_max wiped wiped_with_cands anomalies cands_max "
+               "frames_wipe_matters queries radix_bits_sum").split()
+
+
+def build_model(force=False):
+    if force or not os.path.exists(MODEL_SO) or os.path.getmtime(MODEL_SO) < os.path.getmtime(MODEL_SRC):
+        subprocess.check_call(["g++", "-O2", "-std=c++11", "-ffp-contract=off", "-fPIC", "-shared",
+                               "-o", MODEL_SO, MODEL_SRC])
+
+
+def model_decode(logits, seq_len, beam_width, top_paths, merge_repeated=False, blank_index=0,
+                 blank_label=-1, want_stats=False):
+    build_model()
+    lib = _load(MODEL_SO)
+    logits, seq_len = _check_inputs(logits, seq_len)
+    logits = logits.astype(np.float32, copy=False)
+    T, B, C = logits.shape
+    dec_len, dec, ali_len, ali, logp = _dense_out(B, top_paths, T, np.float32)
+    st = np.zeros(16, np.int64)
+    rc = lib.ctcx_model_decode_f32(_ptr(logits, _c_float_p), T, B, C, _ptr(seq_len, _c_int_p),
+                                   beam_width, top_paths, int(bool(merge_repeated)), blank_index,
+                                   blank_label, _ptr(dec_len, _c_int_p), _ptr(dec, _c_int_p),
+                                   _ptr(ali_len, _c_int_p), _ptr(ali, _c_int_p), _ptr(logp, _c_float_p),
+                                   st.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+    if rc != 0:
+        raise OracleError({2: "max_time is 0", 6: "requested more paths than the beam width.",
+                           7: "Less leaves in the beam search than requested."}.get(rc, "error %d" % rc))
+    res = DenseResult(B, top_paths, T, dec_len, dec, ali_len, ali, logp)
+    return (res, dict(zip(MODEL_STATS, st.tolist()))) if want_stats else res
+
+
+def same_result(a, b, bitwise=True):
+    """Utterance/path pairs where two DenseResults differ (labels, alignments, log-prob bits)."""
+    bad = []
+    for u in range(a.B):
+        for p in range(a.P):
+            lp_ok = (np.asarray(a.logp[u, p]).view(np.uint32 if a.logp.dtype == np.float32 else np.uint64)
+                     == np.asarray(b.logp[u, p]).view(np.uint32 if b.logp.dtype == np.float32 else np.uint64)) \
+                if bitwise and a.logp.dtype == b.logp.dtype else np.isclose(a.logp[u, p], b.logp[u, p], rtol=1e-6, atol=1e-6)
+            if a.decoded(u, p) != b.decoded(u, p) or a.alignment(u, p) != b.alignment(u, p) or not lp_ok:
+                bad.append((u, p))
+    return bad
+
+
+# ----------------------------------------------------------------------------------------------
+# Golden fixtures generated from the reference itself (tests/golden/make_golden.py)
+GOLDEN_NPZ = os.path.join(ROOT, "tests", "golden", "ref_cases.npz")
+GOLDEN_JSON = os.path.join(ROOT, "tests", "golden", "ref_cases.json")
+
+
+class Golden:
+    def __init__(self):
+        import json
+        self.arr = np.load(GOLDEN_NPZ)
+        self.meta = json.load(open(GOLDEN_JSON))
+
+    def result(self, name):
+        g = lambda k: self.arr["%s/%s" % (name, k)]  # noqa: E731
+        dec_len, ali_len = g("dec_len"), g("ali_len")
+        B, P = dec_len.shape
+        T = g("dec").shape[2]
+        r = DenseResult.__new__(DenseResult)
+        r.B, r.P, r.T = B, P, T
+        r.dec_len, r.ali_len, r.dec, r.ali, r.logp = dec_len, ali_len, g("dec"), g("ali"), g("logp")
+        return r
+
+    def tie_free(self, name):
+        k = "%s/tie_free" % name
+        return self.arr[k] if k in self.arr else None
+
+    def random_cases(self):
+        """[(name, x, seq_len, W, P, merge, blank_index, blank_label)]"""
+        out = []
+        for c in self.meta["random"]:
+            name, kind, T, B, C, W, P, merge, blank, bl, seed, sigma, ragged, dt = c
+            x = make_logits(kind, T, B, C, blank, seed, sigma)
+            if dt == "f64":
+                x = x.astype(np.float64)
+            sl = ragged_lengths(T, B, seed) if ragged else np.full(B, T, np.int32)
+            out.append((name, x, sl, W, P, merge, blank, bl))
+        return out
+
+    def literal_cases(self):
+        out = []
+        for name, rows, sl, W, P, merge, blank, bl in self.meta["literal"]:
+            x = np.asarray(rows, np.float32)[:, None, :]
+            out.append((name, x, np.asarray([sl], np.int32), W, P, merge, blank, bl))
+        return out

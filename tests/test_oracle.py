@@ -1,0 +1,184 @@
+"""CPU suite, part 1: pins the oracle (oracle/ctcx_oracle.c) -- and the CPU model of the parallel
+formulation the CUDA kernels implement -- against
+  (1) the reference's own known-answer test (ops_test.py:25-64),
+  (2) golden outputs generated from the reference itself (tests/golden/, make_golden.py),
+  (3) the compiled reference oracle/_ref on seeded random inputs, where it is available,
+  (4) the reference's error behaviour (decoder.h:237-243, kernels.cc:118-138).
+Citations relative to /root/reference/tensorflow_ctc_ext_beam_search_decoder/.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import ctcx_testlib as L
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return L.Golden()
+
+
+# --- (1) the reference's own test, transliterated (python/ops/ctc_ext_beam_search_decoder_ops_test.py:20-100)
+PAPER_DECODED = [[1, 1, 2], [1, 2, 1, 2], [1, 2], [1, 1, 2, 1], [1, 2, 1]]
+PAPER_ALIGNMENT = [[1, 1, 0, 1, 0, 2, 2, 2], [1, 1, 0, 2, 1, 2, 2, 2], [1, 1, 0, 0, 0, 2, 2, 2],
+                   [1, 1, 0, 1, 0, 2, 2, 1], [1, 1, 0, 0, 0, 2, 2, 1]]
+PAPER_LOGP = [-2.0613022, -2.1155741, -2.713197, -2.8770373, -2.9212725]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("impl", ["oracle", "model"])
+def test_paper_known_answer(dtype, impl):
+    if impl == "model" and dtype == np.float64:
+        pytest.skip("the model is float32 only")
+    fn = L.oracle_decode if impl == "oracle" else L.model_decode
+    r = fn(L.paper_logits(dtype), [8], 10, 5, False, 0, 0)
+    raw = L.pack_sparse(r)
+    for p in range(5):
+        np.testing.assert_array_equal(raw[0][p], [[0, i] for i in range(len(PAPER_DECODED[p]))])  # :36-41
+        np.testing.assert_array_equal(raw[1][p], PAPER_DECODED[p])                                 # :49-50
+        np.testing.assert_array_equal(raw[2][p], [1, len(PAPER_DECODED[p])])                       # :58-59
+        np.testing.assert_array_equal(raw[3][p], [[0, i] for i in range(8)])                       # :42-47
+        np.testing.assert_array_equal(raw[4][p], PAPER_ALIGNMENT[p])                               # :51-56
+        np.testing.assert_array_equal(raw[5][p], [1, 8])                                           # :60-61
+    np.testing.assert_allclose(raw[6], [PAPER_LOGP], rtol=1e-6, atol=1e-6)                        # :63-64
+
+
+def test_trace_w3_matches_reference(golden):
+    """Per-frame beams of the paper example at beam_width=3, including the
+    exact tie at t=2: only the set of (score, prefix) per frame is compared at tied positions."""
+    x = L.paper_logits(np.float32)
+    want = golden.meta["trace_w3"]
+    for t in range(1, 9):
+        r = L.oracle_decode(x[:t], [t], 3, 3, False, 0, 0)
+        got = sorted((round(float(r.logp[0, p]), 6), tuple(r.decoded(0, p)), tuple(r.alignment(0, p)))
+                     for p in range(3))
+        exp = sorted((round(lp, 6), tuple(pre), tuple(ali)) for lp, pre, ali in want[t - 1])
+        assert got == exp, "frame %d" % (t - 1)
+
+
+# --- (2) golden outputs of the reference
+def _golden_check(fn, golden, bitwise):
+    for name, x, sl, W, P, merge, blank, bl in golden.random_cases() + golden.literal_cases():
+        if fn is L.model_decode and x.dtype == np.float64:
+            continue
+        want = golden.result(name)
+        got = fn(x, sl, W, P, merge, blank, bl)
+        bad = L.same_result(want, got, bitwise=bitwise)
+        tf = golden.tie_free(name)
+        if tf is not None:  # utterances with an exact tie in an order-deciding comparison are excused
+            bad = [(u, p) for (u, p) in bad if tf[u]]
+        assert not bad, "%s: %s" % (name, bad[:5])
+
+
+def test_oracle_matches_golden(golden):
+    _golden_check(L.oracle_decode, golden, bitwise=True)
+
+
+def test_model_matches_golden(golden):
+    _golden_check(L.model_decode, golden, bitwise=True)
+
+
+def test_paper_golden_is_the_reference_output(golden):
+    for dt, nm in ((np.float64, "paper_f64"), (np.float32, "paper_f32")):
+        assert not L.same_result(golden.result(nm), L.oracle_decode(L.paper_logits(dt), [8], 10, 5, False, 0, 0))
+
+
+# --- (3) the compiled reference, when present (it is built wherever /root/reference exists)
+REF_SWEEP = [("gauss", 50, 16, 29, 10, 3, False, 28, 0, False), ("peaky", 50, 16, 29, 10, 3, True, 28, 1, True),
+             ("peaky", 100, 3, 29, 100, 1, True, 28, 2, False), ("gauss", 40, 4, 32, 64, 4, False, 31, 3, True),
+             ("peaky", 25, 2, 300, 16, 2, False, 299, 4, False), ("gauss", 30, 32, 5, 3, 3, True, 2, 5, True),
+             ("peaky", 30, 32, 16, 3, 1, False, 5, 6, False), ("gauss", 30, 16, 4, 1, 1, False, 0, 7, False)]
+
+
+@pytest.mark.skipif(not L.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("case", REF_SWEEP, ids=lambda c: "%s-T%d-B%d-C%d-W%d" % c[:5])
+def test_oracle_matches_compiled_reference(case):
+    kind, T, B, C, W, P, merge, blank, seed, ragged = case
+    x = L.make_logits(kind, T, B, C, blank, seed)
+    sl = L.ragged_lengths(T, B, seed) if ragged else np.full(B, T, np.int32)
+    ref = L.ref_decode(x, sl, W, P, merge, blank, -1)
+    got, margins = L.oracle_decode(x, sl, W, P, merge, blank, -1, want_margin=True)
+    bad = L.same_result(ref, got)
+    # the reference breaks exact ties by libstdc++ heap order: only tie-free utterances must agree
+    tie_free = margins[:, [1, 2, 4]].min(axis=1) > 0
+    assert not [(u, p) for (u, p) in bad if tie_free[u]], bad[:5]
+    assert len({u for u, _ in bad}) <= max(1, B // 4)
+
+
+# --- the model (the formulation the kernels implement) == the oracle, bit for bit, ties included
+@pytest.mark.parametrize("seed", range(6))
+def test_model_equals_oracle_random_shapes(seed):
+    rng = np.random.default_rng(1000 + seed)
+    for _ in range(8):
+        C = int(rng.integers(2, 40)); W = int(rng.integers(1, 40)); T = int(rng.integers(1, 50))
+        B = int(rng.integers(1, 10)); blank = int(rng.integers(0, C)); merge = bool(rng.integers(0, 2))
+        kind = ["gauss", "peaky"][int(rng.integers(0, 2))]
+        x = L.make_logits(kind, T, B, C, blank, int(rng.integers(0, 10000)), float(rng.choice([0.5, 1, 2, 4])))
+        sl = L.ragged_lengths(T, B, seed)
+        P = int(rng.integers(1, W + 1))
+        try:
+            a = L.oracle_decode(x, sl, W, P, merge, blank, -1)
+        except L.OracleError as e:
+            with pytest.raises(L.OracleError, match=str(e)[:20]):
+                L.model_decode(x, sl, W, P, merge, blank, -1)
+            continue
+        assert not L.same_result(a, L.model_decode(x, sl, W, P, merge, blank, -1))
+
+
+def test_model_equals_oracle_cfg2_scale():
+    x = L.make_logits("peaky", 300, 2, 29, 28, 1)
+    sl = np.full(2, 300, np.int32)
+    assert not L.same_result(L.oracle_decode(x, sl, 100, 1, True, 28, -1),
+                             L.model_decode(x, sl, 100, 1, True, 28, -1))
+    x = L.make_logits("gauss", 200, 2, 29, 28, 1)
+    sl = np.full(2, 200, np.int32)
+    assert not L.same_result(L.oracle_decode(x, sl, 100, 1, True, 28, -1),
+                             L.model_decode(x, sl, 100, 1, True, 28, -1))
+
+
+def test_constant_logits_ties():
+    x = np.zeros((10, 2, 8), np.float32)
+    sl = np.full(2, 10, np.int32)
+    assert not L.same_result(L.oracle_decode(x, sl, 10, 3, False, 7, -1), L.model_decode(x, sl, 10, 3, False, 7, -1))
+
+
+# --- (4) error behaviour
+def test_errors():
+    x = L.paper_logits(np.float32)
+    with pytest.raises(L.OracleError, match="requested more paths than the beam width"):
+        L.oracle_decode(x, [8], 2, 3)
+    with pytest.raises(L.OracleError, match="Less leaves in the beam search than requested"):
+        L.oracle_decode(x[:1], [1], 4, 4)
+    with pytest.raises(L.OracleError, match="Less leaves"):
+        L.oracle_decode(x, [0], 4, 2)
+    with pytest.raises(L.OracleError, match=r"sequence_length\(0\) <= 8"):
+        L.oracle_decode(x, [9], 4, 1)
+    with pytest.raises(L.OracleError, match="inputs is not a 3-Tensor"):
+        L.oracle_decode(x[:, 0, :], [8], 4, 1)
+    with pytest.raises(L.OracleError, match="max_time is 0"):
+        L.oracle_decode(np.zeros((0, 1, 3), np.float32), [0], 4, 1)
+    with pytest.raises(L.OracleError, match="len\\(sequence_length\\) != batch_size"):
+        L.oracle_decode(x, [8, 8], 4, 1)
+    r = L.oracle_decode(x, [0], 4, 1)  # seq_len 0, one path: empty outputs, log-prob 0
+    assert r.decoded(0, 0) == [] and r.alignment(0, 0) == [] and r.logp[0, 0] == 0
+
+
+def test_sparse_packing_layout():
+    """StoreAllDecodedSequences (kernels.cc:163-257): row-major over batch then position."""
+    x = L.make_logits("peaky", 12, 3, 5, 4, 3)
+    sl = np.asarray([12, 7, 0], np.int32)
+    r = L.oracle_decode(x, sl, 4, 1, False, 4, -1)
+    raw = L.pack_sparse(r)
+    assert raw[3][0].shape == (19, 2) and raw[5][0].tolist() == [3, 12]
+    assert raw[3][0][:12, 0].tolist() == [0] * 12 and raw[3][0][12:, 0].tolist() == [1] * 7
+    assert raw[3][0][12:, 1].tolist() == list(range(7))
+    assert raw[2][0].tolist() == [3, max(len(r.decoded(b, 0)) for b in range(3))]
+
+
+def test_libm_port_matches_host_libm_sample():
+    """oracle/libm_port.h (the twin of the device math) against this host's libm, strided sweep."""
+    lib = ctypes.CDLL(L.ORACLE_SO)
+    lib.ctcx_port_mismatches.restype = ctypes.c_longlong
+    out = (ctypes.c_longlong * 3)()
+    assert lib.ctcx_port_mismatches(389, out) == 0, list(out)
