@@ -126,3 +126,197 @@ def test_device_math_is_bit_exact(op):
         torch.cuda.synchronize()
         got = yd.cpu().numpy()
         np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------------
+# The reference's own test, transliterated (ops_test.py:20-100): raw 7-group output, float64 input
+def test_paper_known_answer_like_the_reference(op):
+    logits = L.paper_logits(np.float64)
+    correct_decoded_values = [[1, 1, 2], [1, 2, 1, 2], [1, 2], [1, 1, 2, 1], [1, 2, 1]]
+    correct_alignment_values = [[1, 1, 0, 1, 0, 2, 2, 2], [1, 1, 0, 2, 1, 2, 2, 2], [1, 1, 0, 0, 0, 2, 2, 2],
+                                [1, 1, 0, 1, 0, 2, 2, 1], [1, 1, 0, 0, 0, 2, 2, 1]]
+    correct_log_probs = np.array([[-2.0613022, -2.1155741, -2.713197, -2.8770373, -2.9212725]])
+    out = op.ctc_ext_beam_search_decoder_raw(inputs=logits, sequence_length=[8], beam_width=10,
+                                             blank_index=0, top_paths=5, blank_label=0,
+                                             merge_repeated=False)
+    for p in range(5):
+        np.testing.assert_allclose(out[0][p], [[0, i] for i in range(len(correct_decoded_values[p]))])
+        np.testing.assert_allclose(out[1][p], correct_decoded_values[p])
+        np.testing.assert_allclose(out[2][p], [1, len(correct_decoded_values[p])])
+        np.testing.assert_allclose(out[3][p], [[0, i] for i in range(8)])
+        np.testing.assert_allclose(out[4][p], correct_alignment_values[p])
+        np.testing.assert_allclose(out[5][p], [1, 8])
+    np.testing.assert_allclose(out[6], correct_log_probs, rtol=1e-6, atol=1e-6)
+    assert out[6].dtype == np.float64
+    # documented return value: (decoded, alignment, log_probability) with SparseTensor-like entries
+    dec, ali, lp = op.ctc_ext_beam_search_decoder(logits, [8], beam_width=10, top_paths=5,
+                                                  blank_index=0, blank_label=0)
+    assert dec[0].values.tolist() == [1, 1, 2] and ali[0].dense_shape.tolist() == [1, 8]
+
+
+def test_no_leak_over_many_calls(op):
+    """Counterpart of testCTCExtBeamSearchDecoderMemLeak (ops_test.py:102-123): device memory in
+    use must not grow over repeated calls."""
+    import torch
+    x = torch.from_numpy(L.paper_logits(np.float32)).cuda()
+    sl = torch.tensor([8], dtype=torch.int32).cuda()
+    kw = dict(beam_width=10, top_paths=5, blank_index=0, blank_label=0)
+    op.ctc_ext_beam_search_decoder_raw(x, sl, **kw)
+    torch.cuda.synchronize()
+    before = torch.cuda.memory_allocated()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(300):
+        op.ctc_ext_beam_search_decoder_raw(x, sl, **kw)
+    torch.cuda.synchronize()
+    assert torch.cuda.memory_allocated() <= before
+    assert torch.cuda.mem_get_info()[0] >= free0 - (64 << 20)
+
+
+def test_golden_reference_outputs(op):
+    """Fixtures generated from the reference itself (tests/golden/make_golden.py)."""
+    g = L.Golden()
+    for name, x, sl, W, P, merge, blank, bl in g.random_cases() + g.literal_cases():
+        want = g.result(name)
+        raw = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=W, top_paths=P, merge_repeated=merge,
+                                                 blank_index=blank, blank_label=bl)
+        B, T = x.shape[1], x.shape[0]
+        dec, ali = _dense_from_raw(raw, B, P, T)
+        tf = g.tie_free(name)
+        for b in range(B):
+            if tf is not None and not tf[b]:
+                continue  # exact tie in an order-deciding comparison: reference order unspecified
+            for p in range(P):
+                assert dec[b][p] == want.decoded(b, p), (name, b, p)
+                assert ali[b][p] == want.alignment(b, p), (name, b, p)
+                if x.dtype == np.float32:
+                    assert np.float32(raw[6][b, p]).view(np.uint32) == np.float32(want.logp[b, p]).view(np.uint32)
+                else:  # float64 inputs are computed in float32 (DESIGN.md "next" row f1)
+                    np.testing.assert_allclose(raw[6][b, p], want.logp[b, p], rtol=1e-4)
+
+
+def test_host_buffer_cabi_entry(op):
+    """ctcx_decode_host_f32: what a TF CPU OpKernel would call with host tensors."""
+    x = L.make_logits("peaky", 40, 5, 29, 28, 21)
+    sl = L.ragged_lengths(40, 5, 21)
+    want = L.pack_sparse(L.oracle_decode(x, sl, 10, 2, True, 28, -1))
+    got = op.decode_host_cabi(x, sl, beam_width=10, top_paths=2, merge_repeated=True, blank_index=28)
+    for g in range(6):
+        for p in range(2):
+            np.testing.assert_array_equal(got[g][p], want[g][p])
+    np.testing.assert_array_equal(got[6].view(np.uint32), want[6].view(np.uint32))
+
+
+def test_torch_device_tensors_in_device_tensors_out(op):
+    import torch
+    x = L.make_logits("peaky", 30, 4, 12, 11, 4)
+    sl = np.full(4, 30, np.int32)
+    dec, ali, lp = op.ctc_ext_beam_search_decoder(torch.from_numpy(x).cuda(), torch.from_numpy(sl).cuda(),
+                                                  beam_width=8, top_paths=2, blank_index=11)
+    assert dec[0].indices.is_cuda and ali[1].values.is_cuda and lp.is_cuda and lp.shape == (4, 2)
+    want = L.pack_sparse(L.oracle_decode(x, sl, 8, 2, False, 11, -1))
+    np.testing.assert_array_equal(ali[1].values.cpu().numpy(), want[4][1])
+
+
+def test_edge_cases(op):
+    x = L.make_logits("gauss", 6, 3, 4, 0, 9)
+    # sequence_length 0 with one path: empty sequences, log-prob 0 (SURVEY.md Appendix D)
+    raw = op.ctc_ext_beam_search_decoder_raw(x, [0, 6, 3], beam_width=4, top_paths=1)
+    want = L.pack_sparse(L.oracle_decode(x, np.asarray([0, 6, 3], np.int32), 4, 1, False, 0, -1))
+    for g in range(6):
+        np.testing.assert_array_equal(raw[g][0], want[g][0])
+    assert raw[6][0, 0] == 0.0
+    # empty batch
+    raw = op.ctc_ext_beam_search_decoder_raw(np.zeros((5, 0, 4), np.float32), np.zeros((0,), np.int32),
+                                             beam_width=4, top_paths=2)
+    assert raw[0][0].shape == (0, 2) and raw[6].shape == (0, 2) and raw[2][1].tolist() == [0, 0]
+    # beam wider than anything reachable, blank in the middle, custom blank label
+    check_against_oracle(op, x, np.full(3, 6, np.int32), 64, 3, True, 2, 7)
+
+
+def test_device_side_errors(op):
+    x = L.paper_logits(np.float32)
+    with pytest.raises(op.InvalidArgumentError, match="requested more paths than the beam width"):
+        op.ctc_ext_beam_search_decoder(x, [8], beam_width=2, top_paths=3)
+    with pytest.raises(op.InvalidArgumentError, match="Less leaves in the beam search than requested"):
+        op.ctc_ext_beam_search_decoder(x[:1], [1], beam_width=4, top_paths=4)
+    with pytest.raises(op.InvalidArgumentError, match="Less leaves"):
+        op.ctc_ext_beam_search_decoder(x, [0], beam_width=4, top_paths=2)
+    with pytest.raises(op.FailedPreconditionError, match=r"sequence_length\(0\) <= 8"):
+        op.ctc_ext_beam_search_decoder(x, [9], beam_width=4, top_paths=1)
+    with pytest.raises(op.InvalidArgumentError):  # rejected here, undefined behaviour in the reference
+        op.ctc_ext_beam_search_decoder(x, [8], beam_width=4, top_paths=1, blank_index=3)
+    with pytest.raises(op.InvalidArgumentError):
+        op.ctc_ext_beam_search_decoder(x, [-1], beam_width=4, top_paths=1)
+    with pytest.raises(op.UnsupportedError):
+        op.ctc_ext_beam_search_decoder(x, [8], beam_width=5000, top_paths=1)
+
+
+def test_multi_device_sharding_equals_single(op):
+    """Batch cut into blocks (here: three blocks on the same GPU) and merged on the host."""
+    x = L.make_logits("peaky", 25, 7, 10, 9, 13)
+    sl = L.ragged_lengths(25, 7, 13)
+    whole = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=6, top_paths=2, merge_repeated=True, blank_index=9)
+    parts = op.decode_multi_device(x, sl, 6, 2, True, 9, -1, devices=[0, 0, 0])
+    for g in range(6):
+        for p in range(2):
+            np.testing.assert_array_equal(parts[g][p], whole[g][p])
+    np.testing.assert_array_equal(parts[6], whole[6])
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json sizes: parity on a subset against the oracle + size-independent properties on all
+def _collapse(ali_row, blank_label, merge):
+    out, prev = [], None
+    for s in ali_row:
+        if s != blank_label and s != prev:
+            out.append(s)
+        prev = s
+    if merge:
+        out = [v for i, v in enumerate(out) if i == 0 or v != out[i - 1]]
+    return out
+
+
+FULL = [
+    # name, T, B, C, W, P, merge, blank, oracle utterances
+    ("cfg2", 500, 256, 29, 100, 1, True, 28, 6),
+    ("cfg3", 1500, 64, 32, 64, 4, False, 31, 2),
+    ("cfg4", 400, 128, 1024, 16, 1, False, 1023, 2),
+]
+
+
+@pytest.mark.parametrize("cfg", FULL, ids=lambda c: c[0])
+def test_full_size_properties_and_subset_parity(op, cfg):
+    import torch
+    name, T, B, C, W, P, merge, blank, n_oracle = cfg
+    x = L.make_logits("peaky", T, B, C, blank, seed=31)
+    sl = L.ragged_lengths(T, B, 31)
+    raw = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=W, top_paths=P, merge_repeated=merge,
+                                             blank_index=blank, blank_label=-1)
+    dec, ali = _dense_from_raw(raw, B, P, T)
+    lp = np.asarray(raw[6])
+    for b in range(B):
+        for p in range(P):
+            assert len(ali[b][p]) == sl[b]                       # one alignment symbol per frame
+            # the decoded path is the CTC collapse of its own best alignment (blank_label=-1 is no class)
+            assert dec[b][p] == _collapse(ali[b][p], -1, merge)
+            assert all(0 <= v < C and v != blank for v in dec[b][p])
+        assert all(lp[b, p] >= lp[b, p + 1] for p in range(P - 1))  # paths best-first
+        assert np.all(lp[b] <= 0)
+    for p in range(P):  # shapes = [batch, longest]
+        assert raw[2][p].tolist() == [B, max(len(dec[b][p]) for b in range(B))]
+        assert raw[5][p].tolist() == [B, int(sl.max())]
+    # idempotence / order independence: a permuted batch gives the permuted result
+    perm = np.random.default_rng(0).permutation(B)
+    raw2 = op.ctc_ext_beam_search_decoder_raw(np.ascontiguousarray(x[:, perm]), sl[perm], beam_width=W,
+                                              top_paths=P, merge_repeated=merge, blank_index=blank)
+    dec2, ali2 = _dense_from_raw(raw2, B, P, T)
+    for i, b in enumerate(perm):
+        assert dec2[i] == dec[b] and ali2[i] == ali[b]
+    np.testing.assert_array_equal(np.asarray(raw2[6]), lp[perm])
+    # bit-exact parity against the oracle on the first utterances
+    want = L.oracle_decode(x[:, :n_oracle], sl[:n_oracle], W, P, merge, blank, -1)
+    for b in range(n_oracle):
+        for p in range(P):
+            assert dec[b][p] == want.decoded(b, p) and ali[b][p] == want.alignment(b, p)
+            assert np.float32(lp[b, p]).view(np.uint32) == np.float32(want.logp[b, p]).view(np.uint32)
+    assert op.decoder.last_flags == 0  # no utterance hit the documented rounding anomaly
