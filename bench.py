@@ -288,7 +288,7 @@ def run_own_arm(args, rank, world, local_rank):
                       "trace": float(kern_ms[:, 2].mean()), "scan": float(kern_ms[:, 3].mean()),
                       "wall_ms_per_step": 1e3 * wall_dev / args.steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "kernel": "BeamKernel<128,256>",
+                     "frac": achieved / peak, "traffic": traffic, "kernel": "BeamKernelV2<128,256>",
                      "peak_source": peak_src,
                      "note": "algorithmic bytes = 4*C per frame (logits read once); the kernel is "
                              "bound by the T-long serial recurrence per utterance, not by HBM"},

@@ -73,6 +73,8 @@ def load():
     lib.ctcx_profile_enable.restype = None
     lib.ctcx_profile_get.argtypes = [ctypes.POINTER(ctypes.c_float)]
     lib.ctcx_profile_get.restype = None
+    lib.ctcx_debug_set_cycles_buffer.argtypes = [_vp]
+    lib.ctcx_debug_set_cycles_buffer.restype = None
     lib.ctcx_debug_math_f32.argtypes = [ctypes.c_int, _vp, _vp, ctypes.c_int, _vp]
     _lib = lib
     return lib

@@ -90,7 +90,7 @@ cudaError_t LaunchBeam(const ctcx::BeamParams& p, size_t smem, cudaStream_t stre
 
 template <int WMAX, int NT>
 cudaError_t LaunchBeamV2(const ctcx::BeamParams& p, size_t smem, cudaStream_t stream) {
-  auto kern = ctcx::BeamKernelV2<WMAX, NT>;
+  auto kern = (p.dbg_cycles != nullptr) ? ctcx::BeamKernelV2<WMAX, NT, true> : ctcx::BeamKernelV2<WMAX, NT, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<p.B, NT, smem, stream>>>(p);
@@ -124,6 +124,7 @@ void ProfRecord(int i, cudaStream_t s) {
   cudaEventRecord(g_ev[i], s);
 }
 
+thread_local long long* g_dbg_cycles = nullptr;
 thread_local int g_err_batch = -1;
 thread_local int g_err_max_time = 0;
 thread_local char g_msg[160];
@@ -242,6 +243,7 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
     bp.flags = (int*)(base + ws.flags);
     bp.dbg_totals = nullptr;
     bp.dbg_n = nullptr;
+    bp.dbg_cycles = g_dbg_cycles;  // test/measurement hook (ctcx_debug_set_cycles_buffer)
     const Tier tier = PickTier(W);
     // fast path: narrow vocabulary with the candidate list in shared memory (ctcx_beam_v2.cuh);
     // CTCX_BEAM_IMPL=generic forces the generic kernel (A/B tests)
@@ -509,6 +511,10 @@ void ctcx_profile_enable(int on) { g_profile = on; }
 void ctcx_profile_get(float* out_ms) {
   for (int k = 0; k < 5; ++k) out_ms[k] = g_ms[k];
 }
+
+/* measurement hook: device buffer [B,16] int64 receiving per-phase clock64 cycles of the fast beam
+ * kernel (thread 0 of every CTA, summed over frames); NULL switches it off. */
+void ctcx_debug_set_cycles_buffer(long long* dev_buf) { g_dbg_cycles = dev_buf; }
 
 /* test hook: y = f(x) element-wise with the exact device math; op 0 expf, 1 log1pf, 2 logf */
 int ctcx_debug_math_f32(int op, const float* x_dev, float* y_dev, int n, void* stream_v) {

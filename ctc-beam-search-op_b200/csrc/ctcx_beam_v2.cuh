@@ -21,7 +21,8 @@
 
 namespace ctcx {
 
-constexpr int kBinsV2 = 256;
+constexpr int kBinsV2 = 512;   // score-histogram bins
+constexpr int kBinsLog2V2 = 9;
 constexpr int kBndFast = 32;  // boundary items handled by one warp
 
 struct BeamSmemV2 {
@@ -38,8 +39,9 @@ struct BeamSmemV2 {
   size_t m_pslot;                  // i32 [WMAX]
   size_t risk, risk_new;           // i32 [WMAX]
   size_t wiped;                    // u32 [WMAX]
-  size_t htab;                     // i32 [2*WMAX]
-  size_t hist, offs, bins2;        // u32 [256] each
+  size_t htab;                     // u32 [4*WMAX]  (hash tag << 10 | slot), 0xffffffff = empty
+  size_t hist, offs;               // u32 [kBinsV2] each
+  size_t bins2;                    // u32 [256]
   size_t rowstart;                 // i32 [WMAX+1] list offset of each row's first candidate
   size_t pl;                       // f32 [32]     x[l] - off of the current frame
   size_t wsum;                     // i32 [32]     per-warp candidate counts (block scan)
@@ -73,10 +75,10 @@ struct BeamSmemV2 {
     risk = o; o += w * 4;
     risk_new = o; o += w * 4;
     wiped = o; o += w * 4;
-    htab = o; o += 2 * w * 4;
+    htab = o; o += 4 * w * 4;
     hist = o; o += kBinsV2 * 4;
     offs = o; o += kBinsV2 * 4;
-    bins2 = o; o += kBinsV2 * 4;
+    bins2 = o; o += 256 * 4;
     rowstart = o; o += (w + 1 + 3) / 4 * 4 * 4;
     pl = o; o += 32 * 4;
     wsum = o; o += 32 * 4;
@@ -92,12 +94,12 @@ enum {
   kV2LpMax, kV2Gap, kV2TopBin
 };
 
-template <int WMAX, int NT>
-__global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
-  static_assert(NT >= WMAX && NT >= kBinsV2, "one thread per beam slot and per histogram bin");
+template <int WMAX, int NT, bool TIMING>
+__global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKernelV2(BeamParams p) {
+  static_assert(NT >= WMAX && 2 * NT >= kBinsV2, "one thread per beam slot and per two histogram bins");
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int NWARP = NT / 32;
-  constexpr int TS = 2 * WMAX;
+  constexpr int TS = 4 * WMAX;  // parent look-up table slots (load factor <= 1/4)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   const int W = p.W, C = p.C, T = p.T, B = p.B, blank = p.blank_index;
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
   int* s_risk = (int*)(smem + lay.risk);
   int* s_risk_new = (int*)(smem + lay.risk_new);
   unsigned* s_wiped = (unsigned*)(smem + lay.wiped);
-  int* s_htab = (int*)(smem + lay.htab);
+  unsigned* s_htab = (unsigned*)(smem + lay.htab);
   unsigned* s_hist = (unsigned*)(smem + lay.hist);
   unsigned* s_offs = (unsigned*)(smem + lay.offs);
   unsigned* s_bins2 = (unsigned*)(smem + lay.bins2);
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
 
   // ---- initial state: the root (decoder.h:212-227) ----
   LoadExpTable(s_exptab, tid, NT);
-  for (int i = tid; i < TS; i += NT) s_htab[i] = -1;
+  for (int i = tid; i < TS; i += NT) s_htab[i] = 0xffffffffu;
   for (int i = tid; i < WMAX; i += NT) {
     s_wiped[i] = 0u;
     s_row[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -181,11 +183,22 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
   }
   __syncthreads();
   if (tid == 0) {
-    s_htab[(unsigned)kRootHash & (TS - 1)] = 0;
+    s_htab[(unsigned)kRootHash & (TS - 1)] = ((unsigned)(kRootHash >> 42) << 10) | 0u;
     s_row[0] = make_uint4(__float_as_uint(0.0f), __float_as_uint(0.0f), 0xffffffffu, 0u);
   }
   __syncthreads();
 
+  // optional per-phase clock64 instrumentation (thread 0), compiled out of the production kernel
+  long long cyc[TIMING ? 16 : 1] = {0};
+  long long tprev = 0;
+  const bool timing = TIMING && (p.dbg_cycles != nullptr) && tid == 0;
+#define CTCX_TICK(i)                      \
+  if (TIMING && timing) {                 \
+    const long long now_ = clock64();     \
+    cyc[TIMING ? (i) : 0] += now_ - tprev; \
+    tprev = now_;                         \
+  }
+  if (timing) tprev = clock64();
   for (int t = 0; t < L; ++t) {
     const int cur = t & 1, nxt = cur ^ 1;
     const float* x = s_x + cur * 32;
@@ -199,13 +212,15 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
     const unsigned long long* o_hash = s_hash + cur * WMAX;
     const unsigned long long* o_phash = s_phash + cur * WMAX;
 
-    // prefetch the next frame's row; consumed after the barrier that ends this frame
-    if (t + 1 < L) {
-      if (tid < C) {
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(s_x + nxt * 32 + tid);
+    // prefetch the next frame's row (last warp, idle during PA); consumed after the barrier that
+    // ends this frame
+    if (warp == NWARP - 1 && t + 1 < L) {
+      if (lane < C) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(s_x + nxt * 32 + lane);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa),
-                     "l"(p.logits + ((size_t)(t + 1) * B + b) * C + tid));
-      } else if (tid == 32) {
+                     "l"(p.logits + ((size_t)(t + 1) * B + b) * C + lane));
+      }
+      if (lane == 31) {
         const unsigned sa = (unsigned)__cvta_generic_to_shared((float*)sci + kV2Off0 + nxt);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa),
                      "l"(p.off + (size_t)(t + 1) * B + b));
@@ -218,20 +233,16 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
     const float pl_lane = lane_ok ? __fsub_rn(x[lane], off) : 0.0f;
     const float xb = x[blank];
     const float pb = __fsub_rn(xb, off);
-    if (warp == 0) {
+    if (warp == NWARP - 1) {  // idle during PA
       s_pl[lane] = pl_lane;
-      float mx = lane_ok ? pl_lane : NegInf(), mn = lane_ok ? pl_lane : 0.0f;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
-        mn = fminf(mn, __shfl_xor_sync(kFull, mn, o));
-      }
+      const unsigned kmx = __reduce_max_sync(kFull, lane_ok ? KeyOf(pl_lane) : 0u);
+      const unsigned kmn = __reduce_min_sync(kFull, lane_ok ? KeyOf(pl_lane) : 0xffffffffu);
       if (lane == 0) {
-        ((float*)sci)[kV2LpMax] = mx;
-        ((float*)sci)[kV2LpMin] = mn;
+        ((float*)sci)[kV2LpMax] = (kmx != 0u) ? UnKey(kmx) : NegInf();
+        ((float*)sci)[kV2LpMin] = (kmn != 0xffffffffu) ? UnKey(kmn) : 0.0f;
       }
     }
-
+    CTCX_TICK(7)  // frame setup
     // ---- PA: update the existing members (decoder.h:95-143) ----
     unsigned my_key = 0u;
     if (tid < n) {
@@ -243,12 +254,14 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
       if (lbl >= 0) {
         const unsigned long long ph = o_phash[i];
         unsigned h = (unsigned)ph & (TS - 1);
+        const unsigned tag = (unsigned)(ph >> 42);  // 22 hash bits disjoint from the table index
         for (;;) {  // parent->Active() <=> the parent prefix is in the beam (decoder.h:97)
-          const int s = s_htab[h];
-          if (s < 0) break;
-          if (o_hash[s] == ph) { pslot = s; break; }
+          const unsigned e = s_htab[h];
+          if (e == 0xffffffffu) break;
+          if ((e >> 10) == tag && o_hash[e & 1023u] == ph) { pslot = (int)(e & 1023u); break; }
           h = (h + 1) & (TS - 1);
         }
+        CTCX_TICK(8)  // parent look-up
         const float xl = x[lbl];
         const float pl = __fsub_rn(xl, off);
         const float self_an = __fadd_rn(o_an[i], pl);
@@ -271,10 +284,12 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
           an_src = (unsigned)i;
         }
       }
+      CTCX_TICK(9)  // first LSE + alignment candidates
       const float v_nb = __fsub_rn(__fadd_rn(o_total[i], xb), off);
       const float c1 = __fadd_rn(o_ab[i], pb), c2 = __fadd_rn(o_an[i], pb);
       const unsigned ab_kind = (c2 > c1) ? kAbFromAn : kAbFromAb;
       const float v_nt = LogSumExp(v_nb, v_nl, s_exptab);
+      CTCX_TICK(10)  // second LSE
       m_nt[i] = v_nt;
       m_nb[i] = v_nb;
       m_nl[i] = v_nl;
@@ -292,29 +307,27 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
         }
       }
     }
+    CTCX_TICK(11)  // stores + atomics
     {
-      unsigned kmin = (tid < n) ? my_key : 0xffffffffu, kmax = (tid < n) ? my_key : 0u;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        kmin = min(kmin, __shfl_xor_sync(kFull, kmin, o));
-        kmax = max(kmax, __shfl_xor_sync(kFull, kmax, o));
-      }
+      const unsigned kmin = __reduce_min_sync(kFull, (tid < n) ? my_key : 0xffffffffu);
+      const unsigned kmax = __reduce_max_sync(kFull, (tid < n) ? my_key : 0u);
       if (lane == 0 && warp * 32 < n) {
         atomicMin(&scu[kV2MinKey], kmin);
         atomicMax(&scu[kV2MaxKey], kmax);
       }
     }
+    CTCX_TICK(12)  // min/max reduction
     if (n < W) {  // beam not full: every finite child is admissible; bound the score range
       unsigned kb = 0xffffffffu;
       if (tid < n) {
         const float ob = o_blk[tid], ot = o_total[tid];
         if (ot > NegInf()) kb = KeyOf((ob > NegInf()) ? fminf(ot, ob) : ot);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) kb = min(kb, __shfl_xor_sync(kFull, kb, o));
+      kb = __reduce_min_sync(kFull, kb);
       if (lane == 0 && warp * 32 < n) atomicMin(&scu[kV2MinBase], kb);
     }
     __syncthreads();
+    CTCX_TICK(0)  // PA
 
     // ---- PB: fresh children (decoder.h:146-187) + score histogram ----
     const unsigned minkey_m = scu[kV2MinKey];
@@ -345,26 +358,22 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
     }
     const bool clamped = (lo_key != lo_true);
     const unsigned span = hi_key - lo_key;
-    const int shift = max(0, (32 - __clz(span | 1u)) - 8);  // (key - lo) >> shift < 256
+    const int shift = max(0, (32 - __clz(span | 1u)) - kBinsLog2V2);  // (key - lo) >> shift < kBinsV2
     auto bucket_of = [&](unsigned key) -> int { return (key > lo_key) ? (int)((key - lo_key) >> shift) : 0; };
-    if (tid < n) atomicAdd(&s_hist[bucket_of(my_key)], 1u);
-
-    // pass 1: each thread counts the admissible children in its (row, class slice)
+    // pass 1: each thread scores its (row, class slice) and keeps a bitmask of admissible children
     unsigned okmask = 0u;
-    float r_ot = 0.0f, r_ob = 0.0f;
-    int r_label = -1;
+    float sv[CP];
     if (prow < n) {
       const uint4 ri = s_row[prow];
-      r_ot = __uint_as_float(ri.x);
-      r_ob = __uint_as_float(ri.y);
-      r_label = (int)ri.z;
+      const float r_ot = __uint_as_float(ri.x), r_ob = __uint_as_float(ri.y);
+      const int r_label = (int)ri.z;
       const unsigned vm = ((~ri.w) & class_mask) >> pbase;  // not blank, not already a member
       if ((CP == 32 ? vm : (vm & ((1u << (CP & 31)) - 1u))) && __fadd_rn(lp_max, r_ot) > th0f) {
 #pragma unroll
         for (int k = 0; k < CP; ++k) {
           const int l = pbase + k;
-          const float s = __fadd_rn(s_pl[l], (l == r_label) ? r_ob : r_ot);  // :172-182
-          if (((vm >> k) & 1u) && s > th0f) okmask |= 1u << k;
+          sv[k] = __fadd_rn(s_pl[l], (l == r_label) ? r_ob : r_ot);  // :172-182
+          if (((vm >> k) & 1u) && sv[k] > th0f) okmask |= 1u << k;
         }
       }
     }
@@ -393,20 +402,32 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
       }
       if (prow < n && pbase == 0) s_rowstart[prow] = pos0;
     }
-    // pass 2: write them in visiting order (row, then class) and count them in the histogram
+    // pass 2: write them in visiting order (row, then class) and count them in the histogram.
+    // Everything below the predicted range lands in bin 0: those are counted per warp (one atomic
+    // instead of hundreds on the same address).
     {
-      unsigned m = okmask;
-      int pos = pos0;
-      while (m) {
-        const int k = __ffs(m) - 1;
-        m &= m - 1u;
-        const int l = pbase + k;
-        const unsigned key = KeyOf(__fadd_rn(s_pl[l], (l == r_label) ? r_ob : r_ot));
-        c_list[pos++] = make_uint2(key, ((unsigned)prow << 16) | (unsigned)l);
-        atomicAdd(&s_hist[bucket_of(key)], 1u);
+      int n_clamped = 0;
+      if (okmask) {
+#pragma unroll
+        for (int k = 0; k < CP; ++k) {
+          if ((okmask >> k) & 1u) {
+            const unsigned key = KeyOf(sv[k]);
+            const int pos = pos0 + __popc(okmask & ((1u << k) - 1u));
+            c_list[pos] = make_uint2(key, ((unsigned)prow << 16) | (unsigned)(pbase + k));
+            const int bk = bucket_of(key);
+            if (bk == 0) ++n_clamped; else atomicAdd(&s_hist[bk], 1u);
+          }
+        }
       }
+      if (tid < n) {
+        const int bk = bucket_of(my_key);
+        if (bk == 0) ++n_clamped; else atomicAdd(&s_hist[bk], 1u);
+      }
+      n_clamped = __reduce_add_sync(kFull, n_clamped);
+      if (lane == 0 && n_clamped) atomicAdd(&s_hist[0], (unsigned)n_clamped);
     }
     __syncthreads();
+    CTCX_TICK(1)  // PB
     const int n_cand = sci[kV2NCand];
     const int n_risk = sci[kV2NRisk];
 
@@ -474,42 +495,66 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
       __syncthreads();
     }
 
-    // ---- PD: boundary bin of the W-th item and group offsets (warp 0) ----
-    if (warp == 0) {
-      unsigned h[8];
-      unsigned loc = 0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) { h[q] = s_hist[lane * 8 + q]; loc += h[q]; }
-      unsigned suf = loc;
+    CTCX_TICK(2)  // PC
+    // ---- PD: boundary bin of the W-th item and group offsets (two bins per thread) ----
+    {
+      // suffix sums over bins 511..0: thread `tid` owns bins hi = 511-2*tid and lo = hi-1, so an
+      // inclusive PREFIX scan in thread order is an inclusive SUFFIX scan in bin order
+      const int bin_hi = kBinsV2 - 1 - 2 * tid;
+      unsigned h_hi = 0u, h_lo = 0u;
+      if (bin_hi >= 1) {
+        const uint2 hh = *reinterpret_cast<const uint2*>(&s_hist[bin_hi - 1]);
+        h_lo = hh.x;
+        h_hi = hh.y;
+      }
+      const unsigned h2 = h_hi + h_lo;
+      unsigned incl = h2;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const unsigned v = __shfl_down_sync(kFull, suf, o);
-        if (lane + o < 32) suf += v;
+        const unsigned v = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += v;
       }
-      const unsigned above = suf - loc;
-      const int total = (int)__shfl_sync(kFull, suf, 0);
-      const int K = min(W, total);
+      const unsigned nz = __ballot_sync(kFull, h2 != 0u);
+      if (lane == 31) s_wsum[warp] = (int)incl;
+      {
+        const int l0 = nz ? (__ffs(nz) - 1) : 0;  // first lane (highest bins) holding anything
+        const unsigned hh = __shfl_sync(kFull, h_hi, l0);
+        const int tb = nz ? ((kBinsV2 - 1 - 2 * (warp * 32 + l0)) - (hh ? 0 : 1)) : -1;
+        if (lane == 0) s_wsum[16 + warp] = tb;
+      }
+      __syncthreads();
+      unsigned before = 0u, total = 0u;
       int topbin = -1;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) if (h[q]) topbin = lane * 8 + q;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) topbin = max(topbin, __shfl_xor_sync(kFull, topbin, o));
-      if (lane == 0) sci[kV2TopBin] = topbin;
-      unsigned acc = above;
-#pragma unroll
-      for (int q = 7; q >= 0; --q) {
-        s_offs[lane * 8 + q] = acc;
-        if ((int)(acc + h[q]) >= K && (int)acc < K) {
-          sci[kV2Bstar] = lane * 8 + q;
-          sci[kV2KRem] = K - (int)acc;
-          sci[kV2E] = (int)h[q];
+      for (int w2 = 0; w2 < NWARP; ++w2) {
+        const unsigned v = (unsigned)s_wsum[w2];
+        total += v;
+        if (w2 < warp) before += v;
+        topbin = max(topbin, s_wsum[16 + w2]);
+      }
+      if (bin_hi >= 1) {
+        const int K = min(W, (int)total);
+        const unsigned above_hi = before + incl - h2;  // items in bins above bin_hi
+        const unsigned above_lo = above_hi + h_hi;
+        *reinterpret_cast<uint2*>(&s_offs[bin_hi - 1]) = make_uint2(above_lo, above_hi);
+        *reinterpret_cast<uint2*>(&s_hist[bin_hi - 1]) = make_uint2(0u, 0u);  // re-used as counters in PE
+        if ((int)(above_hi + h_hi) >= K && (int)above_hi < K) {
+          sci[kV2Bstar] = bin_hi;
+          sci[kV2KRem] = K - (int)above_hi;
+          sci[kV2E] = (int)h_hi;
           sci[kV2NNew] = K;
+          sci[kV2TopBin] = topbin;
+        } else if ((int)(above_lo + h_lo) >= K && (int)above_lo < K) {
+          sci[kV2Bstar] = bin_hi - 1;
+          sci[kV2KRem] = K - (int)above_lo;
+          sci[kV2E] = (int)h_lo;
+          sci[kV2NNew] = K;
+          sci[kV2TopBin] = topbin;
         }
-        acc += h[q];
-        s_hist[lane * 8 + q] = 0u;  // re-used as per-group position counters in PE
       }
     }
     __syncthreads();
+    CTCX_TICK(3)  // PD
     const int bstar = sc[kV2Bstar], k_rem = sc[kV2KRem], e_b = sc[kV2E], n_new = sc[kV2NNew];
     const bool bnd_all = (e_b == k_rem);
     // next frame's range prediction: measured top-to-threshold gap; if the prediction missed (the
@@ -530,11 +575,19 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
       }
     };
     if (tid < n) place(my_key, (unsigned)tid);
-    for (int c = tid; c < n_cand; c += NT) {
-      const uint2 e = c_list[c];
-      if (e.x) place(e.x, 0x80000000u | e.y);
+    for (int c0 = tid; c0 < n_cand; c0 += 4 * NT) {  // four independent entries in flight
+      uint2 e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u * NT;
+        e[u] = (c < n_cand) ? c_list[c] : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (e[u].x) place(e[u].x, 0x80000000u | e[u].y);
     }
     __syncthreads();
+    CTCX_TICK(4)  // PE
 
     // ---- PF: cut the boundary bin exactly ----
     if (!bnd_all) {
@@ -620,6 +673,7 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
       __syncthreads();
     }
 
+    CTCX_TICK(5)  // PF
     // ---- PG: rank inside the score group = new slot; write the next beam + back-pointers ----
     {
       float* w_total = s_total + nxt * WMAX;
@@ -631,7 +685,7 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
       unsigned long long* w_hash = s_hash + nxt * WMAX;
       unsigned long long* w_phash = s_phash + nxt * WMAX;
       // clear the parent look-up table (this frame's look-ups happened in PA) before re-filling it
-      for (int i = tid; i < TS; i += NT) s_htab[i] = -1;
+      for (int i = tid; i < TS; i += NT) s_htab[i] = 0xffffffffu;
       unsigned long long comp = 0ull;
       int r = -1;
       if (tid < n_new) {
@@ -642,8 +696,10 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
         for (int j = g0; j < g1; ++j) rank += (s_sorted[j] > comp) ? 1 : 0;
         r = g0 + rank;
       }
+      CTCX_TICK(13)  // PG: rank in group
       __syncthreads();  // table cleared, ranks known; s_hist / scalars no longer needed this frame
-      if (tid < kBinsV2) s_hist[tid] = 0u;
+      CTCX_TICK(14)  // PG: barrier
+      for (int i = tid; i < kBinsV2; i += NT) s_hist[i] = 0u;
       if (tid == 0) {
         sci[kV2NCand] = 0;
         sci[kV2NRisk] = 0;
@@ -699,14 +755,20 @@ __global__ void __launch_bounds__(NT) BeamKernelV2(BeamParams p) {
         p.bp[((size_t)b * T + t) * W + r] = make_uint2(rec, (unsigned)lbl);
         if (p.dbg_totals) p.dbg_totals[((size_t)b * T + t) * W + r] = nt_;
         unsigned h = (unsigned)hsh & (TS - 1);
-        while (atomicCAS(&s_htab[h], -1, r) != -1) h = (h + 1) & (TS - 1);
+        const unsigned entry = ((unsigned)(hsh >> 42) << 10) | (unsigned)r;
+        while (atomicCAS(&s_htab[h], 0xffffffffu, entry) != 0xffffffffu) h = (h + 1) & (TS - 1);
       }
       if (p.dbg_n && tid == 0) p.dbg_n[(size_t)b * T + t] = n_new;
+      CTCX_TICK(15)  // PG: state write
     }
     asm volatile("cp.async.wait_all;\n" ::);
     __syncthreads();
+    CTCX_TICK(6)  // PG
     n = n_new;
   }
+  if (TIMING && timing)
+    for (int i = 0; i < (TIMING ? 16 : 1); ++i) p.dbg_cycles[(size_t)b * 16 + i] = cyc[i];
+#undef CTCX_TICK
 
   // ---- final beam (decoder.h:229-261): sorted, the first P slots are the top paths ----
   {

@@ -106,6 +106,7 @@ struct BeamParams {
   int* flags;        // [B]   bit0 rounding anomaly, bit1 fewer leaves than top_paths
   float* dbg_totals;  // optional [B,T,W]
   int* dbg_n;         // optional [B,T]
+  long long* dbg_cycles;  // optional [B,16]: clock64 cycles per phase (thread 0), summed over frames
 };
 
 // Shared-memory carve-up, computed identically on host and device.

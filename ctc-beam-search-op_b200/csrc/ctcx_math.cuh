@@ -159,13 +159,17 @@ __device__ __forceinline__ float LogfExact(float x) {
   return __double2float_rn(y);
 }
 
-// util/ctc_loss_util.h:33-41
+// util/ctc_loss_util.h:33-41. The reference evaluates (a > b) ? a + f(b - a) : b + f(a - b); the two
+// arms are the same expression max + f(min - max) with the same operands, so it is computed once,
+// without a divergent branch around the (long) exp/log1p chain.
 __device__ __forceinline__ float LogSumExp(float a, float b, const unsigned long long* exp_tab) {
   const float ninf = __int_as_float(0xff800000);
   if (a == ninf) return b;
   if (b == ninf) return a;
-  return (a > b) ? __fadd_rn(a, Log1pfExact(ExpfExact(__fsub_rn(b, a), exp_tab)))
-                 : __fadd_rn(b, Log1pfExact(ExpfExact(__fsub_rn(a, b), exp_tab)));
+  const bool a_gt = a > b;
+  const float hi = a_gt ? a : b;
+  const float d = a_gt ? __fsub_rn(b, a) : __fsub_rn(a, b);
+  return __fadd_rn(hi, Log1pfExact(ExpfExact(d, exp_tab)));
 }
 
 }  // namespace ctcx

@@ -1,0 +1,33 @@
+"""Per-phase latency (clock64, thread 0 of each CTA) of BeamKernelV2: python tools/phase_cycles.py [B] [kind]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+
+import ctcx_testlib as L
+import ctc_beam_search_op_b200 as op
+from ctc_beam_search_op_b200 import _lib
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 148
+kind = sys.argv[2] if len(sys.argv) > 2 else "gauss"
+T, C, W = 500, 29, 100
+lib = _lib.load()
+x = torch.from_numpy(L.make_logits(kind, T, B, C, 28, 1)).cuda()
+sl = torch.full((B,), T, dtype=torch.int32).cuda()
+buf = torch.zeros((B, 16), dtype=torch.int64, device="cuda")
+kw = dict(beam_width=W, top_paths=1, merge_repeated=True, blank_index=28)
+op.ctc_ext_beam_search_decoder_raw(x, sl, **kw)
+lib.ctcx_debug_set_cycles_buffer(buf.data_ptr())
+op.ctc_ext_beam_search_decoder_raw(x, sl, **kw)
+torch.cuda.synchronize()
+lib.ctcx_debug_set_cycles_buffer(None)
+c = buf.cpu().numpy().astype(np.float64) / T
+names = ["PA(end)", "PB", "PC", "PD", "PE", "PF", "PG(end)", "setup", "PA.lookup", "PA.lse1", "PA.lse2",
+         "PA.store", "PA.minmax", "PG.rank", "PG.barrier", "PG.write"]
+m = c.mean(axis=0)
+print("B=%d %s: cycles per frame, thread 0 (mean over CTAs):" % (B, kind))
+print("  " + "  ".join("%s %.0f" % (n, v) for n, v in zip(names, m)) + "  | total %.0f" % m.sum())
