@@ -254,9 +254,14 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
       ctcx::BeamSmemV2 lay2;
       lay2.Init(tier.wmax, bp.cand_cap);
       if (lay2.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
+      const char* nt_env = std::getenv("CTCX_BEAM_THREADS");  // tuning hook: 256 or 512 for the W<=128 tier
+      const int nt128 = (nt_env != nullptr && std::atoi(nt_env) == 512) ? 512 : 256;
       switch (tier.wmax) {
         case 32: e = LaunchBeamV2<32, 256>(bp, lay2.bytes, stream); break;
-        case 128: e = LaunchBeamV2<128, 256>(bp, lay2.bytes, stream); break;
+        case 128:
+          e = (nt128 == 256) ? LaunchBeamV2<128, 256>(bp, lay2.bytes, stream)
+                             : LaunchBeamV2<128, 512>(bp, lay2.bytes, stream);
+          break;
         default: e = LaunchBeamV2<256, 256>(bp, lay2.bytes, stream); break;
       }
     } else {

@@ -57,7 +57,7 @@ struct BeamSmemV2 {
     bnd = o; o += kBndFast * 8;
     exptab = o; o += 32 * 8;
     row = o; o += w * 16;
-    list = o; o += (size_t)cand_cap * 8;
+    list = o; o += ((size_t)cand_cap + 1024) * 8;  // + one scratch slot per thread
     total = o; o += 2 * w * 4;
     blk = o; o += 2 * w * 4;
     lab = o; o += 2 * w * 4;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
   __syncthreads();
 
   // optional per-phase clock64 instrumentation (thread 0), compiled out of the production kernel
-  long long cyc[TIMING ? 16 : 1] = {0};
+  long long cyc[TIMING ? 24 : 1] = {0};
   long long tprev = 0;
   const bool timing = TIMING && (p.dbg_cycles != nullptr) && tid == 0;
 #define CTCX_TICK(i)                      \
@@ -360,6 +360,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     const unsigned span = hi_key - lo_key;
     const int shift = max(0, (32 - __clz(span | 1u)) - kBinsLog2V2);  // (key - lo) >> shift < kBinsV2
     auto bucket_of = [&](unsigned key) -> int { return (key > lo_key) ? (int)((key - lo_key) >> shift) : 0; };
+    CTCX_TICK(16)  // PB: range
     // pass 1: each thread scores its (row, class slice) and keeps a bitmask of admissible children
     unsigned okmask = 0u;
     float sv[CP];
@@ -377,6 +378,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
         }
       }
     }
+    CTCX_TICK(17)  // PB: pass 1
     int pos0;
     {
       const int cnt = __popc(okmask);
@@ -402,26 +404,43 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       }
       if (prow < n && pbase == 0) s_rowstart[prow] = pos0;
     }
-    // pass 2: write them in visiting order (row, then class) and count them in the histogram.
-    // Everything below the predicted range lands in bin 0: those are counted per warp (one atomic
+    CTCX_TICK(18)  // PB: scan
+    // pass 2: write them in visiting order (row, then class). Branch-free: a rejected class stores
+    // into this thread's scratch slot behind the list, so the 16 stores overlap instead of forming 16
+    // divergent regions.
+    {
+      uint2* scratch = c_list + p.cand_cap + tid;
+#pragma unroll
+      for (int k = 0; k < CP; ++k) {
+        const bool ok = (okmask >> k) & 1u;
+        uint2* dst = ok ? (c_list + pos0 + __popc(okmask & ((1u << k) - 1u))) : scratch;
+        *dst = make_uint2(KeyOf(sv[k]), ((unsigned)prow << 16) | (unsigned)(pbase + k));
+      }
+    }
+    __syncthreads();
+    CTCX_TICK(19)  // PB: pass 2
+    // pass 3: histogram of members and listed children, balanced over the threads, four entries in
+    // flight. Everything below the predicted range lands in bin 0 and is counted per warp (one atomic
     // instead of hundreds on the same address).
     {
+      const int n_cand_ = sci[kV2NCand];
       int n_clamped = 0;
-      if (okmask) {
-#pragma unroll
-        for (int k = 0; k < CP; ++k) {
-          if ((okmask >> k) & 1u) {
-            const unsigned key = KeyOf(sv[k]);
-            const int pos = pos0 + __popc(okmask & ((1u << k) - 1u));
-            c_list[pos] = make_uint2(key, ((unsigned)prow << 16) | (unsigned)(pbase + k));
-            const int bk = bucket_of(key);
-            if (bk == 0) ++n_clamped; else atomicAdd(&s_hist[bk], 1u);
-          }
-        }
-      }
       if (tid < n) {
         const int bk = bucket_of(my_key);
         if (bk == 0) ++n_clamped; else atomicAdd(&s_hist[bk], 1u);
+      }
+      for (int c0 = tid; c0 < n_cand_; c0 += 4 * NT) {
+        int bk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u * NT;
+          bk[u] = (c < n_cand_) ? bucket_of(c_list[c].x) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (bk[u] > 0) atomicAdd(&s_hist[bk[u]], 1u);
+          n_clamped += (bk[u] == 0) ? 1 : 0;
+        }
       }
       n_clamped = __reduce_add_sync(kFull, n_clamped);
       if (lane == 0 && n_clamped) atomicAdd(&s_hist[0], (unsigned)n_clamped);
@@ -767,7 +786,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     n = n_new;
   }
   if (TIMING && timing)
-    for (int i = 0; i < (TIMING ? 16 : 1); ++i) p.dbg_cycles[(size_t)b * 16 + i] = cyc[i];
+    for (int i = 0; i < (TIMING ? 24 : 1); ++i) p.dbg_cycles[(size_t)b * 24 + i] = cyc[i];
 #undef CTCX_TICK
 
   // ---- final beam (decoder.h:229-261): sorted, the first P slots are the top paths ----

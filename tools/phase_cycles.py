@@ -18,7 +18,7 @@ T, C, W = 500, 29, 100
 lib = _lib.load()
 x = torch.from_numpy(L.make_logits(kind, T, B, C, 28, 1)).cuda()
 sl = torch.full((B,), T, dtype=torch.int32).cuda()
-buf = torch.zeros((B, 16), dtype=torch.int64, device="cuda")
+buf = torch.zeros((B, 24), dtype=torch.int64, device="cuda")
 kw = dict(beam_width=W, top_paths=1, merge_repeated=True, blank_index=28)
 op.ctc_ext_beam_search_decoder_raw(x, sl, **kw)
 lib.ctcx_debug_set_cycles_buffer(buf.data_ptr())
@@ -26,8 +26,9 @@ op.ctc_ext_beam_search_decoder_raw(x, sl, **kw)
 torch.cuda.synchronize()
 lib.ctcx_debug_set_cycles_buffer(None)
 c = buf.cpu().numpy().astype(np.float64) / T
-names = ["PA(end)", "PB", "PC", "PD", "PE", "PF", "PG(end)", "setup", "PA.lookup", "PA.lse1", "PA.lse2",
-         "PA.store", "PA.minmax", "PG.rank", "PG.barrier", "PG.write"]
+names = ["PA(end)", "PB(end)", "PC", "PD", "PE", "PF", "PG(end)", "setup", "PA.lookup", "PA.lse1", "PA.lse2",
+         "PA.store", "PA.minmax", "PG.rank", "PG.barrier", "PG.write", "PB.range", "PB.pass1", "PB.scan",
+         "PB.pass2+bar", "-", "-", "-", "-"]
 m = c.mean(axis=0)
 print("B=%d %s: cycles per frame, thread 0 (mean over CTAs):" % (B, kind))
 print("  " + "  ".join("%s %.0f" % (n, v) for n, v in zip(names, m)) + "  | total %.0f" % m.sum())
