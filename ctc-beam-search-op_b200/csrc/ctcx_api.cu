@@ -15,6 +15,7 @@
 
 #include "ctcx_kernels.cuh"
 #include "ctcx_beam_v2.cuh"
+#include "ctcx_beam_v3.cuh"
 
 namespace {
 
@@ -91,6 +92,15 @@ cudaError_t LaunchBeam(const ctcx::BeamParams& p, size_t smem, cudaStream_t stre
 template <int WMAX, int NT>
 cudaError_t LaunchBeamV2(const ctcx::BeamParams& p, size_t smem, cudaStream_t stream) {
   auto kern = (p.dbg_cycles != nullptr) ? ctcx::BeamKernelV2<WMAX, NT, true> : ctcx::BeamKernelV2<WMAX, NT, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<p.B, NT, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <int WMAX, int NT>
+cudaError_t LaunchBeamV3(const ctcx::BeamParams& p, size_t smem, cudaStream_t stream) {
+  auto kern = (p.dbg_cycles != nullptr) ? ctcx::BeamKernelV3<WMAX, NT, true> : ctcx::BeamKernelV3<WMAX, NT, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<p.B, NT, smem, stream>>>(p);
@@ -245,24 +255,31 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
     bp.dbg_n = nullptr;
     bp.dbg_cycles = g_dbg_cycles;  // test/measurement hook (ctcx_debug_set_cycles_buffer)
     const Tier tier = PickTier(W);
-    // fast path: narrow vocabulary with the candidate list in shared memory (ctcx_beam_v2.cuh);
-    // CTCX_BEAM_IMPL=generic forces the generic kernel (A/B tests)
+    // fast path: narrow vocabulary with the candidate list in shared memory (ctcx_beam_v3.cuh).
+    // CTCX_BEAM_IMPL=generic | v2 forces the generic kernel / the previous fast kernel (A/B tests).
     const char* impl = std::getenv("CTCX_BEAM_IMPL");
     const bool want_generic = impl != nullptr && std::strcmp(impl, "generic") == 0;
+    const bool want_v2 = impl != nullptr && std::strcmp(impl, "v2") == 0;
     cudaError_t e;
     if (!want_generic && C <= 32 && bp.cand_cap > 0 && tier.wmax <= 256) {
-      ctcx::BeamSmemV2 lay2;
-      lay2.Init(tier.wmax, bp.cand_cap);
-      if (lay2.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
-      const char* nt_env = std::getenv("CTCX_BEAM_THREADS");  // tuning hook: 256 or 512 for the W<=128 tier
-      const int nt128 = (nt_env != nullptr && std::atoi(nt_env) == 512) ? 512 : 256;
-      switch (tier.wmax) {
-        case 32: e = LaunchBeamV2<32, 256>(bp, lay2.bytes, stream); break;
-        case 128:
-          e = (nt128 == 256) ? LaunchBeamV2<128, 256>(bp, lay2.bytes, stream)
-                             : LaunchBeamV2<128, 512>(bp, lay2.bytes, stream);
-          break;
-        default: e = LaunchBeamV2<256, 256>(bp, lay2.bytes, stream); break;
+      if (want_v2) {
+        ctcx::BeamSmemV2 lay2;
+        lay2.Init(tier.wmax, bp.cand_cap);
+        if (lay2.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
+        switch (tier.wmax) {
+          case 32: e = LaunchBeamV2<32, 256>(bp, lay2.bytes, stream); break;
+          case 128: e = LaunchBeamV2<128, 256>(bp, lay2.bytes, stream); break;
+          default: e = LaunchBeamV2<256, 256>(bp, lay2.bytes, stream); break;
+        }
+      } else {
+        ctcx::BeamSmemV3 lay3;
+        lay3.Init(tier.wmax, bp.cand_cap);
+        if (lay3.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
+        switch (tier.wmax) {
+          case 32: e = LaunchBeamV3<32, 256>(bp, lay3.bytes, stream); break;
+          case 128: e = LaunchBeamV3<128, 256>(bp, lay3.bytes, stream); break;
+          default: e = LaunchBeamV3<256, 256>(bp, lay3.bytes, stream); break;
+        }
       }
     } else {
       ctcx::BeamSmem lay;

@@ -10,18 +10,18 @@ import ctcx_testlib as L
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["fast", "generic"])
+@pytest.fixture(scope="module", params=["fast", "v2", "generic"])
 def op(request):
-    """Both beam kernels: the default dispatch (v2 fast path where it applies) and the generic
-    kernel forced through CTCX_BEAM_IMPL=generic."""
+    """All beam kernels: the default dispatch (fast path where it applies), the previous fast kernel
+    and the generic kernel, forced through CTCX_BEAM_IMPL."""
     import os
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import ctc_beam_search_op_b200 as m
     old = os.environ.get("CTCX_BEAM_IMPL")
-    if request.param == "generic":
-        os.environ["CTCX_BEAM_IMPL"] = "generic"
+    if request.param in ("generic", "v2"):
+        os.environ["CTCX_BEAM_IMPL"] = request.param
     else:
         os.environ.pop("CTCX_BEAM_IMPL", None)
     yield m
