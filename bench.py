@@ -94,7 +94,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -208,6 +208,12 @@ def run_own_arm(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks / throttle reasons are sampled from before the warm-up to after the e2e region (the
+    # timed regions themselves last only ~0.1 s; nvidia-smi needs a moment to start)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+
     # ---- warm-up ----
     for i in range(max(args.warmup, 3)):
         step_device(i)
@@ -216,8 +222,6 @@ def run_own_arm(args, rank, world, local_rank):
 
     # ---- device-resident timing (CUDA events per step on the launching stream) ----
     lib.ctcx_profile_enable(1)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
            for _ in range(args.steps)]
     kern_ms = np.zeros((args.steps, 5), np.float32)
@@ -232,7 +236,6 @@ def run_own_arm(args, rank, world, local_rank):
         kern_ms[i] = list(buf)
     barrier()
     wall_dev = time.perf_counter() - wall0
-    clocks = sampler.stop()
     lib.ctcx_profile_enable(0)
     dev_ms = float(sum(e0.elapsed_time(e1) for e0, e1 in evs))
 
@@ -246,6 +249,7 @@ def run_own_arm(args, rank, world, local_rank):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    clocks = sampler.stop()
 
     if world > 1:
         t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -288,7 +292,7 @@ def run_own_arm(args, rank, world, local_rank):
                       "trace": float(kern_ms[:, 2].mean()), "scan": float(kern_ms[:, 3].mean()),
                       "wall_ms_per_step": 1e3 * wall_dev / args.steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "kernel": "BeamKernelV2<128,256>",
+                     "frac": achieved / peak, "traffic": traffic, "kernel": "BeamKernelV3<128,256>",
                      "peak_source": peak_src,
                      "note": "algorithmic bytes = 4*C per frame (logits read once); the kernel is "
                              "bound by the T-long serial recurrence per utterance, not by HBM"},
@@ -307,7 +311,7 @@ def run_own_arm(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kind", default="gauss", choices=["gauss", "peaky"])

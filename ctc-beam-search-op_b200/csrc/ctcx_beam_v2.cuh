@@ -57,7 +57,7 @@ struct BeamSmemV2 {
     bnd = o; o += kBndFast * 8;
     exptab = o; o += 32 * 8;
     row = o; o += w * 16;
-    list = o; o += ((size_t)cand_cap + 1024) * 8;  // + one scratch slot per thread
+    list = o; o += (((size_t)cand_cap + 1024) * 8 + 15) / 16 * 16;  // + one scratch slot per thread
     total = o; o += 2 * w * 4;
     blk = o; o += 2 * w * 4;
     lab = o; o += 2 * w * 4;

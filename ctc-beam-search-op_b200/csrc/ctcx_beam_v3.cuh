@@ -39,12 +39,13 @@ struct BeamSmemV3 {
   size_t m_pslot;                  // i32 [WMAX]
   size_t risk, risk_new;           // i32 [WMAX]
   size_t wiped;                    // u32 [WMAX]
-  size_t htab;                     // u32 [4*WMAX]  (hash tag << 10 | slot), 0xffffffff = empty
+  size_t htab;                     // u32 [8*WMAX]  (hash tag << 10 | slot), 0xffffffff = empty
   size_t hist, offs;               // u32 [kBinsV2] each
   size_t bins2;                    // u32 [256]
   size_t pl;                       // f32 [32]     x[l] - off of the current frame
   size_t wsum;                     // i32 [32]     per-warp candidate counts (block scan)
   size_t pls;                      // f32 [32]     class log-probs sorted descending (-inf padding)
+  size_t plh;                      // f32 [8]      s_plS[0,4,8,...]: heads of the groups of four
   size_t bits;                     // u32 [32]     class bit at each sorted position
   size_t pref;                     // u32 [36]     pref[j] = classes at sorted positions < j
   size_t x;                        // f32 [2][32]
@@ -59,7 +60,7 @@ struct BeamSmemV3 {
     bnd = o; o += kBndFast * 8;
     exptab = o; o += 32 * 8;
     row = o; o += w * 16;
-    list = o; o += (size_t)cand_cap * 8;
+    list = o; o += ((size_t)cand_cap * 8 + 15) / 16 * 16;  // keep the following arrays 16-byte aligned
     total = o; o += 2 * w * 4;
     blk = o; o += 2 * w * 4;
     lab = o; o += 2 * w * 4;
@@ -77,13 +78,14 @@ struct BeamSmemV3 {
     risk = o; o += w * 4;
     risk_new = o; o += w * 4;
     wiped = o; o += w * 4;
-    htab = o; o += 4 * w * 4;
+    htab = o; o += 8 * w * 4;
     hist = o; o += kBinsV2 * 4;
     offs = o; o += kBinsV2 * 4;
     bins2 = o; o += 256 * 4;
     pl = o; o += 32 * 4;
     wsum = o; o += 32 * 4;
     pls = o; o += 32 * 4;
+    plh = o; o += 8 * 4;
     bits = o; o += 32 * 4;
     pref = o; o += 36 * 4;
     x = o; o += 2 * 32 * 4;
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
   static_assert(NT >= WMAX && 2 * NT >= kBinsV2, "one thread per beam slot and per two histogram bins");
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int NWARP = NT / 32;
-  constexpr int TS = 4 * WMAX;  // parent look-up table slots (load factor <= 1/4)
+  constexpr int TS = 8 * WMAX;  // parent look-up table slots (load factor <= 1/8: ~97% of the look-ups miss)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   const int W = p.W, C = p.C, T = p.T, B = p.B, blank = p.blank_index;
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
   unsigned* s_bins2 = (unsigned*)(smem + lay.bins2);
   float* s_pl = (float*)(smem + lay.pl);
   float* s_plS = (float*)(smem + lay.pls);
+  float* s_plH = (float*)(smem + lay.plh);
   unsigned* s_bits = (unsigned*)(smem + lay.bits);
   unsigned* s_pref = (unsigned*)(smem + lay.pref);
   int* s_wsum = (int*)(smem + lay.wsum);
@@ -246,6 +249,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
         rank += (kj > kl || (kj == kl && j < lane)) ? 1 : 0;
       }
       s_plS[rank] = lane_ok ? pl_lane : NegInf();
+      if ((rank & 3) == 0) s_plH[rank >> 2] = lane_ok ? pl_lane : NegInf();
       s_bits[rank] = lane_ok ? (1u << lane) : 0u;
       __syncwarp();
       unsigned incl = s_bits[lane];
@@ -277,10 +281,12 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
         unsigned h = (unsigned)ph & (TS - 1);
         const unsigned tag = (unsigned)(ph >> 42);  // 22 hash bits disjoint from the table index
         for (;;) {  // parent->Active() <=> the parent prefix is in the beam (decoder.h:97)
-          const unsigned e = s_htab[h];
-          if (e == 0xffffffffu) break;
-          if ((e >> 10) == tag && o_hash[e & 1023u] == ph) { pslot = (int)(e & 1023u); break; }
-          h = (h + 1) & (TS - 1);
+          const unsigned e0 = s_htab[h], e1 = s_htab[(h + 1) & (TS - 1)];  // two probes in flight
+          if (e0 == 0xffffffffu) break;
+          if ((e0 >> 10) == tag && o_hash[e0 & 1023u] == ph) { pslot = (int)(e0 & 1023u); break; }
+          if (e1 == 0xffffffffu) break;
+          if ((e1 >> 10) == tag && o_hash[e1 & 1023u] == ph) { pslot = (int)(e1 & 1023u); break; }
+          h = (h + 2) & (TS - 1);
         }
         CTCX_TICK(8)  // parent look-up
         const float xl = x[lbl];
@@ -351,7 +357,6 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     CTCX_TICK(0)  // PA
 
     const int n_risk = sci[kV2NRisk];
-    const int Cv = sci[kV3Cv];  // number of non-blank classes
 
     // Candidates of one row above a threshold, as a class bitmask. The classes are sorted by
     // log-prob and fp addition is monotone, so "(x_l - off) + old total > thr" holds exactly for a
@@ -360,11 +365,25 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     // probability (decoder.h:172-177).
     auto cand_mask = [&](const uint4 ri, const float thr) -> unsigned {
       const float ot = __uint_as_float(ri.x);
+      // prefix length = number of sorted scores above thr (the predicate is monotone): first the
+      // heads of the 8 groups of 4, then the group itself. -inf padding never passes.
+      const float4 ha = *reinterpret_cast<const float4*>(s_plH), hb = *reinterpret_cast<const float4*>(s_plH + 4);
+      int g = 0;
+      g += (__fadd_rn(ha.x, ot) > thr) ? 1 : 0;
+      g += (__fadd_rn(ha.y, ot) > thr) ? 1 : 0;
+      g += (__fadd_rn(ha.z, ot) > thr) ? 1 : 0;
+      g += (__fadd_rn(ha.w, ot) > thr) ? 1 : 0;
+      g += (__fadd_rn(hb.x, ot) > thr) ? 1 : 0;
+      g += (__fadd_rn(hb.y, ot) > thr) ? 1 : 0;
+      g += (__fadd_rn(hb.z, ot) > thr) ? 1 : 0;
+      g += (__fadd_rn(hb.w, ot) > thr) ? 1 : 0;
       int pos = 0;
-#pragma unroll
-      for (int step = 16; step >= 1; step >>= 1) {
-        const int q = pos + step;
-        if (q <= Cv && __fadd_rn(s_plS[q - 1], ot) > thr) pos = q;
+      if (g > 0) {  // group g-1 is the last one whose head passes
+        const float4 q = *reinterpret_cast<const float4*>(s_plS + 4 * (g - 1));
+        pos = 4 * (g - 1) + 1;
+        pos += (__fadd_rn(q.y, ot) > thr) ? 1 : 0;
+        pos += (__fadd_rn(q.z, ot) > thr) ? 1 : 0;
+        pos += (__fadd_rn(q.w, ot) > thr) ? 1 : 0;
       }
       unsigned m = s_pref[pos] & ~ri.w;
       const int lb = (int)ri.z;
@@ -390,6 +409,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
             }
             // children visited before the parent reaches label(m), from rows that are not wiped
             const unsigned below = (1u << o_label[m]) - 1u;
+#pragma unroll 4
             for (int r0 = 0; r0 <= pslot; r0 += 32) {
               const int r = r0 + lane;
               if (r <= pslot && !s_wiped[r]) {
