@@ -303,8 +303,23 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
     tp.dec_len = (int*)(base + ws.dec_len); tp.dec = (int*)(base + ws.dec);
     tp.ali_len = (int*)(base + ws.ali_len); tp.ali = (int*)(base + ws.ali);
     const long long walks = (long long)B * P;
-    ctcx::TraceKernel<<<(unsigned)((walks + 127) / 128), 128, 0, stream>>>(tp);
-    CTCX_CUDA(cudaGetLastError());
+    if (walks >= 4096) {
+      // thousands of independent walks hide the latency of the dependent loads by themselves, and
+      // touch one record per frame instead of whole rows
+      ctcx::TraceKernel<<<(unsigned)((walks + 127) / 128), 128, 0, stream>>>(tp);
+      CTCX_CUDA(cudaGetLastError());
+    } else {
+      // one warp per (utterance, path); two blocks of 2^rows_log2 back-pointer rows per warp in
+      // shared memory (about 26 KB per block)
+      constexpr int kTraceWarps = 2;
+      int rows_log2 = 5;
+      while (rows_log2 > 0 && ((size_t)W << rows_log2) * sizeof(uint2) > 26 * 1024) --rows_log2;
+      const size_t tsm = (size_t)kTraceWarps * 2 * ((size_t)W << rows_log2) * sizeof(uint2);
+      auto tk = ctcx::TraceWarpKernel<kTraceWarps>;
+      CTCX_CUDA(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+      tk<<<(unsigned)((walks + kTraceWarps - 1) / kTraceWarps), kTraceWarps * 32, tsm, stream>>>(tp, rows_log2);
+      CTCX_CUDA(cudaGetLastError());
+    }
     ProfRecord(3, stream);
 
     // kernel 4: per-path offsets and sizes

@@ -394,7 +394,6 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     // ---- PC: revisit-wipe fixed point ----
     if (n_risk > 0) {
       for (;;) {
-        if (tid == 0) sci[kV2Changed] = 0;
         for (int q = warp; q < n_risk; q += NWARP) {  // one warp per at-risk member
           const int m = s_risk[q];
           const int pslot = m_pslot[m];
@@ -424,18 +423,24 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
           if (lane == 0) s_risk_new[q] = verdict;
         }
         __syncthreads();
-        for (int q = tid; q < n_risk; q += NT) {
+        // every thread inspects the (few) verdicts itself: no flag, no extra barrier when nothing
+        // changes -- the common case
+        bool changed = false;
+        int min_wiped = 0x7fffffff, max_parent = -1;
+        for (int q = 0; q < n_risk; ++q) {
           const int m = s_risk[q];
           const unsigned v = (unsigned)s_risk_new[q];
-          if (s_wiped[m] != v) {
-            s_wiped[m] = v;
-            sci[kV2Changed] = 1;
-          }
+          changed |= (s_wiped[m] != v);
+          if (v) min_wiped = min(min_wiped, m);
+          max_parent = max(max_parent, m_pslot[m]);
         }
-        __syncthreads();
-        const int changed = sc[kV2Changed];
-        __syncthreads();
         if (!changed) break;
+        __syncthreads();  // all reads of s_wiped are done
+        for (int q = tid; q < n_risk; q += NT) s_wiped[s_risk[q]] = (unsigned)s_risk_new[q];
+        __syncthreads();
+        // a query only counts rows up to its parent's: if every wiped row lies beyond every parent
+        // row, no count (and no parent) is affected and the verdicts are final
+        if (min_wiped > max_parent) break;
       }
       // documented rounding anomaly: flag, do not model
       for (int q = tid; q < n_risk; q += NT) {

@@ -774,6 +774,115 @@ __global__ void __launch_bounds__(128) TraceKernel(TraceParams p) {
   p.ali_len[idx] = L;
 }
 
+// Warp-cooperative trace-back (used when there are too few walks to hide latency by themselves;
+// TraceKernel above is the simple form). One warp per (utterance, path). The walk is a dependent
+// chain (the slot at frame t-1 comes out of the record at frame t), but WHICH ROWS are needed next is
+// known in advance: the warp streams blocks of `rows` consecutive back-pointer rows [rows x W x 8 B,
+// contiguous in memory] into a double buffer in shared memory with cp.async, one block ahead of the
+// walk, so a step is one shared-memory broadcast read plus a few ALU operations instead of a
+// dependent trip to L2/HBM. Symbols are collected 32 frames at a time in registers and written as
+// coalesced rows; the decoded labels are compacted with warp ballots.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) TraceWarpKernel(TraceParams p, int rows_log2) {
+  extern __shared__ __align__(16) unsigned char tsm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int idx = blockIdx.x * WARPS + warp;
+  if (idx >= p.B * p.P) return;
+  const int b = idx / p.P, path = idx - b * p.P;
+  const int L = p.seq_len[b];
+  int* ali = p.ali + (size_t)idx * p.T;
+  int* dec = p.dec + (size_t)idx * p.T;
+  if (path >= p.fin_n[b] || L <= 0) {
+    if (lane == 0) {
+      p.dec_len[idx] = 0;
+      p.ali_len[idx] = 0;
+    }
+    return;
+  }
+  const int W = p.W;
+  const int R = 1 << rows_log2;
+  uint2* buf = reinterpret_cast<uint2*>(tsm) + (size_t)warp * 2 * R * W;
+  const uint2* bp = p.bp + (size_t)b * p.T * W;
+  // block k holds frames [k*R, min(L, (k+1)*R)); blocks are walked from the last one down
+  auto fetch_block = [&](int k) {
+    if (k >= 0) {
+      const int t0 = k << rows_log2;
+      const int nrec = (min(L, t0 + R) - t0) * W;
+      const uint2* src = bp + (size_t)t0 * W;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + (size_t)(k & 1) * R * W);
+      for (int i = lane; i < nrec; i += 32)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst + 8u * (unsigned)i), "l"(src + i));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  const int last_block = (L - 1) >> rows_log2;
+  fetch_block(last_block);
+  int slot = path;
+  int kind_ab = p.fin_kind[idx];
+  int a_val = 0, d_val = -1;  // this lane's symbols of the current 32-frame store block
+  for (int k = last_block; k >= 0; --k) {
+    fetch_block(k - 1);                               // next block in flight while this one is walked
+    asm volatile("cp.async.wait_group 1;\n" ::);     // block k has landed
+    __syncwarp();
+    const uint2* blk = buf + (size_t)(k & 1) * R * W;
+    const int t_lo = k << rows_log2;
+    for (int t = min(L, t_lo + R) - 1; t >= t_lo; --t) {
+      const uint2 r = blk[(t - t_lo) * W + slot];
+      const unsigned prev_self = r.x & 0x7ffu, an_src = (r.x >> 11) & 0x7ffu;
+      const unsigned ab_kind = (r.x >> 22) & 1u, an_kind = (r.x >> 23) & 3u;
+      int sym_a, sym_d = -1;
+      if (kind_ab) {  // entry.h:133-136: a blank frame
+        sym_a = p.blank_label;
+        kind_ab = (ab_kind == kAbFromAb) ? 1 : 0;
+        slot = (int)prev_self;
+      } else {
+        sym_a = (int)r.y;
+        if (an_kind == kAnSelfAn) {
+          slot = (int)prev_self;
+        } else {
+          sym_d = (int)r.y;  // a new label was emitted at this frame
+          slot = (int)an_src;
+          kind_ab = (an_kind == kAnParAb) ? 1 : 0;
+        }
+      }
+      if (lane == (t & 31)) {
+        a_val = sym_a;
+        d_val = sym_d;
+      }
+      if ((t & 31) == 0) {  // frames [t, t+32) complete: coalesced store
+        const int tt = t + lane;
+        if (tt < L) {
+          ali[tt] = a_val;
+          dec[tt] = d_val;
+        }
+      }
+    }
+    __syncwarp();  // buffer (k & 1) is refilled two iterations from now
+  }
+  __syncwarp();
+  // forward compaction of the new labels (entry.h:123-136, optional repeat merging)
+  int base = 0, carry = -1;
+  for (int t0 = 0; t0 < L; t0 += 32) {
+    const int tt = t0 + lane;
+    const int v = (tt < L) ? dec[tt] : -1;
+    const unsigned mask = __ballot_sync(kFull, v >= 0);
+    const unsigned pm = mask & ((1u << lane) - 1u);
+    const int prev_lane = pm ? (31 - __clz(pm)) : 0;
+    int prev_val = __shfl_sync(kFull, v, prev_lane);
+    if (!pm) prev_val = carry;
+    const bool keep = (v >= 0) && (!p.merge_repeated || v != prev_val);
+    const unsigned kmask = __ballot_sync(kFull, keep);
+    __syncwarp();
+    if (keep) dec[base + __popc(kmask & ((1u << lane) - 1u))] = v;
+    base += __popc(kmask);
+    if (mask) carry = __shfl_sync(kFull, v, 31 - __clz(mask));
+  }
+  if (lane == 0) {
+    p.dec_len[idx] = base;
+    p.ali_len[idx] = L;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Kernels 4/5: sparse packing (kernels.cc:163-257). ScanKernel: per path, exclusive prefix sums of
 // the lengths over the batch + totals + maxima. PackKernel: indices [b,pos], values, shapes.
