@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 rep, frames = sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else 128000.0
-src = open(__file__.rsplit("/tools/", 1)[0] + "/ctc-beam-search-op_b200/csrc/ctcx_beam_v2.cuh").read().splitlines()
+src = open(__file__.rsplit("/tools/", 1)[0] + "/ctc-beam-search-op_b200/csrc/" + (sys.argv[3] if len(sys.argv) > 3 else "ctcx_beam_v3.cuh")).read().splitlines()
 bounds = [(1, "init")]
 for i, ln in enumerate(src, 1):
     m = re.search(r"// ---- (P[A-G])", ln)
@@ -55,7 +55,7 @@ def phase(line):
 
 agg, cur, tot, tots = {}, "init", 0, 0
 for a, f, l, i, s in items:
-    if f == "ctcx_beam_v2.cuh" and l:
+    if f == (sys.argv[3] if len(sys.argv) > 3 else "ctcx_beam_v3.cuh") and l:
         cur = phase(l)
     agg.setdefault(cur, [0, 0])
     agg[cur][0] += i
