@@ -165,7 +165,7 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def run_own_arm(args, rank, world, local_rank):
+def run_own_arm(args, rank, world, local_rank, out_fd=1):
     import torch
     import torch.distributed as dist
     import ctc_beam_search_op_b200 as op
@@ -305,7 +305,8 @@ def run_own_arm(args, rank, world, local_rank):
         line["cpu_baseline"] = {"value": n_utt * T / dt, "unit": "frames/s", "cores": cores, "kind": kind,
                                 "sample": "%d utterances of this workload, one per host thread (%.1f s); "
                                           "1 thread alone: %.0f frames/s" % (n_utt, dt, T / dt1)}
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(out_fd, (json.dumps(line) + "\n").encode())
 
 
 def main():
@@ -323,13 +324,19 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
+    # stdout must carry exactly one JSON line: NCCL prints its version banner there, so fd 1 points
+    # to stderr until the result is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
     try:
-        run_own_arm(args, rank, world, local_rank)
+        run_own_arm(args, rank, world, local_rank, saved_stdout)
     finally:
         if world > 1:
             import torch.distributed as dist
