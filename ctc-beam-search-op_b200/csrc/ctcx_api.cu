@@ -230,9 +230,18 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    long long blocks = (rows + 7) / 8;
-    if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
-    ctcx::LogNormKernel<<<(unsigned)blocks, 256, 0, stream>>>(logits_dev, (float*)(base + ws.off), rows, C);
+    if (C <= 64) {  // thread per row, rows staged through shared memory
+      long long blocks = (rows + ctcx::kLogNormRows - 1) / ctcx::kLogNormRows;
+      if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
+      const size_t lsm = (size_t)ctcx::kLogNormRows * (C | 1) * sizeof(float);
+      CTCX_CUDA(cudaFuncSetAttribute(ctcx::LogNormRowKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+      ctcx::LogNormRowKernel<<<(unsigned)blocks, ctcx::kLogNormRows, lsm, stream>>>(
+          logits_dev, (float*)(base + ws.off), rows, C);
+    } else {  // warp per row
+      long long blocks = (rows + 7) / 8;
+      if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
+      ctcx::LogNormKernel<<<(unsigned)blocks, 256, 0, stream>>>(logits_dev, (float*)(base + ws.off), rows, C);
+    }
     CTCX_CUDA(cudaGetLastError());
     ProfRecord(1, stream);
 

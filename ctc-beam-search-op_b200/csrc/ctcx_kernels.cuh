@@ -88,6 +88,41 @@ __global__ void __launch_bounds__(256) LogNormKernel(const float* __restrict__ l
   }
 }
 
+// Narrow-vocabulary variant (C <= 64): one THREAD per row. A CTA stages 256 consecutive rows (one
+// contiguous, coalesced chunk of 256*C floats) in shared memory with an odd row stride (no bank
+// conflicts), then every thread walks its own row: max, then the exp-sum in index order. 4x fewer
+// issued instructions per row than the warp-per-row form, which is what keeps this kernel off the
+// HBM roofline (the exact expf is ~25 instructions, half of them fp64).
+constexpr int kLogNormRows = 256;
+__global__ void __launch_bounds__(kLogNormRows) LogNormRowKernel(const float* __restrict__ logits,
+                                                                  float* __restrict__ off, long long rows,
+                                                                  int C) {
+  extern __shared__ __align__(16) float lsm[];
+  __shared__ unsigned long long s_tab[32];
+  LoadExpTable(s_tab, threadIdx.x, blockDim.x);
+  const int stride = C | 1;
+  for (long long row0 = (long long)blockIdx.x * kLogNormRows; row0 < rows;
+       row0 += (long long)gridDim.x * kLogNormRows) {
+    const int nrow = (int)min((long long)kLogNormRows, rows - row0);
+    const float* src = logits + row0 * C;
+    const int total = nrow * C;
+    __syncthreads();  // previous tile fully consumed (and the table is loaded)
+    for (int i = threadIdx.x; i < total; i += kLogNormRows) {
+      const int r = i / C, c = i - r * C;
+      lsm[r * stride + c] = src[i];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nrow) {
+      const float* x = lsm + threadIdx.x * stride;
+      float mx = x[0];
+      for (int j = 1; j < C; ++j) mx = fmaxf(mx, x[j]);
+      float sum = 0.0f;
+      for (int j = 0; j < C; ++j) sum = __fadd_rn(sum, ExpfExact(__fsub_rn(x[j], mx), s_tab));
+      off[row0 + threadIdx.x] = __fadd_rn(mx, LogfExact(sum));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Kernel 2: the beam kernel.
 // ---------------------------------------------------------------------------------------------
