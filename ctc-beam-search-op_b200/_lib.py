@@ -31,7 +31,8 @@ class CtcxHostResult(ctypes.Structure):
 # every symbol include/ctcx.h declares (tests check that the library exports all of them)
 EXPORTS = ("ctcx_strerror", "ctcx_last_cuda_error", "ctcx_get_limits", "ctcx_workspace_bytes",
            "ctcx_decode_f32", "ctcx_pack_f32", "ctcx_decode_host_f32", "ctcx_free_host",
-           "ctcx_workspace_views")
+           "ctcx_workspace_views", "ctcx_stream_workspace_bytes", "ctcx_stream_reset",
+           "ctcx_stream_step_f32", "ctcx_stream_top_paths")
 
 _lib = None
 
@@ -69,6 +70,13 @@ def load():
     lib.ctcx_free_host.argtypes = [ctypes.POINTER(CtcxHostResult)]
     lib.ctcx_free_host.restype = None
     lib.ctcx_workspace_views.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [_vp] * 5
+    lib.ctcx_stream_workspace_bytes.restype = ctypes.c_size_t
+    lib.ctcx_stream_workspace_bytes.argtypes = [ctypes.c_int] * 5
+    lib.ctcx_stream_reset.argtypes = [_vp, ctypes.c_size_t] + [ctypes.c_int] * 5 + [_vp]
+    lib.ctcx_stream_step_f32.argtypes = [_vp] + [ctypes.c_int] * 5 + [_vp, ctypes.c_int, _vp, ctypes.c_int, _vp]
+    lib.ctcx_stream_top_paths.argtypes = [_vp] + [ctypes.c_int] * 5 + [ctypes.c_int, ctypes.c_int, _vp,
+                                                                      ctypes.POINTER(CtcxSizes),
+                                                                      ctypes.POINTER(ctypes.c_int32)]
     lib.ctcx_profile_enable.argtypes = [ctypes.c_int]
     lib.ctcx_profile_enable.restype = None
     lib.ctcx_profile_get.argtypes = [ctypes.POINTER(ctypes.c_float)]

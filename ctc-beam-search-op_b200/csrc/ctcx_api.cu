@@ -45,7 +45,7 @@ struct Workspace {
     int T, B, C, W, P;
   };
   size_t header, off, bp, fin_total, fin_kind, fin_n, flags, dec_len, ali_len, dec, ali, dec_off,
-      ali_off, sizes, ptrs, stats, bytes;
+      ali_off, sizes, ptrs, stats, t_done, state, bytes;
   void Init(int T, int B, int C, int W, int P) {
     size_t o = 0;
     const size_t b = (size_t)B, t = (size_t)T, w = (size_t)W, pp = (size_t)P;
@@ -66,6 +66,8 @@ struct Workspace {
     sizes = o; o += Align256(4 * pp * 8);
     ptrs = o; o += Align256(6 * pp * 8);
     stats = o; o += Align256(16 * 4);
+    t_done = o; o += Align256(b * 4);                            // streaming: frames consumed so far
+    state = o; o += Align256(b * ctcx::StreamStateBytes(W));     // streaming: beam between chunks
     bytes = o;
   }
 };
@@ -117,6 +119,7 @@ __global__ void FlagsKernel(const int* flags, const int* seq_len, int B, int T, 
     if (f & 2) atomicMin(&out[1], b);
     if (seq_len[b] > T) atomicMin(&out[2], b);
     if (seq_len[b] < 0) atomicMin(&out[3], b);
+    if (f & 4) atomicMin(&out[4], b);  // streaming: more frames fed than the stream was sized for
   }
 }
 
@@ -135,6 +138,109 @@ void ProfRecord(int i, cudaStream_t s) {
 }
 
 thread_local long long* g_dbg_cycles = nullptr;
+int DeviceSmCount() {
+  int sm_count = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  return sm_count;
+}
+
+// kernel 1: softmax normalisers of `rows` consecutive logit rows
+cudaError_t LaunchLogNorm(const float* logits_dev, float* off_dev, long long rows, int C, cudaStream_t stream) {
+  const int sm_count = DeviceSmCount();
+  if (C <= 64) {  // thread per row, rows staged through shared memory
+    long long blocks = (rows + ctcx::kLogNormRows - 1) / ctcx::kLogNormRows;
+    if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
+    const size_t lsm = (size_t)ctcx::kLogNormRows * (C | 1) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(ctcx::LogNormRowKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
+    if (e != cudaSuccess) return e;
+    ctcx::LogNormRowKernel<<<(unsigned)blocks, ctcx::kLogNormRows, lsm, stream>>>(logits_dev, off_dev, rows, C);
+  } else {  // warp per row
+    long long blocks = (rows + 7) / 8;
+    if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
+    ctcx::LogNormKernel<<<(unsigned)blocks, 256, 0, stream>>>(logits_dev, off_dev, rows, C);
+  }
+  return cudaGetLastError();
+}
+
+// kernel 2: picks the beam kernel for the shape (fast path for narrow vocabularies, generic
+// otherwise; CTCX_BEAM_IMPL=generic | v2 forces the generic / the previous fast kernel for A/B
+// tests). Returns CTCX_OK, CTCX_ERR_UNSUPPORTED or CTCX_ERR_CUDA.
+int LaunchBeamFor(ctcx::BeamParams& bp, cudaStream_t stream) {
+  const int W = bp.W, C = bp.C;
+  bp.kid_words = (C + 31) / 32;
+  const long long full_list = (long long)W * C;
+  bp.cand_cap = (full_list <= kListCapMax) ? (int)full_list : 0;
+  bp.dbg_totals = nullptr;
+  bp.dbg_n = nullptr;
+  bp.dbg_cycles = g_dbg_cycles;  // test/measurement hook (ctcx_debug_set_cycles_buffer)
+  const Tier tier = PickTier(W);
+  const char* impl = std::getenv("CTCX_BEAM_IMPL");
+  const bool want_generic = impl != nullptr && std::strcmp(impl, "generic") == 0;
+  const bool want_v2 = impl != nullptr && std::strcmp(impl, "v2") == 0 && bp.state == nullptr;
+  cudaError_t e;
+  if (!want_generic && C <= 32 && bp.cand_cap > 0 && tier.wmax <= 256) {
+    if (want_v2) {
+      ctcx::BeamSmemV2 lay2;
+      lay2.Init(tier.wmax, bp.cand_cap);
+      if (lay2.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
+      switch (tier.wmax) {
+        case 32: e = LaunchBeamV2<32, 256>(bp, lay2.bytes, stream); break;
+        case 128: e = LaunchBeamV2<128, 256>(bp, lay2.bytes, stream); break;
+        default: e = LaunchBeamV2<256, 256>(bp, lay2.bytes, stream); break;
+      }
+    } else {
+      ctcx::BeamSmemV3 lay3;
+      lay3.Init(tier.wmax, bp.cand_cap);
+      if (lay3.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
+      switch (tier.wmax) {
+        case 32: e = LaunchBeamV3<32, 256>(bp, lay3.bytes, stream); break;
+        case 128: e = LaunchBeamV3<128, 256>(bp, lay3.bytes, stream); break;
+        default: e = LaunchBeamV3<256, 256>(bp, lay3.bytes, stream); break;
+      }
+    }
+  } else {
+    ctcx::BeamSmem lay;
+    lay.Init(tier.wmax, tier.nt, C, bp.kid_words, bp.cand_cap);
+    if (lay.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
+    switch (tier.wmax) {
+      case 32: e = LaunchBeam<32, 128>(bp, lay.bytes, stream); break;
+      case 128: e = LaunchBeam<128, 256>(bp, lay.bytes, stream); break;
+      case 256: e = LaunchBeam<256, 256>(bp, lay.bytes, stream); break;
+      default: e = LaunchBeam<1024, 1024>(bp, lay.bytes, stream); break;
+    }
+  }
+  return Check(e, "beam kernel launch") ? CTCX_OK : CTCX_ERR_CUDA;
+}
+
+// kernels 3 + 4: trace-back of the top paths, per-path offsets and sizes
+cudaError_t LaunchTraceAndScan(const ctcx::TraceParams& tp, const ctcx::ScanParams& sp, cudaStream_t stream,
+                               bool profile) {
+  const int W = tp.W;
+  const long long walks = (long long)tp.B * tp.P;
+  if (walks >= 4096) {
+    // thousands of independent walks hide the latency of the dependent loads by themselves, and
+    // touch one record per frame instead of whole rows
+    ctcx::TraceKernel<<<(unsigned)((walks + 127) / 128), 128, 0, stream>>>(tp);
+  } else {
+    // one warp per (utterance, path); two blocks of 2^rows_log2 back-pointer rows per warp in
+    // shared memory (about 26 KB per block)
+    constexpr int kTraceWarps = 2;
+    int rows_log2 = 5;
+    while (rows_log2 > 0 && ((size_t)W << rows_log2) * sizeof(uint2) > 26 * 1024) --rows_log2;
+    const size_t tsm = (size_t)kTraceWarps * 2 * ((size_t)W << rows_log2) * sizeof(uint2);
+    auto tk = ctcx::TraceWarpKernel<kTraceWarps>;
+    cudaError_t e = cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+    if (e != cudaSuccess) return e;
+    tk<<<(unsigned)((walks + kTraceWarps - 1) / kTraceWarps), kTraceWarps * 32, tsm, stream>>>(tp, rows_log2);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (profile) ProfRecord(3, stream);
+  ctcx::ScanKernel<<<tp.P, 1024, 0, stream>>>(sp);
+  return cudaGetLastError();
+}
+
 thread_local int g_err_batch = -1;
 thread_local int g_err_max_time = 0;
 thread_local char g_msg[160];
@@ -200,7 +306,7 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
 
   // sequence_length range check on the device (the data lives there)
   {
-    const int init[4] = {0, B, B, B};
+    const int init[5] = {0, B, B, B, B};
     CTCX_CUDA(cudaMemcpyAsync(d_stats, init, sizeof(init), cudaMemcpyHostToDevice, stream));
     if (B > 0) {
       FlagsKernel<<<(B + 255) / 256, 256, 0, stream>>>(nullptr, seq_len_dev, B, T, d_stats);
@@ -223,121 +329,37 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
   CTCX_CUDA(cudaMemcpyAsync(base + ws.header, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, stream));
 
   if (B > 0) {
-    // kernel 1: normalisers
     ProfRecord(0, stream);
-    const long long rows = (long long)T * B;
-    int sm_count = 148;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (C <= 64) {  // thread per row, rows staged through shared memory
-      long long blocks = (rows + ctcx::kLogNormRows - 1) / ctcx::kLogNormRows;
-      if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
-      const size_t lsm = (size_t)ctcx::kLogNormRows * (C | 1) * sizeof(float);
-      CTCX_CUDA(cudaFuncSetAttribute(ctcx::LogNormRowKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
-      ctcx::LogNormRowKernel<<<(unsigned)blocks, ctcx::kLogNormRows, lsm, stream>>>(
-          logits_dev, (float*)(base + ws.off), rows, C);
-    } else {  // warp per row
-      long long blocks = (rows + 7) / 8;
-      if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
-      ctcx::LogNormKernel<<<(unsigned)blocks, 256, 0, stream>>>(logits_dev, (float*)(base + ws.off), rows, C);
-    }
-    CTCX_CUDA(cudaGetLastError());
+    CTCX_CUDA(LaunchLogNorm(logits_dev, (float*)(base + ws.off), (long long)T * B, C, stream));
     ProfRecord(1, stream);
 
-    // kernel 2: beam search
     ctcx::BeamParams bp;
     bp.logits = logits_dev;
     bp.off = (const float*)(base + ws.off);
     bp.seq_len = seq_len_dev;
     bp.T = T; bp.B = B; bp.C = C; bp.W = W; bp.P = P;
     bp.blank_index = blank_index;
-    bp.kid_words = (C + 31) / 32;
-    const long long full_list = (long long)W * C;
-    bp.cand_cap = (full_list <= kListCapMax) ? (int)full_list : 0;
     bp.bp = (uint2*)(base + ws.bp);
     bp.fin_total = (float*)(base + ws.fin_total);
     bp.fin_kind = (int*)(base + ws.fin_kind);
     bp.fin_n = (int*)(base + ws.fin_n);
     bp.flags = (int*)(base + ws.flags);
-    bp.dbg_totals = nullptr;
-    bp.dbg_n = nullptr;
-    bp.dbg_cycles = g_dbg_cycles;  // test/measurement hook (ctcx_debug_set_cycles_buffer)
-    const Tier tier = PickTier(W);
-    // fast path: narrow vocabulary with the candidate list in shared memory (ctcx_beam_v3.cuh).
-    // CTCX_BEAM_IMPL=generic | v2 forces the generic kernel / the previous fast kernel (A/B tests).
-    const char* impl = std::getenv("CTCX_BEAM_IMPL");
-    const bool want_generic = impl != nullptr && std::strcmp(impl, "generic") == 0;
-    const bool want_v2 = impl != nullptr && std::strcmp(impl, "v2") == 0;
-    cudaError_t e;
-    if (!want_generic && C <= 32 && bp.cand_cap > 0 && tier.wmax <= 256) {
-      if (want_v2) {
-        ctcx::BeamSmemV2 lay2;
-        lay2.Init(tier.wmax, bp.cand_cap);
-        if (lay2.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
-        switch (tier.wmax) {
-          case 32: e = LaunchBeamV2<32, 256>(bp, lay2.bytes, stream); break;
-          case 128: e = LaunchBeamV2<128, 256>(bp, lay2.bytes, stream); break;
-          default: e = LaunchBeamV2<256, 256>(bp, lay2.bytes, stream); break;
-        }
-      } else {
-        ctcx::BeamSmemV3 lay3;
-        lay3.Init(tier.wmax, bp.cand_cap);
-        if (lay3.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
-        switch (tier.wmax) {
-          case 32: e = LaunchBeamV3<32, 256>(bp, lay3.bytes, stream); break;
-          case 128: e = LaunchBeamV3<128, 256>(bp, lay3.bytes, stream); break;
-          default: e = LaunchBeamV3<256, 256>(bp, lay3.bytes, stream); break;
-        }
-      }
-    } else {
-      ctcx::BeamSmem lay;
-      lay.Init(tier.wmax, tier.nt, C, bp.kid_words, bp.cand_cap);
-      if (lay.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
-      switch (tier.wmax) {
-        case 32: e = LaunchBeam<32, 128>(bp, lay.bytes, stream); break;
-        case 128: e = LaunchBeam<128, 256>(bp, lay.bytes, stream); break;
-        case 256: e = LaunchBeam<256, 256>(bp, lay.bytes, stream); break;
-        default: e = LaunchBeam<1024, 1024>(bp, lay.bytes, stream); break;
-      }
-    }
-    CTCX_CUDA(e);
+    bp.Tcap = T; bp.t_done = nullptr; bp.state = nullptr;  // one-shot decode
+    const int brc = LaunchBeamFor(bp, stream);
+    if (brc != CTCX_OK) return brc;
     ProfRecord(2, stream);
 
-    // kernel 3: trace-back
     ctcx::TraceParams tp;
     tp.bp = bp.bp; tp.seq_len = seq_len_dev; tp.fin_total = bp.fin_total; tp.fin_kind = bp.fin_kind;
     tp.fin_n = bp.fin_n; tp.T = T; tp.B = B; tp.W = W; tp.P = P;
     tp.merge_repeated = merge_repeated ? 1 : 0; tp.blank_label = blank_label;
     tp.dec_len = (int*)(base + ws.dec_len); tp.dec = (int*)(base + ws.dec);
     tp.ali_len = (int*)(base + ws.ali_len); tp.ali = (int*)(base + ws.ali);
-    const long long walks = (long long)B * P;
-    if (walks >= 4096) {
-      // thousands of independent walks hide the latency of the dependent loads by themselves, and
-      // touch one record per frame instead of whole rows
-      ctcx::TraceKernel<<<(unsigned)((walks + 127) / 128), 128, 0, stream>>>(tp);
-      CTCX_CUDA(cudaGetLastError());
-    } else {
-      // one warp per (utterance, path); two blocks of 2^rows_log2 back-pointer rows per warp in
-      // shared memory (about 26 KB per block)
-      constexpr int kTraceWarps = 2;
-      int rows_log2 = 5;
-      while (rows_log2 > 0 && ((size_t)W << rows_log2) * sizeof(uint2) > 26 * 1024) --rows_log2;
-      const size_t tsm = (size_t)kTraceWarps * 2 * ((size_t)W << rows_log2) * sizeof(uint2);
-      auto tk = ctcx::TraceWarpKernel<kTraceWarps>;
-      CTCX_CUDA(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-      tk<<<(unsigned)((walks + kTraceWarps - 1) / kTraceWarps), kTraceWarps * 32, tsm, stream>>>(tp, rows_log2);
-      CTCX_CUDA(cudaGetLastError());
-    }
-    ProfRecord(3, stream);
-
-    // kernel 4: per-path offsets and sizes
     ctcx::ScanParams sp;
     sp.dec_len = tp.dec_len; sp.ali_len = tp.ali_len; sp.B = B; sp.P = P;
     sp.dec_off = (long long*)(base + ws.dec_off); sp.ali_off = (long long*)(base + ws.ali_off);
     sp.sizes = (long long*)(base + ws.sizes);
-    ctcx::ScanKernel<<<P, 1024, 0, stream>>>(sp);
-    CTCX_CUDA(cudaGetLastError());
+    CTCX_CUDA(LaunchTraceAndScan(tp, sp, stream, true));
 
     FlagsKernel<<<(B + 255) / 256, 256, 0, stream>>>(bp.flags, seq_len_dev, B, T, d_stats);
     CTCX_CUDA(cudaGetLastError());
@@ -549,6 +571,112 @@ done:
   cudaFree(d_out);
   cudaStreamDestroy(stream);
   return rc;
+}
+
+/* ---- streaming: Step / TopPaths / Reset of the reference decoder (decoder.h:39-53) ---- */
+
+size_t ctcx_stream_workspace_bytes(int max_time_total, int B, int C, int W, int P) {
+  return ctcx_workspace_bytes(max_time_total, B, C, W, P);
+}
+
+int ctcx_stream_reset(void* workspace, size_t workspace_bytes, int T_total, int B, int C, int W, int P,
+                      void* stream_v) {
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  if (T_total <= 0 || B < 0 || C <= 0 || W < 1 || P < 1) return CTCX_ERR_BAD_ARGUMENT;
+  if (W > kMaxBeamWidth || C > kMaxClasses) return CTCX_ERR_UNSUPPORTED;
+  if (P > W) return CTCX_ERR_TOO_MANY_PATHS;
+  Workspace ws;
+  ws.Init(T_total, B, C, W, P);
+  if (workspace == nullptr || workspace_bytes < ws.bytes || ((uintptr_t)workspace & 255u))
+    return CTCX_ERR_WORKSPACE;
+  unsigned char* base = (unsigned char*)workspace;
+  Workspace::Header hdr = {kMagic, T_total, B, C, W, P};
+  CTCX_CUDA(cudaMemcpyAsync(base + ws.header, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, stream));
+  if (B > 0) {
+    // decoder.h:212-227: with zero frames consumed the kernels start from the root
+    CTCX_CUDA(cudaMemsetAsync(base + ws.t_done, 0, (size_t)B * 4, stream));
+    CTCX_CUDA(cudaMemsetAsync(base + ws.flags, 0, (size_t)B * 4, stream));
+    CTCX_CUDA(cudaMemsetAsync(base + ws.state, 0, (size_t)B * ctcx::StreamStateBytes(W), stream));
+  }
+  CTCX_CUDA(cudaStreamSynchronize(stream));  // the header was staged from the stack
+  return CTCX_OK;
+}
+
+int ctcx_stream_step_f32(void* workspace, int T_total, int B, int C, int W, int P, const float* logits_dev,
+                         int chunk_time, const int32_t* chunk_len_dev, int blank_index, void* stream_v) {
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  if (workspace == nullptr) return CTCX_ERR_WORKSPACE;
+  if (chunk_time <= 0 || chunk_time > T_total || chunk_len_dev == nullptr || blank_index < 0 || blank_index >= C)
+    return CTCX_ERR_BAD_ARGUMENT;
+  if (B == 0) return CTCX_OK;
+  Workspace ws;
+  ws.Init(T_total, B, C, W, P);
+  unsigned char* base = (unsigned char*)workspace;
+  CTCX_CUDA(LaunchLogNorm(logits_dev, (float*)(base + ws.off), (long long)chunk_time * B, C, stream));
+  ctcx::BeamParams bp;
+  bp.logits = logits_dev;
+  bp.off = (const float*)(base + ws.off);
+  bp.seq_len = chunk_len_dev;  // frames of THIS chunk to consume, per utterance
+  bp.T = chunk_time; bp.B = B; bp.C = C; bp.W = W; bp.P = P;
+  bp.blank_index = blank_index;
+  bp.bp = (uint2*)(base + ws.bp);
+  bp.fin_total = (float*)(base + ws.fin_total);
+  bp.fin_kind = (int*)(base + ws.fin_kind);
+  bp.fin_n = (int*)(base + ws.fin_n);
+  bp.flags = (int*)(base + ws.flags);
+  bp.Tcap = T_total;
+  bp.t_done = (int*)(base + ws.t_done);
+  bp.state = base + ws.state;
+  return LaunchBeamFor(bp, stream);
+}
+
+int ctcx_stream_top_paths(void* workspace, int T_total, int B, int C, int W, int P, int merge_repeated,
+                          int blank_label, void* stream_v, ctcx_sizes* sizes, int32_t* flags_out) {
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  if (workspace == nullptr || sizes == nullptr) return CTCX_ERR_WORKSPACE;
+  Workspace ws;
+  ws.Init(T_total, B, C, W, P);
+  unsigned char* base = (unsigned char*)workspace;
+  int* d_stats = (int*)(base + ws.stats);
+  std::vector<long long> h_sizes(4 * (size_t)P, 0);
+  int h_stats[5] = {0, B, B, B, B};
+  if (B > 0) {
+    CTCX_CUDA(cudaMemcpyAsync(d_stats, h_stats, sizeof(h_stats), cudaMemcpyHostToDevice, stream));
+    ctcx::TraceParams tp;
+    tp.bp = (const uint2*)(base + ws.bp);
+    tp.seq_len = (const int*)(base + ws.t_done);  // frames consumed so far
+    tp.fin_total = (const float*)(base + ws.fin_total);
+    tp.fin_kind = (const int*)(base + ws.fin_kind);
+    tp.fin_n = (const int*)(base + ws.fin_n);
+    tp.T = T_total; tp.B = B; tp.W = W; tp.P = P;
+    tp.merge_repeated = merge_repeated ? 1 : 0; tp.blank_label = blank_label;
+    tp.dec_len = (int*)(base + ws.dec_len); tp.dec = (int*)(base + ws.dec);
+    tp.ali_len = (int*)(base + ws.ali_len); tp.ali = (int*)(base + ws.ali);
+    ctcx::ScanParams sp;
+    sp.dec_len = tp.dec_len; sp.ali_len = tp.ali_len; sp.B = B; sp.P = P;
+    sp.dec_off = (long long*)(base + ws.dec_off); sp.ali_off = (long long*)(base + ws.ali_off);
+    sp.sizes = (long long*)(base + ws.sizes);
+    CTCX_CUDA(LaunchTraceAndScan(tp, sp, stream, false));
+    FlagsKernel<<<(B + 255) / 256, 256, 0, stream>>>((const int*)(base + ws.flags), tp.seq_len, B, T_total, d_stats);
+    CTCX_CUDA(cudaGetLastError());
+    CTCX_CUDA(cudaMemcpyAsync(h_sizes.data(), base + ws.sizes, h_sizes.size() * 8, cudaMemcpyDeviceToHost, stream));
+    CTCX_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
+    CTCX_CUDA(cudaStreamSynchronize(stream));
+  }
+  if (h_stats[4] < B) {  // an utterance was fed more frames than the stream holds
+    g_err_batch = h_stats[4];
+    g_err_max_time = T_total;
+    return CTCX_ERR_SEQ_LEN_RANGE;
+  }
+  if (h_stats[1] < B) return CTCX_ERR_TOO_FEW_LEAVES;
+  for (int p = 0; p < P; ++p) {
+    if (sizes->n_decoded) sizes->n_decoded[p] = h_sizes[0 * (size_t)P + p];
+    if (sizes->max_decoded) sizes->max_decoded[p] = h_sizes[1 * (size_t)P + p];
+    if (sizes->n_alignment) sizes->n_alignment[p] = h_sizes[2 * (size_t)P + p];
+    if (sizes->max_alignment) sizes->max_alignment[p] = h_sizes[3 * (size_t)P + p];
+  }
+  if (flags_out) *flags_out = h_stats[0];
+  return CTCX_OK;
 }
 
 /* measurement hook (bench.py): per-kernel device times of this thread's last ctcx_decode_f32, from

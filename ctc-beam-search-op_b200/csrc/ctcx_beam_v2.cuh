@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
         w_label[r] = lbl;
         w_hash[r] = hsh;
         s_row[r] = make_uint4(__float_as_uint(nt_), __float_as_uint(nb_), (unsigned)lbl, 0u);
-        p.bp[((size_t)b * T + t) * W + r] = make_uint2(rec, (unsigned)lbl);
+        p.bp[((size_t)b * p.Tcap + t) * W + r] = make_uint2(rec, (unsigned)lbl);
         if (p.dbg_totals) p.dbg_totals[((size_t)b * T + t) * W + r] = nt_;
         unsigned h = (unsigned)hsh & (TS - 1);
         const unsigned entry = ((unsigned)(hsh >> 42) << 10) | (unsigned)r;

@@ -105,7 +105,10 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   const int W = p.W, C = p.C, T = p.T, B = p.B, blank = p.blank_index;
-  const int L = p.seq_len[b];
+  // streaming: frames already consumed by earlier chunks; this chunk contributes L more
+  const int t_done = (p.t_done != nullptr) ? p.t_done[b] : 0;
+  const int L = max(0, min(p.seq_len[b], p.Tcap - t_done));
+  const bool resume = (p.state != nullptr) && t_done > 0;
 
   BeamSmemV3 lay;
   lay.Init(WMAX, p.cand_cap);
@@ -157,14 +160,16 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
   }
   for (int i = tid; i < kBinsV2; i += NT) s_hist[i] = 0u;
   if (tid == 0) {
-    s_total[0] = 0.0f;
-    s_blk[0] = 0.0f;
-    s_lab[0] = NegInf();
-    s_ab[0] = 0.0f;  // empty alignment with probability 1 (entry.h:204-209)
-    s_an[0] = NegInf();
-    s_label[0] = -1;
-    s_hash[0] = kRootHash;
-    s_phash[0] = 0ull;
+    if (!resume) {
+      s_total[0] = 0.0f;
+      s_blk[0] = 0.0f;
+      s_lab[0] = NegInf();
+      s_ab[0] = 0.0f;  // empty alignment with probability 1 (entry.h:204-209)
+      s_an[0] = NegInf();
+      s_label[0] = -1;
+      s_hash[0] = kRootHash;
+      s_phash[0] = 0ull;
+    }
     sci[kV2Anomaly] = 0;
     sci[kV2NCand] = 0;
     sci[kV2NRisk] = 0;
@@ -187,9 +192,26 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     if (tid == 0) ((float*)sci)[kV2Off0] = p.off[b];
   }
   __syncthreads();
-  if (tid == 0) {
-    s_htab[(unsigned)kRootHash & (TS - 1)] = ((unsigned)(kRootHash >> 42) << 10) | 0u;
-    s_row[0] = make_uint4(__float_as_uint(0.0f), __float_as_uint(0.0f), 0xffffffffu, 0u);
+  if (resume) {  // beam as the previous chunk left it (buffer 0: local frame 0 reads buffer 0)
+    StreamView sv(p.state + (size_t)b * StreamStateBytes(W), W);
+    n = sv.hdr->n;
+    for (int i = tid; i < n; i += NT) {
+      s_total[i] = sv.total[i]; s_blk[i] = sv.blk[i]; s_lab[i] = sv.lab[i];
+      s_ab[i] = sv.ab[i]; s_an[i] = sv.an[i]; s_label[i] = sv.label[i];
+      s_hash[i] = sv.hash[i]; s_phash[i] = sv.phash[i];
+    }
+    if (tid == 0) {
+      scu[kV2Gap] = sv.hdr->gap;
+      sci[kV2Anomaly] = sv.hdr->flags & 1;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += NT) {  // row info + parent look-up table of the initial beam
+    s_row[i] = make_uint4(__float_as_uint(s_total[i]), __float_as_uint(s_blk[i]), (unsigned)s_label[i], 0u);
+    const unsigned long long hsh = s_hash[i];
+    unsigned h = (unsigned)hsh & (TS - 1);
+    const unsigned entry = ((unsigned)(hsh >> 42) << 10) | (unsigned)i;
+    while (atomicCAS(&s_htab[h], 0xffffffffu, entry) != 0xffffffffu) h = (h + 1) & (TS - 1);
   }
   __syncthreads();
 
@@ -809,7 +831,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
         w_label[r] = lbl;
         w_hash[r] = hsh;
         s_row[r] = make_uint4(__float_as_uint(nt_), __float_as_uint(nb_), (unsigned)lbl, 0u);
-        p.bp[((size_t)b * T + t) * W + r] = make_uint2(rec, (unsigned)lbl);
+        p.bp[((size_t)b * p.Tcap + (t_done + t)) * W + r] = make_uint2(rec, (unsigned)lbl);
         if (p.dbg_totals) p.dbg_totals[((size_t)b * T + t) * W + r] = nt_;
         unsigned h = (unsigned)hsh & (TS - 1);
         const unsigned entry = ((unsigned)(hsh >> 42) << 10) | (unsigned)r;
@@ -839,10 +861,26 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
         p.fin_kind[(size_t)b * p.P + tid] = 0;
       }
     }
+    const int overflow = (p.seq_len[b] > p.Tcap - t_done) ? 4 : 0;
     if (tid == 0) {
       p.fin_n[b] = n;
-      p.flags[b] = (sci[kV2Anomaly] ? 1 : 0) | ((p.P > n) ? 2 : 0);
+      p.flags[b] = (sci[kV2Anomaly] ? 1 : 0) | ((p.P > n) ? 2 : 0) | overflow;
     }
+    if (p.state != nullptr) {  // carry the beam (and the score-range prediction) to the next chunk
+      StreamView sv(p.state + (size_t)b * StreamStateBytes(W), W);
+      for (int i = tid; i < n; i += NT) {
+        sv.total[i] = s_total[cur * WMAX + i]; sv.blk[i] = s_blk[cur * WMAX + i];
+        sv.lab[i] = s_lab[cur * WMAX + i]; sv.ab[i] = s_ab[cur * WMAX + i];
+        sv.an[i] = s_an[cur * WMAX + i]; sv.label[i] = s_label[cur * WMAX + i];
+        sv.hash[i] = s_hash[cur * WMAX + i]; sv.phash[i] = s_phash[cur * WMAX + i];
+      }
+      if (tid == 0) {
+        sv.hdr->n = n;
+        sv.hdr->gap = scu[kV2Gap];
+        sv.hdr->flags = (sci[kV2Anomaly] ? 1 : 0) | overflow | (resume ? (sv.hdr->flags & 4) : 0);
+      }
+    }
+    if (p.t_done != nullptr && tid == 0) p.t_done[b] = t_done + L;
   }
 }
 

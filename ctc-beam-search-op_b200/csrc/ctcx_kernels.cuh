@@ -141,7 +141,36 @@ struct BeamParams {
   int* flags;        // [B]   bit0 rounding anomaly, bit1 fewer leaves than top_paths
   float* dbg_totals;  // optional [B,T,W]
   int* dbg_n;         // optional [B,T]
-  long long* dbg_cycles;  // optional [B,16]: clock64 cycles per phase (thread 0), summed over frames
+  long long* dbg_cycles;  // optional [B,24]: clock64 cycles per phase (thread 0), summed over frames
+  // streaming (Step / TopPaths / Reset, decoder.h:39-53); all null / T for a one-shot decode
+  int Tcap;               // frames per utterance the back-pointer array can hold (its row stride)
+  int* t_done;            // [B] frames already consumed per utterance (updated by the kernel), or null
+  unsigned char* state;   // [B] x StreamStateBytes(W): beam state carried between chunks, or null
+};
+
+// Beam state of one utterance between two chunks of a streamed decode.
+struct StreamHdr {
+  int n;         // members in the beam
+  unsigned gap;  // score-range prediction of the fast kernel
+  int flags;     // bit0 rounding anomaly, bit2 more frames than the stream was sized for
+  int pad;
+};
+__host__ __device__ inline size_t StreamStateBytes(int W) {
+  return (sizeof(StreamHdr) + (size_t)W * 40 + 15) / 16 * 16;  // 5 x f32 + label + 2 x u64 per slot
+}
+struct StreamView {
+  StreamHdr* hdr;
+  float *total, *blk, *lab, *ab, *an;
+  int* label;
+  unsigned long long *hash, *phash;
+  __device__ StreamView(unsigned char* base, int W) {
+    hdr = reinterpret_cast<StreamHdr*>(base);
+    total = reinterpret_cast<float*>(base + sizeof(StreamHdr));
+    blk = total + W; lab = blk + W; ab = lab + W; an = ab + W;
+    label = reinterpret_cast<int*>(an + W);
+    hash = reinterpret_cast<unsigned long long*>(label + W);
+    phash = hash + W;
+  }
 };
 
 // Shared-memory carve-up, computed identically on host and device.
@@ -219,7 +248,10 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
   const int b = blockIdx.x;
   const int W = p.W, C = p.C, T = p.T, B = p.B, KW = p.kid_words, blank = p.blank_index;
   const bool list_mode = p.cand_cap > 0;
-  const int L = p.seq_len[b];
+  // streaming: frames already consumed by earlier chunks; this chunk contributes L more
+  const int t_done = (p.t_done != nullptr) ? p.t_done[b] : 0;
+  const int L = max(0, min(p.seq_len[b], p.Tcap - t_done));
+  const bool resume = (p.state != nullptr) && t_done > 0;
 
   BeamSmem lay;
   lay.Init(WMAX, NT, C, KW, p.cand_cap);
@@ -261,7 +293,7 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
   for (int i = tid; i < TS; i += NT) s_htab[i] = -1;
   for (int i = tid; i < WMAX * KW; i += NT) s_kid[i] = 0u;
   for (int i = tid; i < WMAX; i += NT) s_wiped[i] = 0u;
-  if (tid == 0) {
+  if (tid == 0 && !resume) {
     s_total[0] = 0.0f;
     s_blk[0] = 0.0f;
     s_lab[0] = NegInf();
@@ -273,6 +305,16 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
     sci[kScAnomaly] = 0;
   }
   int n = 1;  // members in the beam (uniform across the CTA)
+  if (resume) {  // beam as the previous chunk left it (buffer 0: local frame 0 reads buffer 0)
+    StreamView sv(p.state + (size_t)b * StreamStateBytes(W), W);
+    n = sv.hdr->n;
+    for (int i = tid; i < n; i += NT) {
+      s_total[i] = sv.total[i]; s_blk[i] = sv.blk[i]; s_lab[i] = sv.lab[i];
+      s_ab[i] = sv.ab[i]; s_an[i] = sv.an[i]; s_label[i] = sv.label[i];
+      s_hash[i] = sv.hash[i]; s_phash[i] = sv.phash[i];
+    }
+    if (tid == 0) sci[kScAnomaly] = sv.hdr->flags & 1;
+  }
   // row 0 of the logits
   if (L > 0) {
     const float* g = p.logits + (size_t)b * C;
@@ -280,7 +322,10 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
     if (tid == 0) ((float*)sci)[kScOff0] = p.off[b];
   }
   __syncthreads();
-  if (tid == 0) s_htab[(unsigned)kRootHash & (TS - 1)] = 0;
+  for (int i = tid; i < n; i += NT) {  // parent look-up table of the initial beam (the root, or the resumed one)
+    unsigned h = (unsigned)s_hash[i] & (TS - 1);
+    while (atomicCAS(&s_htab[h], -1, i) != -1) h = (h + 1) & (TS - 1);
+  }
   __syncthreads();
 
   for (int t = 0; t < L; ++t) {
@@ -704,7 +749,7 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
         }
         w_label[r] = lbl;
         w_hash[r] = hsh;
-        p.bp[((size_t)b * T + t) * W + r] = make_uint2(rec, (unsigned)lbl);
+        p.bp[((size_t)b * p.Tcap + (t_done + t)) * W + r] = make_uint2(rec, (unsigned)lbl);
         if (p.dbg_totals) p.dbg_totals[((size_t)b * T + t) * W + r] = w_total[r];
         // next frame's parent look-up table
         unsigned h = (unsigned)hsh & (TS - 1);
@@ -735,10 +780,26 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
         p.fin_kind[(size_t)b * p.P + tid] = 0;
       }
     }
+    const int overflow = (p.seq_len[b] > p.Tcap - t_done) ? 4 : 0;
     if (tid == 0) {
       p.fin_n[b] = n;
-      p.flags[b] = (sci[kScAnomaly] ? 1 : 0) | ((p.P > n) ? 2 : 0);
+      p.flags[b] = (sci[kScAnomaly] ? 1 : 0) | ((p.P > n) ? 2 : 0) | overflow;
     }
+    if (p.state != nullptr) {  // carry the beam to the next chunk
+      StreamView sv(p.state + (size_t)b * StreamStateBytes(W), W);
+      for (int i = tid; i < n; i += NT) {
+        sv.total[i] = s_total[cur * WMAX + i]; sv.blk[i] = s_blk[cur * WMAX + i];
+        sv.lab[i] = s_lab[cur * WMAX + i]; sv.ab[i] = s_ab[cur * WMAX + i];
+        sv.an[i] = s_an[cur * WMAX + i]; sv.label[i] = s_label[cur * WMAX + i];
+        sv.hash[i] = s_hash[cur * WMAX + i]; sv.phash[i] = s_phash[cur * WMAX + i];
+      }
+      if (tid == 0) {
+        sv.hdr->n = n;
+        sv.hdr->gap = 0u;
+        sv.hdr->flags = (sci[kScAnomaly] ? 1 : 0) | overflow | (resume ? (sv.hdr->flags & 4) : 0);
+      }
+    }
+    if (p.t_done != nullptr && tid == 0) p.t_done[b] = t_done + L;
   }
 }
 

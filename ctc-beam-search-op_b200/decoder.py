@@ -71,6 +71,30 @@ def _as_tensor(a):
     return torch.from_numpy(np.ascontiguousarray(a)), True
 
 
+def _pack(lib, ws, T, B, P, counts, device, stream):
+    """Allocate the 6*P sparse tensors from the sizes a decode reported and let ctcx_pack_f32 fill
+    them (StoreAllDecodedSequences, kernels.cc:163-257)."""
+    n_dec, n_ali = counts
+    i64 = dict(dtype=torch.int64, device=device)
+    dec_idx = [torch.empty((int(n_dec[p]), 2), **i64) for p in range(P)]
+    dec_val = [torch.empty((int(n_dec[p]),), **i64) for p in range(P)]
+    dec_shp = [torch.empty((2,), **i64) for p in range(P)]
+    ali_idx = [torch.empty((int(n_ali[p]), 2), **i64) for p in range(P)]
+    ali_val = [torch.empty((int(n_ali[p]),), **i64) for p in range(P)]
+    ali_shp = [torch.empty((2,), **i64) for p in range(P)]
+    logp = torch.empty((B, P), dtype=torch.float32, device=device)
+    ptrs = ctypes.c_void_p * P
+
+    def table(ts):
+        return ptrs(*[t.data_ptr() for t in ts])
+
+    rc = lib.ctcx_pack_f32(ws.data_ptr(), T, B, P, table(dec_idx), table(dec_val), table(dec_shp),
+                           table(ali_idx), table(ali_val), table(ali_shp), logp.data_ptr(), stream)
+    if rc != 0:
+        _raise(lib, rc)
+    return [dec_idx, dec_val, dec_shp, ali_idx, ali_val, ali_shp], logp
+
+
 def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_paths,
                                     merge_repeated=False, blank_index=0, blank_label=-1,
                                     name=None, device=None):
@@ -133,25 +157,8 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
             _raise(lib, rc)
         global last_flags
         last_flags = int(flags.value)
-        i64 = dict(dtype=torch.int64, device=device)
-        dec_idx = [torch.empty((int(n_dec[p]), 2), **i64) for p in range(P)]
-        dec_val = [torch.empty((int(n_dec[p]),), **i64) for p in range(P)]
-        dec_shp = [torch.empty((2,), **i64) for p in range(P)]
-        ali_idx = [torch.empty((int(n_ali[p]), 2), **i64) for p in range(P)]
-        ali_val = [torch.empty((int(n_ali[p]),), **i64) for p in range(P)]
-        ali_shp = [torch.empty((2,), **i64) for p in range(P)]
-        logp = torch.empty((B, P), dtype=torch.float32, device=device)
-        ptrs = ctypes.c_void_p * P
-
-        def table(ts):
-            return ptrs(*[t.data_ptr() for t in ts])
-
-        rc = lib.ctcx_pack_f32(ws.data_ptr(), T, B, P, table(dec_idx), table(dec_val), table(dec_shp),
-                               table(ali_idx), table(ali_val), table(ali_shp), logp.data_ptr(), stream)
-        if rc != 0:
-            _raise(lib, rc)
+        groups, logp = _pack(lib, ws, T, B, P, (n_dec, n_ali), device, stream)
         logp = logp.to(out_dtype)
-        groups = [dec_idx, dec_val, dec_shp, ali_idx, ali_val, ali_shp]
         if host_out:
             groups = [[t.cpu() for t in g] for g in groups]
             logp = logp.cpu()
@@ -172,6 +179,109 @@ def ctc_ext_beam_search_decoder(inputs, sequence_length, beam_width, top_paths,
     decoded = [SparseTensor(i, v, s) for i, v, s in zip(raw[0], raw[1], raw[2])]
     alignment = [SparseTensor(i, v, s) for i, v, s in zip(raw[3], raw[4], raw[5])]
     return decoded, alignment, raw[6]
+
+
+class CTCExtBeamSearchDecoderStream:
+    """Streaming form of the decoder: the reference's `Step / TopPaths / Reset`
+    (cc/util/ctc_ext_beam_search_decoder.h:39-53) for a whole batch, with the beam kept on the
+    device between calls. Feeding the frames of an utterance in any chunking gives bit-identical
+    results to one `ctc_ext_beam_search_decoder` call on the concatenation.
+
+        dec = CTCExtBeamSearchDecoderStream(batch_size=B, num_classes=C, beam_width=100, top_paths=1,
+                                            max_time=3000, merge_repeated=True, blank_index=C - 1)
+        for chunk in chunks:                  # [chunk_time, B, C] logits
+            dec.step(chunk)                   # or dec.step(chunk, lengths) for ragged chunks
+            decoded, alignment, logp = dec.top_paths()   # any time; does not disturb the state
+        dec.reset()
+    """
+
+    def __init__(self, batch_size, num_classes, beam_width, top_paths, max_time, merge_repeated=False,
+                 blank_index=0, blank_label=-1, device=None):
+        if int(beam_width) < 1 or int(top_paths) < 1:
+            raise ValueError("beam_width and top_paths must be >= 1")
+        if not torch.cuda.is_available():
+            raise RuntimeError("ctcx: no CUDA device available and there is no CPU fallback")
+        self._lib = _lib.load()
+        self.B, self.C, self.W, self.P, self.T = (int(batch_size), int(num_classes), int(beam_width),
+                                                  int(top_paths), int(max_time))
+        self.merge_repeated, self.blank_index, self.blank_label = (bool(merge_repeated), int(blank_index),
+                                                                   int(blank_label))
+        self.device = (torch.device(device) if device is not None
+                       else torch.device("cuda", torch.cuda.current_device()))
+        nbytes = self._lib.ctcx_stream_workspace_bytes(self.T, self.B, self.C, self.W, self.P)
+        if nbytes == 0:
+            raise InvalidArgumentError(8, self._lib.ctcx_strerror(8).decode())
+        self._nbytes = nbytes
+        self._ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+        self.reset()
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def reset(self):
+        """Reset() (decoder.h:212-227): back to the empty prefix for every utterance."""
+        with torch.cuda.device(self.device):
+            rc = self._lib.ctcx_stream_reset(self._ws.data_ptr(), self._nbytes, self.T, self.B, self.C,
+                                             self.W, self.P, self._stream())
+        if rc != 0:
+            _raise(self._lib, rc)
+
+    def step(self, inputs, sequence_length=None):
+        """Step() over a chunk: inputs [chunk_time, batch, num_classes]; sequence_length[b] = how many
+        leading frames of the chunk utterance b consumes (default: all)."""
+        x, _ = _as_tensor(inputs)
+        if x.dim() != 3:
+            raise InvalidArgumentError(1, self._lib.ctcx_strerror(1).decode())
+        Tc, B, C = (int(v) for v in x.shape)
+        if B != self.B or C != self.C:
+            raise InvalidArgumentError(8, "chunk shape %s does not match the stream (batch %d, classes %d)"
+                                       % (tuple(x.shape), self.B, self.C))
+        if Tc == 0:
+            return
+        with torch.cuda.device(self.device):
+            xd = x.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+            if sequence_length is None:
+                ld = torch.full((B,), Tc, dtype=torch.int32, device=self.device)
+            else:
+                l, _ = _as_tensor(np.asarray(sequence_length, dtype=np.int32)
+                                  if not isinstance(sequence_length, torch.Tensor) else sequence_length)
+                if l.dim() != 1 or int(l.shape[0]) != B:
+                    raise FailedPreconditionError(4, "len(sequence_length) != batch_size.  ")
+                if bool((l.to("cpu") > Tc).any()) or bool((l.to("cpu") < 0).any()):
+                    raise FailedPreconditionError(5, "sequence_length(b) <= %d" % Tc)
+                ld = l.to(device=self.device, dtype=torch.int32).contiguous()
+            rc = self._lib.ctcx_stream_step_f32(self._ws.data_ptr(), self.T, self.B, self.C, self.W, self.P,
+                                                xd.data_ptr(), Tc, ld.data_ptr(), self.blank_index,
+                                                self._stream())
+            # the kernels read xd / ld asynchronously on this stream; keep them alive until then
+            xd.record_stream(torch.cuda.current_stream(self.device))
+            ld.record_stream(torch.cuda.current_stream(self.device))
+        if rc != 0:
+            _raise(self._lib, rc)
+
+    def top_paths_raw(self):
+        """TopPaths() (decoder.h:229-261) of the frames consumed so far, as the raw 7 output groups
+        (device tensors)."""
+        P = self.P
+        arr = ctypes.c_int64 * P
+        n_dec, max_dec, n_ali, max_ali = arr(), arr(), arr(), arr()
+        sizes = _lib.CtcxSizes(n_dec, max_dec, n_ali, max_ali)
+        flags = ctypes.c_int32(0)
+        with torch.cuda.device(self.device):
+            rc = self._lib.ctcx_stream_top_paths(self._ws.data_ptr(), self.T, self.B, self.C, self.W, P,
+                                                 int(self.merge_repeated), self.blank_label, self._stream(),
+                                                 ctypes.byref(sizes), ctypes.byref(flags))
+            if rc != 0:
+                _raise(self._lib, rc)
+            groups, logp = _pack(self._lib, self._ws, self.T, self.B, P, (n_dec, n_ali), self.device,
+                                 self._stream())
+        return CTCExtBeamSearchDecoder(*groups, logp)
+
+    def top_paths(self):
+        raw = self.top_paths_raw()
+        decoded = [SparseTensor(i, v, s) for i, v, s in zip(raw[0], raw[1], raw[2])]
+        alignment = [SparseTensor(i, v, s) for i, v, s in zip(raw[3], raw[4], raw[5])]
+        return decoded, alignment, raw[6]
 
 
 def decode_host_cabi(inputs, sequence_length, beam_width, top_paths, merge_repeated=False,

@@ -126,6 +126,31 @@ int ctcx_decode_host_f32(const float* logits_host, int max_time, int batch, int 
                          ctcx_host_result** result);
 void ctcx_free_host(ctcx_host_result* result);
 
+/* ---- Streaming: the reference decoder's Step / TopPaths / Reset
+ * (util/ctc_ext_beam_search_decoder.h:39-53) for all utterances of a batch at once. The beam state
+ * lives in the workspace between calls, so logits can be fed in chunks of frames as they arrive:
+ *   ctcx_stream_reset(...)                       Reset():    decoder.h:212-227
+ *   ctcx_stream_step_f32(..., chunk, lens ...)   Step() x lens[b] frames: decoder.h:67-210
+ *   ctcx_stream_top_paths(...) + ctcx_pack_f32   TopPaths(): decoder.h:229-261 (does not disturb the state)
+ * Feeding the same frames in any chunking gives bit-identical results to one ctcx_decode_f32 call.
+ * max_time_total bounds the frames per utterance over the whole stream (feeding more is reported by
+ * ctcx_stream_top_paths as CTCX_ERR_SEQ_LEN_RANGE). The shape arguments must be the same in every
+ * call on one workspace. None of the step calls synchronises. ---- */
+size_t ctcx_stream_workspace_bytes(int max_time_total, int batch, int num_classes, int beam_width,
+                                   int top_paths);
+int ctcx_stream_reset(void* workspace, size_t workspace_bytes, int max_time_total, int batch,
+                      int num_classes, int beam_width, int top_paths, void* stream);
+/* logits_dev [chunk_time, batch, num_classes] float32 DEVICE; chunk_len_dev [batch] int32 DEVICE =
+ * number of leading frames of this chunk to consume per utterance (0 .. chunk_time). */
+int ctcx_stream_step_f32(void* workspace, int max_time_total, int batch, int num_classes,
+                         int beam_width, int top_paths, const float* logits_dev, int chunk_time,
+                         const int32_t* chunk_len_dev, int blank_index, void* stream);
+/* Leaves the dense result in the workspace and reports the sparse sizes; follow with
+ * ctcx_pack_f32(workspace, max_time_total, batch, top_paths, ...). Synchronises `stream` once. */
+int ctcx_stream_top_paths(void* workspace, int max_time_total, int batch, int num_classes,
+                          int beam_width, int top_paths, int merge_repeated, int blank_label,
+                          void* stream, ctcx_sizes* sizes, int32_t* flags_out);
+
 /* Debug/test hook: dense per-(b,p) rows as left in the workspace by ctcx_decode_f32 (device
  * pointers into the workspace; stride max_time per row). Any output pointer may be NULL. */
 int ctcx_workspace_views(const void* workspace, int max_time, int batch, int top_paths,

@@ -320,3 +320,65 @@ def test_full_size_properties_and_subset_parity(op, cfg):
             assert dec[b][p] == want.decoded(b, p) and ali[b][p] == want.alignment(b, p)
             assert np.float32(lp[b, p]).view(np.uint32) == np.float32(want.logp[b, p]).view(np.uint32)
     assert op.decoder.last_flags == 0  # no utterance hit the documented rounding anomaly
+
+
+# ------------------------------------------------------------------------------------------------
+# Streaming: Step / TopPaths / Reset (decoder.h:39-53). Any chunking == one-shot == oracle.
+STREAM_CASES = [
+    # kind, T, B, C, W, P, merge, blank
+    ("peaky", 70, 5, 29, 100, 2, True, 28),    # fast kernel
+    ("gauss", 40, 4, 29, 10, 3, False, 28),    # fast kernel, small tier
+    ("gauss", 30, 3, 40, 24, 2, False, 7),     # generic kernel (C > 32)
+    ("peaky", 24, 2, 1024, 16, 1, False, 1023),  # generic kernel, streaming candidate mode
+]
+
+
+@pytest.mark.parametrize("case", STREAM_CASES, ids=lambda c: "%s-T%d-C%d-W%d" % (c[0], c[1], c[3], c[4]))
+def test_streaming_equals_one_shot_and_oracle(op, case):
+    kind, T, B, C, W, P, merge, blank = case
+    rng = np.random.default_rng(17)
+    x = L.make_logits(kind, T, B, C, blank, seed=23)
+    sl = L.ragged_lengths(T, B, 23)
+    dec = op.CTCExtBeamSearchDecoderStream(batch_size=B, num_classes=C, beam_width=W, top_paths=P,
+                                           max_time=T, merge_repeated=merge, blank_index=blank, blank_label=-1)
+    for rep in range(2):  # the second pass checks reset()
+        t = 0
+        while t < T:
+            ct = int(rng.integers(1, 12))
+            ct = min(ct, T - t)
+            lens = np.clip(sl - t, 0, ct).astype(np.int32)
+            dec.step(x[t:t + ct], lens)
+            t += ct
+            if t in (ct, T) or rng.random() < 0.3:  # TopPaths mid-stream == oracle on the prefix
+                done = np.minimum(sl, t).astype(np.int32)
+                if P == 1 or done.min() >= 2:
+                    raw = dec.top_paths_raw()
+                    want = L.pack_sparse(L.oracle_decode(x[:t], done, W, P, merge, blank, -1))
+                    for g in range(6):
+                        for p in range(P):
+                            np.testing.assert_array_equal(raw[g][p].cpu().numpy(), want[g][p])
+                    np.testing.assert_array_equal(raw[6].cpu().numpy().view(np.uint32), want[6].view(np.uint32))
+        raw = dec.top_paths_raw()
+        one = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=W, top_paths=P, merge_repeated=merge,
+                                                 blank_index=blank)
+        for g in range(6):
+            for p in range(P):
+                np.testing.assert_array_equal(raw[g][p].cpu().numpy(), one[g][p])
+        np.testing.assert_array_equal(raw[6].cpu().numpy().view(np.uint32), np.asarray(one[6]).view(np.uint32))
+        dec.reset()
+
+
+def test_streaming_overflow_and_errors(op):
+    x = L.make_logits("peaky", 12, 2, 6, 5, 3)
+    dec = op.CTCExtBeamSearchDecoderStream(2, 6, 4, 1, max_time=8, blank_index=5)
+    dec.step(x[:6])
+    dec.step(x[6:12])  # 12 frames into a stream sized for 8
+    with pytest.raises(op.FailedPreconditionError, match=r"sequence_length\(0\) <= 8"):
+        dec.top_paths()
+    dec.reset()
+    dec.step(x[:8])
+    d, a, lp = dec.top_paths()
+    want = L.pack_sparse(L.oracle_decode(x[:8], np.full(2, 8, np.int32), 4, 1, False, 5, -1))
+    np.testing.assert_array_equal(a[0].values.cpu().numpy(), want[4][0])
+    with pytest.raises(op.InvalidArgumentError):
+        dec.step(x[:, :1])  # wrong batch
