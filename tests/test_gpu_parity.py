@@ -382,3 +382,14 @@ def test_streaming_overflow_and_errors(op):
     np.testing.assert_array_equal(a[0].values.cpu().numpy(), want[4][0])
     with pytest.raises(op.InvalidArgumentError):
         dec.step(x[:, :1])  # wrong batch
+
+
+def test_reference_import_path(op):
+    """The reference test's own import line and call (ops_test.py:12-15, :67-69) work unchanged."""
+    from tensorflow_ctc_ext_beam_search_decoder.python.ops.ctc_ext_beam_search_decoder_ops import \
+        ctc_ext_beam_search_decoder
+    out = ctc_ext_beam_search_decoder(inputs=L.paper_logits(np.float64), sequence_length=[8], beam_width=10,
+                                      blank_index=0, top_paths=5, blank_label=0, merge_repeated=False)
+    np.testing.assert_allclose(out[1][0], [1, 1, 2])
+    np.testing.assert_allclose(out[6], [[-2.0613022, -2.1155741, -2.713197, -2.8770373, -2.9212725]],
+                               rtol=1e-6, atol=1e-6)
