@@ -27,20 +27,37 @@ def nvcc_path():
     return "nvcc"
 
 
+HASH_PATH = os.path.join(LIB_DIR, "libctcx.srchash")
+
+
+def source_hash():
+    """Hash of everything the library is built from (sources, headers, flags)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in SOURCES + HEADERS:
+        with open(f, "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
 def is_stale():
-    if not os.path.exists(LIB_PATH):
+    """True if lib/libctcx.so is missing or was built from different sources. Content based: file
+    times do not survive copying the tree to another box."""
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.exists(f) and os.path.getmtime(f) > t for f in SOURCES + HEADERS)
+    with open(HASH_PATH) as fh:
+        return fh.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
-    """Compile the library if missing or older than its sources. Returns the .so path."""
+    """Compile the library if missing or built from other sources. Returns the .so path."""
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
     subprocess.check_call(cmd)
+    with open(HASH_PATH, "w") as fh:
+        fh.write(source_hash() + "\n")
     return LIB_PATH
 
 

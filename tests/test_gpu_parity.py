@@ -393,3 +393,52 @@ def test_reference_import_path(op):
     np.testing.assert_allclose(out[1][0], [1, 1, 2])
     np.testing.assert_allclose(out[6], [[-2.0613022, -2.1155741, -2.713197, -2.8770373, -2.9212725]],
                                rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# Shape fuzz: small random configurations around the tier / vocabulary boundaries, every kernel.
+def _fuzz_cases():
+    rng = np.random.default_rng(2024)
+    cases = []
+    fixed = [(1, 1, 2, 1, 1), (3, 2, 2, 4, 2), (5, 1, 1, 3, 1), (9, 3, 32, 32, 4), (7, 2, 33, 33, 3),
+             (6, 2, 31, 128, 5), (6, 2, 32, 129, 2), (5, 2, 17, 256, 3), (4, 1, 9, 257, 2),
+             (12, 2, 29, 159, 1), (8, 2, 64, 72, 2), (8, 2, 65, 70, 2), (10, 2, 3, 100, 7)]
+    for T, B, C, W, P in fixed:
+        cases.append((T, B, C, W, P, int(rng.integers(0, C)), bool(rng.integers(0, 2)),
+                      ["gauss", "peaky"][int(rng.integers(0, 2))], float(rng.choice([0.5, 1, 3])), int(rng.integers(0, 9999))))
+    for _ in range(40):
+        C = int(rng.choice([2, 3, 5, 8, 16, 29, 31, 32, 33, 40, 100]))
+        W = int(rng.choice([1, 2, 3, 7, 16, 31, 32, 33, 64, 100, 128, 130, 200]))
+        T = int(rng.integers(1, 40))
+        B = int(rng.integers(1, 6))
+        P = int(rng.integers(1, min(W, 4) + 1))
+        cases.append((T, B, C, W, P, int(rng.integers(0, C)), bool(rng.integers(0, 2)),
+                      ["gauss", "peaky"][int(rng.integers(0, 2))], float(rng.choice([0.5, 1, 3])), int(rng.integers(0, 9999))))
+    return cases
+
+
+def test_fuzz_shapes(op):
+    n_err = 0
+    for T, B, C, W, P, blank, merge, kind, sigma, seed in _fuzz_cases():
+        if C == 1:
+            x = np.random.default_rng(seed).standard_normal((T, B, 1)).astype(np.float32)
+        else:
+            x = L.make_logits(kind, T, B, C, blank, seed, sigma)
+        sl = L.ragged_lengths(T, B, seed)
+        try:
+            want = L.oracle_decode(x, sl, W, P, merge, blank, -1)
+        except L.OracleError as e:
+            with pytest.raises(op.CtcxError, match=str(e)[:24]):
+                op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=W, top_paths=P, merge_repeated=merge,
+                                                   blank_index=blank)
+            n_err += 1
+            continue
+        raw = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=W, top_paths=P, merge_repeated=merge,
+                                                 blank_index=blank, blank_label=-1)
+        packed = L.pack_sparse(want)
+        for g in range(6):
+            for p in range(P):
+                np.testing.assert_array_equal(np.asarray(raw[g][p]), packed[g][p],
+                                              err_msg="T=%d B=%d C=%d W=%d P=%d blank=%d" % (T, B, C, W, P, blank))
+        np.testing.assert_array_equal(np.asarray(raw[6]).view(np.uint32), packed[6].view(np.uint32))
+    assert n_err < 30
