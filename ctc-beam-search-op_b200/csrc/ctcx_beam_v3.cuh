@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       }
     }
     CTCX_TICK(12)  // min/max reduction
-    if (n < W) {  // beam not full: every finite child is admissible; bound the score range
+    if (__builtin_expect(n < W, 0)) {  // beam not full: every finite child is admissible; bound the score range
       unsigned kb = 0xffffffffu;
       if (tid < n) {
         const float ob = o_blk[tid], ot = o_total[tid];
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     };
 
     // ---- PC: revisit-wipe fixed point ----
-    if (n_risk > 0) {
+    if (__builtin_expect(n_risk > 0, 0)) {
       for (;;) {
         for (int q = warp; q < n_risk; q += NWARP) {  // one warp per at-risk member
           const int m = s_risk[q];
@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       }
       __syncthreads();
       CTCX_TICK(3)  // PD
-      if (sc[kV3Found]) break;  // otherwise the prediction missed: run again over the full range
+      if (__builtin_expect(sc[kV3Found] != 0, 1)) break;  // otherwise the prediction missed: run again over the full range
     }
     const bool member_in = !clamped || my_key > lo_key;
     const int bstar = sc[kV2Bstar], k_rem = sc[kV2KRem], e_b = sc[kV2E], n_new = sc[kV2NNew];
@@ -669,7 +669,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
 
     // ---- PF: cut the boundary bin exactly ----
     if (!bnd_all) {
-      if (e_b <= kBndFast) {
+      if (__builtin_expect(e_b <= kBndFast, 1)) {
         if (warp == 0) {
           const unsigned long long mine = (lane < e_b) ? s_bnd[lane] : 0ull;
           const unsigned mlo = (unsigned)mine, mhi = (unsigned)(mine >> 32);
