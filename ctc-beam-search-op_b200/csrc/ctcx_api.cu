@@ -6,8 +6,11 @@
 // StoreAllDecodedSequences :163-257.
 #include "../../include/ctcx.h"
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -107,6 +110,13 @@ cudaError_t LaunchBeamV3(const ctcx::BeamParams& p, size_t smem, cudaStream_t st
   if (e != cudaSuccess) return e;
   kern<<<p.B, NT, smem, stream>>>(p);
   return cudaGetLastError();
+}
+
+// Exact upcast of half-precision logits to the float32 the decoder computes in.
+template <typename H>
+__global__ void UpcastKernel(const H* __restrict__ in, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (float)in[i];
 }
 
 // Reduces the per-utterance flags to {anomaly, too_few_leaves, first bad utterance}.
@@ -571,6 +581,30 @@ done:
   cudaFree(d_out);
   cudaStreamDestroy(stream);
   return rc;
+}
+
+/* fp16 / bf16 logits (what an acoustic model's projection typically emits): upcast exactly to
+ * float32 into `scratch_dev` ([T*B*C] float32, caller-allocated device memory), then decode as
+ * ctcx_decode_f32 does. dtype: 0 = IEEE half, 1 = bfloat16. */
+int ctcx_decode_half(const void* logits_dev, int dtype, float* scratch_dev, int T, int B, int C,
+                     const int32_t* seq_len_dev, int W, int P, int merge_repeated, int blank_index,
+                     int blank_label, void* workspace, size_t workspace_bytes, void* stream_v,
+                     ctcx_sizes* sizes, int32_t* flags_out) {
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  if (T == 0) return CTCX_ERR_MAX_TIME_ZERO;
+  if (T < 0 || B < 0 || C <= 0 || (dtype != 0 && dtype != 1) || (scratch_dev == nullptr && B > 0))
+    return CTCX_ERR_BAD_ARGUMENT;
+  const long long n = (long long)T * B * C;
+  if (n > 0) {
+    const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, 148LL * 32);
+    if (dtype == 0)
+      UpcastKernel<__half><<<blocks, 256, 0, stream>>>((const __half*)logits_dev, scratch_dev, n);
+    else
+      UpcastKernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)logits_dev, scratch_dev, n);
+    CTCX_CUDA(cudaGetLastError());
+  }
+  return ctcx_decode_f32(scratch_dev, T, B, C, seq_len_dev, W, P, merge_repeated, blank_index, blank_label,
+                         workspace, workspace_bytes, stream_v, sizes, flags_out);
 }
 
 /* ---- streaming: Step / TopPaths / Reset of the reference decoder (decoder.h:39-53) ---- */

@@ -100,9 +100,9 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
                                     name=None, device=None):
     """The raw op: returns a 7-field namedtuple of (lists of) tensors, exactly the op's outputs.
 
-    inputs            [max_time, batch, num_classes] float32 (float64 is accepted: computed in
-                      float32, log_probability returned as float64), numpy array or torch tensor on
-                      any device
+    inputs            [max_time, batch, num_classes] float32; float64 is accepted (computed in float32,
+                      log_probability returned as float64); torch float16 / bfloat16 are accepted and
+                      upcast exactly on the device; numpy array or torch tensor on any device
     sequence_length   [batch] int32
     beam_width >= 1, top_paths >= 1, merge_repeated=False, blank_index=0, blank_label=-1
     Outputs live where the inputs live (numpy in -> numpy out).
@@ -138,8 +138,10 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
         device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
     device = torch.device(device)
     host_out = not x.is_cuda
+    half = x.dtype in (torch.float16, torch.bfloat16)
     with torch.cuda.device(device):
-        xd = x.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+        # fp16 / bf16 logits cross the bus as they are and are upcast (exactly) on the device
+        xd = x.to(device=device, dtype=(x.dtype if half else torch.float32), non_blocking=True).contiguous()
         sd = seq.to(device=device, dtype=torch.int32, non_blocking=True).contiguous()
         stream = torch.cuda.current_stream(device).cuda_stream
         P = int(top_paths)
@@ -149,10 +151,18 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
         n_dec, max_dec, n_ali, max_ali = arr(), arr(), arr(), arr()
         sizes = _lib.CtcxSizes(n_dec, max_dec, n_ali, max_ali)
         flags = ctypes.c_int32(0)
-        rc = lib.ctcx_decode_f32(xd.data_ptr(), T, B, C, sd.data_ptr(), int(beam_width), P,
-                                 int(bool(merge_repeated)), int(blank_index), int(blank_label),
-                                 ws.data_ptr(), ws_bytes, stream, ctypes.byref(sizes),
-                                 ctypes.byref(flags))
+        if half:
+            scratch = torch.empty((T, B, C), dtype=torch.float32, device=device)
+            rc = lib.ctcx_decode_half(xd.data_ptr(), 0 if x.dtype == torch.float16 else 1,
+                                      scratch.data_ptr(), T, B, C, sd.data_ptr(), int(beam_width), P,
+                                      int(bool(merge_repeated)), int(blank_index), int(blank_label),
+                                      ws.data_ptr(), ws_bytes, stream, ctypes.byref(sizes),
+                                      ctypes.byref(flags))
+        else:
+            rc = lib.ctcx_decode_f32(xd.data_ptr(), T, B, C, sd.data_ptr(), int(beam_width), P,
+                                     int(bool(merge_repeated)), int(blank_index), int(blank_label),
+                                     ws.data_ptr(), ws_bytes, stream, ctypes.byref(sizes),
+                                     ctypes.byref(flags))
         if rc != 0:
             _raise(lib, rc)
         global last_flags

@@ -126,6 +126,15 @@ int ctcx_decode_host_f32(const float* logits_host, int max_time, int batch, int 
                          ctcx_host_result** result);
 void ctcx_free_host(ctcx_host_result* result);
 
+/* Half-precision logits: logits_dev is [max_time, batch, num_classes] IEEE half (dtype 0) or bfloat16
+ * (dtype 1) in DEVICE memory. They are upcast exactly to float32 into scratch_dev (caller-allocated
+ * device memory, max_time*batch*num_classes floats) and decoded like ctcx_decode_f32, i.e. the result
+ * equals the reference op run on the upcast values. Everything else as ctcx_decode_f32. */
+int ctcx_decode_half(const void* logits_dev, int dtype, float* scratch_dev, int max_time, int batch,
+                     int num_classes, const int32_t* seq_len_dev, int beam_width, int top_paths,
+                     int merge_repeated, int blank_index, int blank_label, void* workspace,
+                     size_t workspace_bytes, void* stream, ctcx_sizes* sizes, int32_t* flags_out);
+
 /* ---- Streaming: the reference decoder's Step / TopPaths / Reset
  * (util/ctc_ext_beam_search_decoder.h:39-53) for all utterances of a batch at once. The beam state
  * lives in the workspace between calls, so logits can be fed in chunks of frames as they arrive:

@@ -442,3 +442,22 @@ def test_fuzz_shapes(op):
                                               err_msg="T=%d B=%d C=%d W=%d P=%d blank=%d" % (T, B, C, W, P, blank))
         np.testing.assert_array_equal(np.asarray(raw[6]).view(np.uint32), packed[6].view(np.uint32))
     assert n_err < 30
+
+
+@pytest.mark.parametrize("dt", ["float16", "bfloat16"])
+def test_half_precision_logits(op, dt):
+    """fp16 / bf16 logits: the result must equal the oracle run on the (exactly) upcast values."""
+    import torch
+    tdt = getattr(torch, dt)
+    x32 = L.make_logits("peaky", 40, 5, 29, 28, 41)
+    xh = torch.from_numpy(x32).to(tdt)
+    up = xh.to(torch.float32).numpy()
+    sl = L.ragged_lengths(40, 5, 41)
+    want = L.pack_sparse(L.oracle_decode(up, sl, 20, 2, True, 28, -1))
+    for inp in (xh, xh.cuda()):
+        raw = op.ctc_ext_beam_search_decoder_raw(inp, sl, beam_width=20, top_paths=2, merge_repeated=True,
+                                                 blank_index=28)
+        for g in range(6):
+            for p in range(2):
+                np.testing.assert_array_equal(raw[g][p].cpu().numpy(), want[g][p])
+        np.testing.assert_array_equal(raw[6].cpu().numpy().view(np.uint32), want[6].view(np.uint32))
