@@ -9,6 +9,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libctcx.so")
 SOURCES = [os.path.join(CSRC, "ctcx_api.cu")]
 HEADERS = [os.path.join(CSRC, "ctcx_kernels.cuh"), os.path.join(CSRC, "ctcx_beam_v2.cuh"),
            os.path.join(CSRC, "ctcx_beam_v3.cuh"),
+           os.path.join(CSRC, "ctcx_beam_wide.cuh"),
            os.path.join(CSRC, "ctcx_math.cuh"),
            os.path.join(os.path.dirname(PKG_DIR), "include", "ctcx.h")]
 

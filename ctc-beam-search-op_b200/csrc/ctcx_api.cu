@@ -19,6 +19,7 @@
 #include "ctcx_kernels.cuh"
 #include "ctcx_beam_v2.cuh"
 #include "ctcx_beam_v3.cuh"
+#include "ctcx_beam_wide.cuh"
 
 namespace {
 
@@ -41,6 +42,27 @@ constexpr uint32_t kMagic = 0x43544358u;  // "CTCX"
 
 size_t Align256(size_t v) { return (v + 255) / 256 * 256; }
 
+struct Tier {
+  int wmax, nt;
+};
+Tier PickTier(int W) {
+  if (W <= 32) return {32, 128};
+  if (W <= 128) return {128, 256};
+  if (W <= 256) return {256, 256};
+  return {1024, 1024};
+}
+
+// Wide-vocabulary fast path (ctcx_beam_wide.cuh): 32 < C <= 2048 and the whole candidate list
+// (beam_width * num_classes entries in the worst frame) fits in shared memory.
+bool UseWide(int W, int C) {
+  if (C <= 32 || C > 2048 || W > 256) return false;
+  const char* impl = std::getenv("CTCX_BEAM_IMPL");
+  if (impl != nullptr && std::strcmp(impl, "generic") == 0) return false;
+  ctcx::BeamSmemWide lay;
+  lay.Init(PickTier(W).wmax, W * C, C, (C + 7) / 8 * 8);
+  return lay.bytes <= 200 * 1024;
+}
+
 // Everything a decode leaves behind for pack, at fixed offsets inside the caller's workspace.
 struct Workspace {
   struct Header {
@@ -48,7 +70,8 @@ struct Workspace {
     int T, B, C, W, P;
   };
   size_t header, off, bp, fin_total, fin_kind, fin_n, flags, dec_len, ali_len, dec, ali, dec_off,
-      ali_off, sizes, ptrs, stats, t_done, state, bytes;
+      ali_off, sizes, ptrs, stats, t_done, state, srt_pl, srt_cls, bytes;
+  int Cs;  // row stride of the sorted-class arrays (0 when the wide fast path does not apply)
   void Init(int T, int B, int C, int W, int P) {
     size_t o = 0;
     const size_t b = (size_t)B, t = (size_t)T, w = (size_t)W, pp = (size_t)P;
@@ -71,19 +94,12 @@ struct Workspace {
     stats = o; o += Align256(16 * 4);
     t_done = o; o += Align256(b * 4);                            // streaming: frames consumed so far
     state = o; o += Align256(b * ctcx::StreamStateBytes(W));     // streaming: beam between chunks
+    Cs = UseWide(W, C) ? (C + 7) / 8 * 8 : 0;                    // wide fast path: classes sorted per frame
+    srt_pl = o; o += Align256(t * b * (size_t)Cs * 4);
+    srt_cls = o; o += Align256(t * b * (size_t)Cs * 2);
     bytes = o;
   }
 };
-
-struct Tier {
-  int wmax, nt;
-};
-Tier PickTier(int W) {
-  if (W <= 32) return {32, 128};
-  if (W <= 128) return {128, 256};
-  if (W <= 256) return {256, 256};
-  return {1024, 1024};
-}
 
 template <int WMAX, int NT>
 cudaError_t LaunchBeam(const ctcx::BeamParams& p, size_t smem, cudaStream_t stream) {
@@ -117,6 +133,15 @@ template <typename H>
 __global__ void UpcastKernel(const H* __restrict__ in, float* __restrict__ out, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = (float)in[i];
+}
+
+template <int WMAX, int NT>
+cudaError_t LaunchBeamWide(const ctcx::BeamParams& p, size_t smem, cudaStream_t stream) {
+  auto kern = ctcx::BeamKernelWide<WMAX, NT, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<p.B, NT, smem, stream>>>(p);
+  return cudaGetLastError();
 }
 
 // Reduces the per-utterance flags to {anomaly, too_few_leaves, first bad utterance}.
@@ -173,6 +198,17 @@ cudaError_t LaunchLogNorm(const float* logits_dev, float* off_dev, long long row
   return cudaGetLastError();
 }
 
+// kernel 1b (wide vocabularies): classes of every row ordered by log-prob
+cudaError_t LaunchSortClasses(const float* logits_dev, const float* off_dev, long long rows, int C, int blank,
+                              int Cs, float* srt_pl, unsigned short* srt_cls, cudaStream_t stream) {
+  int n_pow2 = 64;
+  while (n_pow2 < C) n_pow2 <<= 1;
+  long long blocks = std::min<long long>(rows, (long long)DeviceSmCount() * 16);
+  ctcx::SortClassesKernel<<<(unsigned)blocks, 256, (size_t)n_pow2 * 8, stream>>>(logits_dev, off_dev, rows, C, blank,
+                                                                              Cs, n_pow2, srt_pl, srt_cls);
+  return cudaGetLastError();
+}
+
 // kernel 2: picks the beam kernel for the shape (fast path for narrow vocabularies, generic
 // otherwise; CTCX_BEAM_IMPL=generic | v2 forces the generic / the previous fast kernel for A/B
 // tests). Returns CTCX_OK, CTCX_ERR_UNSUPPORTED or CTCX_ERR_CUDA.
@@ -189,7 +225,16 @@ int LaunchBeamFor(ctcx::BeamParams& bp, cudaStream_t stream) {
   const bool want_generic = impl != nullptr && std::strcmp(impl, "generic") == 0;
   const bool want_v2 = impl != nullptr && std::strcmp(impl, "v2") == 0 && bp.state == nullptr;
   cudaError_t e;
-  if (!want_generic && C <= 32 && bp.cand_cap > 0 && tier.wmax <= 256) {
+  if (bp.srt_pl != nullptr) {  // wide-vocabulary fast path (the caller ran SortClassesKernel)
+    bp.cand_cap = W * C;
+    ctcx::BeamSmemWide layw;
+    layw.Init(tier.wmax, bp.cand_cap, C, bp.Cs);
+    switch (tier.wmax) {
+      case 32: e = LaunchBeamWide<32, 256>(bp, layw.bytes, stream); break;
+      case 128: e = LaunchBeamWide<128, 256>(bp, layw.bytes, stream); break;
+      default: e = LaunchBeamWide<256, 256>(bp, layw.bytes, stream); break;
+    }
+  } else if (!want_generic && C <= 32 && bp.cand_cap > 0 && tier.wmax <= 256) {
     if (want_v2) {
       ctcx::BeamSmemV2 lay2;
       lay2.Init(tier.wmax, bp.cand_cap);
@@ -355,6 +400,13 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
     bp.fin_n = (int*)(base + ws.fin_n);
     bp.flags = (int*)(base + ws.flags);
     bp.Tcap = T; bp.t_done = nullptr; bp.state = nullptr;  // one-shot decode
+    bp.srt_pl = nullptr; bp.srt_cls = nullptr; bp.Cs = ws.Cs;
+    if (ws.Cs > 0) {
+      bp.srt_pl = (const float*)(base + ws.srt_pl);
+      bp.srt_cls = (const unsigned short*)(base + ws.srt_cls);
+      CTCX_CUDA(LaunchSortClasses(logits_dev, bp.off, (long long)T * B, C, blank_index, ws.Cs,
+                                  (float*)(base + ws.srt_pl), (unsigned short*)(base + ws.srt_cls), stream));
+    }
     const int brc = LaunchBeamFor(bp, stream);
     if (brc != CTCX_OK) return brc;
     ProfRecord(2, stream);
@@ -661,6 +713,13 @@ int ctcx_stream_step_f32(void* workspace, int T_total, int B, int C, int W, int 
   bp.Tcap = T_total;
   bp.t_done = (int*)(base + ws.t_done);
   bp.state = base + ws.state;
+  bp.srt_pl = nullptr; bp.srt_cls = nullptr; bp.Cs = ws.Cs;
+  if (ws.Cs > 0) {
+    bp.srt_pl = (const float*)(base + ws.srt_pl);
+    bp.srt_cls = (const unsigned short*)(base + ws.srt_cls);
+    CTCX_CUDA(LaunchSortClasses(logits_dev, bp.off, (long long)chunk_time * B, C, blank_index, ws.Cs,
+                                (float*)(base + ws.srt_pl), (unsigned short*)(base + ws.srt_cls), stream));
+  }
   return LaunchBeamFor(bp, stream);
 }
 

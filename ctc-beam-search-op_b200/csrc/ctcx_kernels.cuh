@@ -123,6 +123,52 @@ __global__ void __launch_bounds__(kLogNormRows) LogNormRowKernel(const float* __
   }
 }
 
+// Pre-pass for wide vocabularies (32 < C <= 2048): per (t,b) row, the non-blank classes ordered by
+// log-prob x_l - off, descending -- the per-frame candidate-class ordering of the north star. With it
+// the children of a beam entry above ANY threshold are a prefix of this order (fp addition is
+// monotone), so the beam kernel finds them by binary search instead of scoring all C classes.
+// One CTA per row (grid-stride), bitonic sort of (score key << 16 | class) in shared memory.
+// Runs after LogNorm*Kernel (needs off).
+__global__ void __launch_bounds__(256) SortClassesKernel(const float* __restrict__ logits,
+                                                         const float* __restrict__ off, long long rows,
+                                                         int C, int blank, int Cs, int n_pow2,
+                                                         float* __restrict__ srt_pl,
+                                                         unsigned short* __restrict__ srt_cls) {
+  extern __shared__ __align__(16) unsigned long long skeys[];
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float* x = logits + row * C;
+    const float o = off[row];
+    __syncthreads();  // previous row fully written out
+    for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+      unsigned long long k = 0ull;  // blank and padding sort last
+      if (i < C && i != blank) k = ((unsigned long long)KeyOf(__fsub_rn(x[i], o)) << 16) | (unsigned long long)i;
+      skeys[i] = k;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const unsigned long long a = skeys[i], bb = skeys[ixj];
+            const bool desc = ((i & k) == 0);  // descending overall
+            if (desc ? (a < bb) : (a > bb)) {
+              skeys[i] = bb;
+              skeys[ixj] = a;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (int i = threadIdx.x; i < Cs; i += blockDim.x) {
+      const unsigned long long k = (i < n_pow2) ? skeys[i] : 0ull;
+      srt_pl[row * Cs + i] = k ? UnKey((unsigned)(k >> 16)) : NegInf();
+      srt_cls[row * Cs + i] = k ? (unsigned short)(k & 0xffffull) : (unsigned short)0xffff;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Kernel 2: the beam kernel.
 // ---------------------------------------------------------------------------------------------
@@ -146,6 +192,10 @@ struct BeamParams {
   int Tcap;               // frames per utterance the back-pointer array can hold (its row stride)
   int* t_done;            // [B] frames already consumed per utterance (updated by the kernel), or null
   unsigned char* state;   // [B] x StreamStateBytes(W): beam state carried between chunks, or null
+  // wide-vocabulary fast path (ctcx_beam_wide.cuh): per frame, the classes sorted by log-prob
+  const float* srt_pl;           // [T,B,Cs] x_l - off, descending (blank / padding = -inf at the end)
+  const unsigned short* srt_cls; // [T,B,Cs] class index at each sorted position
+  int Cs;                        // row stride of the two arrays (C rounded up to a multiple of 8)
 };
 
 // Beam state of one utterance between two chunks of a streamed decode.
