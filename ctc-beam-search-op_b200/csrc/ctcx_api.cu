@@ -52,14 +52,19 @@ Tier PickTier(int W) {
   return {1024, 1024};
 }
 
-// Wide-vocabulary fast path (ctcx_beam_wide.cuh): 32 < C <= 2048 and the whole candidate list
-// (beam_width * num_classes entries in the worst frame) fits in shared memory.
+// Wide-vocabulary fast path (ctcx_beam_wide.cuh): 32 < C <= 2048 and the candidate list of the worst
+// frame (beam_width rows x the Kc = min(C-1, 2*beam_width+2) best classes of the frame) fits in
+// shared memory. WideKc = sorted classes the beam kernel uses, WideKs = row stride of the sorted
+// arrays (Kc + one sentinel when classes are left out, rounded up to 8).
+int WideKc(int W, int C) { return std::min(C - 1, 2 * W + 2); }
+int WideKe(int W, int C) { return std::min(C - 1, WideKc(W, C) + 1); }
+int WideKs(int W, int C) { return (WideKe(W, C) + 7) / 8 * 8; }
 bool UseWide(int W, int C) {
   if (C <= 32 || C > 2048 || W > 256) return false;
   const char* impl = std::getenv("CTCX_BEAM_IMPL");
   if (impl != nullptr && std::strcmp(impl, "generic") == 0) return false;
   ctcx::BeamSmemWide lay;
-  lay.Init(PickTier(W).wmax, W * C, C, (C + 7) / 8 * 8);
+  lay.Init(PickTier(W).wmax, W * WideKc(W, C), C, WideKs(W, C));
   return lay.bytes <= 200 * 1024;
 }
 
@@ -94,7 +99,7 @@ struct Workspace {
     stats = o; o += Align256(16 * 4);
     t_done = o; o += Align256(b * 4);                            // streaming: frames consumed so far
     state = o; o += Align256(b * ctcx::StreamStateBytes(W));     // streaming: beam between chunks
-    Cs = UseWide(W, C) ? (C + 7) / 8 * 8 : 0;                    // wide fast path: classes sorted per frame
+    Cs = UseWide(W, C) ? WideKs(W, C) : 0;                       // wide fast path: best classes per frame, sorted
     srt_pl = o; o += Align256(t * b * (size_t)Cs * 4);
     srt_cls = o; o += Align256(t * b * (size_t)Cs * 2);
     bytes = o;
@@ -198,15 +203,29 @@ cudaError_t LaunchLogNorm(const float* logits_dev, float* off_dev, long long row
   return cudaGetLastError();
 }
 
-// kernel 1b (wide vocabularies): classes of every row ordered by log-prob
-cudaError_t LaunchSortClasses(const float* logits_dev, const float* off_dev, long long rows, int C, int blank,
-                              int Cs, float* srt_pl, unsigned short* srt_cls, cudaStream_t stream) {
-  int n_pow2 = 64;
-  while (n_pow2 < C) n_pow2 <<= 1;
-  long long blocks = std::min<long long>(rows, (long long)DeviceSmCount() * 16);
-  ctcx::SortClassesKernel<<<(unsigned)blocks, 256, (size_t)n_pow2 * 8, stream>>>(logits_dev, off_dev, rows, C, blank,
-                                                                              Cs, n_pow2, srt_pl, srt_cls);
+// kernel 1b (wide vocabularies): the best classes of every row ordered by log-prob
+template <int NI>
+cudaError_t LaunchTopClassesNI(const float* logits_dev, const float* off_dev, long long rows, int C, int blank,
+                               int Ke, int Ks, float* srt_pl, unsigned short* srt_cls, cudaStream_t stream) {
+  auto kern = ctcx::TopClassesKernel<NI>;
+  const size_t smem = (size_t)8 * Ke * 8;  // one Ke-entry buffer per warp
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  long long blocks = std::min<long long>((rows + 7) / 8, (long long)DeviceSmCount() * 16);
+  kern<<<(unsigned)blocks, 256, smem, stream>>>(logits_dev, off_dev, rows, C, blank, Ke, Ks, srt_pl, srt_cls);
   return cudaGetLastError();
+}
+cudaError_t LaunchTopClasses(const float* logits_dev, const float* off_dev, long long rows, int C, int blank,
+                             int W, float* srt_pl, unsigned short* srt_cls, cudaStream_t stream) {
+  const int Ke = WideKe(W, C), Ks = WideKs(W, C), ni = (C + 31) / 32;
+#define CTCX_TOPC(N) LaunchTopClassesNI<N>(logits_dev, off_dev, rows, C, blank, Ke, Ks, srt_pl, srt_cls, stream)
+  if (ni <= 2) return CTCX_TOPC(2);
+  if (ni <= 4) return CTCX_TOPC(4);
+  if (ni <= 8) return CTCX_TOPC(8);
+  if (ni <= 16) return CTCX_TOPC(16);
+  if (ni <= 32) return CTCX_TOPC(32);
+  return CTCX_TOPC(64);
+#undef CTCX_TOPC
 }
 
 // kernel 2: picks the beam kernel for the shape (fast path for narrow vocabularies, generic
@@ -225,8 +244,9 @@ int LaunchBeamFor(ctcx::BeamParams& bp, cudaStream_t stream) {
   const bool want_generic = impl != nullptr && std::strcmp(impl, "generic") == 0;
   const bool want_v2 = impl != nullptr && std::strcmp(impl, "v2") == 0 && bp.state == nullptr;
   cudaError_t e;
-  if (bp.srt_pl != nullptr) {  // wide-vocabulary fast path (the caller ran SortClassesKernel)
-    bp.cand_cap = W * C;
+  if (bp.srt_pl != nullptr) {  // wide-vocabulary fast path (the caller ran TopClassesKernel)
+    bp.Kc = WideKc(W, C);
+    bp.cand_cap = W * bp.Kc;
     ctcx::BeamSmemWide layw;
     layw.Init(tier.wmax, bp.cand_cap, C, bp.Cs);
     switch (tier.wmax) {
@@ -400,12 +420,12 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
     bp.fin_n = (int*)(base + ws.fin_n);
     bp.flags = (int*)(base + ws.flags);
     bp.Tcap = T; bp.t_done = nullptr; bp.state = nullptr;  // one-shot decode
-    bp.srt_pl = nullptr; bp.srt_cls = nullptr; bp.Cs = ws.Cs;
+    bp.srt_pl = nullptr; bp.srt_cls = nullptr; bp.Cs = ws.Cs; bp.Kc = 0;
     if (ws.Cs > 0) {
       bp.srt_pl = (const float*)(base + ws.srt_pl);
       bp.srt_cls = (const unsigned short*)(base + ws.srt_cls);
-      CTCX_CUDA(LaunchSortClasses(logits_dev, bp.off, (long long)T * B, C, blank_index, ws.Cs,
-                                  (float*)(base + ws.srt_pl), (unsigned short*)(base + ws.srt_cls), stream));
+      CTCX_CUDA(LaunchTopClasses(logits_dev, bp.off, (long long)T * B, C, blank_index, W,
+                                 (float*)(base + ws.srt_pl), (unsigned short*)(base + ws.srt_cls), stream));
     }
     const int brc = LaunchBeamFor(bp, stream);
     if (brc != CTCX_OK) return brc;
@@ -713,12 +733,12 @@ int ctcx_stream_step_f32(void* workspace, int T_total, int B, int C, int W, int 
   bp.Tcap = T_total;
   bp.t_done = (int*)(base + ws.t_done);
   bp.state = base + ws.state;
-  bp.srt_pl = nullptr; bp.srt_cls = nullptr; bp.Cs = ws.Cs;
+  bp.srt_pl = nullptr; bp.srt_cls = nullptr; bp.Cs = ws.Cs; bp.Kc = 0;
   if (ws.Cs > 0) {
     bp.srt_pl = (const float*)(base + ws.srt_pl);
     bp.srt_cls = (const unsigned short*)(base + ws.srt_cls);
-    CTCX_CUDA(LaunchSortClasses(logits_dev, bp.off, (long long)chunk_time * B, C, blank_index, ws.Cs,
-                                (float*)(base + ws.srt_pl), (unsigned short*)(base + ws.srt_cls), stream));
+    CTCX_CUDA(LaunchTopClasses(logits_dev, bp.off, (long long)chunk_time * B, C, blank_index, W,
+                               (float*)(base + ws.srt_pl), (unsigned short*)(base + ws.srt_cls), stream));
   }
   return LaunchBeamFor(bp, stream);
 }

@@ -1,15 +1,25 @@
-// Beam kernel for WIDE vocabularies (32 < num_classes <= 2048, beam_width * num_classes small enough
-// for the candidate list to live in shared memory: BASELINE's Conformer-BPE shape C=1024, W=16).
-// Derived from BeamKernelV3 (ctcx_beam_v3.cuh): same phases, same total order, bit-identical results
-// as the generic BeamKernel. What differs is how candidates are found: the pre-pass
-// (SortClassesKernel) orders every frame's classes by log-prob; the children of a row above ANY
-// threshold are then a PREFIX of that order (fp addition is monotone), whose length an exact binary
-// search finds in ~log2(C) steps -- instead of scoring W*C children and issuing W*C shared-memory
-// histogram atomics per pass, as the generic kernel's streaming mode does.
+// Beam kernel for WIDE vocabularies (32 < num_classes <= 2048: BASELINE's Conformer-BPE shape
+// C=1024, W=16). Derived from BeamKernelV3 (ctcx_beam_v3.cuh): same phases, same total order,
+// bit-identical results as the generic BeamKernel. What differs is how candidates are found: the
+// pre-pass (TopClassesKernel) orders every frame's best classes by log-prob; the children of a row
+// above ANY threshold are then a PREFIX of that order (fp addition is monotone), whose length an
+// exact binary search finds in ~log2(Kc) steps -- instead of scoring W*C children and issuing W*C
+// shared-memory histogram atomics per pass, as the generic kernel's streaming mode does.
 //   * member-children are a bitmap [row][class] (few members have their parent in the beam);
 //   * the repeated label (base = old blank mass) is re-tested individually;
 //   * a revisit-wipe query sums prefix lengths over the rows visited before the parent's turn and
 //     scans only the parent's own row for the "labels below label(m)" part.
+//
+// Why Kc = 2W+2 sorted classes per frame are enough (W = beam_width). A row's children enter the
+// next beam in the order (score desc, label asc), at most W of them. Up to W-1 classes of a row are
+// already members (skipped) and the repeated label scores lower than its position suggests, so the
+// W best children of a row sit in its first 2W sorted positions -- unless scores that differ as
+// log-probs round to the SAME sum, in which case the label order can prefer a class further down.
+// All classes past position Kc score <= the sentinel (position Kc) <= the W-th best item, so only an
+// exact tie with the lowest selected item can matter; the kernel detects that after the cut (rows
+// whose prefix hit Kc) and swaps such classes in one by one from the raw row, in order. The
+// revisit-wipe counts saturate at W, and a capped row alone contributes >= W+2, so they are exact
+// as well (the own-row part falls back to the raw row when capped).
 #pragma once
 #include "ctcx_beam_v3.cuh"
 
@@ -24,7 +34,6 @@ struct BeamSmemWide {
   size_t row;                      // uint4 [WMAX] {old total, old blank, label, -}
   size_t kid;                      // u32 [WMAX][KW] member-children bitmap
   size_t kids;                     // u32 [WMAX]     the same as a list (parent row << 16 | label)
-  size_t pos;                      // u16 [Cs]     sorted position of each class (this frame)
   size_t cls;                      // u16 [2][Cs]  class at each sorted position (double-buffered)
   size_t list;                     // uint2 [cand_cap] {score key, (row<<16)|label}
   size_t total, blk, lab, ab, an;  // f32 [2][WMAX]
@@ -39,7 +48,7 @@ struct BeamSmemWide {
   size_t bins2;                    // u32 [256]
   size_t wsum;                     // i32 [32]     per-warp candidate counts (block scan)
   size_t pls;                      // f32 [2][Cs]  class log-probs sorted descending (double-buffered)
-  size_t x;                        // f32 [2][Cs]
+  size_t x;                        // f32 [2][Cx]  raw logit row (double-buffered), Cx = C rounded up to 4
   size_t scal;                     // 32 x 4 B
   size_t bytes;
   __host__ __device__ void Init(int wmax, int cand_cap, int C, int Cs) {
@@ -54,7 +63,6 @@ struct BeamSmemWide {
     row = o; o += w * 16;
     kid = o; o += w * kw * 4;
     kids = o; o += w * 4;
-    pos = o; o += ((size_t)Cs * 2 + 15) / 16 * 16;
     cls = o; o += 2 * (size_t)Cs * 2;
     list = o; o += ((size_t)cand_cap * 8 + 15) / 16 * 16;  // keep the following arrays 16-byte aligned
     total = o; o += 2 * w * 4;
@@ -80,13 +88,13 @@ struct BeamSmemWide {
     bins2 = o; o += 256 * 4;
     wsum = o; o += 32 * 4;
     pls = o; o += 2 * (size_t)Cs * 4;
-    x = o; o += 2 * (size_t)Cs * 4;
+    x = o; o += 2 * ((size_t)C + 3) / 4 * 4 * 4;
     scal = o; o += 32 * 4;
     bytes = (o + 15) / 16 * 16;
   }
 };
 
-enum { kWNKid = 23 };  // scalar slot in addition to the kV2* / kV3* ones
+enum { kWNKid = 23, kWCapped = 24, kWBest = 25 };  // scalar slots in addition to the kV2* / kV3* ones
 
 template <int WMAX, int NT, bool TIMING>
 __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKernelWide(BeamParams p) {
@@ -134,11 +142,13 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
   unsigned* s_bins2 = (unsigned*)(smem + lay.bins2);
   float* s_plS2 = (float*)(smem + lay.pls);
   unsigned short* s_cls2 = (unsigned short*)(smem + lay.cls);
-  unsigned short* s_pos = (unsigned short*)(smem + lay.pos);
   unsigned* s_kid = (unsigned*)(smem + lay.kid);
   unsigned* s_kids = (unsigned*)(smem + lay.kids);
-  const int Cs = p.Cs, KW = (C + 31) / 32;
-  const int Cv = C - 1;  // non-blank classes = length of the sorted order
+  const int Cs = p.Cs, KW = (C + 31) / 32, Cx = (C + 3) / 4 * 4;
+  const int Cv = min(C - 1, p.Kc);      // length of the sorted order the kernel works with
+  const bool trunc = Cv < C - 1;        // classes were left out; s_plS[Cv] is the best of them
+  int P2 = 1;                           // largest power of two <= Cv (binary search start)
+  while (2 * P2 <= Cv) P2 *= 2;
   int* s_wsum = (int*)(smem + lay.wsum);
   float* s_x = (float*)(smem + lay.x);
   volatile int* sc = (volatile int*)(smem + lay.scal);
@@ -174,6 +184,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     scu[kV2Gap] = 0u;
     sci[kV3Found] = 0;
     sci[kWNKid] = 0;
+    sci[kWCapped] = 0;
   }
   int n = 1;
   // thread -> (row, class slice) mapping of the candidate pass
@@ -226,7 +237,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
   if (timing) tprev = clock64();
   for (int t = 0; t < L; ++t) {
     const int cur = t & 1, nxt = cur ^ 1;
-    const float* x = s_x + cur * Cs;
+    const float* x = s_x + cur * Cx;
     const float* s_plS = s_plS2 + cur * Cs;          // this frame's classes, best first
     const unsigned short* s_cls = s_cls2 + cur * Cs;
     const float off = ((const float*)sci)[kV2Off0 + cur];
@@ -244,9 +255,16 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     if (warp == NWARP - 1 && t + 1 < L) {
       const size_t r1 = (size_t)(t + 1) * B + b;
       const float* g = p.logits + r1 * C;
-      for (int l = lane; l < C; l += 32) {
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(s_x + nxt * Cs + l);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(g + l));
+      if ((C & 3) == 0) {  // rows 16-byte aligned
+        for (int l = lane * 4; l < C; l += 128) {
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(s_x + nxt * Cx + l);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g + l));
+        }
+      } else {
+        for (int l = lane; l < C; l += 32) {
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(s_x + nxt * Cx + l);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(g + l));
+        }
       }
       const float* gp = p.srt_pl + r1 * Cs;            // rows are 16-byte aligned (Cs % 8 == 0)
       for (int j = lane * 4; j < Cs; j += 128) {
@@ -267,9 +285,6 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
 
     const float xb = x[blank];
     const float pb = __fsub_rn(xb, off);
-    // sorted position of every class (needed to tell whether a given class lies inside a prefix);
-    // threads beyond the members do it while PA runs
-    for (int j = tid; j < Cv; j += NT) s_pos[s_cls[j]] = (unsigned short)j;
     if (tid == NT - 1) {
       ((float*)sci)[kV2LpMax] = (Cv > 0) ? s_plS[0] : NegInf();
       ((float*)sci)[kV2LpMin] = (Cv > 0) ? s_plS[Cv - 1] : 0.0f;
@@ -371,8 +386,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     // branch-free binary search for its length (decoder.h:172-182).
     auto prefix_len = [&](const float ot, const float thr) -> int {
       int pos = 0;
-#pragma unroll
-      for (int step = 1024; step >= 1; step >>= 1) {
+      for (int step = P2; step >= 1; step >>= 1) {
         const int q = pos + step;
         if (q <= Cv && __fadd_rn(s_plS[q - 1], ot) > thr) pos = q;
       }
@@ -387,20 +401,23 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       s_out = __fadd_rn(s_plS[j], base);
       return s_out > thr;
     };
-    // number of candidates of a row above thr: prefix length minus the member-children inside the
-    // prefix minus the repeated label if its own (lower) score fails
+    // number of candidates of a row above thr: prefix length minus the member-children above thr
+    // minus the repeated label if its own (lower) score fails. A class lies in the prefix exactly
+    // when its log-prob + old total exceeds thr. For a capped row (len == Cv < C-1) the result is a
+    // lower bound that is still >= W+2, all a revisit-wipe verdict needs (header comment).
     auto cand_count = [&](int row, const uint4 ri, const float thr) -> int {
-      const int len = prefix_len(__uint_as_float(ri.x), thr);
-      int cnt = len;
+      const float ot = __uint_as_float(ri.x);
+      int cnt = prefix_len(ot, thr);
       const int nk = sci[kWNKid];
       for (int k = 0; k < nk; ++k) {  // members whose parent is in the beam: a handful
         const unsigned kd = s_kids[k];
-        if ((int)(kd >> 16) == row && (int)s_pos[kd & 0xffffu] < len) --cnt;
+        if ((int)(kd >> 16) == row && __fadd_rn(__fsub_rn(x[kd & 0xffffu], off), ot) > thr) --cnt;
       }
       const int lb = (int)ri.z;
-      if (lb >= 0 && lb != blank && (int)s_pos[lb] < len && !is_kid(row, lb) &&
-          !(__fadd_rn(s_plS[s_pos[lb]], __uint_as_float(ri.y)) > thr))
-        --cnt;
+      if (lb >= 0 && lb != blank && !is_kid(row, lb)) {
+        const float pl = __fsub_rn(x[lb], off);
+        if (__fadd_rn(pl, ot) > thr && !(__fadd_rn(pl, __uint_as_float(ri.y)) > thr)) --cnt;
+      }
       return cnt;
     };
 
@@ -430,10 +447,18 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
               const uint4 rp = s_row[pslot];
               const int len = prefix_len(__uint_as_float(rp.x), v);
               const int lblm = o_label[m];
-              for (int j = lane; j < len; j += 32) {
-                const int c = (int)s_cls[j];
-                float sv_;
-                cnt += (c < lblm && cand_ok(pslot, rp, c, j, v, sv_)) ? 1 : 0;
+              if (trunc && len == Cv) {  // capped prefix: the raw row has every class
+                for (int c = lane; c < lblm; c += 32) {
+                  if (c == blank || is_kid(pslot, c)) continue;
+                  const float base = (c == (int)rp.z) ? __uint_as_float(rp.y) : __uint_as_float(rp.x);
+                  cnt += (__fadd_rn(__fsub_rn(x[c], off), base) > v) ? 1 : 0;
+                }
+              } else {
+                for (int j = lane; j < len; j += 32) {
+                  const int c = (int)s_cls[j];
+                  float sv_;
+                  cnt += (c < lblm && cand_ok(pslot, rp, c, j, v, sv_)) ? 1 : 0;
+                }
               }
             }
             cnt = __reduce_add_sync(kFull, cnt);
@@ -516,6 +541,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
         if (s_wiped[row]) continue;
         const uint4 ri = s_row[row];
         const int len = (__fadd_rn(lp_max, __uint_as_float(ri.x)) > thr) ? prefix_len(__uint_as_float(ri.x), thr) : 0;
+        if (trunc && len == Cv && lane == 0) sci[kWCapped] = 1;  // classes beyond the sorted ones exist
         for (int j0 = 0; j0 < len; j0 += 32) {
           const int j = j0 + lane;
           float sc_ = 0.0f;
@@ -728,6 +754,50 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       __syncthreads();
     }
 
+    // ---- capped rows: classes beyond the sorted ones that TIE with the lowest selected item and
+    // precede it in (row, label) order replace it, one at a time in that order (header comment).
+    // Every class left out scores <= the sentinel <= that item, so nothing else can be missing. ----
+    if (__builtin_expect(trunc && sc[kWCapped] != 0, 0)) {
+      const unsigned lastkey = KeyOf(s_plS[Cv - 1]);
+      const int lastcls = (int)s_cls[Cv - 1];
+      unsigned done_upto = 0u;  // left-out children up to this order key are in already
+      for (;;) {
+        unsigned long long mn = (tid < n_new) ? s_sorted[tid] : ~0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long v = __shfl_xor_sync(kFull, mn, o);
+          mn = (v < mn) ? v : mn;
+        }
+        if (lane == 0) s_bnd[warp] = mn;
+        if (tid == 0) scu[kWBest] = 0xffffffffu;
+        __syncthreads();
+        unsigned long long cutc = ~0ull;
+#pragma unroll
+        for (int w2 = 0; w2 < NWARP; ++w2) cutc = (s_bnd[w2] < cutc) ? s_bnd[w2] : cutc;
+        const unsigned keyc = (unsigned)(cutc >> 32), okc = ~(unsigned)(cutc & 0xffffffffull);
+        if (!(okc & 0x80000000u)) break;  // a member: members precede children on equal scores
+        const int rowc = (int)((okc & 0x7fffffffu) >> 16);
+        for (int idx = tid; idx < (rowc + 1) * C; idx += NT) {
+          const int r = idx / C, c = idx - r * C;
+          const unsigned ok = 0x80000000u | ((unsigned)r << 16) | (unsigned)c;
+          if (c == blank || ok >= okc || ok <= done_upto || s_wiped[r]) continue;
+          const float pl = __fsub_rn(x[c], off);
+          const unsigned pk = KeyOf(pl);
+          if (pk > lastkey || (pk == lastkey && c <= lastcls)) continue;  // among the sorted classes
+          if (is_kid(r, c)) continue;
+          const uint4 ri = s_row[r];
+          const float base = (c == (int)ri.z) ? __uint_as_float(ri.y) : __uint_as_float(ri.x);
+          if (KeyOf(__fadd_rn(pl, base)) == keyc) atomicMin(&scu[kWBest], ok);
+        }
+        __syncthreads();
+        const unsigned best = scu[kWBest];
+        if (best == 0xffffffffu) break;
+        if (tid < n_new && s_sorted[tid] == cutc)
+          s_sorted[tid] = ((unsigned long long)keyc << 32) | (unsigned long long)(~best);
+        done_upto = best;
+        __syncthreads();
+      }
+    }
     CTCX_TICK(5)  // PF
     // ---- PG: rank inside the score group = new slot; write the next beam + back-pointers ----
     {
@@ -765,6 +835,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
         scu[kV2Gap] = gap_next;
         sci[kV3Found] = 0;
         sci[kWNKid] = 0;
+        sci[kWCapped] = 0;
       }
       if (tid < n) {
         s_wiped[tid] = 0u;

@@ -123,48 +123,85 @@ __global__ void __launch_bounds__(kLogNormRows) LogNormRowKernel(const float* __
   }
 }
 
-// Pre-pass for wide vocabularies (32 < C <= 2048): per (t,b) row, the non-blank classes ordered by
-// log-prob x_l - off, descending -- the per-frame candidate-class ordering of the north star. With it
-// the children of a beam entry above ANY threshold are a prefix of this order (fp addition is
-// monotone), so the beam kernel finds them by binary search instead of scoring all C classes.
-// One CTA per row (grid-stride), bitonic sort of (score key << 16 | class) in shared memory.
-// Runs after LogNorm*Kernel (needs off).
-__global__ void __launch_bounds__(256) SortClassesKernel(const float* __restrict__ logits,
-                                                         const float* __restrict__ off, long long rows,
-                                                         int C, int blank, int Cs, int n_pow2,
-                                                         float* __restrict__ srt_pl,
-                                                         unsigned short* __restrict__ srt_cls) {
-  extern __shared__ __align__(16) unsigned long long skeys[];
-  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+// Pre-pass for wide vocabularies (32 < C <= 2048): per (t,b) row, the `Ke` best non-blank classes
+// ordered by (log-prob x_l - off descending, class ascending) -- the per-frame candidate-class
+// ordering of the north star. The children of a beam entry above ANY threshold are a prefix of this
+// order (fp addition is monotone), so the beam kernel finds them by binary search instead of scoring
+// all C classes; and no entry can place more than beam_width children in the next beam, so the first
+// Kc = 2*beam_width+2 classes (+1 sentinel, Ke = Kc+1) are all it ever needs (ctcx_beam_wide.cuh has
+// the argument and the exact handling of the one tie case that reaches past the cut).
+// One warp per row: keys in registers (NI per lane), the Ke-th largest key by a bitwise search with
+// warp-wide counts, compaction by ballots, final order by rank counting. Runs after LogNorm*Kernel.
+template <int NI>
+__global__ void __launch_bounds__(256) TopClassesKernel(const float* __restrict__ logits,
+                                                        const float* __restrict__ off, long long rows,
+                                                        int C, int blank, int Ke, int Ks,
+                                                        float* __restrict__ srt_pl,
+                                                        unsigned short* __restrict__ srt_cls) {
+  extern __shared__ __align__(16) unsigned long long tbuf[];  // [warps][Ke]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long* buf = tbuf + (size_t)warp * Ke;
+  const unsigned lt = (1u << lane) - 1u;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp_global; row < rows; row += nwarps) {
     const float* x = logits + row * C;
     const float o = off[row];
-    __syncthreads();  // previous row fully written out
-    for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
-      unsigned long long k = 0ull;  // blank and padding sort last
-      if (i < C && i != blank) k = ((unsigned long long)KeyOf(__fsub_rn(x[i], o)) << 16) | (unsigned long long)i;
-      skeys[i] = k;
+    unsigned k[NI];  // 0 = blank / padding (every real key is > 0)
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int j = i * 32 + lane;
+      k[i] = (j < C && j != blank) ? KeyOf(__fsub_rn(x[j], o)) : 0u;
     }
-    __syncthreads();
-    for (int k = 2; k <= n_pow2; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
-          const int ixj = i ^ j;
-          if (ixj > i) {
-            const unsigned long long a = skeys[i], bb = skeys[ixj];
-            const bool desc = ((i & k) == 0);  // descending overall
-            if (desc ? (a < bb) : (a > bb)) {
-              skeys[i] = bb;
-              skeys[ixj] = a;
-            }
-          }
-        }
-        __syncthreads();
+    // the Ke-th largest key, most significant bit first; stop early once some threshold separates
+    // exactly Ke keys (the usual case long before bit 0)
+    unsigned kth = 0u;
+    bool exact = false;
+    for (int bit = 31; bit >= 0; --bit) {
+      const unsigned trial = kth | (1u << bit);
+      int cnt = 0;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) cnt += (k[i] >= trial) ? 1 : 0;
+      cnt = __reduce_add_sync(kFull, cnt);
+      if (cnt >= Ke) {
+        kth = trial;
+        if (cnt == Ke) { exact = true; break; }
       }
     }
-    for (int i = threadIdx.x; i < Cs; i += blockDim.x) {
-      const unsigned long long k = (i < n_pow2) ? skeys[i] : 0ull;
-      srt_pl[row * Cs + i] = k ? UnKey((unsigned)(k >> 16)) : NegInf();
-      srt_cls[row * Cs + i] = k ? (unsigned short)(k & 0xffffull) : (unsigned short)0xffff;
+    int ties_left = 0;  // keys equal to kth to take, lowest classes first (only if !exact)
+    if (!exact) {
+      int g = 0;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) g += (k[i] > kth) ? 1 : 0;
+      ties_left = Ke - __reduce_add_sync(kFull, g);
+    }
+    __syncwarp();  // the previous row's rank pass is done with buf
+    int base = 0;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      bool take = exact ? (k[i] >= kth) : (k[i] > kth);
+      if (!exact) {
+        const unsigned tm = __ballot_sync(kFull, k[i] == kth);
+        if (k[i] == kth && __popc(tm & lt) < ties_left) take = true;
+        ties_left -= min(ties_left, __popc(tm));
+      }
+      const unsigned sm = __ballot_sync(kFull, take);
+      if (take)
+        buf[base + __popc(sm & lt)] = ((unsigned long long)k[i] << 16) | (unsigned long long)(0xffff - (i * 32 + lane));
+      base += __popc(sm);
+    }
+    __syncwarp();
+    for (int e = lane; e < Ks; e += 32) {
+      if (e < Ke) {
+        const unsigned long long mine = buf[e];
+        int rank = 0;
+        for (int q = 0; q < Ke; ++q) rank += (buf[q] > mine) ? 1 : 0;
+        srt_pl[row * Ks + rank] = UnKey((unsigned)(mine >> 16));
+        srt_cls[row * Ks + rank] = (unsigned short)(0xffff - (unsigned)(mine & 0xffffull));
+      } else {
+        srt_pl[row * Ks + e] = NegInf();
+        srt_cls[row * Ks + e] = (unsigned short)0xffff;
+      }
     }
   }
 }
@@ -193,9 +230,11 @@ struct BeamParams {
   int* t_done;            // [B] frames already consumed per utterance (updated by the kernel), or null
   unsigned char* state;   // [B] x StreamStateBytes(W): beam state carried between chunks, or null
   // wide-vocabulary fast path (ctcx_beam_wide.cuh): per frame, the classes sorted by log-prob
-  const float* srt_pl;           // [T,B,Cs] x_l - off, descending (blank / padding = -inf at the end)
+  const float* srt_pl;           // [T,B,Cs] x_l - off of the best classes, descending (padding = -inf)
   const unsigned short* srt_cls; // [T,B,Cs] class index at each sorted position
-  int Cs;                        // row stride of the two arrays (C rounded up to a multiple of 8)
+  int Cs;                        // row stride of the two arrays (a multiple of 8)
+  int Kc;                        // sorted classes per frame the kernel may use (entry Kc, if < C-1
+                                 // classes are listed, is a sentinel: the best class left out)
 };
 
 // Beam state of one utterance between two chunks of a streamed decode.

@@ -102,6 +102,64 @@ def test_constant_logits_pathological_ties(op):
     check_against_oracle(op, x, np.full(4, 15, np.int32), 20, 4, True, 0, -1)
 
 
+def _micro_spaced(T, B, C, seed, step, levels=None, ascending=True):
+    """Logits whose classes differ by ~1e-6: after a few dozen frames the running scores are large
+    enough that DIFFERENT log-probs round to the SAME sum, so the (score, label) order of a row's
+    children is no longer the per-frame order of the log-probs."""
+    rng = np.random.default_rng(seed)
+    if levels is None:
+        base = np.arange(C, dtype=np.float64) * step
+        if not ascending:
+            base = base[::-1]
+        x = np.tile(base, (T, B, 1))
+        for t in range(T):
+            for b in range(B):
+                if rng.random() < 0.5:  # some frames: a random class -> value assignment
+                    x[t, b] = rng.permutation(base)
+    else:
+        x = rng.integers(0, levels, (T, B, C)).astype(np.float64) * step
+    return x.astype(np.float32)
+
+
+WIDE_CASES = [
+    # kind, T, B, C, W, P, merge, blank  (all with 2W+2 < C-1: the beam kernel sees a truncated order)
+    ("gauss", 60, 4, 100, 4, 2, False, 99),
+    ("peaky", 60, 4, 300, 8, 3, True, 0),
+    ("gauss", 50, 3, 1024, 16, 1, False, 1023),   # BASELINE cfg4 shape
+    ("peaky", 40, 2, 2048, 5, 2, False, 17),
+    ("gauss", 40, 3, 37, 1, 1, False, 5),
+    ("gauss", 40, 3, 700, 40, 2, False, 3),       # WMAX=128 tier
+]
+
+
+@pytest.mark.parametrize("case", WIDE_CASES, ids=lambda c: "%s-T%d-C%d-W%d" % (c[0], c[1], c[3], c[4]))
+def test_wide_vocabulary_truncated_order(op, case):
+    kind, T, B, C, W, P, merge, blank = case
+    x = L.make_logits(kind, T, B, C, blank, seed=31)
+    check_against_oracle(op, x, L.ragged_lengths(T, B, 31), W, P, merge, blank, -1)
+
+
+def test_wide_vocabulary_ties_beyond_the_sorted_classes(op):
+    """Wide kernel corner: classes that were left out of the per-frame top-Kc order but tie exactly
+    (after rounding) with the lowest selected item and precede it in label order must be swapped in."""
+    full = lambda T, B: np.full(B, T, np.int32)
+    # constant logits: every class of every row ties, every prefix is capped
+    for (T, B, C, W, P) in [(20, 2, 64, 3, 3), (12, 2, 200, 16, 2), (10, 1, 1024, 2, 1)]:
+        check_against_oracle(op, np.zeros((T, B, C), np.float32), full(T, B), W, P, False, C - 1, -1)
+    # log-probs 1e-6 apart, higher label = higher log-prob: the sorted order starts at the highest
+    # labels while the reference's order prefers the lowest label among equal sums
+    for (T, B, C, W, P, step, asc, blank) in [(90, 3, 100, 2, 2, 1e-6, True, 0), (90, 3, 100, 2, 1, 1e-6, True, 99),
+                                              (120, 2, 64, 4, 3, 3e-6, True, 10), (80, 2, 150, 3, 2, 1e-6, False, 7),
+                                              (100, 2, 1024, 16, 2, 2e-7, True, 1023)]:
+        x = _micro_spaced(T, B, C, 5, step, ascending=asc)
+        check_against_oracle(op, x, full(T, B), W, P, False, blank, -1)
+    # few distinct levels, tiny and coarse spacing (many exact ties + revisits)
+    for (T, B, C, W, P, step, levels) in [(80, 3, 90, 3, 3, 1e-6, 3), (40, 3, 48, 6, 4, 1.0, 3),
+                                          (60, 2, 120, 5, 2, 0.5, 2), (100, 2, 70, 2, 2, 5e-7, 4)]:
+        x = _micro_spaced(T, B, C, 9, step, levels=levels)
+        check_against_oracle(op, x, full(T, B), W, P, True, 1, -1)
+
+
 def test_device_math_is_bit_exact(op):
     """ExpfExact / Log1pfExact / LogfExact on the device == the portable twin == host libm."""
     import ctypes
@@ -328,8 +386,9 @@ STREAM_CASES = [
     # kind, T, B, C, W, P, merge, blank
     ("peaky", 70, 5, 29, 100, 2, True, 28),    # fast kernel
     ("gauss", 40, 4, 29, 10, 3, False, 28),    # fast kernel, small tier
-    ("gauss", 30, 3, 40, 24, 2, False, 7),     # generic kernel (C > 32)
-    ("peaky", 24, 2, 1024, 16, 1, False, 1023),  # generic kernel, streaming candidate mode
+    ("gauss", 30, 3, 40, 24, 2, False, 7),     # wide kernel, all classes sorted (generic when forced)
+    ("peaky", 24, 2, 1024, 16, 1, False, 1023),  # wide kernel (generic: streaming candidate mode)
+    ("gauss", 36, 3, 120, 6, 2, True, 0),        # wide kernel, truncated class order
 ]
 
 
