@@ -142,7 +142,7 @@ __global__ void UpcastKernel(const H* __restrict__ in, float* __restrict__ out, 
 
 template <int WMAX, int NT>
 cudaError_t LaunchBeamWide(const ctcx::BeamParams& p, size_t smem, cudaStream_t stream) {
-  auto kern = ctcx::BeamKernelWide<WMAX, NT, false>;
+  auto kern = (p.dbg_cycles != nullptr) ? ctcx::BeamKernelWide<WMAX, NT, true> : ctcx::BeamKernelWide<WMAX, NT, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<p.B, NT, smem, stream>>>(p);

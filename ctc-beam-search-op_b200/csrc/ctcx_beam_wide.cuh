@@ -436,17 +436,61 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
               const unsigned kj = m_key[j];
               cnt += (kj > vkey || (kj == vkey && j < m)) ? 1 : 0;
             }
-            // children visited before the parent's turn, from rows that are not wiped: whole prefixes
-            for (int r0 = 0; r0 < pslot; r0 += 32) {
-              const int r = r0 + lane;
-              if (r < pslot && !s_wiped[r]) cnt += cand_count(r, s_row[r], v);
-            }
-            // ... and, in the parent's own row, the classes below label(m) (an index condition, not a
-            // prefix one: scan the row's prefix)
-            {
-              const uint4 rp = s_row[pslot];
+            const uint4 rp = s_row[pslot];
+            const int lblm = o_label[m];
+            if (Cv <= 64) {
+              // short sorted order (small beam widths): the lanes hold the sorted log-probs, a row's
+              // prefix length is one or two ballots -- no dependent shared-memory search per row
+              const float pl0 = (lane < Cv) ? s_plS[lane] : NegInf();
+              const float pl1 = (32 + lane < Cv) ? s_plS[32 + lane] : NegInf();
+              int tot = 0;  // warp-uniform
+              for (int r = 0; r < pslot; ++r) {
+                if (s_wiped[r]) continue;
+                const float ot = o_total[r];
+                tot += __popc(__ballot_sync(kFull, __fadd_rn(pl0, ot) > v));
+                if (Cv > 32) tot += __popc(__ballot_sync(kFull, __fadd_rn(pl1, ot) > v));
+              }
+              if (lane == 0) cnt += tot;
+              // corrections as in cand_count: member-children above v, repeated labels that fail
+              const int nk = sci[kWNKid];
+              for (int k = lane; k < nk; k += 32) {
+                const unsigned kd = s_kids[k];
+                const int r = (int)(kd >> 16);
+                if (r < pslot && !s_wiped[r] && __fadd_rn(__fsub_rn(x[kd & 0xffffu], off), o_total[r]) > v) --cnt;
+              }
+              for (int r = lane; r < pslot; r += 32) {
+                if (s_wiped[r]) continue;
+                const uint4 ri = s_row[r];
+                const int lb = (int)ri.z;
+                if (lb >= 0 && lb != blank && !is_kid(r, lb)) {
+                  const float pl = __fsub_rn(x[lb], off);
+                  if (__fadd_rn(pl, __uint_as_float(ri.x)) > v && !(__fadd_rn(pl, __uint_as_float(ri.y)) > v)) --cnt;
+                }
+              }
+              // the parent's own row: classes below label(m) (an index condition, not a prefix one)
+              const float otp = __uint_as_float(rp.x);
+              const bool in0 = __fadd_rn(pl0, otp) > v, in1 = __fadd_rn(pl1, otp) > v;
+              const unsigned pm_last = __ballot_sync(kFull, (Cv > 32) ? in1 : in0);
+              if (trunc && ((pm_last >> ((Cv - 1) & 31)) & 1u)) {  // capped prefix: the raw row has every class
+                for (int c = lane; c < lblm; c += 32) {
+                  if (c == blank || is_kid(pslot, c)) continue;
+                  const float base = (c == (int)rp.z) ? __uint_as_float(rp.y) : __uint_as_float(rp.x);
+                  cnt += (__fadd_rn(__fsub_rn(x[c], off), base) > v) ? 1 : 0;
+                }
+              } else {
+                float sv_;
+                if (in0) { const int c = (int)s_cls[lane]; cnt += (c < lblm && cand_ok(pslot, rp, c, lane, v, sv_)) ? 1 : 0; }
+                if (in1) { const int c = (int)s_cls[32 + lane]; cnt += (c < lblm && cand_ok(pslot, rp, c, 32 + lane, v, sv_)) ? 1 : 0; }
+              }
+            } else {
+              // children visited before the parent's turn, from rows that are not wiped: whole prefixes
+              for (int r0 = 0; r0 < pslot; r0 += 32) {
+                const int r = r0 + lane;
+                if (r < pslot && !s_wiped[r]) cnt += cand_count(r, s_row[r], v);
+              }
+              // ... and, in the parent's own row, the classes below label(m) (an index condition, not a
+              // prefix one: scan the row's prefix)
               const int len = prefix_len(__uint_as_float(rp.x), v);
-              const int lblm = o_label[m];
               if (trunc && len == Cv) {  // capped prefix: the raw row has every class
                 for (int c = lane; c < lblm; c += 32) {
                   if (c == blank || is_kid(pslot, c)) continue;
@@ -536,22 +580,28 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       const bool member_in = !clamped || my_key > lo_key;
       CTCX_TICK(16)  // PB: range
 
-      // PB: one warp per row (round robin); the row's candidates are a prefix of the sorted classes
+      // PB: one warp per row (round robin); the row's candidates are a prefix of the sorted classes:
+      // 32 positions per step, until a position fails
       for (int row = warp; row < n; row += NWARP) {
         if (s_wiped[row]) continue;
         const uint4 ri = s_row[row];
-        const int len = (__fadd_rn(lp_max, __uint_as_float(ri.x)) > thr) ? prefix_len(__uint_as_float(ri.x), thr) : 0;
-        if (trunc && len == Cv && lane == 0) sci[kWCapped] = 1;  // classes beyond the sorted ones exist
-        for (int j0 = 0; j0 < len; j0 += 32) {
+        const float ot = __uint_as_float(ri.x);
+        for (int j0 = 0; j0 < Cv; j0 += 32) {
           const int j = j0 + lane;
           float sc_ = 0.0f;
           int c = 0;
-          bool ok = false;
-          if (j < len) {
-            c = (int)s_cls[j];
-            ok = cand_ok(row, ri, c, j, thr, sc_);
+          bool inp = false, ok = false;
+          if (j < Cv) {
+            inp = __fadd_rn(s_plS[j], ot) > thr;
+            if (inp) {
+              c = (int)s_cls[j];
+              ok = cand_ok(row, ri, c, j, thr, sc_);
+            }
           }
+          const unsigned pm = __ballot_sync(kFull, inp);
           const unsigned mk = __ballot_sync(kFull, ok);
+          // the last sorted position is inside the prefix: classes beyond the sorted ones may be too
+          if (trunc && j0 + 32 >= Cv && ((pm >> (Cv - 1 - j0)) & 1u) && lane == 0) sci[kWCapped] = 1;
           if (mk) {
             int base = 0;
             if (lane == 0) base = atomicAdd(&sci[kV2NCand], __popc(mk));  // one atomic per 32 positions
@@ -562,6 +612,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
               atomicAdd(&s_hist[bucket_of(key)], 1u);
             }
           }
+          if (pm != kFull) break;
         }
       }
       if (tid < n && member_in) atomicAdd(&s_hist[bucket_of(my_key)], 1u);
@@ -643,6 +694,12 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     // next frame's range prediction: the measured top-to-threshold gap
     const unsigned gap_next = (unsigned)(sc[kV2TopBin] - bstar + 1) << shift;
 
+    if (TIMING && timing) {  // event counters next to the cycle counters (slots 20-23)
+      cyc[TIMING ? 20 : 0] += (!bnd_all && e_b > kBndFast) ? 1 : 0;  // slow boundary cut
+      cyc[TIMING ? 21 : 0] += clamped ? 0 : 1;                        // full-range histogram (miss or no prediction)
+      cyc[TIMING ? 22 : 0] += (sc[kWCapped] != 0) ? 1 : 0;           // some row's prefix hit Kc
+      cyc[TIMING ? 23 : 0] += n_cand;                                 // listed candidates
+    }
     // ---- PE: scatter every item at or above the boundary bin into its score group ----
     auto place = [&](unsigned key, unsigned okey) {
       const int bucket = bucket_of(key);
@@ -777,6 +834,9 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
         const unsigned keyc = (unsigned)(cutc >> 32), okc = ~(unsigned)(cutc & 0xffffffffull);
         if (!(okc & 0x80000000u)) break;  // a member: members precede children on equal scores
         const int rowc = (int)((okc & 0x7fffffffu) >> 16);
+        // a left-out class of row r scores <= sentinel + old total(r): no tie there, no tie at all
+        const bool may_tie = tid <= rowc && !s_wiped[tid] && KeyOf(__fadd_rn(s_plS[Cv], o_total[tid])) == keyc;
+        if (!__syncthreads_or(may_tie ? 1 : 0)) break;
         for (int idx = tid; idx < (rowc + 1) * C; idx += NT) {
           const int r = idx / C, c = idx - r * C;
           const unsigned ok = 0x80000000u | ((unsigned)r << 16) | (unsigned)c;

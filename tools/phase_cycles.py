@@ -1,4 +1,5 @@
-"""Per-phase latency (clock64, thread 0 of each CTA) of BeamKernelV2: python tools/phase_cycles.py [B] [kind]"""
+"""Per-phase latency (clock64, thread 0 of each CTA) of the fast beam kernels:
+python tools/phase_cycles.py [B] [kind] [cfg2|cfg4]"""
 import os
 import sys
 
@@ -14,12 +15,13 @@ from ctc_beam_search_op_b200 import _lib
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 148
 kind = sys.argv[2] if len(sys.argv) > 2 else "gauss"
-T, C, W = 500, 29, 100
+cfg = sys.argv[3] if len(sys.argv) > 3 else "cfg2"
+T, C, W, BLANK, MERGE = (500, 29, 100, 28, True) if cfg == "cfg2" else (400, 1024, 16, 1023, False)
 lib = _lib.load()
-x = torch.from_numpy(L.make_logits(kind, T, B, C, 28, 1)).cuda()
+x = torch.from_numpy(L.make_logits(kind, T, B, C, BLANK, 1)).cuda()
 sl = torch.full((B,), T, dtype=torch.int32).cuda()
 buf = torch.zeros((B, 24), dtype=torch.int64, device="cuda")
-kw = dict(beam_width=W, top_paths=1, merge_repeated=True, blank_index=28)
+kw = dict(beam_width=W, top_paths=1, merge_repeated=MERGE, blank_index=BLANK)
 op.ctc_ext_beam_search_decoder_raw(x, sl, **kw)
 lib.ctcx_debug_set_cycles_buffer(buf.data_ptr())
 op.ctc_ext_beam_search_decoder_raw(x, sl, **kw)
@@ -28,7 +30,7 @@ lib.ctcx_debug_set_cycles_buffer(None)
 c = buf.cpu().numpy().astype(np.float64) / T
 names = ["PA(end)", "PB(end)", "PC", "PD", "PE", "PF", "PG(end)", "setup", "PA.lookup", "PA.lse1", "PA.lse2",
          "PA.store", "PA.minmax", "PG.rank", "PG.barrier", "PG.write", "PB.range", "PB.pass1", "PB.scan",
-         "PB.pass2+bar", "-", "-", "-", "-"]
+         "PB.pass2+bar", "ev.slowcut", "ev.fullrange", "ev.capped", "ev.ncand"]
 m = c.mean(axis=0)
 print("B=%d %s: cycles per frame, thread 0 (mean over CTAs):" % (B, kind))
-print("  " + "  ".join("%s %.0f" % (n, v) for n, v in zip(names, m)) + "  | total %.0f" % m.sum())
+print("  " + "  ".join(("%s %.3f" if n.startswith("ev.") else "%s %.0f") % (n, v) for n, v in zip(names, m)) + "  | total %.0f" % m[:20].sum())
