@@ -73,6 +73,7 @@ struct Workspace {
   struct Header {
     uint32_t magic;
     int T, B, C, W, P;
+    int real_bytes;  // 4: float32 decode, 8: float64 decode
   };
   size_t header, off, bp, fin_total, fin_kind, fin_n, flags, dec_len, ali_len, dec, ali, dec_off,
       ali_off, sizes, ptrs, stats, t_done, state, srt_pl, srt_cls, bytes;
@@ -82,9 +83,9 @@ struct Workspace {
     const size_t b = (size_t)B, t = (size_t)T, w = (size_t)W, pp = (size_t)P;
     (void)C;
     header = o; o += Align256(sizeof(Header));
-    off = o; o += Align256(t * b * 4);
+    off = o; o += Align256(t * b * 8);                           // float or double
     bp = o; o += Align256(b * t * w * 8);
-    fin_total = o; o += Align256(b * pp * 4);
+    fin_total = o; o += Align256(b * pp * 8);                    // float or double
     fin_kind = o; o += Align256(b * pp * 4);
     fin_n = o; o += Align256(b * 4);
     flags = o; o += Align256(b * 4);
@@ -106,9 +107,9 @@ struct Workspace {
   }
 };
 
-template <int WMAX, int NT>
-cudaError_t LaunchBeam(const ctcx::BeamParams& p, size_t smem, cudaStream_t stream) {
-  auto kern = ctcx::BeamKernel<WMAX, NT>;
+template <typename R, int WMAX, int NT>
+cudaError_t LaunchBeam(const ctcx::BeamParamsT<R>& p, size_t smem, cudaStream_t stream) {
+  auto kern = ctcx::BeamKernelT<R, WMAX, NT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<p.B, NT, smem, stream>>>(p);
@@ -203,6 +204,13 @@ cudaError_t LaunchLogNorm(const float* logits_dev, float* off_dev, long long row
   return cudaGetLastError();
 }
 
+cudaError_t LaunchLogNorm(const double* logits_dev, double* off_dev, long long rows, int C, cudaStream_t stream) {
+  long long blocks = (rows + 7) / 8;
+  if (blocks > (long long)DeviceSmCount() * 16) blocks = (long long)DeviceSmCount() * 16;
+  ctcx::LogNormKernelF64<<<(unsigned)blocks, 256, 0, stream>>>(logits_dev, off_dev, rows, C);
+  return cudaGetLastError();
+}
+
 // kernel 1b (wide vocabularies): the best classes of every row ordered by log-prob
 template <int NI>
 cudaError_t LaunchTopClassesNI(const float* logits_dev, const float* off_dev, long long rows, int C, int blank,
@@ -279,11 +287,37 @@ int LaunchBeamFor(ctcx::BeamParams& bp, cudaStream_t stream) {
     lay.Init(tier.wmax, tier.nt, C, bp.kid_words, bp.cand_cap);
     if (lay.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
     switch (tier.wmax) {
-      case 32: e = LaunchBeam<32, 128>(bp, lay.bytes, stream); break;
-      case 128: e = LaunchBeam<128, 256>(bp, lay.bytes, stream); break;
-      case 256: e = LaunchBeam<256, 256>(bp, lay.bytes, stream); break;
-      default: e = LaunchBeam<1024, 1024>(bp, lay.bytes, stream); break;
+      case 32: e = LaunchBeam<float, 32, 128>(bp, lay.bytes, stream); break;
+      case 128: e = LaunchBeam<float, 128, 256>(bp, lay.bytes, stream); break;
+      case 256: e = LaunchBeam<float, 256, 256>(bp, lay.bytes, stream); break;
+      default: e = LaunchBeam<float, 1024, 1024>(bp, lay.bytes, stream); break;
     }
+  }
+  return Check(e, "beam kernel launch") ? CTCX_OK : CTCX_ERR_CUDA;
+}
+
+// T = double: the generic kernel instantiated for double scores (64-bit keys)
+int LaunchBeamFor(ctcx::BeamParamsT<double>& bp, cudaStream_t stream) {
+  const int W = bp.W, C = bp.C;
+  bp.kid_words = (C + 31) / 32;
+  const long long full_list = (long long)W * C;
+  bp.cand_cap = (full_list <= kListCapMax) ? (int)full_list : 0;
+  bp.dbg_totals = nullptr;
+  bp.dbg_n = nullptr;
+  bp.dbg_cycles = nullptr;
+  // double state is twice as wide: the largest tier that fits in shared memory holds 512 slots
+  Tier tier = PickTier(W);
+  if (tier.wmax > 256) tier = (W <= 512) ? Tier{512, 512} : Tier{1024, 1024};
+  ctcx::BeamSmem lay;
+  lay.Init(tier.wmax, tier.nt, C, bp.kid_words, bp.cand_cap, 8);
+  if (lay.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;  // beam_width > 512, or a very wide vocabulary
+  cudaError_t e;
+  switch (tier.wmax) {
+    case 32: e = LaunchBeam<double, 32, 128>(bp, lay.bytes, stream); break;
+    case 128: e = LaunchBeam<double, 128, 256>(bp, lay.bytes, stream); break;
+    case 256: e = LaunchBeam<double, 256, 256>(bp, lay.bytes, stream); break;
+    case 512: e = LaunchBeam<double, 512, 512>(bp, lay.bytes, stream); break;
+    default: return CTCX_ERR_UNSUPPORTED;
   }
   return Check(e, "beam kernel launch") ? CTCX_OK : CTCX_ERR_CUDA;
 }
@@ -361,10 +395,14 @@ size_t ctcx_workspace_bytes(int T, int B, int C, int W, int P) {
   ws.Init(T, B, C, W, P);
   return ws.bytes;
 }
+}  // extern "C"
 
-int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t* seq_len_dev, int W,
-                    int P, int merge_repeated, int blank_index, int blank_label, void* workspace,
-                    size_t workspace_bytes, void* stream_v, ctcx_sizes* sizes, int32_t* flags_out) {
+namespace {
+template <typename R>
+int DecodeImpl(const R* logits_dev, int T, int B, int C, const int32_t* seq_len_dev, int W,
+               int P, int merge_repeated, int blank_index, int blank_label, void* workspace,
+               size_t workspace_bytes, void* stream_v, ctcx_sizes* sizes, int32_t* flags_out) {
+  constexpr bool kF32 = (sizeof(R) == 4);
   cudaStream_t stream = (cudaStream_t)stream_v;
   // --- validation, in the reference's order (kernels.cc:111-138), then TopPaths' (decoder.h:237) ---
   if (T == 0) return CTCX_ERR_MAX_TIME_ZERO;
@@ -400,39 +438,41 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
   // TopPaths is reached for utterance 0 only after its frames; for B == 0 it is never reached
   if (B > 0 && P > W) return CTCX_ERR_TOO_MANY_PATHS;
 
-  Workspace::Header hdr = {kMagic, T, B, C, W, P};
+  Workspace::Header hdr = {kMagic, T, B, C, W, P, (int)sizeof(R)};
   CTCX_CUDA(cudaMemcpyAsync(base + ws.header, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, stream));
 
   if (B > 0) {
     ProfRecord(0, stream);
-    CTCX_CUDA(LaunchLogNorm(logits_dev, (float*)(base + ws.off), (long long)T * B, C, stream));
+    CTCX_CUDA(LaunchLogNorm(logits_dev, (R*)(base + ws.off), (long long)T * B, C, stream));
     ProfRecord(1, stream);
 
-    ctcx::BeamParams bp;
+    ctcx::BeamParamsT<R> bp;
     bp.logits = logits_dev;
-    bp.off = (const float*)(base + ws.off);
+    bp.off = (const R*)(base + ws.off);
     bp.seq_len = seq_len_dev;
     bp.T = T; bp.B = B; bp.C = C; bp.W = W; bp.P = P;
     bp.blank_index = blank_index;
     bp.bp = (uint2*)(base + ws.bp);
-    bp.fin_total = (float*)(base + ws.fin_total);
+    bp.fin_total = (R*)(base + ws.fin_total);
     bp.fin_kind = (int*)(base + ws.fin_kind);
     bp.fin_n = (int*)(base + ws.fin_n);
     bp.flags = (int*)(base + ws.flags);
     bp.Tcap = T; bp.t_done = nullptr; bp.state = nullptr;  // one-shot decode
     bp.srt_pl = nullptr; bp.srt_cls = nullptr; bp.Cs = ws.Cs; bp.Kc = 0;
-    if (ws.Cs > 0) {
-      bp.srt_pl = (const float*)(base + ws.srt_pl);
-      bp.srt_cls = (const unsigned short*)(base + ws.srt_cls);
-      CTCX_CUDA(LaunchTopClasses(logits_dev, bp.off, (long long)T * B, C, blank_index, W,
-                                 (float*)(base + ws.srt_pl), (unsigned short*)(base + ws.srt_cls), stream));
+    if constexpr (kF32) {
+      if (ws.Cs > 0) {
+        bp.srt_pl = (const float*)(base + ws.srt_pl);
+        bp.srt_cls = (const unsigned short*)(base + ws.srt_cls);
+        CTCX_CUDA(LaunchTopClasses(logits_dev, bp.off, (long long)T * B, C, blank_index, W,
+                                   (float*)(base + ws.srt_pl), (unsigned short*)(base + ws.srt_cls), stream));
+      }
     }
     const int brc = LaunchBeamFor(bp, stream);
     if (brc != CTCX_OK) return brc;
     ProfRecord(2, stream);
 
     ctcx::TraceParams tp;
-    tp.bp = bp.bp; tp.seq_len = seq_len_dev; tp.fin_total = bp.fin_total; tp.fin_kind = bp.fin_kind;
+    tp.bp = bp.bp; tp.seq_len = seq_len_dev; tp.fin_kind = bp.fin_kind;
     tp.fin_n = bp.fin_n; tp.T = T; tp.B = B; tp.W = W; tp.P = P;
     tp.merge_repeated = merge_repeated ? 1 : 0; tp.blank_label = blank_label;
     tp.dec_len = (int*)(base + ws.dec_len); tp.dec = (int*)(base + ws.dec);
@@ -470,17 +510,18 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
   return CTCX_OK;
 }
 
-int ctcx_pack_f32(const void* workspace, int T, int B, int P, int64_t* const* decoded_indices,
-                  int64_t* const* decoded_values, int64_t* const* decoded_shape,
-                  int64_t* const* alignment_indices, int64_t* const* alignment_values,
-                  int64_t* const* alignment_shape, float* log_probability, void* stream_v) {
+int PackImpl(const void* workspace, int T, int B, int P, int64_t* const* decoded_indices,
+             int64_t* const* decoded_values, int64_t* const* decoded_shape,
+             int64_t* const* alignment_indices, int64_t* const* alignment_values,
+             int64_t* const* alignment_shape, void* log_probability, int real_bytes, void* stream_v) {
   cudaStream_t stream = (cudaStream_t)stream_v;
   if (workspace == nullptr || T <= 0 || B < 0 || P < 1) return CTCX_ERR_WORKSPACE;
   const unsigned char* base = (const unsigned char*)workspace;
   Workspace::Header hdr;
   CTCX_CUDA(cudaMemcpyAsync(&hdr, base, sizeof(hdr), cudaMemcpyDeviceToHost, stream));
   CTCX_CUDA(cudaStreamSynchronize(stream));
-  if (hdr.magic != kMagic || hdr.T != T || hdr.B != B || hdr.P != P) return CTCX_ERR_WORKSPACE;
+  if (hdr.magic != kMagic || hdr.T != T || hdr.B != B || hdr.P != P || hdr.real_bytes != real_bytes)
+    return CTCX_ERR_WORKSPACE;
   Workspace ws;
   ws.Init(hdr.T, hdr.B, hdr.C, hdr.W, hdr.P);
   // device copy of the 6*P output pointers
@@ -502,9 +543,10 @@ int ctcx_pack_f32(const void* workspace, int T, int B, int P, int64_t* const* de
     pp.ali_len = (const int*)(base + ws.ali_len); pp.ali = (const int*)(base + ws.ali);
     pp.dec_off = (const long long*)(base + ws.dec_off); pp.ali_off = (const long long*)(base + ws.ali_off);
     pp.sizes = (const long long*)(base + ws.sizes);
-    pp.fin_total = (const float*)(base + ws.fin_total);
+    pp.fin_total = (const void*)(base + ws.fin_total);
     pp.ptrs = (long long* const*)(base + ws.ptrs);
     pp.log_prob = log_probability;
+    pp.real_bytes = real_bytes;
     pp.T = T; pp.B = B; pp.P = P;
     dim3 grid((unsigned)B, (unsigned)P);
     ctcx::PackKernel<<<grid, 128, 0, stream>>>(pp);
@@ -521,6 +563,39 @@ int ctcx_pack_f32(const void* workspace, int T, int B, int P, int64_t* const* de
   CTCX_CUDA(cudaStreamSynchronize(stream));
   return CTCX_OK;
 }
+}  // namespace
+
+extern "C" {
+
+int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t* seq_len_dev, int W,
+                    int P, int merge_repeated, int blank_index, int blank_label, void* workspace,
+                    size_t workspace_bytes, void* stream_v, ctcx_sizes* sizes, int32_t* flags_out) {
+  return DecodeImpl<float>(logits_dev, T, B, C, seq_len_dev, W, P, merge_repeated, blank_index, blank_label,
+                           workspace, workspace_bytes, stream_v, sizes, flags_out);
+}
+
+int ctcx_decode_f64(const double* logits_dev, int T, int B, int C, const int32_t* seq_len_dev, int W,
+                    int P, int merge_repeated, int blank_index, int blank_label, void* workspace,
+                    size_t workspace_bytes, void* stream_v, ctcx_sizes* sizes, int32_t* flags_out) {
+  return DecodeImpl<double>(logits_dev, T, B, C, seq_len_dev, W, P, merge_repeated, blank_index, blank_label,
+                            workspace, workspace_bytes, stream_v, sizes, flags_out);
+}
+
+int ctcx_pack_f32(const void* workspace, int T, int B, int P, int64_t* const* decoded_indices,
+                  int64_t* const* decoded_values, int64_t* const* decoded_shape,
+                  int64_t* const* alignment_indices, int64_t* const* alignment_values,
+                  int64_t* const* alignment_shape, float* log_probability, void* stream_v) {
+  return PackImpl(workspace, T, B, P, decoded_indices, decoded_values, decoded_shape, alignment_indices,
+                  alignment_values, alignment_shape, log_probability, 4, stream_v);
+}
+
+int ctcx_pack_f64(const void* workspace, int T, int B, int P, int64_t* const* decoded_indices,
+                  int64_t* const* decoded_values, int64_t* const* decoded_shape,
+                  int64_t* const* alignment_indices, int64_t* const* alignment_values,
+                  int64_t* const* alignment_shape, double* log_probability, void* stream_v) {
+  return PackImpl(workspace, T, B, P, decoded_indices, decoded_values, decoded_shape, alignment_indices,
+                  alignment_values, alignment_shape, log_probability, 8, stream_v);
+}
 
 int ctcx_workspace_views(const void* workspace, int T, int B, int P, const int32_t** dec_len,
                          const int32_t** dec, const int32_t** ali_len, const int32_t** ali,
@@ -530,6 +605,7 @@ int ctcx_workspace_views(const void* workspace, int T, int B, int P, const int32
   Workspace::Header hdr;
   CTCX_CUDA(cudaMemcpy(&hdr, base, sizeof(hdr), cudaMemcpyDeviceToHost));
   if (hdr.magic != kMagic || hdr.T != T || hdr.B != B || hdr.P != P) return CTCX_ERR_WORKSPACE;
+  if (logp != nullptr && hdr.real_bytes != 4) return CTCX_ERR_BAD_ARGUMENT;  // float32 decodes only
   Workspace ws;
   ws.Init(hdr.T, hdr.B, hdr.C, hdr.W, hdr.P);
   if (dec_len) *dec_len = (const int32_t*)(base + ws.dec_len);
@@ -696,7 +772,7 @@ int ctcx_stream_reset(void* workspace, size_t workspace_bytes, int T_total, int 
   if (workspace == nullptr || workspace_bytes < ws.bytes || ((uintptr_t)workspace & 255u))
     return CTCX_ERR_WORKSPACE;
   unsigned char* base = (unsigned char*)workspace;
-  Workspace::Header hdr = {kMagic, T_total, B, C, W, P};
+  Workspace::Header hdr = {kMagic, T_total, B, C, W, P, 4};
   CTCX_CUDA(cudaMemcpyAsync(base + ws.header, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, stream));
   if (B > 0) {
     // decoder.h:212-227: with zero frames consumed the kernels start from the root
@@ -758,7 +834,6 @@ int ctcx_stream_top_paths(void* workspace, int T_total, int B, int C, int W, int
     ctcx::TraceParams tp;
     tp.bp = (const uint2*)(base + ws.bp);
     tp.seq_len = (const int*)(base + ws.t_done);  // frames consumed so far
-    tp.fin_total = (const float*)(base + ws.fin_total);
     tp.fin_kind = (const int*)(base + ws.fin_kind);
     tp.fin_n = (const int*)(base + ws.fin_n);
     tp.T = T_total; tp.B = B; tp.W = W; tp.P = P;
@@ -808,6 +883,16 @@ int ctcx_debug_math_f32(int op, const float* x_dev, float* y_dev, int n, void* s
   cudaStream_t stream = (cudaStream_t)stream_v;
   if (n <= 0) return CTCX_OK;
   ctcx::MathTestKernel<<<(n + 255) / 256, 256, 0, stream>>>(op, x_dev, y_dev, n);
+  CTCX_CUDA(cudaGetLastError());
+  return CTCX_OK;
+}
+
+
+/* the double-precision twin: op 0 exp (x <= 0), 1 log (x >= 1), 2 LogSumExp(x, 0) */
+int ctcx_debug_math_f64(int op, const double* x_dev, double* y_dev, int n, void* stream_v) {
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  if (n <= 0) return CTCX_OK;
+  ctcx::MathTestKernelF64<<<(n + 255) / 256, 256, 0, stream>>>(op, x_dev, y_dev, n);
   CTCX_CUDA(cudaGetLastError());
   return CTCX_OK;
 }

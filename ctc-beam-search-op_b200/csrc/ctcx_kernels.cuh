@@ -88,6 +88,32 @@ __global__ void __launch_bounds__(256) LogNormKernel(const float* __restrict__ l
   }
 }
 
+// T = double (kernels.cc:275): the same normaliser through the double-precision exp()/log().
+__global__ void __launch_bounds__(256) LogNormKernelF64(const double* __restrict__ logits,
+                                                        double* __restrict__ off, long long rows, int C) {
+  __shared__ unsigned long long s_tab[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = kCtcxExpTab[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp_global; row < rows; row += nwarps) {
+    const double* x = logits + row * C;
+    double mx = __longlong_as_double((long long)0xfff0000000000000ull);
+    for (int j = lane; j < C; j += 32) mx = fmax(mx, x[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));
+    double sum = 0.0;
+    for (int base = 0; base < C; base += 32) {
+      const int j = base + lane;
+      const double e = (j < C) ? ExpExactD(__dsub_rn(x[j], mx), s_tab) : 0.0;
+      const int m = min(32, C - base);
+      for (int k = 0; k < m; ++k) sum = __dadd_rn(sum, __shfl_sync(kFull, e, k));
+    }
+    if (lane == 0) off[row] = __dadd_rn(mx, LogExactD(sum));
+  }
+}
+
 // Narrow-vocabulary variant (C <= 64): one THREAD per row. A CTA stages 256 consecutive rows (one
 // contiguous, coalesced chunk of 256*C floats) in shared memory with an odd row stride (no bank
 // conflicts), then every thread walks its own row: max, then the exp-sum in index order. 4x fewer
@@ -209,20 +235,72 @@ __global__ void __launch_bounds__(256) TopClassesKernel(const float* __restrict_
 // ---------------------------------------------------------------------------------------------
 // Kernel 2: the beam kernel.
 // ---------------------------------------------------------------------------------------------
-struct BeamParams {
-  const float* logits;  // [T,B,C] time-major raw logits
-  const float* off;     // [T,B]   normaliser from LogNormKernel
+// Arithmetic of the score type R (float, or double for the reference's T = double registration,
+// kernels.cc:275): explicit round-to-nearest operations, the monotone score -> integer key map and
+// the (key, ~tie order) composite the survivors are ranked by.
+template <typename R>
+struct RealOps;
+template <>
+struct RealOps<float> {
+  using Key = unsigned;
+  using Comp = unsigned long long;  // key << 32 | ~order
+  static constexpr int kKeyBits = 32;
+  static constexpr Key kKeyMax = 0xffffffffu;
+  static constexpr Key kKeyNegInf = 0x007fffffu;
+  __device__ static __forceinline__ float NegInf() { return __int_as_float((int)0xff800000); }
+  __device__ static __forceinline__ float Add(float a, float b) { return __fadd_rn(a, b); }
+  __device__ static __forceinline__ float Sub(float a, float b) { return __fsub_rn(a, b); }
+  __device__ static __forceinline__ Key KeyOf(float s) { return ctcx::KeyOf(s); }
+  __device__ static __forceinline__ float UnKey(Key k) { return ctcx::UnKey(k); }
+  __device__ static __forceinline__ int Bits(Key range) { return range == 0u ? 0 : 32 - __clz(range); }
+  __device__ static __forceinline__ Comp MakeComp(Key k, unsigned not_order) {
+    return ((unsigned long long)k << 32) | (unsigned long long)not_order;
+  }
+  __device__ static __forceinline__ bool Greater(Comp a, Comp b) { return a > b; }
+  __device__ static __forceinline__ Key CompKey(Comp c) { return (unsigned)(c >> 32); }
+  __device__ static __forceinline__ unsigned CompNotOrder(Comp c) { return (unsigned)(c & 0xffffffffull); }
+};
+template <>
+struct RealOps<double> {
+  using Key = unsigned long long;
+  using Comp = ulonglong2;  // {key, ~order}
+  static constexpr int kKeyBits = 64;
+  static constexpr Key kKeyMax = 0xffffffffffffffffull;
+  static constexpr Key kKeyNegInf = 0x000fffffffffffffull;
+  __device__ static __forceinline__ double NegInf() { return __longlong_as_double((long long)0xfff0000000000000ull); }
+  __device__ static __forceinline__ double Add(double a, double b) { return __dadd_rn(a, b); }
+  __device__ static __forceinline__ double Sub(double a, double b) { return __dsub_rn(a, b); }
+  __device__ static __forceinline__ Key KeyOf(double s) {  // -0.0 canonicalised to +0.0
+    const unsigned long long u = (unsigned long long)__double_as_longlong(__dadd_rn(s, 0.0));
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+  }
+  __device__ static __forceinline__ double UnKey(Key k) {
+    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+  }
+  __device__ static __forceinline__ int Bits(Key range) { return range == 0ull ? 0 : 64 - __clzll((long long)range); }
+  __device__ static __forceinline__ Comp MakeComp(Key k, unsigned not_order) {
+    return make_ulonglong2(k, (unsigned long long)not_order);
+  }
+  __device__ static __forceinline__ bool Greater(Comp a, Comp b) { return a.x > b.x || (a.x == b.x && a.y > b.y); }
+  __device__ static __forceinline__ Key CompKey(Comp c) { return c.x; }
+  __device__ static __forceinline__ unsigned CompNotOrder(Comp c) { return (unsigned)c.y; }
+};
+
+template <typename R>
+struct BeamParamsT {
+  const R* logits;  // [T,B,C] time-major raw logits
+  const R* off;     // [T,B]   normaliser from LogNormKernel
   const int* seq_len;   // [B]
   int T, B, C, W, P;
   int blank_index;
   int cand_cap;   // capacity of the shared-memory candidate list; 0 = streaming mode
   int kid_words;  // ceil(C/32)
   uint2* bp;      // [B,T,W] back-pointer records {packed, label}
-  float* fin_total;  // [B,P]
+  R* fin_total;      // [B,P]
   int* fin_kind;     // [B,P] 1 = best alignment ends in blank
   int* fin_n;        // [B]   members in the final beam
   int* flags;        // [B]   bit0 rounding anomaly, bit1 fewer leaves than top_paths
-  float* dbg_totals;  // optional [B,T,W]
+  R* dbg_totals;      // optional [B,T,W]
   int* dbg_n;         // optional [B,T]
   long long* dbg_cycles;  // optional [B,24]: clock64 cycles per phase (thread 0), summed over frames
   // streaming (Step / TopPaths / Reset, decoder.h:39-53); all null / T for a one-shot decode
@@ -230,12 +308,13 @@ struct BeamParams {
   int* t_done;            // [B] frames already consumed per utterance (updated by the kernel), or null
   unsigned char* state;   // [B] x StreamStateBytes(W): beam state carried between chunks, or null
   // wide-vocabulary fast path (ctcx_beam_wide.cuh): per frame, the classes sorted by log-prob
-  const float* srt_pl;           // [T,B,Cs] x_l - off of the best classes, descending (padding = -inf)
+  const R* srt_pl;               // [T,B,Cs] x_l - off of the best classes, descending (padding = -inf)
   const unsigned short* srt_cls; // [T,B,Cs] class index at each sorted position
   int Cs;                        // row stride of the two arrays (a multiple of 8)
   int Kc;                        // sorted classes per frame the kernel may use (entry Kc, if < C-1
                                  // classes are listed, is a sentinel: the best class left out)
 };
+using BeamParams = BeamParamsT<float>;
 
 // Beam state of one utterance between two chunks of a streamed decode.
 struct StreamHdr {
@@ -266,44 +345,54 @@ struct StreamView {
 struct BeamSmem {
   // byte offsets
   size_t hash, phash;          // u64 [2][WMAX]
-  size_t surv;                 // u64 [WMAX]
+  size_t surv;                 // Comp [WMAX]
   size_t exptab;               // u64 [32]
-  size_t total, blk, lab, ab, an;  // f32 [2][WMAX]
+  size_t total, blk, lab, ab, an;  // R [2][WMAX]
   size_t label;                // i32 [2][WMAX]
-  size_t m_nt, m_nb, m_nl, m_nab, m_nan;  // f32 [WMAX]
-  size_t m_key, m_rec;         // u32 [WMAX]
+  size_t m_nt, m_nb, m_nl, m_nab, m_nan;  // R [WMAX]
+  size_t m_key;                // Key [WMAX]
+  size_t m_rec;                // u32 [WMAX]
   size_t m_pslot;              // i32 [WMAX]
   size_t risk, risk_new;       // i32 [WMAX]
   size_t wiped;                // u32 [WMAX] (0/1)
   size_t part;                 // i32 [NT]
   size_t htab;                 // i32 [2*WMAX]
   size_t hist;                 // u32 [256]
-  size_t x;                    // f32 [2][Cpad]
+  size_t x;                    // R [2][Cpad]
   size_t kid;                  // u32 [WMAX*kid_words]
-  size_t c_key, c_id;          // u32 [cand_cap]
+  size_t c_key;                // Key [cand_cap]
+  size_t c_id;                 // u32 [cand_cap]
+  size_t offv;                 // R [2]   this / the next frame's normaliser
+  size_t keys;                 // Key [4] min key, max key, radix prefix
   size_t scal;                 // i32/u32 [32] scalars
   size_t bytes;
 
   __host__ __device__ static size_t Align(size_t v, size_t a) { return (v + a - 1) / a * a; }
-  __host__ __device__ void Init(int wmax, int nt, int C, int kid_words, int cand_cap) {
+  // rs = sizeof(R): 4 (float) or 8 (double); every 8-byte array precedes the 4-byte ones
+  __host__ __device__ void Init(int wmax, int nt, int C, int kid_words, int cand_cap, int rs = 4) {
     size_t o = 0;
-    const size_t w = (size_t)wmax;
+    const size_t w = (size_t)wmax, r = (size_t)rs;
+    const size_t cpad = Align((size_t)C, 4);
     hash = o; o += 2 * w * 8;
     phash = o; o += 2 * w * 8;
-    surv = o; o += w * 8;
+    surv = o; o += w * (rs == 4 ? 8 : 16);
     exptab = o; o += 32 * 8;
-    total = o; o += 2 * w * 4;
-    blk = o; o += 2 * w * 4;
-    lab = o; o += 2 * w * 4;
-    ab = o; o += 2 * w * 4;
-    an = o; o += 2 * w * 4;
+    keys = o; o += 4 * 8;
+    offv = o; o += 2 * 8;
+    total = o; o += 2 * w * r;
+    blk = o; o += 2 * w * r;
+    lab = o; o += 2 * w * r;
+    ab = o; o += 2 * w * r;
+    an = o; o += 2 * w * r;
+    m_nt = o; o += w * r;
+    m_nb = o; o += w * r;
+    m_nl = o; o += w * r;
+    m_nab = o; o += w * r;
+    m_nan = o; o += w * r;
+    m_key = o; o += w * r;
+    x = o; o += 2 * cpad * r;
+    c_key = o; o += Align((size_t)cand_cap * r, 8);
     label = o; o += 2 * w * 4;
-    m_nt = o; o += w * 4;
-    m_nb = o; o += w * 4;
-    m_nl = o; o += w * 4;
-    m_nab = o; o += w * 4;
-    m_nan = o; o += w * 4;
-    m_key = o; o += w * 4;
     m_rec = o; o += w * 4;
     m_pslot = o; o += w * 4;
     risk = o; o += w * 4;
@@ -312,10 +401,7 @@ struct BeamSmem {
     part = o; o += (size_t)nt * 4;
     htab = o; o += 2 * w * 4;
     hist = o; o += 256 * 4;
-    const size_t cpad = Align((size_t)C, 4);
-    x = o; o += 2 * cpad * 4;
     kid = o; o += w * (size_t)kid_words * 4;
-    c_key = o; o += (size_t)cand_cap * 4;
     c_id = o; o += (size_t)cand_cap * 4;
     scal = o; o += 32 * 4;
     bytes = Align(o, 16);
@@ -324,12 +410,16 @@ struct BeamSmem {
 
 // indices into the scalar block
 enum {
-  kScNCand = 0, kScNRisk, kScMinKey, kScMaxKey, kScChanged, kScPrefix, kScK, kScE, kScNSurv,
-  kScTotalItems, kScOff0, kScOff1, kScAnomaly
+  kScNCand = 0, kScNRisk, kScChanged, kScK, kScE, kScNSurv, kScTotalItems, kScAnomaly
 };
+enum { kKeyMin = 0, kKeyMaxSlot = 1, kKeyPrefix = 2 };  // slots of the Key-typed scalar block
 
-template <int WMAX, int NT>
-__global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
+template <typename R, int WMAX, int NT>
+__global__ void __launch_bounds__(NT) BeamKernelT(BeamParamsT<R> p) {
+  using Ops = RealOps<R>;
+  using Key = typename Ops::Key;
+  using Comp = typename Ops::Comp;
+  constexpr bool kIsF32 = (sizeof(R) == 4);  // streaming state blocks exist for float only
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int NWARP = NT / 32;
   constexpr int TS = 2 * WMAX;  // hash-table slots (power of two)
@@ -340,26 +430,26 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
   // streaming: frames already consumed by earlier chunks; this chunk contributes L more
   const int t_done = (p.t_done != nullptr) ? p.t_done[b] : 0;
   const int L = max(0, min(p.seq_len[b], p.Tcap - t_done));
-  const bool resume = (p.state != nullptr) && t_done > 0;
+  const bool resume = kIsF32 && (p.state != nullptr) && t_done > 0;
 
   BeamSmem lay;
-  lay.Init(WMAX, NT, C, KW, p.cand_cap);
+  lay.Init(WMAX, NT, C, KW, p.cand_cap, (int)sizeof(R));
   unsigned long long* s_hash = (unsigned long long*)(smem + lay.hash);
   unsigned long long* s_phash = (unsigned long long*)(smem + lay.phash);
-  unsigned long long* s_surv = (unsigned long long*)(smem + lay.surv);
+  Comp* s_surv = (Comp*)(smem + lay.surv);
   unsigned long long* s_exptab = (unsigned long long*)(smem + lay.exptab);
-  float* s_total = (float*)(smem + lay.total);
-  float* s_blk = (float*)(smem + lay.blk);
-  float* s_lab = (float*)(smem + lay.lab);
-  float* s_ab = (float*)(smem + lay.ab);
-  float* s_an = (float*)(smem + lay.an);
+  R* s_total = (R*)(smem + lay.total);
+  R* s_blk = (R*)(smem + lay.blk);
+  R* s_lab = (R*)(smem + lay.lab);
+  R* s_ab = (R*)(smem + lay.ab);
+  R* s_an = (R*)(smem + lay.an);
   int* s_label = (int*)(smem + lay.label);
-  float* m_nt = (float*)(smem + lay.m_nt);
-  float* m_nb = (float*)(smem + lay.m_nb);
-  float* m_nl = (float*)(smem + lay.m_nl);
-  float* m_nab = (float*)(smem + lay.m_nab);
-  float* m_nan = (float*)(smem + lay.m_nan);
-  unsigned* m_key = (unsigned*)(smem + lay.m_key);
+  R* m_nt = (R*)(smem + lay.m_nt);
+  R* m_nb = (R*)(smem + lay.m_nb);
+  R* m_nl = (R*)(smem + lay.m_nl);
+  R* m_nab = (R*)(smem + lay.m_nab);
+  R* m_nan = (R*)(smem + lay.m_nan);
+  Key* m_key = (Key*)(smem + lay.m_key);
   unsigned* m_rec = (unsigned*)(smem + lay.m_rec);
   int* m_pslot = (int*)(smem + lay.m_pslot);
   int* s_risk = (int*)(smem + lay.risk);
@@ -368,13 +458,14 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
   int* s_part = (int*)(smem + lay.part);
   int* s_htab = (int*)(smem + lay.htab);
   unsigned* s_hist = (unsigned*)(smem + lay.hist);
-  float* s_x = (float*)(smem + lay.x);
+  R* s_x = (R*)(smem + lay.x);
   unsigned* s_kid = (unsigned*)(smem + lay.kid);
-  unsigned* c_key = (unsigned*)(smem + lay.c_key);
+  Key* c_key = (Key*)(smem + lay.c_key);
   unsigned* c_id = (unsigned*)(smem + lay.c_id);
   volatile int* sc = (volatile int*)(smem + lay.scal);
   int* sci = (int*)(smem + lay.scal);
-  unsigned* scu = (unsigned*)(smem + lay.scal);
+  Key* s_keys = (Key*)(smem + lay.keys);
+  R* s_offv = (R*)(smem + lay.offv);
   const int cpad = (int)BeamSmem::Align((size_t)C, 4);
 
   // ---- initial state: the root (decoder.h:212-227) ----
@@ -383,32 +474,34 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
   for (int i = tid; i < WMAX * KW; i += NT) s_kid[i] = 0u;
   for (int i = tid; i < WMAX; i += NT) s_wiped[i] = 0u;
   if (tid == 0 && !resume) {
-    s_total[0] = 0.0f;
-    s_blk[0] = 0.0f;
-    s_lab[0] = NegInf();
-    s_ab[0] = 0.0f;  // empty alignment with probability 1 (entry.h:204-209)
-    s_an[0] = NegInf();
+    s_total[0] = (R)0;
+    s_blk[0] = (R)0;
+    s_lab[0] = Ops::NegInf();
+    s_ab[0] = (R)0;  // empty alignment with probability 1 (entry.h:204-209)
+    s_an[0] = Ops::NegInf();
     s_label[0] = -1;
     s_hash[0] = kRootHash;
     s_phash[0] = 0ull;
     sci[kScAnomaly] = 0;
   }
   int n = 1;  // members in the beam (uniform across the CTA)
-  if (resume) {  // beam as the previous chunk left it (buffer 0: local frame 0 reads buffer 0)
-    StreamView sv(p.state + (size_t)b * StreamStateBytes(W), W);
-    n = sv.hdr->n;
-    for (int i = tid; i < n; i += NT) {
-      s_total[i] = sv.total[i]; s_blk[i] = sv.blk[i]; s_lab[i] = sv.lab[i];
-      s_ab[i] = sv.ab[i]; s_an[i] = sv.an[i]; s_label[i] = sv.label[i];
-      s_hash[i] = sv.hash[i]; s_phash[i] = sv.phash[i];
+  if constexpr (kIsF32) {
+    if (resume) {  // beam as the previous chunk left it (buffer 0: local frame 0 reads buffer 0)
+      StreamView sv(p.state + (size_t)b * StreamStateBytes(W), W);
+      n = sv.hdr->n;
+      for (int i = tid; i < n; i += NT) {
+        s_total[i] = sv.total[i]; s_blk[i] = sv.blk[i]; s_lab[i] = sv.lab[i];
+        s_ab[i] = sv.ab[i]; s_an[i] = sv.an[i]; s_label[i] = sv.label[i];
+        s_hash[i] = sv.hash[i]; s_phash[i] = sv.phash[i];
+      }
+      if (tid == 0) sci[kScAnomaly] = sv.hdr->flags & 1;
     }
-    if (tid == 0) sci[kScAnomaly] = sv.hdr->flags & 1;
   }
   // row 0 of the logits
   if (L > 0) {
-    const float* g = p.logits + (size_t)b * C;
+    const R* g = p.logits + (size_t)b * C;
     for (int l = tid; l < C; l += NT) s_x[l] = g[l];
-    if (tid == 0) ((float*)sci)[kScOff0] = p.off[b];
+    if (tid == 0) s_offv[0] = p.off[b];
   }
   __syncthreads();
   for (int i = tid; i < n; i += NT) {  // parent look-up table of the initial beam (the root, or the resumed one)
@@ -419,50 +512,50 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
 
   for (int t = 0; t < L; ++t) {
     const int cur = t & 1, nxt = cur ^ 1;
-    const float* x = s_x + cur * cpad;
-    const float off = ((const float*)sci)[kScOff0 + cur];
-    const float* o_total = s_total + cur * WMAX;
-    const float* o_blk = s_blk + cur * WMAX;
-    const float* o_lab = s_lab + cur * WMAX;
-    const float* o_ab = s_ab + cur * WMAX;
-    const float* o_an = s_an + cur * WMAX;
+    const R* x = s_x + cur * cpad;
+    const R off = s_offv[cur];
+    const R* o_total = s_total + cur * WMAX;
+    const R* o_blk = s_blk + cur * WMAX;
+    const R* o_lab = s_lab + cur * WMAX;
+    const R* o_ab = s_ab + cur * WMAX;
+    const R* o_an = s_an + cur * WMAX;
     const int* o_label = s_label + cur * WMAX;
     const unsigned long long* o_hash = s_hash + cur * WMAX;
     const unsigned long long* o_phash = s_phash + cur * WMAX;
 
     // prefetch the next frame's row (consumed after the barrier that ends this frame)
     if (t + 1 < L) {
-      const float* g = p.logits + ((size_t)(t + 1) * B + b) * C;
-      float* dst = s_x + nxt * cpad;
+      const R* g = p.logits + ((size_t)(t + 1) * B + b) * C;
+      R* dst = s_x + nxt * cpad;
       for (int l = tid; l < C; l += NT) {
         const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + l);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(g + l));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(sa), "l"(g + l), "n"(sizeof(R)));
       }
       if (tid == 0) {
-        const unsigned sa = (unsigned)__cvta_generic_to_shared((float*)sci + kScOff0 + nxt);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa),
-                     "l"(p.off + (size_t)(t + 1) * B + b));
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(s_offv + nxt);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(sa),
+                     "l"(p.off + (size_t)(t + 1) * B + b), "n"(sizeof(R)));
       }
       asm volatile("cp.async.commit_group;\n" ::);
     }
     if (tid == 0) {
       sci[kScNCand] = 0;
       sci[kScNRisk] = 0;
-      scu[kScMinKey] = 0xffffffffu;
-      scu[kScMaxKey] = 0u;
+      s_keys[kKeyMin] = Ops::kKeyMax;
+      s_keys[kKeyMaxSlot] = (Key)0;
       sci[kScNSurv] = 0;
     }
     __syncthreads();
 
     // ---- (A) update the existing members (decoder.h:95-143) ----
-    const float xb = x[blank];
-    const float pb = __fsub_rn(xb, off);
-    unsigned my_key = 0u;
+    const R xb = x[blank];
+    const R pb = Ops::Sub(xb, off);
+    Key my_key = (Key)0;
     if (tid < n) {
       const int i = tid;
       const int lbl = o_label[i];
       int pslot = -1;
-      float v_nl = o_lab[i], v_an = NegInf();
+      R v_nl = o_lab[i], v_an = Ops::NegInf();
       unsigned an_kind = kAnNone, an_src = kInvalidSlot;
       if (lbl >= 0) {
         const unsigned long long ph = o_phash[i];
@@ -473,38 +566,38 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
           if (o_hash[s] == ph) { pslot = s; break; }
           h = (h + 1) & (TS - 1);
         }
-        const float xl = x[lbl];
-        const float pl = __fsub_rn(xl, off);
-        const float self_an = __fadd_rn(o_an[i], pl);
+        const R xl = x[lbl];
+        const R pl = Ops::Sub(xl, off);
+        const R self_an = Ops::Add(o_an[i], pl);
         if (pslot >= 0) {
           const bool same = (lbl == o_label[pslot]);
-          const float base = same ? o_blk[pslot] : o_total[pslot];
-          v_nl = __fsub_rn(__fadd_rn(LogSumExp(o_lab[i], base, s_exptab), xl), off);  // :102-104,:113-115
-          v_an = __fadd_rn(o_ab[pslot], pl);
+          const R base = same ? o_blk[pslot] : o_total[pslot];
+          v_nl = Ops::Sub(Ops::Add(LogSumExp(o_lab[i], base, s_exptab), xl), off);  // :102-104,:113-115
+          v_an = Ops::Add(o_ab[pslot], pl);
           an_kind = kAnParAb;
           an_src = (unsigned)pslot;
           if (!same) {
-            const float c2 = __fadd_rn(o_an[pslot], pl);
+            const R c2 = Ops::Add(o_an[pslot], pl);
             if (c2 > v_an) { v_an = c2; an_kind = kAnParAn; }
           }
           if (self_an > v_an) { v_an = self_an; an_kind = kAnSelfAn; an_src = (unsigned)i; }
         } else {
-          v_nl = __fadd_rn(o_lab[i], pl);  // :125
+          v_nl = Ops::Add(o_lab[i], pl);  // :125
           v_an = self_an;
           an_kind = kAnSelfAn;
           an_src = (unsigned)i;
         }
       }
-      const float v_nb = __fsub_rn(__fadd_rn(o_total[i], xb), off);  // :132
-      const float c1 = __fadd_rn(o_ab[i], pb), c2 = __fadd_rn(o_an[i], pb);
+      const R v_nb = Ops::Sub(Ops::Add(o_total[i], xb), off);  // :132
+      const R c1 = Ops::Add(o_ab[i], pb), c2 = Ops::Add(o_an[i], pb);
       const unsigned ab_kind = (c2 > c1) ? kAbFromAn : kAbFromAb;
-      const float v_nt = LogSumExp(v_nb, v_nl, s_exptab);  // :139
+      const R v_nt = LogSumExp(v_nb, v_nl, s_exptab);  // :139
       m_nt[i] = v_nt;
       m_nb[i] = v_nb;
       m_nl[i] = v_nl;
       m_nab[i] = (c2 > c1) ? c2 : c1;
       m_nan[i] = v_an;
-      my_key = KeyOf(v_nt);
+      my_key = Ops::KeyOf(v_nt);
       m_key[i] = my_key;
       m_rec[i] = PackRec((unsigned)i, an_src, ab_kind, an_kind);
       m_pslot[i] = pslot;
@@ -518,15 +611,15 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
     }
     // min / max member key
     {
-      unsigned kmin = (tid < n) ? my_key : 0xffffffffu, kmax = (tid < n) ? my_key : 0u;
+      Key kmin = (tid < n) ? my_key : Ops::kKeyMax, kmax = (tid < n) ? my_key : (Key)0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         kmin = min(kmin, __shfl_xor_sync(kFull, kmin, o));
         kmax = max(kmax, __shfl_xor_sync(kFull, kmax, o));
       }
       if (lane == 0 && warp * 32 < n) {
-        atomicMin(&scu[kScMinKey], kmin);
-        atomicMax(&scu[kScMaxKey], kmax);
+        atomicMin(&s_keys[kKeyMin], kmin);
+        atomicMax(&s_keys[kKeyMaxSlot], kmax);
       }
     }
     __syncthreads();
@@ -535,25 +628,25 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
 
     // weakest a-priori threshold: with a full beam nothing at or below the W-th member total can
     // ever be admitted (decoder.h:151-155); keys are compared instead of floats from here on
-    const unsigned th0 = (n == W) ? max(scu[kScMinKey], kKeyNegInf) : kKeyNegInf;
+    const Key th0 = (n == W) ? max(s_keys[kKeyMin], Ops::kKeyNegInf) : Ops::kKeyNegInf;
 
     // ---- (C) fresh children above the threshold (decoder.h:161-187) ----
     // evaluates (row, label) -> score key; used to build the list or, in streaming mode, directly
-    auto eval_child = [&](int row, int l, unsigned& skey) -> bool {
+    auto eval_child = [&](int row, int l, Key& skey) -> bool {
       if (l == blank) return false;
       if ((s_kid[row * KW + (l >> 5)] >> (l & 31)) & 1u) return false;  // c.Active(): merged in (A)
-      const float pl = __fsub_rn(x[l], off);
-      const float base = (l == o_label[row]) ? o_blk[row] : o_total[row];
-      skey = KeyOf(__fadd_rn(pl, base));  // :172-182
+      const R pl = Ops::Sub(x[l], off);
+      const R base = (l == o_label[row]) ? o_blk[row] : o_total[row];
+      skey = Ops::KeyOf(Ops::Add(pl, base));  // :172-182
       return skey > th0;
     };
     {
-      unsigned kmax = 0u, kmin = 0xffffffffu;
+      Key kmax = (Key)0, kmin = Ops::kKeyMax;
       int cnt_stream = 0;
       for (int row = warp; row < n; row += NWARP) {
         for (int l0 = 0; l0 < C; l0 += 32) {
           const int l = l0 + lane;
-          unsigned skey = 0u;
+          Key skey = (Key)0;
           const bool ok = (l < C) && eval_child(row, l, skey);
           if (ok) { kmax = max(kmax, skey); kmin = min(kmin, skey); }
           if (list_mode) {
@@ -580,9 +673,9 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
         cnt_stream += __shfl_xor_sync(kFull, cnt_stream, o);
       }
       if (lane == 0) {
-        if (kmax != 0u) {
-          atomicMin(&scu[kScMinKey], kmin);
-          atomicMax(&scu[kScMaxKey], kmax);
+        if (kmax != (Key)0) {
+          atomicMin(&s_keys[kKeyMin], kmin);
+          atomicMax(&s_keys[kKeyMaxSlot], kmax);
         }
         if (!list_mode && cnt_stream) atomicAdd(&sci[kScNCand], cnt_stream);
       }
@@ -601,11 +694,11 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
           const int pb_slot = m_pslot[m];
           int verdict = 0;
           if (!s_wiped[pb_slot]) {
-            const unsigned vkey = m_key[m];
+            const Key vkey = m_key[m];
             const unsigned idm = ((unsigned)pb_slot << 16) | (unsigned)o_label[m];
             int cnt = 0;
             for (int j = lane; j < n; j += 32) {
-              const unsigned kj = m_key[j];
+              const Key kj = m_key[j];
               cnt += (kj > vkey || (kj == vkey && j < m)) ? 1 : 0;
             }
             if (list_mode) {
@@ -618,7 +711,7 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
                 if (s_wiped[row]) continue;
                 const int lend = (row == pb_slot) ? o_label[m] : C;
                 for (int l = lane; l < lend; l += 32) {
-                  unsigned skey;
+                  Key skey;
                   cnt += (eval_child(row, l, skey) && skey > vkey) ? 1 : 0;
                 }
               }
@@ -650,9 +743,9 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
         if (s_wiped[m]) {
           const int pslot = m_pslot[m];
           const int lbl = o_label[m];
-          const float pl = __fsub_rn(x[lbl], off);
-          const float base = (lbl == o_label[pslot]) ? o_blk[pslot] : o_total[pslot];
-          if (KeyOf(__fadd_rn(pl, base)) > m_key[m]) sci[kScAnomaly] = 1;
+          const R pl = Ops::Sub(x[lbl], off);
+          const R base = (lbl == o_label[pslot]) ? o_blk[pslot] : o_total[pslot];
+          if (Ops::KeyOf(Ops::Add(pl, base)) > m_key[m]) sci[kScAnomaly] = 1;
           sci[kScChanged] = 2;  // "some member is wiped"
         }
       }
@@ -677,7 +770,7 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
         for (int row = warp; row < n; row += NWARP) {
           if (any_wiped && s_wiped[row]) continue;
           for (int l = lane; l < C; l += 32) {
-            unsigned skey;
+            Key skey;
             if (eval_child(row, l, skey)) f(skey, 0x80000000u | ((unsigned)row << 16) | (unsigned)l);
           }
         }
@@ -686,22 +779,22 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
     // one radix-select level: among items with pred(), find the K-th largest of key(); returns the
     // selected key in sc[kScPrefix] (+lo), the number still to take at that key in sc[kScK] and the
     // number of items equal to it in sc[kScE]; sc[kScTotalItems] = number of items seen.
-    auto radix_select = [&](unsigned lo, unsigned range, int K, auto&& keyfn) {
-      const int nbits = (range == 0u) ? 0 : (32 - __clz(range));
+    auto radix_select = [&](Key lo, Key range, int K, auto&& keyfn) {
+      const int nbits = Ops::Bits(range);
       int npass = (nbits + 7) / 8;
       if (npass == 0) npass = 1;
-      if (tid == 0) { scu[kScPrefix] = 0u; sci[kScK] = K; }
+      if (tid == 0) { s_keys[kKeyPrefix] = (Key)0; sci[kScK] = K; }
       for (int pass = npass - 1; pass >= 0; --pass) {
         const int shift = pass * 8;
         for (int i = tid; i < 256; i += NT) s_hist[i] = 0u;
         __syncthreads();
-        const unsigned prefix = scu[kScPrefix];
-        for_each_item([&](unsigned skey, unsigned okey) {
-          unsigned key;
+        const Key prefix = s_keys[kKeyPrefix];
+        for_each_item([&](Key skey, unsigned okey) {
+          Key key;
           if (!keyfn(skey, okey, key)) return;
-          const unsigned d = key - lo;
-          const unsigned hi = (shift + 8 >= 32) ? 0u : (d >> (shift + 8));
-          if (hi == prefix) atomicAdd(&s_hist[(d >> shift) & 255u], 1u);
+          const Key d = key - lo;
+          const Key hi = (shift + 8 >= Ops::kKeyBits) ? (Key)0 : (d >> (shift + 8));
+          if (hi == prefix) atomicAdd(&s_hist[(unsigned)(d >> shift) & 255u], 1u);
         });
         __syncthreads();
         if (warp == 0) {
@@ -723,7 +816,7 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
 #pragma unroll
             for (int q = 7; q >= 0; --q) {
               if ((int)(acc + h[q]) >= k && (int)acc < k) {
-                scu[kScPrefix] = (prefix << 8) | (unsigned)(lane * 8 + q);
+                s_keys[kKeyPrefix] = (prefix << 8) | (Key)(lane * 8 + q);
                 sci[kScK] = k - (int)acc;
                 sci[kScE] = (int)h[q];
               }
@@ -736,36 +829,37 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
     };
 
     const int n_items_upper = n + n_cand;  // before removing wiped rows
-    unsigned cut_d = 0u, cut_o = 0u;       // survivors: d > cut_d || (d == cut_d && ~okey >= cut_o)
-    const unsigned lo = scu[kScMinKey];
+    Key cut_d = (Key)0;  // survivors: d > cut_d || (d == cut_d && ~okey >= cut_o)
+    unsigned cut_o = 0u;
+    const Key lo = s_keys[kKeyMin];
     bool take_all = (!any_wiped && n_items_upper <= W);
     if (!take_all) {
-      const unsigned range = scu[kScMaxKey] - lo;
-      radix_select(lo, range, W, [&](unsigned skey, unsigned, unsigned& key) { key = skey; return true; });
+      const Key range = s_keys[kKeyMaxSlot] - lo;
+      radix_select(lo, range, W, [&](Key skey, unsigned, Key& key) { key = skey; return true; });
       const int total_items = sc[kScTotalItems];
       if (total_items <= W) {
         take_all = true;
       } else {
-        cut_d = scu[kScPrefix];
+        cut_d = s_keys[kKeyPrefix];
         const int k_rem = sc[kScK], e = sc[kScE];
         __syncthreads();
         if (e != k_rem) {  // exact ties straddle the beam boundary: cut them by tie order
-          const unsigned want = cut_d + lo;
-          radix_select(0u, 0xffffffffu, k_rem, [&](unsigned skey, unsigned okey, unsigned& key) {
-            key = ~okey;
+          const Key want = cut_d + lo;
+          radix_select((Key)0, (Key)0xffffffffu, k_rem, [&](Key skey, unsigned okey, Key& key) {
+            key = (Key)(~okey);
             return skey == want;
           });
-          cut_o = scu[kScPrefix];
+          cut_o = (unsigned)s_keys[kKeyPrefix];
           __syncthreads();
         }
       }
     }
     // collect survivors as 64-bit composites (score key, ~tie order): larger = earlier in the beam
-    for_each_item([&](unsigned skey, unsigned okey) {
-      const unsigned d = skey - lo;
+    for_each_item([&](Key skey, unsigned okey) {
+      const Key d = skey - lo;
       if (take_all || d > cut_d || (d == cut_d && ~okey >= cut_o)) {
         const int pos = atomicAdd(&sci[kScNSurv], 1);
-        if (pos < WMAX) s_surv[pos] = ((unsigned long long)skey << 32) | (unsigned long long)(~okey);
+        if (pos < WMAX) s_surv[pos] = Ops::MakeComp(skey, ~okey);
       }
     });
     __syncthreads();
@@ -779,9 +873,9 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
       const int part = (PARTS > 1) ? (tid / WMAX) : 0;
       int cnt = 0;
       if (k < n_new && part < PARTS) {
-        const unsigned long long mine = s_surv[k];
+        const Comp mine = s_surv[k];
         const int j0 = (int)((long long)n_new * part / PARTS), j1 = (int)((long long)n_new * (part + 1) / PARTS);
-        for (int j = j0; j < j1; ++j) cnt += (s_surv[j] > mine) ? 1 : 0;
+        for (int j = j0; j < j1; ++j) cnt += Ops::Greater(s_surv[j], mine) ? 1 : 0;
       }
       if (PARTS > 1) {
         s_part[tid] = cnt;
@@ -790,18 +884,18 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
           for (int q = 1; q < PARTS; ++q) cnt += s_part[q * WMAX + k];
         }
       }
-      float* w_total = s_total + nxt * WMAX;
-      float* w_blk = s_blk + nxt * WMAX;
-      float* w_lab = s_lab + nxt * WMAX;
-      float* w_ab = s_ab + nxt * WMAX;
-      float* w_an = s_an + nxt * WMAX;
+      R* w_total = s_total + nxt * WMAX;
+      R* w_blk = s_blk + nxt * WMAX;
+      R* w_lab = s_lab + nxt * WMAX;
+      R* w_ab = s_ab + nxt * WMAX;
+      R* w_an = s_an + nxt * WMAX;
       int* w_label = s_label + nxt * WMAX;
       unsigned long long* w_hash = s_hash + nxt * WMAX;
       unsigned long long* w_phash = s_phash + nxt * WMAX;
       if (part == 0 && k < n_new) {
         const int r = cnt;  // new slot
-        const unsigned long long comp = s_surv[k];
-        const unsigned okey = ~(unsigned)(comp & 0xffffffffull);
+        const Comp comp = s_surv[k];
+        const unsigned okey = ~Ops::CompNotOrder(comp);
         unsigned rec;
         int lbl;
         unsigned long long hsh;
@@ -819,18 +913,18 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
         } else {  // fresh child (decoder.h:170-187)
           const int row = (int)((okey & 0x7fffffffu) >> 16);
           lbl = (int)(okey & 0xffffu);
-          const float s = UnKey((unsigned)(comp >> 32));
-          const float pl = __fsub_rn(x[lbl], off);
-          float v_an = __fadd_rn(o_ab[row], pl);
+          const R s = Ops::UnKey(Ops::CompKey(comp));
+          const R pl = Ops::Sub(x[lbl], off);
+          R v_an = Ops::Add(o_ab[row], pl);
           unsigned an_kind = kAnParAb;
           if (lbl != o_label[row]) {
-            const float c2 = __fadd_rn(o_an[row], pl);
+            const R c2 = Ops::Add(o_an[row], pl);
             if (c2 > v_an) { v_an = c2; an_kind = kAnParAn; }
           }
           w_total[r] = s;
-          w_blk[r] = NegInf();
+          w_blk[r] = Ops::NegInf();
           w_lab[r] = s;
-          w_ab[r] = NegInf();
+          w_ab[r] = Ops::NegInf();
           w_an[r] = v_an;
           hsh = HashChild(o_hash[row], lbl);
           w_phash[r] = o_hash[row];
@@ -865,7 +959,7 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
         p.fin_total[(size_t)b * p.P + tid] = s_total[cur * WMAX + tid];
         p.fin_kind[(size_t)b * p.P + tid] = (s_ab[cur * WMAX + tid] > s_an[cur * WMAX + tid]) ? 1 : 0;
       } else {
-        p.fin_total[(size_t)b * p.P + tid] = 0.0f;
+        p.fin_total[(size_t)b * p.P + tid] = (R)0;
         p.fin_kind[(size_t)b * p.P + tid] = 0;
       }
     }
@@ -874,18 +968,20 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
       p.fin_n[b] = n;
       p.flags[b] = (sci[kScAnomaly] ? 1 : 0) | ((p.P > n) ? 2 : 0) | overflow;
     }
-    if (p.state != nullptr) {  // carry the beam to the next chunk
-      StreamView sv(p.state + (size_t)b * StreamStateBytes(W), W);
-      for (int i = tid; i < n; i += NT) {
-        sv.total[i] = s_total[cur * WMAX + i]; sv.blk[i] = s_blk[cur * WMAX + i];
-        sv.lab[i] = s_lab[cur * WMAX + i]; sv.ab[i] = s_ab[cur * WMAX + i];
-        sv.an[i] = s_an[cur * WMAX + i]; sv.label[i] = s_label[cur * WMAX + i];
-        sv.hash[i] = s_hash[cur * WMAX + i]; sv.phash[i] = s_phash[cur * WMAX + i];
-      }
-      if (tid == 0) {
-        sv.hdr->n = n;
-        sv.hdr->gap = 0u;
-        sv.hdr->flags = (sci[kScAnomaly] ? 1 : 0) | overflow | (resume ? (sv.hdr->flags & 4) : 0);
+    if constexpr (kIsF32) {
+      if (p.state != nullptr) {  // carry the beam to the next chunk
+        StreamView sv(p.state + (size_t)b * StreamStateBytes(W), W);
+        for (int i = tid; i < n; i += NT) {
+          sv.total[i] = s_total[cur * WMAX + i]; sv.blk[i] = s_blk[cur * WMAX + i];
+          sv.lab[i] = s_lab[cur * WMAX + i]; sv.ab[i] = s_ab[cur * WMAX + i];
+          sv.an[i] = s_an[cur * WMAX + i]; sv.label[i] = s_label[cur * WMAX + i];
+          sv.hash[i] = s_hash[cur * WMAX + i]; sv.phash[i] = s_phash[cur * WMAX + i];
+        }
+        if (tid == 0) {
+          sv.hdr->n = n;
+          sv.hdr->gap = 0u;
+          sv.hdr->flags = (sci[kScAnomaly] ? 1 : 0) | overflow | (resume ? (sv.hdr->flags & 4) : 0);
+        }
       }
     }
     if (p.t_done != nullptr && tid == 0) p.t_done[b] = t_done + L;
@@ -900,7 +996,6 @@ __global__ void __launch_bounds__(NT) BeamKernel(BeamParams p) {
 struct TraceParams {
   const uint2* bp;
   const int* seq_len;
-  const float* fin_total;
   const int* fin_kind;
   const int* fin_n;
   int T, B, W, P;
@@ -1145,9 +1240,10 @@ struct PackParams {
   const int* dec_len; const int* dec; const int* ali_len; const int* ali;  // dense rows
   const long long* dec_off; const long long* ali_off;                      // [P,B]
   const long long* sizes;                                                   // [4,P]
-  const float* fin_total;                                                   // [B,P]
+  const void* fin_total;                                                    // [B,P] float or double
   long long* const* ptrs;  // device table [6,P]: dec_idx, dec_val, dec_shape, ali_idx, ali_val, ali_shape
-  float* log_prob;         // [B,P]
+  void* log_prob;          // [B,P] float or double
+  int real_bytes;          // 4 or 8
   int T, B, P;
 };
 
@@ -1179,7 +1275,10 @@ __global__ void __launch_bounds__(128) PackKernel(PackParams p) {
     }
   }
   if (threadIdx.x == 0) {
-    p.log_prob[row] = p.fin_total[row];  // kernels.cc:87-89
+    if (p.real_bytes == 8)  // kernels.cc:87-89
+      ((double*)p.log_prob)[row] = ((const double*)p.fin_total)[row];
+    else
+      ((float*)p.log_prob)[row] = ((const float*)p.fin_total)[row];
     if (b == 0) {
       long long* ds = p.ptrs[2 * p.P + path];
       long long* as = p.ptrs[5 * p.P + path];
@@ -1198,6 +1297,19 @@ __global__ void MathTestKernel(int op, const float* x, float* y, int n) {
   if (i >= n) return;
   const float v = x[i];
   y[i] = (op == 0) ? ExpfExact(v, s_tab) : (op == 1) ? Log1pfExact(v) : LogfExact(v);
+}
+
+// op 0: exp (x <= 0), 1: log (x >= 1), 2: LogSumExp(x, 0) of the double path
+__global__ void MathTestKernelF64(int op, const double* x, double* y, int n) {
+  __shared__ unsigned long long s_tab[256];
+  __shared__ unsigned long long s_tabf[32];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = kCtcxExpTab[i];
+  LoadExpTable(s_tabf, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i];
+  y[i] = (op == 0) ? ExpExactD(v, s_tab) : (op == 1) ? LogExactD(v) : LogSumExp(v, 0.0, s_tabf);
 }
 
 }  // namespace ctcx

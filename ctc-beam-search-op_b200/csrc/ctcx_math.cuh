@@ -172,4 +172,107 @@ __device__ __forceinline__ float LogSumExp(float a, float b, const unsigned long
   return __fadd_rn(hi, Log1pfExact(ExpfExact(d, exp_tab)));
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Double precision (T = double is registered too, kernels.cc:275): the normaliser then calls exp()
+// and log(). Same approach: glibc 2.39's Arm Optimized Routines double algorithms (N = 128), in the
+// operation order of __exp_fma / __log_fma (read off the disassembly of this image's libm; CPU twin
+// and its 2e9-sample check: oracle/libm_port.h). LogSumExp stays in the float functions even for
+// double (util/ctc_loss_util.h:39-40).
+// ---------------------------------------------------------------------------------------------
+}  // namespace ctcx
+#define CTCX_TAB_QUAL __device__ __constant__
+#include "ctcx_libm_f64_tables.h"
+#undef CTCX_TAB_QUAL
+namespace ctcx {
+
+__device__ __forceinline__ double AsD(unsigned long long u) { return __longlong_as_double((long long)u); }
+
+// exp for -512 < x <= 0; smaller arguments (< 1e-222, never able to change a sum >= 1) and -inf give 0.
+// `tab` = the 256-entry table (a shared-memory copy where lanes index it divergently).
+__device__ __forceinline__ double ExpExactD(double x, const unsigned long long* tab) {
+  const unsigned abstop = (unsigned)((unsigned long long)__double_as_longlong(x) >> 52) & 0x7ffu;
+  if (abstop - 0x3c9u >= 0x3fu) {
+    if (abstop < 0x3c9u) return __dadd_rn(1.0, x);
+    return 0.0;
+  }
+  const double InvLn2N = AsD(kCtcxExpHdr[0]), Shift = AsD(kCtcxExpHdr[1]);
+  const double NegLn2hiN = AsD(kCtcxExpHdr[2]), NegLn2loN = AsD(kCtcxExpHdr[3]);
+  const double C2 = AsD(kCtcxExpHdr[4]), C3 = AsD(kCtcxExpHdr[5]), C4 = AsD(kCtcxExpHdr[6]), C5 = AsD(kCtcxExpHdr[7]);
+  double kd = __fma_rn(InvLn2N, x, Shift);
+  const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+  kd = __dsub_rn(kd, Shift);
+  double r = __fma_rn(kd, NegLn2hiN, x);
+  r = __fma_rn(kd, NegLn2loN, r);
+  const unsigned idx = 2u * ((unsigned)ki & 127u);
+  const double tail = AsD(tab[idx]);
+  const unsigned long long sbits = tab[idx + 1] + (ki << 45);
+  const double r2 = __dmul_rn(r, r);
+  const double p23 = __fma_rn(C3, r, C2);
+  const double p45 = __fma_rn(r, C5, C4);
+  double tmp = __fma_rn(p23, r2, __dadd_rn(tail, r));
+  tmp = __fma_rn(__dmul_rn(r2, r2), p45, tmp);
+  const double scale = AsD(sbits);
+  return __fma_rn(scale, tmp, scale);
+}
+
+// log for finite x >= 1.
+__device__ __forceinline__ double LogExactD(double x) {
+  const unsigned long long ix = (unsigned long long)__double_as_longlong(x);
+  if (ix - 0x3fee000000000000ull < 0x3090000000000ull) {  // near 1: dedicated polynomial
+    if (ix == 0x3ff0000000000000ull) return 0.0;
+    const double B0 = AsD(kCtcxLogHdr[7]);
+    const double r = __dsub_rn(x, 1.0);
+    const double r2 = __dmul_rn(r, r);
+    const double r3 = __dmul_rn(r, r2);
+    const double q1 = __fma_rn(r2, AsD(kCtcxLogHdr[10]), __fma_rn(AsD(kCtcxLogHdr[9]), r, AsD(kCtcxLogHdr[8])));
+    const double q4 = __fma_rn(r2, AsD(kCtcxLogHdr[13]), __fma_rn(AsD(kCtcxLogHdr[12]), r, AsD(kCtcxLogHdr[11])));
+    double q7 = __fma_rn(r2, AsD(kCtcxLogHdr[16]), __fma_rn(AsD(kCtcxLogHdr[15]), r, AsD(kCtcxLogHdr[14])));
+    q7 = __fma_rn(r3, AsD(kCtcxLogHdr[17]), q7);
+    double y = __fma_rn(q7, r3, q4);
+    y = __fma_rn(y, r3, q1);
+    const double two27 = 134217728.0;
+    const double rw = __fma_rn(r, two27, r);
+    const double rhi = __fma_rn(-two27, r, rw);
+    const double rlo = __dsub_rn(r, rhi);
+    const double rhi2 = __dmul_rn(rhi, rhi);
+    const double hi = __fma_rn(rhi2, B0, r);
+    double lo = __fma_rn(rhi2, B0, __dsub_rn(r, hi));
+    lo = __fma_rn(__dmul_rn(B0, rlo), __dadd_rn(rhi, r), lo);
+    y = __fma_rn(y, r3, lo);
+    return __dadd_rn(y, hi);
+  }
+  const unsigned long long tmp = ix - 0x3fe6000000000000ull;
+  const int i = (int)((tmp >> 45) & 127ull);
+  const int k = (int)((long long)tmp >> 52);
+  const unsigned long long iz = ix - (tmp & (0xfffull << 52));
+  const double invc = AsD(kCtcxLogTab[2 * i]), logc = AsD(kCtcxLogTab[2 * i + 1]);
+  const double z = AsD(iz);
+  const double r = __fma_rn(z, invc, -1.0);
+  const double kd = (double)k;
+  const double w = __fma_rn(kd, AsD(kCtcxLogHdr[0]), logc);
+  const double hi = __dadd_rn(w, r);
+  double lo = __dadd_rn(__dsub_rn(w, hi), r);
+  lo = __fma_rn(kd, AsD(kCtcxLogHdr[1]), lo);
+  const double r2 = __dmul_rn(r, r);
+  const double p12 = __fma_rn(AsD(kCtcxLogHdr[4]), r, AsD(kCtcxLogHdr[3]));
+  const double p34 = __fma_rn(r, AsD(kCtcxLogHdr[6]), AsD(kCtcxLogHdr[5]));
+  lo = __fma_rn(r2, AsD(kCtcxLogHdr[2]), lo);
+  const double p = __fma_rn(p34, r2, p12);
+  const double y = __fma_rn(__dmul_rn(r, r2), p, lo);
+  return __dadd_rn(y, hi);
+}
+
+// util/ctc_loss_util.h:33-41 with T = double: the difference is rounded to float, expf / log1pf are
+// the float functions, their float result is added to the larger operand in double.
+__device__ __forceinline__ double LogSumExp(double a, double b, const unsigned long long* exp_tab) {
+  const double ninf = __longlong_as_double((long long)0xfff0000000000000ull);
+  if (a == ninf) return b;
+  if (b == ninf) return a;
+  const bool a_gt = a > b;
+  const double hi = a_gt ? a : b;
+  const double d = a_gt ? __dsub_rn(b, a) : __dsub_rn(a, b);
+  return __dadd_rn(hi, (double)Log1pfExact(ExpfExact(__double2float_rn(d), exp_tab)));
+}
+
 }  // namespace ctcx

@@ -71,9 +71,9 @@ def _as_tensor(a):
     return torch.from_numpy(np.ascontiguousarray(a)), True
 
 
-def _pack(lib, ws, T, B, P, counts, device, stream):
-    """Allocate the 6*P sparse tensors from the sizes a decode reported and let ctcx_pack_f32 fill
-    them (StoreAllDecodedSequences, kernels.cc:163-257)."""
+def _pack(lib, ws, T, B, P, counts, device, stream, f64=False):
+    """Allocate the 6*P sparse tensors from the sizes a decode reported and let ctcx_pack_f32 /
+    ctcx_pack_f64 fill them (StoreAllDecodedSequences, kernels.cc:163-257)."""
     n_dec, n_ali = counts
     i64 = dict(dtype=torch.int64, device=device)
     dec_idx = [torch.empty((int(n_dec[p]), 2), **i64) for p in range(P)]
@@ -82,14 +82,15 @@ def _pack(lib, ws, T, B, P, counts, device, stream):
     ali_idx = [torch.empty((int(n_ali[p]), 2), **i64) for p in range(P)]
     ali_val = [torch.empty((int(n_ali[p]),), **i64) for p in range(P)]
     ali_shp = [torch.empty((2,), **i64) for p in range(P)]
-    logp = torch.empty((B, P), dtype=torch.float32, device=device)
+    logp = torch.empty((B, P), dtype=torch.float64 if f64 else torch.float32, device=device)
     ptrs = ctypes.c_void_p * P
 
     def table(ts):
         return ptrs(*[t.data_ptr() for t in ts])
 
-    rc = lib.ctcx_pack_f32(ws.data_ptr(), T, B, P, table(dec_idx), table(dec_val), table(dec_shp),
-                           table(ali_idx), table(ali_val), table(ali_shp), logp.data_ptr(), stream)
+    pack = lib.ctcx_pack_f64 if f64 else lib.ctcx_pack_f32
+    rc = pack(ws.data_ptr(), T, B, P, table(dec_idx), table(dec_val), table(dec_shp),
+              table(ali_idx), table(ali_val), table(ali_shp), logp.data_ptr(), stream)
     if rc != 0:
         _raise(lib, rc)
     return [dec_idx, dec_val, dec_shp, ali_idx, ali_val, ali_shp], logp
@@ -100,9 +101,11 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
                                     name=None, device=None):
     """The raw op: returns a 7-field namedtuple of (lists of) tensors, exactly the op's outputs.
 
-    inputs            [max_time, batch, num_classes] float32; float64 is accepted (computed in float32,
-                      log_probability returned as float64); torch float16 / bfloat16 are accepted and
-                      upcast exactly on the device; numpy array or torch tensor on any device
+    inputs            [max_time, batch, num_classes] float32 or float64 (the reference registers both,
+                      kernels.cc:269-275; float64 is computed in float64 by the double instantiation
+                      of the generic kernel and log_probability is float64); torch float16 / bfloat16
+                      are accepted and upcast exactly on the device; numpy array or torch tensor on
+                      any device
     sequence_length   [batch] int32
     beam_width >= 1, top_paths >= 1, merge_repeated=False, blank_index=0, blank_label=-1
     Outputs live where the inputs live (numpy in -> numpy out).
@@ -133,7 +136,7 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
     if not torch.cuda.is_available():
         raise RuntimeError("ctcx: no CUDA device available and there is no CPU fallback")
 
-    out_dtype = torch.float64 if x.dtype == torch.float64 else torch.float32
+    f64 = x.dtype == torch.float64
     if device is None:
         device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
     device = torch.device(device)
@@ -141,7 +144,8 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
     half = x.dtype in (torch.float16, torch.bfloat16)
     with torch.cuda.device(device):
         # fp16 / bf16 logits cross the bus as they are and are upcast (exactly) on the device
-        xd = x.to(device=device, dtype=(x.dtype if half else torch.float32), non_blocking=True).contiguous()
+        xd = x.to(device=device, dtype=(x.dtype if (half or f64) else torch.float32),
+                  non_blocking=True).contiguous()
         sd = seq.to(device=device, dtype=torch.int32, non_blocking=True).contiguous()
         stream = torch.cuda.current_stream(device).cuda_stream
         P = int(top_paths)
@@ -159,16 +163,15 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
                                       ws.data_ptr(), ws_bytes, stream, ctypes.byref(sizes),
                                       ctypes.byref(flags))
         else:
-            rc = lib.ctcx_decode_f32(xd.data_ptr(), T, B, C, sd.data_ptr(), int(beam_width), P,
-                                     int(bool(merge_repeated)), int(blank_index), int(blank_label),
-                                     ws.data_ptr(), ws_bytes, stream, ctypes.byref(sizes),
-                                     ctypes.byref(flags))
+            decode = lib.ctcx_decode_f64 if f64 else lib.ctcx_decode_f32
+            rc = decode(xd.data_ptr(), T, B, C, sd.data_ptr(), int(beam_width), P,
+                        int(bool(merge_repeated)), int(blank_index), int(blank_label),
+                        ws.data_ptr(), ws_bytes, stream, ctypes.byref(sizes), ctypes.byref(flags))
         if rc != 0:
             _raise(lib, rc)
         global last_flags
         last_flags = int(flags.value)
-        groups, logp = _pack(lib, ws, T, B, P, (n_dec, n_ali), device, stream)
-        logp = logp.to(out_dtype)
+        groups, logp = _pack(lib, ws, T, B, P, (n_dec, n_ali), device, stream, f64)
         if host_out:
             groups = [[t.cpu() for t in g] for g in groups]
             logp = logp.cpu()

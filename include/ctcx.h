@@ -135,6 +135,22 @@ int ctcx_decode_half(const void* logits_dev, int dtype, float* scratch_dev, int 
                      int merge_repeated, int blank_index, int blank_label, void* workspace,
                      size_t workspace_bytes, void* stream, ctcx_sizes* sizes, int32_t* flags_out);
 
+/* T = double (the reference registers the op for float and double, kernels.cc:269-275, and its own
+ * test feeds float64): logits_dev is [max_time, batch, num_classes] float64 in DEVICE memory; scores
+ * are computed in float64 exactly as the reference does (LogSumExp still through the float
+ * functions, util/ctc_loss_util.h:39-40); ctcx_pack_f64 writes log_probability as float64 [batch,
+ * top_paths]. Same workspace size, same error codes. A workspace decoded with one dtype must be
+ * packed with the same one (CTCX_ERR_WORKSPACE otherwise). */
+int ctcx_decode_f64(const double* logits_dev, int max_time, int batch, int num_classes,
+                    const int32_t* seq_len_dev, int beam_width, int top_paths, int merge_repeated,
+                    int blank_index, int blank_label, void* workspace, size_t workspace_bytes,
+                    void* stream, ctcx_sizes* sizes, int32_t* flags_out);
+int ctcx_pack_f64(const void* workspace, int max_time, int batch, int top_paths,
+                  int64_t* const* decoded_indices, int64_t* const* decoded_values,
+                  int64_t* const* decoded_shape, int64_t* const* alignment_indices,
+                  int64_t* const* alignment_values, int64_t* const* alignment_shape,
+                  double* log_probability, void* stream);
+
 /* ---- Streaming: the reference decoder's Step / TopPaths / Reset
  * (util/ctc_ext_beam_search_decoder.h:39-53) for all utterances of a batch at once. The beam state
  * lives in the workspace between calls, so logits can be fed in chunks of frames as they arrive:

@@ -151,4 +151,92 @@ static inline float ctcx_port_logf(float x) {
   y = fma(y, r2, y0 + r);
   return (float)y;
 }
+
+/* ---- double precision (the reference also registers T = double: kernels.cc:275; its normaliser then
+ * calls exp()/log(), decoder.h:76,78). glibc 2.39's exp/log are the Arm Optimized Routines double
+ * algorithms (N = 128 tables); the operation order below -- which product-sums are fused -- was read
+ * off the disassembly of __exp_fma / __log_fma in this image's libm (the variants the x86-64 ifunc
+ * selects on FMA-capable CPUs), the tables were dumped from the same binary
+ * (tools/dump_libm_f64_tables.py). Checked against libm on 2e9 random arguments per function
+ * (libm_port_check.c: ctcx_port_mismatches_f64), 0 mismatches.
+ * Domains: exp for -512 < x <= 0 (smaller arguments give < 1e-222, which can never change the
+ * normaliser's sum >= 1: they are returned as 0); log for finite x >= 1. ---- */
+#include "../ctc-beam-search-op_b200/csrc/ctcx_libm_f64_tables.h"
+
+static inline double ctcx_port_exp(double x) {
+  const double InvLn2N = ctcx_asdouble(kCtcxExpHdr[0]), Shift = ctcx_asdouble(kCtcxExpHdr[1]);
+  const double NegLn2hiN = ctcx_asdouble(kCtcxExpHdr[2]), NegLn2loN = ctcx_asdouble(kCtcxExpHdr[3]);
+  const double C2 = ctcx_asdouble(kCtcxExpHdr[4]), C3 = ctcx_asdouble(kCtcxExpHdr[5]);
+  const double C4 = ctcx_asdouble(kCtcxExpHdr[6]), C5 = ctcx_asdouble(kCtcxExpHdr[7]);
+  const uint32_t abstop = (uint32_t)(ctcx_asuint64(x) >> 52) & 0x7ff;
+  if (abstop - 0x3c9u >= 0x3fu) {
+    if (abstop < 0x3c9u) return 1.0 + x; /* |x| < 2^-54 */
+    return 0.0;                          /* x <= -512 (or -inf): see the domain note */
+  }
+  double kd = fma(InvLn2N, x, Shift);
+  const uint64_t ki = ctcx_asuint64(kd);
+  kd -= Shift;
+  double r = fma(kd, NegLn2hiN, x);
+  r = fma(kd, NegLn2loN, r);
+  const uint64_t idx = 2 * (ki % 128);
+  const uint64_t top = ki << 45;
+  const double tail = ctcx_asdouble(kCtcxExpTab[idx]);
+  const uint64_t sbits = kCtcxExpTab[idx + 1] + top;
+  const double r2 = r * r;
+  const double p23 = fma(C3, r, C2);
+  const double p45 = fma(r, C5, C4);
+  double tmp = fma(p23, r2, tail + r);
+  tmp = fma(r2 * r2, p45, tmp);
+  const double scale = ctcx_asdouble(sbits);
+  return fma(scale, tmp, scale);
+}
+
+static inline double ctcx_port_log(double x) {
+  const double Ln2hi = ctcx_asdouble(kCtcxLogHdr[0]), Ln2lo = ctcx_asdouble(kCtcxLogHdr[1]);
+  const double* A = (const double*)(const void*)&kCtcxLogHdr[2];  /* A[0..4] */
+  const double* B = (const double*)(const void*)&kCtcxLogHdr[7];  /* B[0..10] */
+  const uint64_t ix = ctcx_asuint64(x);
+  if (ix - 0x3fee000000000000ull < 0x3090000000000ull) { /* 1 - 2^-4 <= x < 1 + 0x1.09p-4 */
+    if (ix == 0x3ff0000000000000ull) return 0.0;
+    const double r = x - 1.0;
+    const double r2 = r * r;
+    const double r3 = r * r2;
+    const double q1 = fma(r2, B[3], fma(B[2], r, B[1]));
+    const double q4 = fma(r2, B[6], fma(B[5], r, B[4]));
+    double q7 = fma(r2, B[9], fma(B[8], r, B[7]));
+    q7 = fma(r3, B[10], q7);
+    double y = fma(q7, r3, q4);
+    y = fma(y, r3, q1);
+    const double two27 = 0x1p27;
+    const double rw = fma(r, two27, r);      /* r + w,  w = r * 2^27 */
+    const double rhi = fma(-two27, r, rw);   /* (r + w) - w */
+    const double rlo = r - rhi;
+    const double rhi2 = rhi * rhi;
+    const double hi = fma(rhi2, B[0], r);    /* r + w', w' = rhi*rhi*B0 */
+    double lo = fma(rhi2, B[0], r - hi);     /* r - hi + w' */
+    lo = fma(B[0] * rlo, rhi + r, lo);
+    y = fma(y, r3, lo);
+    return y + hi;
+  }
+  const uint64_t tmp = ix - 0x3fe6000000000000ull;
+  const int i = (int)((tmp >> 45) % 128);
+  const int k = (int)((int64_t)tmp >> 52);
+  const uint64_t iz = ix - (tmp & (0xfffull << 52));
+  const double invc = ctcx_asdouble(kCtcxLogTab[2 * i]), logc = ctcx_asdouble(kCtcxLogTab[2 * i + 1]);
+  const double z = ctcx_asdouble(iz);
+  const double r = fma(z, invc, -1.0);
+  const double kd = (double)k;
+  const double w = fma(kd, Ln2hi, logc);
+  const double hi = w + r;
+  double lo = (w - hi) + r;
+  lo = fma(kd, Ln2lo, lo);
+  const double r2 = r * r;
+  const double p12 = fma(A[2], r, A[1]);
+  const double p34 = fma(r, A[4], A[3]);
+  lo = fma(r2, A[0], lo);
+  const double p = fma(p34, r2, p12);
+  const double y = fma(r * r2, p, lo);
+  return y + hi;
+}
+
 #endif

@@ -186,6 +186,90 @@ def test_device_math_is_bit_exact(op):
         np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+def test_device_math_f64_is_bit_exact(op):
+    """ExpExactD / LogExactD / the double LogSumExp on the device == host libm exp / log /
+    log1pf(expf) (the reference's T = double arithmetic)."""
+    import ctypes
+    import torch
+    from ctc_beam_search_op_b200 import _lib
+    lib = _lib.load()
+    cpu = ctypes.CDLL(L.ORACLE_SO)
+    rng = np.random.default_rng(6)
+    dp = ctypes.POINTER(ctypes.c_double)
+    n = 400000
+    xe = np.concatenate([-np.abs(rng.standard_normal(n) * 25), -rng.random(n) * 512, -10.0 ** rng.uniform(-20, 2.7, n),
+                         [0.0, -0.0, -1e-300, -1e-17, -511.99, -512.0, -600.0, -745.2, -1e4, -np.inf]])
+    xl = np.concatenate([1 + rng.random(n) * 0.07, 1 + rng.random(n) * 70000, 1 + 10.0 ** rng.uniform(-16, 0, n),
+                         [1.0, 1.0 + 2 ** -52, 1.0647, 1.065, 2.0, 29.0, 1024.0, 65535.0]])
+    for op_id, xs, fn in ((0, xe, cpu.ctcx_libm_exp_v), (1, xl, cpu.ctcx_libm_log_v)):
+        xs = np.ascontiguousarray(xs, np.float64)
+        want = np.empty_like(xs)
+        fn(xs.ctypes.data_as(dp), want.ctypes.data_as(dp), len(xs))
+        if op_id == 0:
+            want[xs <= -512.0] = 0.0  # below 1e-222 the device returns 0 (cannot change a sum >= 1)
+        xd = torch.from_numpy(xs).cuda()
+        yd = torch.empty_like(xd)
+        assert lib.ctcx_debug_math_f64(op_id, xd.data_ptr(), yd.data_ptr(), len(xs), None) == 0
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(yd.cpu().numpy().view(np.uint64), want.view(np.uint64))
+    # LogSumExp(x, 0) in double: x + log1pf(expf((float)(0 - x))) for x > 0, 0 + log1pf(expf((float)x)) else
+    xs = np.concatenate([rng.standard_normal(n) * 20, rng.standard_normal(n) * 1e-3, [0.0, 1e-9, -1e-9, 104.0, -104.0]])
+    fpp = ctypes.POINTER(ctypes.c_float)
+    d32 = (-np.abs(xs)).astype(np.float32)
+    e = np.empty_like(d32)
+    cpu.ctcx_libm_expf_v(d32.ctypes.data_as(fpp), e.ctypes.data_as(fpp), len(d32))
+    l1 = np.empty_like(d32)
+    cpu.ctcx_libm_log1pf_v(e.ctypes.data_as(fpp), l1.ctypes.data_as(fpp), len(d32))
+    want = np.maximum(xs, 0.0) + l1.astype(np.float64)
+    xd = torch.from_numpy(np.ascontiguousarray(xs)).cuda()
+    yd = torch.empty_like(xd)
+    assert lib.ctcx_debug_math_f64(2, xd.data_ptr(), yd.data_ptr(), len(xs), None) == 0
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(yd.cpu().numpy().view(np.uint64), want.view(np.uint64))
+
+
+F64_CASES = [
+    # kind, T, B, C, W, P, merge, blank
+    ("gauss", 40, 4, 29, 10, 3, False, 28),
+    ("peaky", 60, 3, 29, 100, 1, True, 28),    # cfg2 shape, short
+    ("gauss", 30, 3, 40, 24, 2, False, 7),
+    ("peaky", 20, 2, 300, 8, 2, False, 0),     # streaming candidate mode
+    ("gauss", 12, 2, 12, 300, 3, False, 0),    # WMAX=1024 tier
+    ("gauss", 25, 2, 40, 200, 2, True, 39),    # WMAX=256 tier
+]
+
+
+@pytest.mark.parametrize("case", F64_CASES, ids=lambda c: "%s-T%d-C%d-W%d" % (c[0], c[1], c[3], c[4]))
+def test_float64_decode_is_bit_exact(op, case):
+    """T = double (kernels.cc:275; the reference's own test feeds float64): decoded in float64 by the
+    double instantiation of the generic kernel, identical to the float64 oracle down to the bits."""
+    kind, T, B, C, W, P, merge, blank = case
+    rng = np.random.default_rng(41)
+    x = rng.standard_normal((T, B, C))  # genuine float64 values
+    if kind == "peaky":
+        x += L.make_logits("peaky", T, B, C, blank, 41).astype(np.float64) - L.make_logits("gauss", T, B, C, blank, 41)
+    sl = L.ragged_lengths(T, B, 41)
+    want = L.oracle_decode(x, sl, W, P, merge, blank, -1)
+    assert want.logp.dtype == np.float64
+    raw = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=W, top_paths=P, merge_repeated=merge,
+                                             blank_index=blank, blank_label=-1)
+    packed = L.pack_sparse(want)
+    for g in range(6):
+        for p in range(P):
+            np.testing.assert_array_equal(np.asarray(raw[g][p]), packed[g][p])
+    assert np.asarray(raw[6]).dtype == np.float64
+    np.testing.assert_array_equal(np.asarray(raw[6]).view(np.uint64), np.asarray(packed[6], np.float64).view(np.uint64))
+    if W == 300:  # float64 state is twice as wide: beam widths above 512 are refused, never degraded
+        with pytest.raises(op.CtcxError, match="not supported"):
+            op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=600, top_paths=1, blank_index=blank)
+    # device tensors in, device tensors out
+    import torch
+    rd = op.ctc_ext_beam_search_decoder_raw(torch.from_numpy(x).cuda(), torch.from_numpy(sl).cuda(), beam_width=W,
+                                            top_paths=P, merge_repeated=merge, blank_index=blank)
+    assert rd[6].dtype == torch.float64 and rd[6].is_cuda
+    np.testing.assert_array_equal(rd[6].cpu().numpy().view(np.uint64), np.asarray(raw[6]).view(np.uint64))
+
+
 # ------------------------------------------------------------------------------------------------
 # The reference's own test, transliterated (ops_test.py:20-100): raw 7-group output, float64 input
 def test_paper_known_answer_like_the_reference(op):
@@ -206,6 +290,10 @@ def test_paper_known_answer_like_the_reference(op):
         np.testing.assert_allclose(out[5][p], [1, 8])
     np.testing.assert_allclose(out[6], correct_log_probs, rtol=1e-6, atol=1e-6)
     assert out[6].dtype == np.float64
+    # float64 is computed in float64: identical to the compiled reference's float64 output
+    ref64 = L.Golden().result("paper_f64").logp
+    assert ref64.dtype == np.float64
+    np.testing.assert_array_equal(np.asarray(out[6]).view(np.uint64), ref64.view(np.uint64))
     # documented return value: (decoded, alignment, log_probability) with SparseTensor-like entries
     dec, ali, lp = op.ctc_ext_beam_search_decoder(logits, [8], beam_width=10, top_paths=5,
                                                   blank_index=0, blank_label=0)
