@@ -25,12 +25,12 @@ class CtcxHostResult(ctypes.Structure):
                 ("decoded_indices", _i64pp), ("decoded_values", _i64pp), ("decoded_shape", _i64pp),
                 ("alignment_indices", _i64pp), ("alignment_values", _i64pp),
                 ("alignment_shape", _i64pp), ("log_probability", ctypes.POINTER(ctypes.c_float)),
-                ("flags", ctypes.c_int32)]
+                ("flags", ctypes.c_int32), ("log_probability_f64", ctypes.POINTER(ctypes.c_double))]
 
 
 # every symbol include/ctcx.h declares (tests check that the library exports all of them)
 EXPORTS = ("ctcx_strerror", "ctcx_last_cuda_error", "ctcx_get_limits", "ctcx_workspace_bytes",
-           "ctcx_decode_f32", "ctcx_decode_f64", "ctcx_decode_half", "ctcx_pack_f32", "ctcx_pack_f64", "ctcx_decode_host_f32", "ctcx_free_host",
+           "ctcx_decode_f32", "ctcx_decode_f64", "ctcx_decode_half", "ctcx_pack_f32", "ctcx_pack_f64", "ctcx_decode_host_f32", "ctcx_decode_host_f64", "ctcx_free_host",
            "ctcx_workspace_views", "ctcx_stream_workspace_bytes", "ctcx_stream_reset",
            "ctcx_stream_step_f32", "ctcx_stream_top_paths")
 
@@ -73,6 +73,7 @@ def load():
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_int,
                                          ctypes.POINTER(ctypes.POINTER(CtcxHostResult))]
+    lib.ctcx_decode_host_f64.argtypes = lib.ctcx_decode_host_f32.argtypes
     lib.ctcx_free_host.argtypes = [ctypes.POINTER(CtcxHostResult)]
     lib.ctcx_free_host.restype = None
     lib.ctcx_workspace_views.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [_vp] * 5

@@ -632,12 +632,13 @@ void ctcx_free_host(ctcx_host_result* r) {
   std::free(r->n_decoded);
   std::free(r->n_alignment);
   std::free(r->log_probability);
+  std::free(r->log_probability_f64);
   std::free(r);
 }
 
-int ctcx_decode_host_f32(const float* logits_host, int T, int B, int C, const int32_t* seq_len_host,
-                         int W, int P, int merge_repeated, int blank_index, int blank_label,
-                         int device, ctcx_host_result** result) {
+static int DecodeHostImpl(const void* logits_host, int rb, int T, int B, int C, const int32_t* seq_len_host,
+                          int W, int P, int merge_repeated, int blank_index, int blank_label,
+                          int device, ctcx_host_result** result) {
   if (result == nullptr) return CTCX_ERR_BAD_ARGUMENT;
   *result = nullptr;
   if (T == 0) return CTCX_ERR_MAX_TIME_ZERO;
@@ -647,7 +648,7 @@ int ctcx_decode_host_f32(const float* logits_host, int T, int B, int C, const in
   CTCX_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   const size_t n_logits = (size_t)T * B * C;
   const size_t ws_bytes = ctcx_workspace_bytes(T, B, C, W, P);
-  float* d_logits = nullptr;
+  void* d_logits = nullptr;
   int32_t* d_seq = nullptr;
   void* d_ws = nullptr;
   unsigned char* d_out = nullptr;
@@ -662,13 +663,15 @@ int ctcx_decode_host_f32(const float* logits_host, int T, int B, int C, const in
   do {                                                        \
     if (!Check((call), #call)) { rc = CTCX_ERR_CUDA; goto done; } \
   } while (0)
-  CTCX_TRY(cudaMalloc(&d_logits, n_logits * 4 + 4));
+  CTCX_TRY(cudaMalloc(&d_logits, n_logits * rb + 8));
   CTCX_TRY(cudaMalloc(&d_seq, (size_t)B * 4 + 4));
   CTCX_TRY(cudaMalloc(&d_ws, ws_bytes));
-  CTCX_TRY(cudaMemcpyAsync(d_logits, logits_host, n_logits * 4, cudaMemcpyHostToDevice, stream));
+  CTCX_TRY(cudaMemcpyAsync(d_logits, logits_host, n_logits * rb, cudaMemcpyHostToDevice, stream));
   CTCX_TRY(cudaMemcpyAsync(d_seq, seq_len_host, (size_t)B * 4, cudaMemcpyHostToDevice, stream));
-  rc = ctcx_decode_f32(d_logits, T, B, C, d_seq, W, P, merge_repeated, blank_index, blank_label, d_ws,
-                       ws_bytes, stream, &sizes, &flags);
+  rc = (rb == 8) ? ctcx_decode_f64((const double*)d_logits, T, B, C, d_seq, W, P, merge_repeated, blank_index,
+                                   blank_label, d_ws, ws_bytes, stream, &sizes, &flags)
+                 : ctcx_decode_f32((const float*)d_logits, T, B, C, d_seq, W, P, merge_repeated, blank_index,
+                                   blank_label, d_ws, ws_bytes, stream, &sizes, &flags);
   if (rc != CTCX_OK) goto done;
   {
     // one device block for all outputs, then one D2H copy
@@ -681,15 +684,17 @@ int ctcx_decode_host_f32(const float* logits_host, int T, int B, int C, const in
       o_ai[p] = take((size_t)n_ali[p] * 2); o_av[p] = take((size_t)n_ali[p]); o_as[p] = take(2);
     }
     const size_t o_lp = o;
-    o += Align256((size_t)B * P * 4);
+    o += Align256((size_t)B * P * rb);
     out_bytes = o;
     CTCX_TRY(cudaMalloc(&d_out, out_bytes + 256));
     for (int p = 0; p < P; ++p) {
       p_di[p] = (int64_t*)(d_out + o_di[p]); p_dv[p] = (int64_t*)(d_out + o_dv[p]); p_ds[p] = (int64_t*)(d_out + o_ds[p]);
       p_ai[p] = (int64_t*)(d_out + o_ai[p]); p_av[p] = (int64_t*)(d_out + o_av[p]); p_as[p] = (int64_t*)(d_out + o_as[p]);
     }
-    rc = ctcx_pack_f32(d_ws, T, B, P, p_di.data(), p_dv.data(), p_ds.data(), p_ai.data(), p_av.data(),
-                       p_as.data(), (float*)(d_out + o_lp), stream);
+    rc = (rb == 8) ? ctcx_pack_f64(d_ws, T, B, P, p_di.data(), p_dv.data(), p_ds.data(), p_ai.data(), p_av.data(),
+                                   p_as.data(), (double*)(d_out + o_lp), stream)
+                   : ctcx_pack_f32(d_ws, T, B, P, p_di.data(), p_dv.data(), p_ds.data(), p_ai.data(), p_av.data(),
+                                   p_as.data(), (float*)(d_out + o_lp), stream);
     if (rc != CTCX_OK) goto done;
     std::vector<unsigned char> h_out(out_bytes);
     CTCX_TRY(cudaMemcpyAsync(h_out.data(), d_out, out_bytes, cudaMemcpyDeviceToHost, stream));
@@ -717,8 +722,9 @@ int ctcx_decode_host_f32(const float* logits_host, int T, int B, int C, const in
       r->alignment_values[p] = dup(o_av[p], (size_t)n_ali[p]);
       r->alignment_shape[p] = dup(o_as[p], 2);
     }
-    r->log_probability = (float*)std::malloc((size_t)B * P * 4 + 4);
-    std::memcpy(r->log_probability, h_out.data() + o_lp, (size_t)B * P * 4);
+    void* lp = std::malloc((size_t)B * P * rb + 8);
+    std::memcpy(lp, h_out.data() + o_lp, (size_t)B * P * rb);
+    if (rb == 8) r->log_probability_f64 = (double*)lp; else r->log_probability = (float*)lp;
     *result = r;
   }
 done:
@@ -729,6 +735,20 @@ done:
   cudaFree(d_out);
   cudaStreamDestroy(stream);
   return rc;
+}
+
+int ctcx_decode_host_f32(const float* logits_host, int T, int B, int C, const int32_t* seq_len_host,
+                         int W, int P, int merge_repeated, int blank_index, int blank_label,
+                         int device, ctcx_host_result** result) {
+  return DecodeHostImpl(logits_host, 4, T, B, C, seq_len_host, W, P, merge_repeated, blank_index, blank_label,
+                        device, result);
+}
+
+int ctcx_decode_host_f64(const double* logits_host, int T, int B, int C, const int32_t* seq_len_host,
+                         int W, int P, int merge_repeated, int blank_index, int blank_label,
+                         int device, ctcx_host_result** result) {
+  return DecodeHostImpl(logits_host, 8, T, B, C, seq_len_host, W, P, merge_repeated, blank_index, blank_label,
+                        device, result);
 }
 
 /* fp16 / bf16 logits (what an acoustic model's projection typically emits): upcast exactly to

@@ -299,10 +299,12 @@ class CTCExtBeamSearchDecoderStream:
 
 def decode_host_cabi(inputs, sequence_length, beam_width, top_paths, merge_repeated=False,
                      blank_index=0, blank_label=-1, device=0):
-    """The host-buffer C-ABI entry (ctcx_decode_host_f32) exactly as a TensorFlow CPU OpKernel
-    would call it: numpy in, numpy out, all copies inside the call."""
+    """The host-buffer C-ABI entry (ctcx_decode_host_f32, or ctcx_decode_host_f64 for float64
+    inputs) exactly as a TensorFlow CPU OpKernel would call it: numpy in, numpy out, all copies inside
+    the call."""
     lib = _lib.load()
-    x = np.ascontiguousarray(inputs, dtype=np.float32)
+    f64 = np.asarray(inputs).dtype == np.float64
+    x = np.ascontiguousarray(inputs, dtype=np.float64 if f64 else np.float32)
     if x.ndim != 3:
         raise InvalidArgumentError(1, lib.ctcx_strerror(1).decode())
     seq = np.ascontiguousarray(sequence_length, dtype=np.int32)
@@ -314,9 +316,9 @@ def decode_host_cabi(inputs, sequence_length, beam_width, top_paths, merge_repea
             4, "len(sequence_length) != batch_size.  len(sequence_length):  %d batch_size: %d"
             % (seq.shape[0], B))
     res = ctypes.POINTER(_lib.CtcxHostResult)()
-    rc = lib.ctcx_decode_host_f32(x.ctypes.data, T, B, C, seq.ctypes.data, int(beam_width),
-                                  int(top_paths), int(bool(merge_repeated)), int(blank_index),
-                                  int(blank_label), int(device), ctypes.byref(res))
+    entry = lib.ctcx_decode_host_f64 if f64 else lib.ctcx_decode_host_f32
+    rc = entry(x.ctypes.data, T, B, C, seq.ctypes.data, int(beam_width), int(top_paths),
+               int(bool(merge_repeated)), int(blank_index), int(blank_label), int(device), ctypes.byref(res))
     if rc != 0:
         _raise(lib, rc)
     try:
@@ -335,8 +337,9 @@ def decode_host_cabi(inputs, sequence_length, beam_width, top_paths, merge_repea
             out[3].append(arr(r.alignment_indices[p], na * 2).reshape(na, 2))
             out[4].append(arr(r.alignment_values[p], na))
             out[5].append(arr(r.alignment_shape[p], 2))
-        logp = (np.ctypeslib.as_array(r.log_probability, shape=(B * P,)).copy().reshape(B, P)
-                if B * P else np.zeros((B, P), np.float32))
+        lp_ptr = r.log_probability_f64 if f64 else r.log_probability
+        logp = (np.ctypeslib.as_array(lp_ptr, shape=(B * P,)).copy().reshape(B, P)
+                if B * P else np.zeros((B, P), np.float64 if f64 else np.float32))
     finally:
         lib.ctcx_free_host(res)
     return CTCExtBeamSearchDecoder(*out, logp)

@@ -116,11 +116,17 @@ typedef struct {
   int64_t** alignment_indices; /* [P] -> [n_alignment[p]*2] */
   int64_t** alignment_values;  /* [P] -> [n_alignment[p]] */
   int64_t** alignment_shape;   /* [P] -> [2]              */
-  float* log_probability;      /* [batch*top_paths]       */
+  float* log_probability;      /* [batch*top_paths]; NULL after ctcx_decode_host_f64 */
   int32_t flags;
+  double* log_probability_f64; /* [batch*top_paths]; NULL after ctcx_decode_host_f32 */
 } ctcx_host_result;
 
 int ctcx_decode_host_f32(const float* logits_host, int max_time, int batch, int num_classes,
+                         const int32_t* seq_len_host, int beam_width, int top_paths,
+                         int merge_repeated, int blank_index, int blank_label, int device,
+                         ctcx_host_result** result);
+/* T = double registration (kernels.cc:275): float64 host logits, log_probability_f64 in the result. */
+int ctcx_decode_host_f64(const double* logits_host, int max_time, int batch, int num_classes,
                          const int32_t* seq_len_host, int beam_width, int top_paths,
                          int merge_repeated, int blank_index, int blank_label, int device,
                          ctcx_host_result** result);

@@ -259,6 +259,12 @@ def test_float64_decode_is_bit_exact(op, case):
             np.testing.assert_array_equal(np.asarray(raw[g][p]), packed[g][p])
     assert np.asarray(raw[6]).dtype == np.float64
     np.testing.assert_array_equal(np.asarray(raw[6]).view(np.uint64), np.asarray(packed[6], np.float64).view(np.uint64))
+    host = op.decode_host_cabi(x, sl, W, P, merge, blank, -1)  # ctcx_decode_host_f64
+    assert host[6].dtype == np.float64
+    np.testing.assert_array_equal(host[6].view(np.uint64), np.asarray(raw[6]).view(np.uint64))
+    for g in range(6):
+        for p in range(P):
+            np.testing.assert_array_equal(host[g][p], packed[g][p])
     if W == 300:  # float64 state is twice as wide: beam widths above 512 are refused, never degraded
         with pytest.raises(op.CtcxError, match="not supported"):
             op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=600, top_paths=1, blank_index=blank)

@@ -182,3 +182,14 @@ def test_libm_port_matches_host_libm_sample():
     lib.ctcx_port_mismatches.restype = ctypes.c_longlong
     out = (ctypes.c_longlong * 3)()
     assert lib.ctcx_port_mismatches(389, out) == 0, list(out)
+
+
+def test_libm_port_f64_matches_host_libm_sample():
+    """The double-precision twin (exp / log in glibc's FMA operation order, used by the float64
+    decode) against this host's libm on 2 x 2e6 pseudo-random arguments per function."""
+    lib = ctypes.CDLL(L.ORACLE_SO)
+    lib.ctcx_port_mismatches_f64.restype = ctypes.c_longlong
+    lib.ctcx_port_mismatches_f64.argtypes = [ctypes.c_longlong, ctypes.c_ulonglong,
+                                             ctypes.POINTER(ctypes.c_longlong)]
+    out = (ctypes.c_longlong * 2)()
+    assert lib.ctcx_port_mismatches_f64(2000000, 12345, out) == 0, list(out)

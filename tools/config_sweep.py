@@ -1,4 +1,5 @@
-"""Device-resident timing of the BASELINE.json shapes: python tools/config_sweep.py"""
+"""Device-resident timing of the BASELINE.json shapes: python tools/config_sweep.py [--f64]
+(--f64: float64 logits through ctcx_decode_f64, the reference's T = double registration)"""
 import ctypes
 import os
 import sys
@@ -14,6 +15,7 @@ import ctcx_testlib as L
 import ctc_beam_search_op_b200 as op
 from ctc_beam_search_op_b200 import _lib
 
+F64 = "--f64" in sys.argv
 lib = _lib.load()
 lib.ctcx_profile_enable(1)
 CFGS = [("cfg1", 50, 8, 29, 10, 3, False, 28), ("cfg2", 500, 256, 29, 100, 1, True, 28),
@@ -21,6 +23,8 @@ CFGS = [("cfg1", 50, 8, 29, 10, 3, False, 28), ("cfg2", 500, 256, 29, 100, 1, Tr
 for kind in ("gauss", "peaky"):
     for name, T, B, C, W, P, merge, blank in CFGS:
         x = torch.from_numpy(L.make_logits(kind, T, B, C, blank, 3)).cuda()
+        if F64:
+            x = x.double()
         sl = torch.full((B,), T, dtype=torch.int32).cuda()
         ms = []
         for i in range(4):
@@ -33,5 +37,5 @@ for kind in ("gauss", "peaky"):
             lib.ctcx_profile_get(buf)
             ms.append(list(buf) + [wall])
         m = np.array(ms[1:]).mean(axis=0)
-        print("%s %-5s T=%4d B=%3d C=%4d W=%3d P=%d: lognorm %.3f beam %.3f trace %.3f | call %.3f ms -> %.2f M frames/s"
+        print(("f64 " if F64 else "") + "%s %-5s T=%4d B=%3d C=%4d W=%3d P=%d: lognorm %.3f beam %.3f trace %.3f | call %.3f ms -> %.2f M frames/s"
               % (kind, name, T, B, C, W, P, m[0], m[1], m[2], m[5], T * B / m[5] / 1e3))
