@@ -12,6 +12,7 @@ from .decoder import (CTCExtBeamSearchDecoder, CTCExtBeamSearchDecoderStream, Ct
                       ctc_ext_beam_search_decoder, ctc_ext_beam_search_decoder_raw,
                       decode_host_cabi)
 
+from . import torch_op  # noqa: F401,E402  (registers torch.ops.ctcx.ctc_ext_beam_search_decoder)
 from .sharding import decode_distributed, decode_multi_device, merge_raw, shard_bounds  # noqa: F401,E402
 
 __all__ = ["CTCExtBeamSearchDecoderStream", "decode_multi_device", "decode_distributed", "shard_bounds", "merge_raw","ctc_ext_beam_search_decoder", "ctc_ext_beam_search_decoder_raw", "decode_host_cabi",

@@ -614,3 +614,21 @@ def test_half_precision_logits(op, dt):
             for p in range(2):
                 np.testing.assert_array_equal(raw[g][p].cpu().numpy(), want[g][p])
         np.testing.assert_array_equal(raw[6].cpu().numpy().view(np.uint32), want[6].view(np.uint32))
+
+
+def test_torch_library_op(op):
+    """torch.ops.ctcx.ctc_ext_beam_search_decoder == the raw Python entry; opcheck validates the
+    schema / fake-tensor registration against the real kernels."""
+    import torch
+    T, B, C, W, P = 40, 5, 29, 10, 3
+    x = torch.from_numpy(L.make_logits("peaky", T, B, C, 28, 7)).cuda()
+    sl = torch.from_numpy(L.ragged_lengths(T, B, 7)).cuda()
+    flat = torch.ops.ctcx.ctc_ext_beam_search_decoder(x, sl, W, P, True, 28, -1)
+    got = op.torch_op.unflatten(flat, P)
+    want = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=W, top_paths=P, merge_repeated=True, blank_index=28)
+    for g in range(6):
+        for p in range(P):
+            assert torch.equal(got[g][p], want[g][p])
+    assert torch.equal(got[6], want[6])
+    torch.library.opcheck(torch.ops.ctcx.ctc_ext_beam_search_decoder.default, (x, sl, W, P, True, 28, -1),
+                          test_utils=("test_schema", "test_faketensor"))

@@ -121,3 +121,29 @@ def test_shard_bounds_and_merge():
         for p in range(2):
             np.testing.assert_array_equal(merged[g][p], whole[g][p])
     np.testing.assert_array_equal(merged[6], whole[6])
+
+
+def test_torch_library_registration_traces_with_fake_tensors():
+    """torch.ops.ctcx.ctc_ext_beam_search_decoder exists, has the reference op's argument order
+    (ops.cc:10-16) and infers its output shapes without a device (ops.cc:41-61: data-dependent
+    numbers of sparse entries, [batch, top_paths] log-probabilities)."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from torch.fx.experimental.symbolic_shapes import ShapeEnv
+    import ctc_beam_search_op_b200 as m  # noqa: F401
+    op = torch.ops.ctcx.ctc_ext_beam_search_decoder
+    schema = str(op.default._schema)
+    for a in ("Tensor inputs", "Tensor sequence_length", "Int beam_width", "Int top_paths",
+              "bool merge_repeated=False", "Int blank_index=0", "Int blank_label=-1"):
+        assert a in schema, schema
+    with FakeTensorMode(shape_env=ShapeEnv()):
+        for dt in (torch.float32, torch.float64):
+            x = torch.empty((50, 8, 29), device="cuda", dtype=dt)
+            sl = torch.empty((8,), dtype=torch.int32, device="cuda")
+            out = op(x, sl, 10, 3, True, 28, -1)
+            assert len(out) == 19
+            assert out[0].shape[1] == 2 and out[0].dtype == torch.int64 and out[6].shape == (2,)
+            assert out[18].shape == (8, 3) and out[18].dtype == dt
+    # the flat list maps back onto the raw namedtuple
+    r = m.torch_op.unflatten(list(range(19)), 3)
+    assert r.decoded_indices == [0, 1, 2] and r.alignment_shape == [15, 16, 17] and r.log_probability == 18
