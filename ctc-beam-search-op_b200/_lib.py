@@ -30,7 +30,7 @@ class CtcxHostResult(ctypes.Structure):
 
 # every symbol include/ctcx.h declares (tests check that the library exports all of them)
 EXPORTS = ("ctcx_strerror", "ctcx_last_cuda_error", "ctcx_get_limits", "ctcx_workspace_bytes",
-           "ctcx_decode_f32", "ctcx_decode_f64", "ctcx_decode_half", "ctcx_pack_f32", "ctcx_pack_f64", "ctcx_decode_host_f32", "ctcx_decode_host_f64", "ctcx_free_host",
+           "ctcx_decode_f32", "ctcx_decode_f64", "ctcx_decode_scorer_f32", "ctcx_decode_half", "ctcx_pack_f32", "ctcx_pack_f64", "ctcx_decode_host_f32", "ctcx_decode_host_f64", "ctcx_free_host",
            "ctcx_workspace_views", "ctcx_stream_workspace_bytes", "ctcx_stream_reset",
            "ctcx_stream_step_f32", "ctcx_stream_top_paths")
 
@@ -63,6 +63,10 @@ def load():
                                     ctypes.c_size_t, _vp, ctypes.POINTER(CtcxSizes),
                                     ctypes.POINTER(ctypes.c_int32)]
     lib.ctcx_decode_f64.argtypes = lib.ctcx_decode_f32.argtypes
+    lib.ctcx_decode_scorer_f32.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp,
+                                           ctypes.c_size_t, _vp, ctypes.POINTER(CtcxSizes),
+                                           ctypes.POINTER(ctypes.c_int32)]
     lib.ctcx_decode_half.argtypes = [_vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      _vp, ctypes.c_size_t, _vp, ctypes.POINTER(CtcxSizes),

@@ -150,6 +150,12 @@ cudaError_t LaunchBeamWide(const ctcx::BeamParams& p, size_t smem, cudaStream_t 
   return cudaGetLastError();
 }
 
+// flag = 1 if any entry is positive or NaN (scorer tables hold log-probabilities)
+__global__ void PositiveKernel(const float* v, long long n, int* flag) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!(v[i] <= 0.0f)) *flag = 1;
+}
+
 // Reduces the per-utterance flags to {anomaly, too_few_leaves, first bad utterance}.
 __global__ void FlagsKernel(const int* flags, const int* seq_len, int B, int T, int* out) {
   // out[0] = OR of anomaly bits, out[1] = first b with too few leaves (or B), out[2] = first b with
@@ -249,10 +255,11 @@ int LaunchBeamFor(ctcx::BeamParams& bp, cudaStream_t stream) {
   bp.dbg_cycles = g_dbg_cycles;  // test/measurement hook (ctcx_debug_set_cycles_buffer)
   const Tier tier = PickTier(W);
   const char* impl = std::getenv("CTCX_BEAM_IMPL");
-  const bool want_generic = impl != nullptr && std::strcmp(impl, "generic") == 0;
+  // a scorer table breaks the fast kernels' monotone-prefix argument: generic kernel only
+  const bool want_generic = (impl != nullptr && std::strcmp(impl, "generic") == 0) || bp.lm != nullptr;
   const bool want_v2 = impl != nullptr && std::strcmp(impl, "v2") == 0 && bp.state == nullptr;
   cudaError_t e;
-  if (bp.srt_pl != nullptr) {  // wide-vocabulary fast path (the caller ran TopClassesKernel)
+  if (bp.srt_pl != nullptr && bp.lm == nullptr) {  // wide-vocabulary fast path (the caller ran TopClassesKernel)
     bp.Kc = WideKc(W, C);
     bp.cand_cap = W * bp.Kc;
     ctcx::BeamSmemWide layw;
@@ -401,7 +408,8 @@ namespace {
 template <typename R>
 int DecodeImpl(const R* logits_dev, int T, int B, int C, const int32_t* seq_len_dev, int W,
                int P, int merge_repeated, int blank_index, int blank_label, void* workspace,
-               size_t workspace_bytes, void* stream_v, ctcx_sizes* sizes, int32_t* flags_out) {
+               size_t workspace_bytes, void* stream_v, ctcx_sizes* sizes, int32_t* flags_out,
+               const R* lm_dev = nullptr) {
   constexpr bool kF32 = (sizeof(R) == 4);
   cudaStream_t stream = (cudaStream_t)stream_v;
   // --- validation, in the reference's order (kernels.cc:111-138), then TopPaths' (decoder.h:237) ---
@@ -459,8 +467,9 @@ int DecodeImpl(const R* logits_dev, int T, int B, int C, const int32_t* seq_len_
     bp.flags = (int*)(base + ws.flags);
     bp.Tcap = T; bp.t_done = nullptr; bp.state = nullptr;  // one-shot decode
     bp.srt_pl = nullptr; bp.srt_cls = nullptr; bp.Cs = ws.Cs; bp.Kc = 0;
+    bp.lm = lm_dev;
     if constexpr (kF32) {
-      if (ws.Cs > 0) {
+      if (ws.Cs > 0 && lm_dev == nullptr) {
         bp.srt_pl = (const float*)(base + ws.srt_pl);
         bp.srt_cls = (const unsigned short*)(base + ws.srt_cls);
         CTCX_CUDA(LaunchTopClasses(logits_dev, bp.off, (long long)T * B, C, blank_index, W,
@@ -572,6 +581,32 @@ int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t*
                     size_t workspace_bytes, void* stream_v, ctcx_sizes* sizes, int32_t* flags_out) {
   return DecodeImpl<float>(logits_dev, T, B, C, seq_len_dev, W, P, merge_repeated, blank_index, blank_label,
                            workspace, workspace_bytes, stream_v, sizes, flags_out);
+}
+
+/* Decode with a scorer plugged into the reference's extension point (util/ctc_beam_scorer.h:31-65). */
+int ctcx_decode_scorer_f32(const float* logits_dev, int T, int B, int C, const int32_t* seq_len_dev, int W,
+                           int P, int merge_repeated, int blank_index, int blank_label,
+                           const float* expansion_scores_dev, void* workspace, size_t workspace_bytes,
+                           void* stream_v, ctcx_sizes* sizes, int32_t* flags_out) {
+  if (expansion_scores_dev != nullptr && C > 0) {  // expansion scores are log-probabilities: <= 0
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    int* d_flag = nullptr;
+    if (workspace == nullptr || ((uintptr_t)workspace & 255u)) return CTCX_ERR_WORKSPACE;
+    Workspace ws;
+    ws.Init(T > 0 ? T : 1, B > 0 ? B : 0, C, W > 0 ? W : 1, P > 0 ? P : 1);
+    if (workspace_bytes < ws.bytes) return CTCX_ERR_WORKSPACE;
+    d_flag = (int*)((unsigned char*)workspace + ws.stats) + 8;
+    CTCX_CUDA(cudaMemsetAsync(d_flag, 0, 4, stream));
+    const long long n = (long long)(C + 1) * C;
+    PositiveKernel<<<(unsigned)std::min<long long>((n + 255) / 256, 1024), 256, 0, stream>>>(expansion_scores_dev, n, d_flag);
+    CTCX_CUDA(cudaGetLastError());
+    int h_flag = 0;
+    CTCX_CUDA(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, stream));
+    CTCX_CUDA(cudaStreamSynchronize(stream));
+    if (h_flag) return CTCX_ERR_BAD_ARGUMENT;
+  }
+  return DecodeImpl<float>(logits_dev, T, B, C, seq_len_dev, W, P, merge_repeated, blank_index, blank_label,
+                           workspace, workspace_bytes, stream_v, sizes, flags_out, expansion_scores_dev);
 }
 
 int ctcx_decode_f64(const double* logits_dev, int T, int B, int C, const int32_t* seq_len_dev, int W,
@@ -829,7 +864,7 @@ int ctcx_stream_step_f32(void* workspace, int T_total, int B, int C, int W, int 
   bp.Tcap = T_total;
   bp.t_done = (int*)(base + ws.t_done);
   bp.state = base + ws.state;
-  bp.srt_pl = nullptr; bp.srt_cls = nullptr; bp.Cs = ws.Cs; bp.Kc = 0;
+  bp.srt_pl = nullptr; bp.srt_cls = nullptr; bp.Cs = ws.Cs; bp.Kc = 0; bp.lm = nullptr;
   if (ws.Cs > 0) {
     bp.srt_pl = (const float*)(base + ws.srt_pl);
     bp.srt_cls = (const unsigned short*)(base + ws.srt_cls);

@@ -313,6 +313,10 @@ struct BeamParamsT {
   int Cs;                        // row stride of the two arrays (a multiple of 8)
   int Kc;                        // sorted classes per frame the kernel may use (entry Kc, if < C-1
                                  // classes are listed, is a sentinel: the best class left out)
+  // scorer extension point (util/ctc_beam_scorer.h:31-65), generic kernel only: null = the default
+  // scorer; otherwise a [C+1, C] table of expansion scores (<= 0), row = label of the expanded
+  // entry + 1 (row 0: the root), column = new label: GetStateExpansionScore(state, s) = s + entry
+  const R* lm;
 };
 using BeamParams = BeamParamsT<float>;
 
@@ -571,7 +575,9 @@ __global__ void __launch_bounds__(NT) BeamKernelT(BeamParamsT<R> p) {
         const R self_an = Ops::Add(o_an[i], pl);
         if (pslot >= 0) {
           const bool same = (lbl == o_label[pslot]);
-          const R base = same ? o_blk[pslot] : o_total[pslot];
+          R base = same ? o_blk[pslot] : o_total[pslot];
+          if (p.lm != nullptr)  // GetStateExpansionScore(b->state, .), decoder.h:103,114
+            base = Ops::Add(base, p.lm[(size_t)(o_label[pslot] + 1) * C + lbl]);
           v_nl = Ops::Sub(Ops::Add(LogSumExp(o_lab[i], base, s_exptab), xl), off);  // :102-104,:113-115
           v_an = Ops::Add(o_ab[pslot], pl);
           an_kind = kAnParAb;
@@ -636,7 +642,8 @@ __global__ void __launch_bounds__(NT) BeamKernelT(BeamParamsT<R> p) {
       if (l == blank) return false;
       if ((s_kid[row * KW + (l >> 5)] >> (l & 31)) & 1u) return false;  // c.Active(): merged in (A)
       const R pl = Ops::Sub(x[l], off);
-      const R base = (l == o_label[row]) ? o_blk[row] : o_total[row];
+      R base = (l == o_label[row]) ? o_blk[row] : o_total[row];
+      if (p.lm != nullptr) base = Ops::Add(base, p.lm[(size_t)(o_label[row] + 1) * C + l]);  // :171,:176,:182
       skey = Ops::KeyOf(Ops::Add(pl, base));  // :172-182
       return skey > th0;
     };
@@ -744,7 +751,8 @@ __global__ void __launch_bounds__(NT) BeamKernelT(BeamParamsT<R> p) {
           const int pslot = m_pslot[m];
           const int lbl = o_label[m];
           const R pl = Ops::Sub(x[lbl], off);
-          const R base = (lbl == o_label[pslot]) ? o_blk[pslot] : o_total[pslot];
+          R base = (lbl == o_label[pslot]) ? o_blk[pslot] : o_total[pslot];
+          if (p.lm != nullptr) base = Ops::Add(base, p.lm[(size_t)(o_label[pslot] + 1) * C + lbl]);
           if (Ops::KeyOf(Ops::Add(pl, base)) > m_key[m]) sci[kScAnomaly] = 1;
           sci[kScChanged] = 2;  // "some member is wiped"
         }

@@ -98,7 +98,7 @@ def _pack(lib, ws, T, B, P, counts, device, stream, f64=False):
 
 def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_paths,
                                     merge_repeated=False, blank_index=0, blank_label=-1,
-                                    name=None, device=None):
+                                    name=None, device=None, expansion_scores=None):
     """The raw op: returns a 7-field namedtuple of (lists of) tensors, exactly the op's outputs.
 
     inputs            [max_time, batch, num_classes] float32 or float64 (the reference registers both,
@@ -108,6 +108,11 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
                       any device
     sequence_length   [batch] int32
     beam_width >= 1, top_paths >= 1, merge_repeated=False, blank_index=0, blank_label=-1
+    expansion_scores  optional [num_classes + 1, num_classes] float32 table (entries <= 0) for the
+                      reference's scorer extension point (util/ctc_beam_scorer.h): extending an entry
+                      whose last label is f (row f + 1; row 0 = empty prefix) by label l adds
+                      table[f + 1, l] to the score carried over -- a bigram LM / insertion penalty.
+                      float32 inputs only; None = the op's default scorer.
     Outputs live where the inputs live (numpy in -> numpy out).
     """
     del name
@@ -141,7 +146,7 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
         device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
     device = torch.device(device)
     host_out = not x.is_cuda
-    half = x.dtype in (torch.float16, torch.bfloat16)
+    half = x.dtype in (torch.float16, torch.bfloat16) and expansion_scores is None
     with torch.cuda.device(device):
         # fp16 / bf16 logits cross the bus as they are and are upcast (exactly) on the device
         xd = x.to(device=device, dtype=(x.dtype if (half or f64) else torch.float32),
@@ -162,6 +167,17 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
                                       int(bool(merge_repeated)), int(blank_index), int(blank_label),
                                       ws.data_ptr(), ws_bytes, stream, ctypes.byref(sizes),
                                       ctypes.byref(flags))
+        elif expansion_scores is not None:
+            if f64:
+                raise TypeError("expansion_scores is supported for float32 inputs only")
+            es, _ = _as_tensor(expansion_scores)
+            if tuple(es.shape) != (C + 1, C):
+                raise InvalidArgumentError(8, "expansion_scores must have shape [num_classes + 1, num_classes]")
+            esd = es.to(device=device, dtype=torch.float32).contiguous()
+            rc = lib.ctcx_decode_scorer_f32(xd.data_ptr(), T, B, C, sd.data_ptr(), int(beam_width), P,
+                                            int(bool(merge_repeated)), int(blank_index), int(blank_label),
+                                            esd.data_ptr(), ws.data_ptr(), ws_bytes, stream,
+                                            ctypes.byref(sizes), ctypes.byref(flags))
         else:
             decode = lib.ctcx_decode_f64 if f64 else lib.ctcx_decode_f32
             rc = decode(xd.data_ptr(), T, B, C, sd.data_ptr(), int(beam_width), P,
@@ -183,12 +199,13 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
 
 def ctc_ext_beam_search_decoder(inputs, sequence_length, beam_width, top_paths,
                                 merge_repeated=False, blank_index=0, blank_label=-1, name=None,
-                                device=None):
+                                device=None, expansion_scores=None):
     """`(decoded, alignment, log_probability)` as documented by the reference (README.md:19-31):
     decoded[j] / alignment[j] are SparseTensor(indices [N,2] rows [batch, position], values [N],
     dense_shape [batch, max length]) for path j; log_probability is [batch, top_paths]."""
     raw = ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_paths,
-                                          merge_repeated, blank_index, blank_label, name, device)
+                                          merge_repeated, blank_index, blank_label, name, device,
+                                          expansion_scores)
     decoded = [SparseTensor(i, v, s) for i, v, s in zip(raw[0], raw[1], raw[2])]
     alignment = [SparseTensor(i, v, s) for i, v, s in zip(raw[3], raw[4], raw[5])]
     return decoded, alignment, raw[6]

@@ -157,6 +157,24 @@ int ctcx_pack_f64(const void* workspace, int max_time, int batch, int top_paths,
                   int64_t* const* alignment_values, int64_t* const* alignment_shape,
                   double* log_probability, void* stream);
 
+/* Scorer extension point. The reference's decoder takes a BaseBeamScorer (util/ctc_beam_scorer.h:
+ * 31-65; call sites decoder.h:103,114,171,176,182) whose GetStateExpansionScore(state, s) is applied
+ * whenever a beam entry is extended by a label; the op itself only ever passes the default scorer
+ * (kernels.cc:260-265), i.e. s unchanged. This entry point plugs a table-driven scorer in:
+ *   expansion_scores_dev  [num_classes + 1, num_classes] float32, DEVICE memory, every entry <= 0
+ *                         (log-probabilities; CTCX_ERR_BAD_ARGUMENT otherwise): row = label of the
+ *                         entry being extended + 1 (row 0: the empty prefix), column = the new label;
+ *                         GetStateExpansionScore(state, s) = s + entry  -- e.g. a label-bigram LM with
+ *                         its weight folded in, or a constant insertion penalty.
+ * NULL gives ctcx_decode_f32. With a table the generic beam kernel is used (the fast kernels'
+ * candidate search assumes scores monotone in the frame's log-probs). A constant table reproduces
+ * the reference compiled with a stateless scorer subclass bit for bit (tests/test_oracle.py). */
+int ctcx_decode_scorer_f32(const float* logits_dev, int max_time, int batch, int num_classes,
+                           const int32_t* seq_len_dev, int beam_width, int top_paths,
+                           int merge_repeated, int blank_index, int blank_label,
+                           const float* expansion_scores_dev, void* workspace, size_t workspace_bytes,
+                           void* stream, ctcx_sizes* sizes, int32_t* flags_out);
+
 /* ---- Streaming: the reference decoder's Step / TopPaths / Reset
  * (util/ctc_ext_beam_search_decoder.h:39-53) for all utterances of a batch at once. The beam state
  * lives in the workspace between calls, so logits can be fed in chunks of frames as they arrive:

@@ -77,7 +77,17 @@ int ctcx_oracle_decode_f32(const float* logits, int T, int B, int C, const int* 
                            int* dec_len, int* dec, int* ali_len, int* ali, float* logp,
                            double* margins, ctcx_oracle_stats* stats, char* err, int errcap) {
   return decode_f32(logits, T, B, C, seq_len, W, P, merge_repeated, blank_index, blank_label,
-                    dec_len, dec, ali_len, ali, logp, margins, stats, err, errcap);
+                    dec_len, dec, ali_len, ali, logp, margins, stats, err, errcap, NULL);
+}
+
+/* the same with a scorer: lm = [C+1, C] expansion-score table (see ctcx_oracle_impl.h), or NULL */
+int ctcx_oracle_decode_lm_f32(const float* logits, int T, int B, int C, const int* seq_len, int W,
+                              int P, int merge_repeated, int blank_index, int blank_label,
+                              const float* lm, int* dec_len, int* dec, int* ali_len, int* ali,
+                              float* logp, double* margins, ctcx_oracle_stats* stats, char* err,
+                              int errcap) {
+  return decode_f32(logits, T, B, C, seq_len, W, P, merge_repeated, blank_index, blank_label,
+                    dec_len, dec, ali_len, ali, logp, margins, stats, err, errcap, lm);
 }
 
 int ctcx_oracle_decode_f64(const double* logits, int T, int B, int C, const int* seq_len, int W,
@@ -85,5 +95,5 @@ int ctcx_oracle_decode_f64(const double* logits, int T, int B, int C, const int*
                            int* dec_len, int* dec, int* ali_len, int* ali, double* logp,
                            double* margins, ctcx_oracle_stats* stats, char* err, int errcap) {
   return decode_f64(logits, T, B, C, seq_len, W, P, merge_repeated, blank_index, blank_label,
-                    dec_len, dec, ali_len, ali, logp, margins, stats, err, errcap);
+                    dec_len, dec, ali_len, ali, logp, margins, stats, err, errcap, NULL);
 }

@@ -62,7 +62,18 @@ typedef struct {
   int frame;
   double margin[CTCX_N_MARGINS];
   ctcx_oracle_stats* stats;
+  /* scorer extension point (util/ctc_beam_scorer.h:31-65): NULL = the default scorer
+   * (GetStateExpansionScore returns previous_score unchanged); otherwise a [C+1, C] table of
+   * expansion scores, row = label of the expanded entry + 1 (row 0: the root), column = new label:
+   * ExpandState caches table[from_label + 1][to_label] in the child (decoder.h:171) and
+   * GetStateExpansionScore returns previous_score + that value (decoder.h:103,114,176,182). */
+  const REAL* lm;
 } SUF(Dec);
+
+static REAL SUF(expansion)(const SUF(Dec)* d, int from_label, int to_label, REAL previous_score) {
+  if (!d->lm) return previous_score;
+  return previous_score + d->lm[(size_t)(from_label + 1) * (size_t)d->C + (size_t)to_label];
+}
 
 #define NEG_INF ((REAL)(-INFINITY))
 
@@ -311,11 +322,11 @@ static void SUF(step)(SUF(Dec)* d, const REAL* x) {
       const REAL p = x[b->label] - off;
       if (par->n_total != NEG_INF) { /* parent->Active(), decoder.h:97 */
         if (b->label == par->label) { /* :98-108 */
-          b->n_label = SUF(lse)(b->n_label, par->o_blank) + x[b->label] - off;
+          b->n_label = SUF(lse)(b->n_label, SUF(expansion)(d, par->label, b->label, par->o_blank)) + x[b->label] - off;
           SUF(add_cand)(d, bi, b->parent, 1, 0, b->label, p);
           SUF(add_cand)(d, bi, bi, 0, 0, b->label, p);
         } else { /* :109-121 */
-          b->n_label = SUF(lse)(b->n_label, par->o_total) + x[b->label] - off;
+          b->n_label = SUF(lse)(b->n_label, SUF(expansion)(d, par->label, b->label, par->o_total)) + x[b->label] - off;
           SUF(add_cand)(d, bi, b->parent, 1, 0, b->label, p);
           SUF(add_cand)(d, bi, b->parent, 0, 0, b->label, p);
           SUF(add_cand)(d, bi, bi, 0, 0, b->label, p);
@@ -346,7 +357,7 @@ static void SUF(step)(SUF(Dec)* d, const REAL* x) {
         if (l == blank) continue;
         int c = SUF(get_child)(d, br[i], l, 0);
         if (c >= 0 && d->nodes[c].stamp == d->frame) continue; /* a member */
-        REAL s = x[l] - off + ((l == b->label) ? b->o_blank : b->o_total);
+        REAL s = x[l] - off + SUF(expansion)(d, b->label, l, (l == b->label) ? b->o_blank : b->o_total);
         if (s > th0) ++rel;
       }
     }
@@ -368,7 +379,7 @@ static void SUF(step)(SUF(Dec)* d, const REAL* x) {
         if (l == blank) continue;
         int c = SUF(get_child)(d, bi, l, 0);
         if (c >= 0 && d->nodes[c].n_total != NEG_INF) continue;
-        REAL s = x[l] - off + ((l == b->label) ? b->shadow_blank : b->shadow_total);
+        REAL s = x[l] - off + SUF(expansion)(d, b->label, l, (l == b->label) ? b->shadow_blank : b->shadow_total);
         if (SUF(is_candidate)(d, s, 0)) eff = 1;
       }
       if (eff) {
@@ -387,10 +398,10 @@ static void SUF(step)(SUF(Dec)* d, const REAL* x) {
       const REAL p = x[ind] - off;
       c->n_blank = NEG_INF; /* :170 */
       if (c->label == b->label) { /* :172-177 */
-        c->n_label = p + b->o_blank;
+        c->n_label = p + SUF(expansion)(d, b->label, ind, b->o_blank);
         SUF(add_cand)(d, ci, bi, 1, 0, ind, p);
       } else { /* :178-185 */
-        c->n_label = p + b->o_total;
+        c->n_label = p + SUF(expansion)(d, b->label, ind, b->o_total);
         SUF(add_cand)(d, ci, bi, 1, 0, ind, p);
         SUF(add_cand)(d, ci, bi, 0, 0, ind, p);
       }
@@ -502,7 +513,7 @@ static int SUF(top_paths)(SUF(Dec)* d, int P, int merge_repeated, int max_time, 
 static int SUF(decode)(const REAL* logits, int T, int B, int C, const int* seq_len, int W, int P,
                        int merge_repeated, int blank_index, int blank_label, int* dec_len, int* dec,
                        int* ali_len, int* ali, REAL* logp, double* margins,
-                       ctcx_oracle_stats* stats, char* err, int errcap) {
+                       ctcx_oracle_stats* stats, char* err, int errcap, const REAL* lm) {
   if (T == 0) { /* kernels.cc:118-120 */
     snprintf(err, (size_t)errcap, "max_time is 0");
     return 2;
@@ -520,6 +531,7 @@ static int SUF(decode)(const REAL* logits, int T, int B, int C, const int* seq_l
   d.blank_index = blank_index;
   d.blank_label = blank_label;
   d.stats = stats;
+  d.lm = lm;
   d.leaves = (int*)malloc(sizeof(int) * (size_t)(W + 1));
   d.branches = (int*)malloc(sizeof(int) * (size_t)(W + 1));
   SUF(tab_grow)(&d);

@@ -41,13 +41,38 @@ void SetErr(char* err, int errcap, const std::string& msg) {
   }
 }
 
+// A scorer for the reference's extension point (util/ctc_beam_scorer.h:14-20, "a thin layer for
+// integrating language model scoring"). Only STATELESS scorers compile against the reference as it
+// is: BeamEntry::AddAlignmentCandidate takes a BeamEntry<T>* (util/ctc_beam_entry.h:190), i.e. the
+// default EmptyBeamState, so a decoder instantiated with any other state type is ill-formed. A
+// stateless scorer sees no labels; what it can express is a constant expansion score per new label
+// (a label insertion penalty): GetStateExpansionScore(state, previous) = previous + penalty.
+template <typename T>
+class ConstScorer : public tensorflow::ctc::BaseBeamScorer<T, tensorflow::ctc::ctc_beam_search::EmptyBeamState> {
+ public:
+  explicit ConstScorer(T penalty) : penalty_(penalty) {}
+  T GetStateExpansionScore(const tensorflow::ctc::ctc_beam_search::EmptyBeamState& state,
+                           T previous_score) const override {
+    (void)state;
+    return previous_score + penalty_;
+  }
+
+ private:
+  T penalty_;
+};
+
 // Decodes utterances [b_begin, b_end) of a time-major [T,B,C] tensor. Outputs are dense rows with
 // stride T per (b, p): dec[(b*P+p)*T + i], ali[(b*P+p)*T + i]; logp[b*P+p].
+template <typename T, typename Decoder>
+int RunBatch(Decoder& decoder, const T* logits, int max_time, int batch, int num_classes, const int* seq_len,
+             int b_begin, int b_end, int top_paths, bool merge_repeated, int* dec_len, int* dec,
+             int* ali_len, int* ali, T* logp, char* err, int errcap);
+
 template <typename T>
 int Decode(const T* logits, int max_time, int batch, int num_classes, const int* seq_len,
            int b_begin, int b_end, int beam_width, int top_paths, bool merge_repeated,
            int blank_index, int blank_label, int* dec_len, int* dec, int* ali_len, int* ali,
-           T* logp, char* err, int errcap) {
+           T* logp, char* err, int errcap, const T* penalty = nullptr) {
   using tensorflow::ctc::CTCExtBeamSearchDecoder;
   // kernels.cc:118-120
   if (max_time == 0) {
@@ -61,10 +86,25 @@ int Decode(const T* logits, int max_time, int batch, int num_classes, const int*
       return 5;
     }
   }
+  if (penalty != nullptr) {  // the same loops with a scorer plugged into the extension point
+    ConstScorer<T> scorer(*penalty);
+    CTCExtBeamSearchDecoder<T> decoder(num_classes, blank_index, beam_width, &scorer, blank_label, 1,
+                                       merge_repeated);
+    return RunBatch<T>(decoder, logits, max_time, batch, num_classes, seq_len, b_begin, b_end, top_paths,
+                       merge_repeated, dec_len, dec, ali_len, ali, logp, err, errcap);
+  }
   typename CTCExtBeamSearchDecoder<T>::DefaultBeamScorer scorer;
   // kernels.cc:55-57: ONE decoder with batch_size=1, re-used across the batch after Reset().
   CTCExtBeamSearchDecoder<T> decoder(num_classes, blank_index, beam_width, &scorer, blank_label, 1,
                                      merge_repeated);
+  return RunBatch<T>(decoder, logits, max_time, batch, num_classes, seq_len, b_begin, b_end, top_paths,
+                     merge_repeated, dec_len, dec, ali_len, ali, logp, err, errcap);
+}
+
+template <typename T, typename Decoder>
+int RunBatch(Decoder& decoder, const T* logits, int max_time, int batch, int num_classes, const int* seq_len,
+             int b_begin, int b_end, int top_paths, bool merge_repeated, int* dec_len, int* dec,
+             int* ali_len, int* ali, T* logp, char* err, int errcap) {
   std::vector<std::vector<int> > paths, alignments;
   std::vector<T> log_probs;
   for (int b = b_begin; b < b_end; ++b) {
@@ -145,6 +185,17 @@ int ctcx_ref_trace_f32(const float* logits, int T, int C, int W, int merge_repea
                        int* dec, int* ali) {
   return Trace<float>(logits, T, C, W, merge_repeated != 0, blank_index, blank_label, n_out, logp,
                       dec_len, dec, ali);
+}
+
+
+/* the reference decoder with a stateless scorer (constant expansion score) plugged into its
+ * BaseBeamScorer extension point */
+int ctcx_ref_decode_penalty_f32(const float* logits, int T, int B, int C, const int* seq_len, int b_begin,
+                                int b_end, int W, int P, int merge_repeated, int blank_index,
+                                int blank_label, float penalty, int* dec_len, int* dec, int* ali_len,
+                                int* ali, float* logp, char* err, int errcap) {
+  return Decode<float>(logits, T, B, C, seq_len, b_begin, b_end, W, P, merge_repeated != 0,
+                       blank_index, blank_label, dec_len, dec, ali_len, ali, logp, err, errcap, &penalty);
 }
 
 }  // extern "C"

@@ -94,11 +94,27 @@ def _check_inputs(logits, seq_len):
 
 
 def ref_decode(logits, seq_len, beam_width, top_paths, merge_repeated=False, blank_index=0,
-               blank_label=-1, b_range=None):
-    """The reference's own decoder (compiled from /root/reference into oracle/_ref)."""
+               blank_label=-1, b_range=None, penalty=None):
+    """The reference's own decoder (compiled from /root/reference into oracle/_ref). penalty: a
+    stateless scorer (constant expansion score) plugged into the reference's BaseBeamScorer
+    extension point, float32 only."""
     lib = _load(REF_SO)
     logits, seq_len = _check_inputs(logits, seq_len)
     T, B, C = logits.shape
+    if penalty is not None:
+        logits = logits.astype(np.float32, copy=False)
+        b0, b1 = b_range if b_range is not None else (0, B)
+        dec_len, dec, ali_len, ali, logp = _dense_out(B, top_paths, T, np.float32)
+        err = ctypes.create_string_buffer(256)
+        lib.ctcx_ref_decode_penalty_f32.argtypes = [_c_float_p] + [ctypes.c_int] * 3 + [_c_int_p] + \
+            [ctypes.c_int] * 7 + [ctypes.c_float] + [_c_int_p] * 4 + [_c_float_p, ctypes.c_char_p, ctypes.c_int]
+        rc = lib.ctcx_ref_decode_penalty_f32(
+            _ptr(logits, _c_float_p), T, B, C, _ptr(seq_len, _c_int_p), b0, b1, beam_width, top_paths,
+            int(bool(merge_repeated)), blank_index, blank_label, float(penalty), _ptr(dec_len, _c_int_p),
+            _ptr(dec, _c_int_p), _ptr(ali_len, _c_int_p), _ptr(ali, _c_int_p), _ptr(logp, _c_float_p), err, 256)
+        if rc != 0:
+            raise OracleError(err.value.decode())
+        return DenseResult(B, top_paths, T, dec_len, dec, ali_len, ali, logp)
     if logits.dtype == np.float64:
         fn, fp, dt = lib.ctcx_ref_decode_f64, _c_double_p, np.float64
     else:
@@ -165,12 +181,31 @@ class OracleStats(ctypes.Structure):
 
 
 def oracle_decode(logits, seq_len, beam_width, top_paths, merge_repeated=False, blank_index=0,
-                  blank_label=-1, want_margin=False, want_stats=False):
+                  blank_label=-1, want_margin=False, want_stats=False, lm=None):
     """This repo's plain-C restatement (oracle/ctcx_oracle.c). Returns DenseResult; with
-    want_margin also a float64 [B,5] array with each utterance's minimum decision margins."""
+    want_margin also a float64 [B,5] array with each utterance's minimum decision margins.
+    lm: optional [C+1, C] float32 expansion-score table of the scorer extension point."""
     lib = _load(ORACLE_SO)
     logits, seq_len = _check_inputs(logits, seq_len)
     T, B, C = logits.shape
+    if lm is not None:
+        logits = logits.astype(np.float32, copy=False)
+        lm = np.ascontiguousarray(lm, np.float32)
+        assert lm.shape == (C + 1, C)
+        dec_len, dec, ali_len, ali, logp = _dense_out(B, top_paths, T, np.float32)
+        margin = np.full((max(B, 1), N_MARGINS), np.inf, np.float64)
+        stats = OracleStats()
+        err = ctypes.create_string_buffer(256)
+        rc = lib.ctcx_oracle_decode_lm_f32(
+            _ptr(logits, _c_float_p), T, B, C, _ptr(seq_len, _c_int_p), beam_width, top_paths,
+            int(bool(merge_repeated)), blank_index, blank_label, _ptr(lm, _c_float_p), _ptr(dec_len, _c_int_p),
+            _ptr(dec, _c_int_p), _ptr(ali_len, _c_int_p), _ptr(ali, _c_int_p), _ptr(logp, _c_float_p),
+            _ptr(margin, _c_double_p), ctypes.byref(stats), err, 256)
+        if rc != 0:
+            raise OracleError(err.value.decode())
+        res = DenseResult(B, top_paths, T, dec_len, dec, ali_len, ali, logp)
+        out = [res] + ([margin[:B]] if want_margin else []) + ([stats] if want_stats else [])
+        return out[0] if len(out) == 1 else tuple(out)
     if logits.dtype == np.float64:
         fn, fp, dt = lib.ctcx_oracle_decode_f64, _c_double_p, np.float64
     else:

@@ -632,3 +632,40 @@ def test_torch_library_op(op):
     assert torch.equal(got[6], want[6])
     torch.library.opcheck(torch.ops.ctcx.ctc_ext_beam_search_decoder.default, (x, sl, W, P, True, 28, -1),
                           test_utils=("test_schema", "test_faketensor"))
+
+
+def test_scorer_extension_point(op):
+    """ctcx_decode_scorer_f32: a [C+1, C] expansion-score table plugged into the reference's
+    BaseBeamScorer call sites (decoder.h:103,114,171-182). GPU == oracle bit-for-bit for random
+    bigram tables; the constant-table case is pinned against the compiled reference in
+    tests/test_oracle.py."""
+    rng = np.random.default_rng(77)
+    for (kind, T, B, C, W, P, merge, blank) in [("gauss", 50, 5, 29, 10, 3, False, 28), ("peaky", 60, 4, 29, 100, 2, True, 28),
+                                                ("peaky", 30, 3, 120, 6, 2, False, 0), ("gauss", 25, 2, 40, 200, 2, False, 7)]:
+        x = L.make_logits(kind, T, B, C, blank, 13)
+        sl = L.ragged_lengths(T, B, 13)
+        for table in (-np.abs(rng.standard_normal((C + 1, C))).astype(np.float32) * 2,
+                      np.full((C + 1, C), -1.25, np.float32)):
+            want = L.oracle_decode(x, sl, W, P, merge, blank, -1, lm=table)
+            raw = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=W, top_paths=P, merge_repeated=merge,
+                                                     blank_index=blank, blank_label=-1, expansion_scores=table)
+            packed = L.pack_sparse(want)
+            for g in range(6):
+                for p in range(P):
+                    np.testing.assert_array_equal(np.asarray(raw[g][p]), packed[g][p])
+            np.testing.assert_array_equal(np.asarray(raw[6]).view(np.uint32), packed[6].view(np.uint32))
+        # a zero table is the default scorer
+        zero = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=W, top_paths=P, merge_repeated=merge,
+                                                  blank_index=blank, expansion_scores=np.zeros((C + 1, C), np.float32))
+        plain = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=W, top_paths=P, merge_repeated=merge, blank_index=blank)
+        np.testing.assert_array_equal(np.asarray(zero[6]).view(np.uint32), np.asarray(plain[6]).view(np.uint32))
+        assert all(np.array_equal(zero[4][p], plain[4][p]) for p in range(P))
+    # positive entries are refused (the gate decoder.h:157 is only redundant for log-probabilities)
+    bad = np.zeros((30, 29), np.float32)
+    bad[3, 4] = 0.5
+    with pytest.raises(op.CtcxError):
+        op.ctc_ext_beam_search_decoder_raw(L.make_logits("gauss", 10, 2, 29, 28, 1), [10, 10], beam_width=4, top_paths=1,
+                                           blank_index=28, expansion_scores=bad)
+    with pytest.raises(op.CtcxError):
+        op.ctc_ext_beam_search_decoder_raw(L.make_logits("gauss", 10, 2, 29, 28, 1), [10, 10], beam_width=4, top_paths=1,
+                                           blank_index=28, expansion_scores=np.zeros((29, 29), np.float32))

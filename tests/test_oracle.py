@@ -7,6 +7,7 @@ formulation the CUDA kernels implement -- against
 Citations relative to /root/reference/tensorflow_ctc_ext_beam_search_decoder/.
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -193,3 +194,29 @@ def test_libm_port_f64_matches_host_libm_sample():
                                              ctypes.POINTER(ctypes.c_longlong)]
     out = (ctypes.c_longlong * 2)()
     assert lib.ctcx_port_mismatches_f64(2000000, 12345, out) == 0, list(out)
+
+
+def test_scorer_extension_point_constant_table_is_the_reference_with_a_stateless_scorer():
+    """The reference's BaseBeamScorer extension point (util/ctc_beam_scorer.h:31-65). As the
+    reference is written only stateless scorers compile (BeamEntry::AddAlignmentCandidate takes a
+    BeamEntry<T>*, ctc_beam_entry.h:190), so what can be pinned against the compiled reference is a
+    constant expansion score: oracle(table == const) must equal reference(ConstScorer(const))."""
+    if not os.path.exists(L.REF_SO):
+        pytest.skip("compiled reference not available")
+    for (kind, T, B, C, W, P, merge, blank, pen) in [("gauss", 50, 6, 29, 10, 3, False, 28, -0.7),
+                                                     ("peaky", 60, 4, 29, 100, 2, True, 28, -2.5),
+                                                     ("gauss", 40, 3, 12, 5, 2, False, 0, -0.1),
+                                                     ("peaky", 40, 4, 40, 16, 3, False, 39, -4.0)]:
+        x = L.make_logits(kind, T, B, C, blank, 3)
+        sl = L.ragged_lengths(T, B, 3)
+        ref = L.ref_decode(x, sl, W, P, merge, blank, -1, penalty=pen)
+        got, margin = L.oracle_decode(x, sl, W, P, merge, blank, -1, lm=np.full((C + 1, C), pen, np.float32),
+                                      want_margin=True)
+        bad = [bp for bp in L.same_result(ref, got) if margin[bp[0]].min() > 0]  # exact ties: DESIGN section 5
+        assert not bad, bad
+        assert L.same_result(ref, L.ref_decode(x, sl, W, P, merge, blank, -1))  # and the scorer matters
+    # a zero table is the default scorer
+    x = L.make_logits("peaky", 30, 3, 12, 11, 4)
+    sl = np.full(3, 30, np.int32)
+    assert not L.same_result(L.oracle_decode(x, sl, 8, 2, False, 11, -1),
+                             L.oracle_decode(x, sl, 8, 2, False, 11, -1, lm=np.zeros((13, 12), np.float32)))
