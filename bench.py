@@ -3,6 +3,7 @@
 decoded per second at beam=100).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--kind gauss|peaky]
+                  [--workload cfg1|cfg2|cfg3|cfg4|cfg5]   (default cfg2, the shape the metric is quoted on)
 
 One "step" = one decode of one batch of synthetic logits: the LibriSpeech char-CTC shape the metric
 is quoted on (BASELINE.json configs[1]): T=500, B=256 per GPU, C=29 (blank=28), beam_width=100,
@@ -36,8 +37,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-CFG = dict(workload="librispeech-char-ctc (BASELINE configs[1])", T=500, B=256, C=29, blank_index=28,
-           beam_width=100, top_paths=1, merge_repeated=True, blank_label=-1)
+# BASELINE.json configs[0..4]; the metric is quoted on cfg2, the others are selectable for the
+# per-shape table in DESIGN.md (B is per GPU)
+WORKLOADS = {
+    "cfg1": dict(workload="repo test scale (BASELINE configs[0])", T=50, B=8, C=29, blank_index=28,
+                 beam_width=10, top_paths=3, merge_repeated=False, blank_label=-1),
+    "cfg2": dict(workload="librispeech-char-ctc (BASELINE configs[1])", T=500, B=256, C=29, blank_index=28,
+                 beam_width=100, top_paths=1, merge_repeated=True, blank_label=-1),
+    "cfg3": dict(workload="wav2vec2-base char head (BASELINE configs[2])", T=1500, B=64, C=32, blank_index=31,
+                 beam_width=64, top_paths=4, merge_repeated=False, blank_label=-1),
+    "cfg4": dict(workload="conformer-bpe head (BASELINE configs[3])", T=400, B=128, C=1024, blank_index=1023,
+                 beam_width=16, top_paths=1, merge_repeated=False, blank_label=-1),
+    "cfg5": dict(workload="throughput sweep (BASELINE configs[4], 1024 utterances per GPU)", T=500, B=1024, C=29,
+                 blank_index=28, beam_width=100, top_paths=1, merge_repeated=True, blank_label=-1),
+}
+CFG = dict(WORKLOADS["cfg2"])
 L2_BYTES = 126 * 1024 * 1024
 
 
@@ -287,12 +301,13 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": bytes_per_batch + B * 4,
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": 7 * args.steps,
+        "gpu_launches": (8 if (32 < C <= 2048) else 7) * args.steps,  # +1: TopClassesKernel for wide vocabularies
         "kernel_ms": {"lognorm": float(kern_ms[:, 0].mean()), "beam": beam_ms,
                       "trace": float(kern_ms[:, 2].mean()), "scan": float(kern_ms[:, 3].mean()),
                       "wall_ms_per_step": 1e3 * wall_dev / args.steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "kernel": "BeamKernelV3<128,256>",
+                     "frac": achieved / peak, "traffic": traffic if args.workload == "cfg2" else None,
+                     "kernel": "BeamKernelWide" if (32 < C <= 2048) else "BeamKernelV3",
                      "peak_source": peak_src,
                      "note": "algorithmic bytes = 4*C per frame (logits read once); the kernel is "
                              "bound by the T-long serial recurrence per utterance, not by HBM"},
@@ -317,7 +332,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kind", default="gauss", choices=["gauss", "peaky"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    CFG.clear()
+    CFG.update(WORKLOADS[args.workload])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
