@@ -71,29 +71,60 @@ def _as_tensor(a):
     return torch.from_numpy(np.ascontiguousarray(a)), True
 
 
-def _pack(lib, ws, T, B, P, counts, device, stream, f64=False):
-    """Allocate the 6*P sparse tensors from the sizes a decode reported and let ctcx_pack_f32 /
-    ctcx_pack_f64 fill them (StoreAllDecodedSequences, kernels.cc:163-257)."""
+def _carve(buf, B, P, counts, f64):
+    """Views of one int64 buffer: the 6*P sparse tensors (ops.cc:17-22) followed by log_probability."""
     n_dec, n_ali = counts
-    i64 = dict(dtype=torch.int64, device=device)
-    dec_idx = [torch.empty((int(n_dec[p]), 2), **i64) for p in range(P)]
-    dec_val = [torch.empty((int(n_dec[p]),), **i64) for p in range(P)]
-    dec_shp = [torch.empty((2,), **i64) for p in range(P)]
-    ali_idx = [torch.empty((int(n_ali[p]), 2), **i64) for p in range(P)]
-    ali_val = [torch.empty((int(n_ali[p]),), **i64) for p in range(P)]
-    ali_shp = [torch.empty((2,), **i64) for p in range(P)]
-    logp = torch.empty((B, P), dtype=torch.float64 if f64 else torch.float32, device=device)
+    o = 0
+    groups = [[], [], [], [], [], []]
+
+    def take(n, shape):
+        nonlocal o
+        t = buf[o:o + n].view(shape)
+        o += n
+        return t
+
+    for p in range(P):
+        nd, na = int(n_dec[p]), int(n_ali[p])
+        groups[0].append(take(2 * nd, (nd, 2)))
+        groups[1].append(take(nd, (nd,)))
+        groups[2].append(take(2, (2,)))
+        groups[3].append(take(2 * na, (na, 2)))
+        groups[4].append(take(na, (na,)))
+        groups[5].append(take(2, (2,)))
+    n_lp = B * P if f64 else (B * P + 1) // 2  # in int64 units
+    lp = buf[o:o + n_lp].view(torch.float64 if f64 else torch.float32)[:B * P].view(B, P)
+    return groups, lp
+
+
+def _pack_elems(B, P, counts, f64):
+    n_dec, n_ali = counts
+    return sum(3 * int(n_dec[p]) + 3 * int(n_ali[p]) + 4 for p in range(P)) + (B * P if f64 else (B * P + 1) // 2)
+
+
+def _pack(lib, ws, T, B, P, counts, device, stream, f64=False, host_out=False):
+    """Allocate the 6*P sparse tensors from the sizes a decode reported and let ctcx_pack_f32 /
+    ctcx_pack_f64 fill them (StoreAllDecodedSequences, kernels.cc:163-257). All outputs are views of
+    ONE buffer, so results for host callers cross the bus in a single copy into pinned memory (from
+    torch's caching host allocator) instead of 6*P+1 pageable ones."""
+    n = _pack_elems(B, P, counts, f64)
+    buf = torch.empty((n,), dtype=torch.int64, device=device)
+    groups, logp = _carve(buf, B, P, counts, f64)
     ptrs = ctypes.c_void_p * P
 
     def table(ts):
         return ptrs(*[t.data_ptr() for t in ts])
 
     pack = lib.ctcx_pack_f64 if f64 else lib.ctcx_pack_f32
-    rc = pack(ws.data_ptr(), T, B, P, table(dec_idx), table(dec_val), table(dec_shp),
-              table(ali_idx), table(ali_val), table(ali_shp), logp.data_ptr(), stream)
+    rc = pack(ws.data_ptr(), T, B, P, table(groups[0]), table(groups[1]), table(groups[2]),
+              table(groups[3]), table(groups[4]), table(groups[5]), logp.data_ptr(), stream)
     if rc != 0:
         _raise(lib, rc)
-    return [dec_idx, dec_val, dec_shp, ali_idx, ali_val, ali_shp], logp
+    if host_out:
+        hbuf = torch.empty((n,), dtype=torch.int64, pin_memory=True)
+        hbuf.copy_(buf, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        groups, logp = _carve(hbuf, B, P, counts, f64)
+    return groups, logp
 
 
 def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_paths,
@@ -187,13 +218,10 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
             _raise(lib, rc)
         global last_flags
         last_flags = int(flags.value)
-        groups, logp = _pack(lib, ws, T, B, P, (n_dec, n_ali), device, stream, f64)
-        if host_out:
-            groups = [[t.cpu() for t in g] for g in groups]
-            logp = logp.cpu()
-            if x_np:
-                groups = [[t.numpy() for t in g] for g in groups]
-                logp = logp.numpy()
+        groups, logp = _pack(lib, ws, T, B, P, (n_dec, n_ali), device, stream, f64, host_out)
+        if host_out and x_np:
+            groups = [[t.numpy() for t in g] for g in groups]
+            logp = logp.numpy()
     return CTCExtBeamSearchDecoder(*groups, logp)
 
 

@@ -24,10 +24,11 @@ def _ctc_ext_beam_search_decoder(inputs: torch.Tensor, sequence_length: torch.Te
     raw = _decoder.ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width=beam_width,
                                                    top_paths=top_paths, merge_repeated=merge_repeated,
                                                    blank_index=blank_index, blank_label=blank_label)
+    # the raw entry returns views of one packed buffer; a registered op's outputs must not alias
     flat = []
     for g in range(6):
-        flat.extend(raw[g])
-    flat.append(raw[6])
+        flat.extend(t.clone() for t in raw[g])
+    flat.append(raw[6].clone())
     return flat
 
 

@@ -1,0 +1,40 @@
+"""Where the end-to-end (host in, host out) time of the cfg2 workload goes: python tools/e2e_breakdown.py"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+
+import ctcx_testlib as L
+import ctc_beam_search_op_b200 as op
+
+T, B, C, W = 500, 256, 29, 100
+kw = dict(beam_width=W, top_paths=1, merge_repeated=True, blank_index=28, blank_label=-1)
+xs = [torch.from_numpy(L.make_logits("gauss", T, B, C, 28, s)).pin_memory() for s in range(10)]
+sl = torch.full((B,), T, dtype=torch.int32).pin_memory()
+dev = torch.device("cuda", 0)
+
+
+def timed(f, n=30):
+    for i in range(3):
+        f(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n):
+        f(i)
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / n * 1e3
+
+
+xd = [x.to(dev) for x in xs]
+sd = sl.to(dev)
+print("h2d logits only      %.3f ms" % timed(lambda i: xs[i % 10].to(dev, non_blocking=True)))
+print("decode, device in/out %.3f ms" % timed(lambda i: op.ctc_ext_beam_search_decoder_raw(xd[i % 10], sd, **kw)))
+out = op.ctc_ext_beam_search_decoder_raw(xd[0], sd, **kw)
+nbytes = sum(t.numel() * t.element_size() for g in out[:6] for t in g) + out[6].numel() * 4
+print("d2h outputs only (%.2f MB, .cpu() per tensor) %.3f ms" % (nbytes / 1e6, timed(lambda i: [[t.cpu() for t in g] for g in out[:6]] + [out[6].cpu()])))
+print("e2e (host in, host out) %.3f ms" % timed(lambda i: op.ctc_ext_beam_search_decoder_raw(xs[i % 10], sl, **kw)))
