@@ -425,14 +425,17 @@ int DecodeImpl(const R* logits_dev, int T, int B, int C, const int32_t* seq_len_
   unsigned char* base = (unsigned char*)workspace;
   int* d_stats = (int*)(base + ws.stats);
 
-  // sequence_length range check on the device (the data lives there)
+  // sequence_length lives on the device: its range check (kernels.cc:134-138) is folded into the
+  // flags reduction at the end -- every kernel clamps the lengths it walks -- so that a decode has
+  // ONE host round trip. Only when top_paths > beam_width (an error either way) is it evaluated
+  // first, because the reference reports a bad length before TopPaths' own error (decoder.h:237).
   {
     const int init[5] = {0, B, B, B, B};
     CTCX_CUDA(cudaMemcpyAsync(d_stats, init, sizeof(init), cudaMemcpyHostToDevice, stream));
-    if (B > 0) {
-      FlagsKernel<<<(B + 255) / 256, 256, 0, stream>>>(nullptr, seq_len_dev, B, T, d_stats);
-      CTCX_CUDA(cudaGetLastError());
-    }
+  }
+  if (B > 0 && P > W) {
+    FlagsKernel<<<(B + 255) / 256, 256, 0, stream>>>(nullptr, seq_len_dev, B, T, d_stats);
+    CTCX_CUDA(cudaGetLastError());
     int h[4];
     CTCX_CUDA(cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, stream));
     CTCX_CUDA(cudaStreamSynchronize(stream));
@@ -442,9 +445,9 @@ int DecodeImpl(const R* logits_dev, int T, int B, int C, const int32_t* seq_len_
       return CTCX_ERR_SEQ_LEN_RANGE;
     }
     if (h[3] < B) return CTCX_ERR_BAD_ARGUMENT;
+    // TopPaths is reached for utterance 0 only after its frames; for B == 0 it is never reached
+    return CTCX_ERR_TOO_MANY_PATHS;
   }
-  // TopPaths is reached for utterance 0 only after its frames; for B == 0 it is never reached
-  if (B > 0 && P > W) return CTCX_ERR_TOO_MANY_PATHS;
 
   Workspace::Header hdr = {kMagic, T, B, C, W, P, (int)sizeof(R)};
   CTCX_CUDA(cudaMemcpyAsync(base + ws.header, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, stream));
@@ -508,6 +511,12 @@ int DecodeImpl(const R* logits_dev, int T, int B, int C, const int32_t* seq_len_
     for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&g_ms[k], g_ev[k], g_ev[k + 1]);
     cudaEventElapsedTime(&g_ms[4], g_ev[0], g_ev[4]);
   }
+  if (h_stats[2] < B) {  // kernels.cc:134-138
+    g_err_batch = h_stats[2];
+    g_err_max_time = T;
+    return CTCX_ERR_SEQ_LEN_RANGE;
+  }
+  if (h_stats[3] < B) return CTCX_ERR_BAD_ARGUMENT;  // negative sequence_length
   if (h_stats[1] < B) return CTCX_ERR_TOO_FEW_LEAVES;
   for (int p = 0; p < P; ++p) {
     if (sizes->n_decoded) sizes->n_decoded[p] = h_sizes[0 * (size_t)P + p];
@@ -568,8 +577,8 @@ int PackImpl(const void* workspace, int T, int B, int P, int64_t* const* decoded
       CTCX_CUDA(cudaMemcpyAsync(alignment_shape[p], zeros, 16, cudaMemcpyHostToDevice, stream));
     }
   }
-  // the pointer table was staged from a stack/heap vector: make sure the copy has been consumed
-  CTCX_CUDA(cudaStreamSynchronize(stream));
+  // the pointer table lives in a host vector: a cudaMemcpyAsync from pageable memory returns only
+  // after the source has been copied to the driver's staging buffer, so no synchronisation is needed
   return CTCX_OK;
 }
 }  // namespace

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   const int W = p.W, C = p.C, T = p.T, B = p.B, blank = p.blank_index;
-  const int L = p.seq_len[b];
+  const int L = max(0, min(p.seq_len[b], p.T));
 
   BeamSmemV2 lay;
   lay.Init(WMAX, p.cand_cap);

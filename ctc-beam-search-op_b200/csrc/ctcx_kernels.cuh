@@ -1018,7 +1018,7 @@ __global__ void __launch_bounds__(128) TraceKernel(TraceParams p) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p.B * p.P) return;
   const int b = idx / p.P, path = idx - b * p.P;
-  const int L = p.seq_len[b];
+  const int L = max(0, min(p.seq_len[b], p.T));  // out-of-range lengths are reported by the host, not walked
   int* ali = p.ali + (size_t)idx * p.T;
   int* dec = p.dec + (size_t)idx * p.T;
   if (path >= p.fin_n[b] || L <= 0) {
@@ -1077,7 +1077,7 @@ __global__ void __launch_bounds__(WARPS * 32) TraceWarpKernel(TraceParams p, int
   const int idx = blockIdx.x * WARPS + warp;
   if (idx >= p.B * p.P) return;
   const int b = idx / p.P, path = idx - b * p.P;
-  const int L = p.seq_len[b];
+  const int L = max(0, min(p.seq_len[b], p.T));  // out-of-range lengths are reported by the host, not walked
   int* ali = p.ali + (size_t)idx * p.T;
   int* dec = p.dec + (size_t)idx * p.T;
   if (path >= p.fin_n[b] || L <= 0) {

@@ -92,7 +92,8 @@ int ctcx_decode_f32(const float* logits_dev, int max_time, int batch, int num_cl
  *   decoded_shape[p]     int64 [2] = [batch, max_decoded[p]]
  *   alignment_*          likewise
  *   log_probability      float32 [batch, top_paths]
- * Does not synchronise. */
+ * Synchronises `stream` once at entry (it validates the workspace header); the pack kernel itself is
+ * only enqueued. */
 int ctcx_pack_f32(const void* workspace, int max_time, int batch, int top_paths,
                   int64_t* const* decoded_indices, int64_t* const* decoded_values,
                   int64_t* const* decoded_shape, int64_t* const* alignment_indices,
