@@ -669,3 +669,35 @@ def test_scorer_extension_point(op):
     with pytest.raises(op.CtcxError):
         op.ctc_ext_beam_search_decoder_raw(L.make_logits("gauss", 10, 2, 29, 28, 1), [10, 10], beam_width=4, top_paths=1,
                                            blank_index=28, expansion_scores=np.zeros((29, 29), np.float32))
+
+
+def test_masked_logits_minus_infinity(op):
+    """-inf logits (vocabulary masking): probability exactly 0 for those classes. The reference
+    handles them through kLogZero (loss_util.h:19-22, decoder.h:151 `total > kLogZero`); oracle ==
+    compiled reference on such inputs (checked on the CPU), GPU == oracle here. The blank stays
+    finite (a frame with every class at -inf is NaN in the reference as well)."""
+    rng = np.random.default_rng(0)
+    for (kind, T, B, C, W, P, merge, blank, frac) in [("gauss", 40, 6, 12, 8, 3, False, 11, 0.2),
+                                                      ("peaky", 60, 4, 29, 20, 2, True, 28, 0.3),
+                                                      ("gauss", 30, 4, 40, 16, 2, False, 0, 0.5),
+                                                      ("gauss", 30, 4, 8, 100, 4, False, 7, 0.4),
+                                                      ("peaky", 40, 3, 200, 6, 2, False, 199, 0.9),   # wide, few finite classes
+                                                      ("gauss", 30, 2, 1024, 16, 1, False, 1023, 0.5),
+                                                      ("gauss", 50, 3, 29, 100, 1, True, 28, 0.6)]:
+        x = L.make_logits(kind, T, B, C, blank, 5)
+        mask = rng.random((T, B, C)) < frac
+        mask[..., blank] = False
+        x = np.where(mask, -np.inf, x).astype(np.float32)
+        check_against_oracle(op, x, L.ragged_lengths(T, B, 5), W, P, merge, blank, -1)
+    # a label that is masked in every frame never appears; float64 path too
+    x = L.make_logits("gauss", 30, 3, 10, 9, 8).astype(np.float64)
+    x[:, :, 4] = -np.inf
+    sl = np.full(3, 30, np.int32)
+    want = L.oracle_decode(x, sl, 12, 3, False, 9, -1)
+    raw = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=12, top_paths=3, blank_index=9)
+    packed = L.pack_sparse(want)
+    for g in range(6):
+        for p in range(3):
+            np.testing.assert_array_equal(np.asarray(raw[g][p]), packed[g][p])
+    np.testing.assert_array_equal(np.asarray(raw[6]).view(np.uint64), packed[6].view(np.uint64))
+    assert all(4 not in np.asarray(raw[1][p]).tolist() for p in range(3))

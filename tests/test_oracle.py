@@ -220,3 +220,23 @@ def test_scorer_extension_point_constant_table_is_the_reference_with_a_stateless
     sl = np.full(3, 30, np.int32)
     assert not L.same_result(L.oracle_decode(x, sl, 8, 2, False, 11, -1),
                              L.oracle_decode(x, sl, 8, 2, False, 11, -1, lm=np.zeros((13, 12), np.float32)))
+
+
+def test_minus_infinity_logits_oracle_equals_reference():
+    """Vocabulary masking (-inf logits, blank finite): the oracle follows the compiled reference."""
+    if not os.path.exists(L.REF_SO):
+        pytest.skip("compiled reference not available")
+    rng = np.random.default_rng(0)
+    for (kind, T, B, C, W, P, merge, blank, frac) in [("gauss", 40, 6, 12, 8, 3, False, 11, 0.2),
+                                                      ("peaky", 60, 4, 29, 20, 2, True, 28, 0.3),
+                                                      ("gauss", 30, 4, 40, 16, 2, False, 0, 0.5),
+                                                      ("peaky", 40, 3, 200, 6, 2, False, 199, 0.9)]:
+        x = L.make_logits(kind, T, B, C, blank, 5)
+        mask = rng.random((T, B, C)) < frac
+        mask[..., blank] = False
+        x = np.where(mask, -np.inf, x).astype(np.float32)
+        sl = L.ragged_lengths(T, B, 5)
+        ref = L.ref_decode(x, sl, W, P, merge, blank, -1)
+        got, margin = L.oracle_decode(x, sl, W, P, merge, blank, -1, want_margin=True)
+        assert not [bp for bp in L.same_result(ref, got) if margin[bp[0]].min() > 0]
+        assert not L.same_result(got, L.model_decode(x, sl, W, P, merge, blank, -1))
