@@ -636,6 +636,18 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     }
     const bool member_in = !clamped || my_key > lo_key;
     const int bstar = sc[kV2Bstar], k_rem = sc[kV2KRem], e_b = sc[kV2E], n_new = sc[kV2NNew];
+    if (TIMING && timing) {  // event counters (slots 20-23): how selective would a "below the cut" filter be?
+      int below = 0, wiped = 0;
+      for (int q = 0; q < n_risk; ++q) {
+        const int m = s_risk[q];
+        below += (bucket_of(m_key[m]) <= bstar || (clamped && m_key[m] <= lo_key)) ? 1 : 0;
+        wiped += s_wiped[m] ? 1 : 0;
+      }
+      cyc[TIMING ? 20 : 0] += n_risk;
+      cyc[TIMING ? 21 : 0] += below;
+      cyc[TIMING ? 22 : 0] += wiped;
+      cyc[TIMING ? 23 : 0] += (n_risk > 0) ? 1 : 0;
+    }
     const bool bnd_all = (e_b == k_rem);
     // next frame's range prediction: the measured top-to-threshold gap
     const unsigned gap_next = (unsigned)(sc[kV2TopBin] - bstar + 1) << shift;

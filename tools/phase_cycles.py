@@ -30,7 +30,8 @@ lib.ctcx_debug_set_cycles_buffer(None)
 c = buf.cpu().numpy().astype(np.float64) / T
 names = ["PA(end)", "PB(end)", "PC", "PD", "PE", "PF", "PG(end)", "setup", "PA.lookup", "PA.lse1", "PA.lse2",
          "PA.store", "PA.minmax", "PG.rank", "PG.barrier", "PG.write", "PB.range", "PB.pass1", "PB.scan",
-         "PB.pass2+bar", "ev.slowcut", "ev.fullrange", "ev.capped", "ev.ncand"]
+         "PB.pass2+bar"] + (["ev.n_risk", "ev.risk_below_cut", "ev.wiped", "ev.frames_with_risk"] if cfg == "cfg2"
+                                 else ["ev.slowcut", "ev.fullrange", "ev.capped", "ev.ncand"])
 m = c.mean(axis=0)
 print("B=%d %s: cycles per frame, thread 0 (mean over CTAs):" % (B, kind))
 print("  " + "  ".join(("%s %.3f" if n.startswith("ev.") else "%s %.0f") % (n, v) for n, v in zip(names, m)) + "  | total %.0f" % m[:20].sum())
