@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       s_pl[lane] = pl_lane;
       const unsigned kl = lane_ok ? KeyOf(pl_lane) : 0u;  // blank / padding sort last
       int rank = 0;
-#pragma unroll
+#pragma unroll 4  // code size: the frame loop must stay inside the 32 KB instruction cache
       for (int j = 0; j < 32; ++j) {
         const unsigned kj = __shfl_sync(kFull, kl, j);
         rank += (kj > kl || (kj == kl && j < lane)) ? 1 : 0;
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
             }
             // children visited before the parent reaches label(m), from rows that are not wiped
             const unsigned below = (1u << o_label[m]) - 1u;
-#pragma unroll 4
+#pragma unroll 1
             for (int r0 = 0; r0 <= pslot; r0 += 32) {
               const int r = r0 + lane;
               if (r <= pslot && !s_wiped[r]) {
