@@ -21,8 +21,8 @@
 
 namespace ctcx {
 
-constexpr int kBinsV2 = 512;   // score-histogram bins
-constexpr int kBinsLog2V2 = 9;
+constexpr int kBinsV2 = 256;   // score-histogram bins (256 measured best: 512 costs scan work, 128 crowds the boundary bin)
+constexpr int kBinsLog2V2 = 8;
 constexpr int kBndFast = 32;  // boundary items handled by one warp
 
 struct BeamSmemV2 {
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     CTCX_TICK(2)  // PC
     // ---- PD: boundary bin of the W-th item and group offsets (two bins per thread) ----
     {
-      // suffix sums over bins 511..0: thread `tid` owns bins hi = 511-2*tid and lo = hi-1, so an
+      // suffix sums over bins kBinsV2-1..0: thread `tid` owns bins hi = kBinsV2-1-2*tid and lo = hi-1, so an
       // inclusive PREFIX scan in thread order is an inclusive SUFFIX scan in bin order
       const int bin_hi = kBinsV2 - 1 - 2 * tid;
       unsigned h_hi = 0u, h_lo = 0u;

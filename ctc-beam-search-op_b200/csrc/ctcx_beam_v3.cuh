@@ -10,7 +10,7 @@
 //       bitmask: pref[L(v)] & ~member-children, L found by a 5-step exact binary search over the
 //       sorted class scores (fp add is monotone); a wipe query is a sum of popcounts -- no list.
 //   PB  only candidates inside the predicted score range (previous top-to-threshold gap x2) are
-//       listed and histogrammed (512 bins); wiped rows are skipped                 decoder.h:146-187
+//       listed and histogrammed (256 bins); wiped rows are skipped                 decoder.h:146-187
 //   PD  parallel suffix scan -> boundary bin of the W-th item; if the prediction missed (fewer than
 //       W items in range) PB/PD run again over the full admissible range
 //   PE  items above the boundary bin are scattered into score groups
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
 
       // ---- PD: boundary bin of the W-th item and group offsets (two bins per thread) ----
       {
-        // suffix sums over bins 511..0: thread `tid` owns bins hi = 511-2*tid and lo = hi-1, so an
+        // suffix sums over bins kBinsV2-1..0: thread `tid` owns bins hi = kBinsV2-1-2*tid and lo = hi-1, so an
         // inclusive PREFIX scan in thread order is an inclusive SUFFIX scan in bin order
         const int bin_hi = kBinsV2 - 1 - 2 * tid;
         unsigned h_hi = 0u, h_lo = 0u;
