@@ -291,7 +291,7 @@ int LaunchBeamFor(ctcx::BeamParams& bp, cudaStream_t stream) {
     }
   } else {
     ctcx::BeamSmem lay;
-    lay.Init(tier.wmax, tier.nt, C, bp.kid_words, bp.cand_cap);
+    lay.Init(tier.wmax, tier.nt, C, bp.kid_words, bp.cand_cap, 4, W);
     if (lay.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
     switch (tier.wmax) {
       case 32: e = LaunchBeam<float, 32, 128>(bp, lay.bytes, stream); break;
@@ -316,7 +316,7 @@ int LaunchBeamFor(ctcx::BeamParamsT<double>& bp, cudaStream_t stream) {
   Tier tier = PickTier(W);
   if (tier.wmax > 256) tier = (W <= 512) ? Tier{512, 512} : Tier{1024, 1024};
   ctcx::BeamSmem lay;
-  lay.Init(tier.wmax, tier.nt, C, bp.kid_words, bp.cand_cap, 8);
+  lay.Init(tier.wmax, tier.nt, C, bp.kid_words, bp.cand_cap, 8, W);
   if (lay.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;  // beam_width > 512, or a very wide vocabulary
   cudaError_t e;
   switch (tier.wmax) {

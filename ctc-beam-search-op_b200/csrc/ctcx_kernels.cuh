@@ -375,7 +375,7 @@ struct BeamSmem {
   size_t htab;                 // i32 [2*WMAX]
   size_t hist;                 // u32 [256]
   size_t x;                    // R [2][Cpad]
-  size_t kid;                  // u32 [WMAX*kid_words]
+  size_t kid;                  // u32 [kid_rows*kid_words], kid_rows = beam_width rounded up to 32
   size_t c_key;                // Key [cand_cap]
   size_t c_id;                 // u32 [cand_cap]
   size_t offv;                 // R [2]   this / the next frame's normaliser
@@ -385,7 +385,8 @@ struct BeamSmem {
 
   __host__ __device__ static size_t Align(size_t v, size_t a) { return (v + a - 1) / a * a; }
   // rs = sizeof(R): 4 (float) or 8 (double); every 8-byte array precedes the 4-byte ones
-  __host__ __device__ void Init(int wmax, int nt, int C, int kid_words, int cand_cap, int rs = 4) {
+  __host__ __device__ static int KidRows(int W) { return (W + 31) / 32 * 32; }
+  __host__ __device__ void Init(int wmax, int nt, int C, int kid_words, int cand_cap, int rs, int W) {
     size_t o = 0;
     const size_t w = (size_t)wmax, r = (size_t)rs;
     const size_t cpad = Align((size_t)C, 4);
@@ -417,7 +418,7 @@ struct BeamSmem {
     part = o; o += (size_t)nt * 4;
     htab = o; o += 2 * w * 4;
     hist = o; o += 256 * 4;
-    kid = o; o += w * (size_t)kid_words * 4;
+    kid = o; o += (size_t)KidRows(W) * (size_t)kid_words * 4;  // sized by the beam width, not the tier
     c_id = o; o += (size_t)cand_cap * 4;
     scal = o; o += 32 * 4;
     bytes = Align(o, 16);
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(NT) BeamKernelT(BeamParamsT<R> p) {
   const bool resume = kIsF32 && (p.state != nullptr) && t_done > 0;
 
   BeamSmem lay;
-  lay.Init(WMAX, NT, C, KW, p.cand_cap, (int)sizeof(R));
+  lay.Init(WMAX, NT, C, KW, p.cand_cap, (int)sizeof(R), W);
   unsigned long long* s_hash = (unsigned long long*)(smem + lay.hash);
   unsigned long long* s_phash = (unsigned long long*)(smem + lay.phash);
   Comp* s_surv = (Comp*)(smem + lay.surv);
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(NT) BeamKernelT(BeamParamsT<R> p) {
   // ---- initial state: the root (decoder.h:212-227) ----
   LoadExpTable(s_exptab, tid, NT);
   for (int i = tid; i < TS; i += NT) s_htab[i] = -1;
-  for (int i = tid; i < WMAX * KW; i += NT) s_kid[i] = 0u;
+  for (int i = tid; i < BeamSmem::KidRows(W) * KW; i += NT) s_kid[i] = 0u;
   for (int i = tid; i < WMAX; i += NT) s_wiped[i] = 0u;
   if (tid == 0 && !resume) {
     s_total[0] = (R)0;
