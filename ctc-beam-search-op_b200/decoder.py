@@ -317,6 +317,25 @@ class CTCExtBeamSearchDecoderStream:
         if rc != 0:
             _raise(self._lib, rc)
 
+    def step_device(self, inputs_dev, lengths_dev):
+        """Step() on buffers that already live on the device -- float32 [chunk_time, batch, num_classes]
+        and int32 [batch], both contiguous -- without any conversion, allocation or synchronisation: the
+        call only enqueues kernels on the current stream, so it can be captured into a CUDA graph
+        (`with torch.cuda.graph(g): dec.step_device(x_static, len_static)`) and replayed per chunk,
+        which removes the launch overhead that dominates small chunks."""
+        x, ln = inputs_dev, lengths_dev
+        if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3 and
+                int(x.shape[1]) == self.B and int(x.shape[2]) == self.C):
+            raise InvalidArgumentError(8, "step_device needs a contiguous CUDA float32 [chunk_time, %d, %d] tensor"
+                                       % (self.B, self.C))
+        if not (ln.is_cuda and ln.dtype == torch.int32 and ln.is_contiguous() and tuple(ln.shape) == (self.B,)):
+            raise InvalidArgumentError(8, "step_device needs a contiguous CUDA int32 [%d] tensor" % self.B)
+        rc = self._lib.ctcx_stream_step_f32(self._ws.data_ptr(), self.T, self.B, self.C, self.W, self.P,
+                                            x.data_ptr(), int(x.shape[0]), ln.data_ptr(), self.blank_index,
+                                            self._stream())
+        if rc != 0:
+            _raise(self._lib, rc)
+
     def top_paths_raw(self):
         """TopPaths() (decoder.h:229-261) of the frames consumed so far, as the raw 7 output groups
         (device tensors)."""

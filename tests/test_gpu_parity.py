@@ -701,3 +701,37 @@ def test_masked_logits_minus_infinity(op):
             np.testing.assert_array_equal(np.asarray(raw[g][p]), packed[g][p])
     np.testing.assert_array_equal(np.asarray(raw[6]).view(np.uint64), packed[6].view(np.uint64))
     assert all(4 not in np.asarray(raw[1][p]).tolist() for p in range(3))
+
+
+def test_streaming_steps_replayed_from_a_cuda_graph(op):
+    """The step call only enqueues kernels (no synchronisation, no allocation), so a chunk step can be
+    captured once into a CUDA graph and replayed for every chunk: same result as the one-shot decode."""
+    import torch
+    for (T, B, C, W, P, blank, Tc) in [(64, 6, 29, 20, 2, 28, 8), (48, 3, 300, 8, 1, 0, 6)]:
+        x = L.make_logits("peaky", T, B, C, blank, 19)
+        sl = np.full(B, T, np.int32)
+        dec = op.CTCExtBeamSearchDecoderStream(batch_size=B, num_classes=C, beam_width=W, top_paths=P,
+                                               max_time=T, merge_repeated=True, blank_index=blank)
+        x_static = torch.zeros((Tc, B, C), dtype=torch.float32, device="cuda")
+        l_static = torch.full((B,), Tc, dtype=torch.int32, device="cuda")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up outside the capture (module loading, attributes)
+            dec.step_device(x_static, l_static)
+        torch.cuda.current_stream().wait_stream(side)
+        dec.reset()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            dec.step_device(x_static, l_static)
+        dec.reset()  # the capture itself does not run the step
+        xd = torch.from_numpy(x).cuda()
+        for t in range(0, T, Tc):
+            x_static.copy_(xd[t:t + Tc])
+            g.replay()
+        raw = dec.top_paths_raw()
+        one = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=W, top_paths=P, merge_repeated=True,
+                                                 blank_index=blank)
+        for gi in range(6):
+            for p in range(P):
+                np.testing.assert_array_equal(raw[gi][p].cpu().numpy(), one[gi][p])
+        np.testing.assert_array_equal(raw[6].cpu().numpy().view(np.uint32), np.asarray(one[6]).view(np.uint32))
