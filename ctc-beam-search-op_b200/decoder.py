@@ -36,6 +36,9 @@ class CtcxError(ValueError):
         super().__init__(message)
         self.code = code
 
+    def __reduce__(self):  # picklable: errors travel between ranks (sharding.decode_distributed)
+        return (type(self), (self.code, str(self)))
+
 
 class InvalidArgumentError(CtcxError):
     """tf.errors.InvalidArgumentError counterpart."""

@@ -147,3 +147,12 @@ def test_torch_library_registration_traces_with_fake_tensors():
     # the flat list maps back onto the raw namedtuple
     r = m.torch_op.unflatten(list(range(19)), 3)
     assert r.decoded_indices == [0, 1, 2] and r.alignment_shape == [15, 16, 17] and r.log_probability == 18
+
+
+def test_error_classes_survive_pickling():
+    """decode_distributed ships a rank's exception to the gathering rank: code and text must survive."""
+    import pickle
+    import ctc_beam_search_op_b200 as m
+    for cls, code in ((m.InvalidArgumentError, 6), (m.FailedPreconditionError, 5), (m.UnsupportedError, 9)):
+        e = pickle.loads(pickle.dumps(cls(code, "sequence_length(3) <= 8")))
+        assert type(e) is cls and e.code == code and str(e) == "sequence_length(3) <= 8"
