@@ -408,11 +408,22 @@ def test_multi_device_sharding_equals_single(op):
     x = L.make_logits("peaky", 25, 7, 10, 9, 13)
     sl = L.ragged_lengths(25, 7, 13)
     whole = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=6, top_paths=2, merge_repeated=True, blank_index=9)
-    parts = op.decode_multi_device(x, sl, 6, 2, True, 9, -1, devices=[0, 0, 0])
-    for g in range(6):
-        for p in range(2):
-            np.testing.assert_array_equal(parts[g][p], whole[g][p])
-    np.testing.assert_array_equal(parts[6], whole[6])
+    import torch
+    layouts = [[0, 0, 0]]
+    if torch.cuda.device_count() >= 2:  # really different devices where the box has them
+        layouts += [[0, 1], [1, 0, 1]]
+    for devices in layouts:
+        parts = op.decode_multi_device(x, sl, 6, 2, True, 9, -1, devices=devices)
+        for g in range(6):
+            for p in range(2):
+                np.testing.assert_array_equal(parts[g][p], whole[g][p])
+        np.testing.assert_array_equal(parts[6], whole[6])
+    if torch.cuda.device_count() >= 2:  # a tensor living on the second device is decoded there
+        r1 = op.ctc_ext_beam_search_decoder_raw(torch.from_numpy(x).to("cuda:1"), torch.from_numpy(sl).to("cuda:1"),
+                                                beam_width=6, top_paths=2, merge_repeated=True, blank_index=9)
+        assert r1[6].device == torch.device("cuda", 1)
+        np.testing.assert_array_equal(r1[6].cpu().numpy(), np.asarray(whole[6]))
+        np.testing.assert_array_equal(r1[4][0].cpu().numpy(), np.asarray(whole[4][0]))
 
 
 # ------------------------------------------------------------------------------------------------
