@@ -746,3 +746,29 @@ def test_streaming_steps_replayed_from_a_cuda_graph(op):
             for p in range(P):
                 np.testing.assert_array_equal(raw[gi][p].cpu().numpy(), one[gi][p])
         np.testing.assert_array_equal(raw[6].cpu().numpy().view(np.uint32), np.asarray(one[6]).view(np.uint32))
+
+
+def test_side_stream_and_non_contiguous_inputs(op):
+    """The op runs on the caller's current stream and accepts strided views (host and device)."""
+    import torch
+    T, B, C, W, P = 40, 6, 29, 12, 2
+    big = L.make_logits("peaky", T, 2 * B, C, 28, 29)
+    x = big[:, ::2, :]                       # non-contiguous numpy view
+    sl = L.ragged_lengths(T, B, 29)
+    want = L.pack_sparse(L.oracle_decode(np.ascontiguousarray(x), sl, W, P, True, 28, -1))
+    kw = dict(beam_width=W, top_paths=P, merge_repeated=True, blank_index=28)
+    for raw in (op.ctc_ext_beam_search_decoder_raw(x, sl, **kw),
+                op.ctc_ext_beam_search_decoder_raw(torch.from_numpy(big).cuda()[:, ::2, :], torch.from_numpy(sl).cuda(), **kw)):
+        for g in range(6):
+            for p in range(P):
+                np.testing.assert_array_equal(np.asarray(raw[g][p].cpu() if hasattr(raw[g][p], "cpu") else raw[g][p]), want[g][p])
+    side = torch.cuda.Stream()
+    xd, sd = torch.from_numpy(np.ascontiguousarray(x)).cuda(), torch.from_numpy(sl).cuda()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        xs = xd * 1.0                        # produced on the side stream: the decode must be ordered after it
+        raw = op.ctc_ext_beam_search_decoder_raw(xs, sd, **kw)
+        lp = raw[6].clone()
+    side.synchronize()
+    np.testing.assert_array_equal(lp.cpu().numpy().view(np.uint32), want[6].view(np.uint32))
+    np.testing.assert_array_equal(raw[4][0].cpu().numpy(), want[4][0])
