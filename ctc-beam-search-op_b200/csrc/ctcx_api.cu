@@ -217,22 +217,22 @@ cudaError_t LaunchLogNorm(const double* logits_dev, double* off_dev, long long r
   return cudaGetLastError();
 }
 
-// kernel 1b (wide vocabularies): the best classes of every row ordered by log-prob
+// kernel 1 for wide vocabularies: fused normaliser + the best classes of every row ordered by log-prob
 template <int NI>
-cudaError_t LaunchTopClassesNI(const float* logits_dev, const float* off_dev, long long rows, int C, int blank,
-                               int Ke, int Ks, float* srt_pl, unsigned short* srt_cls, cudaStream_t stream) {
-  auto kern = ctcx::TopClassesKernel<NI>;
-  const size_t smem = (size_t)8 * Ke * 8;  // one Ke-entry buffer per warp
+cudaError_t LaunchNormTopClassesNI(const float* logits_dev, float* off_dev, long long rows, int C, int blank,
+                                   int Ke, int Ks, float* srt_pl, unsigned short* srt_cls, cudaStream_t stream) {
+  auto kern = ctcx::NormTopClassesKernel<NI>;
+  const size_t smem = (size_t)8 * NI * 32 * sizeof(float) + (size_t)8 * Ke * 8;  // exp terms + selection buffer per warp
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   long long blocks = std::min<long long>((rows + 7) / 8, (long long)DeviceSmCount() * 16);
   kern<<<(unsigned)blocks, 256, smem, stream>>>(logits_dev, off_dev, rows, C, blank, Ke, Ks, srt_pl, srt_cls);
   return cudaGetLastError();
 }
-cudaError_t LaunchTopClasses(const float* logits_dev, const float* off_dev, long long rows, int C, int blank,
-                             int W, float* srt_pl, unsigned short* srt_cls, cudaStream_t stream) {
+cudaError_t LaunchNormTopClasses(const float* logits_dev, float* off_dev, long long rows, int C, int blank,
+                                 int W, float* srt_pl, unsigned short* srt_cls, cudaStream_t stream) {
   const int Ke = WideKe(W, C), Ks = WideKs(W, C), ni = (C + 31) / 32;
-#define CTCX_TOPC(N) LaunchTopClassesNI<N>(logits_dev, off_dev, rows, C, blank, Ke, Ks, srt_pl, srt_cls, stream)
+#define CTCX_TOPC(N) LaunchNormTopClassesNI<N>(logits_dev, off_dev, rows, C, blank, Ke, Ks, srt_pl, srt_cls, stream)
   if (ni <= 2) return CTCX_TOPC(2);
   if (ni <= 4) return CTCX_TOPC(4);
   if (ni <= 8) return CTCX_TOPC(8);
@@ -454,8 +454,9 @@ int DecodeImpl(const R* logits_dev, int T, int B, int C, const int32_t* seq_len_
 
   if (B > 0) {
     ProfRecord(0, stream);
-    CTCX_CUDA(LaunchLogNorm(logits_dev, (R*)(base + ws.off), (long long)T * B, C, stream));
-    ProfRecord(1, stream);
+    bool fused_prepass = false;
+    if constexpr (kF32) fused_prepass = (ws.Cs > 0 && lm_dev == nullptr);
+    if (!fused_prepass) CTCX_CUDA(LaunchLogNorm(logits_dev, (R*)(base + ws.off), (long long)T * B, C, stream));
 
     ctcx::BeamParamsT<R> bp;
     bp.logits = logits_dev;
@@ -472,13 +473,14 @@ int DecodeImpl(const R* logits_dev, int T, int B, int C, const int32_t* seq_len_
     bp.srt_pl = nullptr; bp.srt_cls = nullptr; bp.Cs = ws.Cs; bp.Kc = 0;
     bp.lm = lm_dev;
     if constexpr (kF32) {
-      if (ws.Cs > 0 && lm_dev == nullptr) {
+      if (fused_prepass) {  // wide vocabulary: normaliser and candidate classes in one pass over the logits
         bp.srt_pl = (const float*)(base + ws.srt_pl);
         bp.srt_cls = (const unsigned short*)(base + ws.srt_cls);
-        CTCX_CUDA(LaunchTopClasses(logits_dev, bp.off, (long long)T * B, C, blank_index, W,
-                                   (float*)(base + ws.srt_pl), (unsigned short*)(base + ws.srt_cls), stream));
+        CTCX_CUDA(LaunchNormTopClasses(logits_dev, (float*)(base + ws.off), (long long)T * B, C, blank_index, W,
+                                       (float*)(base + ws.srt_pl), (unsigned short*)(base + ws.srt_cls), stream));
       }
     }
+    ProfRecord(1, stream);
     const int brc = LaunchBeamFor(bp, stream);
     if (brc != CTCX_OK) return brc;
     ProfRecord(2, stream);
@@ -858,7 +860,7 @@ int ctcx_stream_step_f32(void* workspace, int T_total, int B, int C, int W, int 
   Workspace ws;
   ws.Init(T_total, B, C, W, P);
   unsigned char* base = (unsigned char*)workspace;
-  CTCX_CUDA(LaunchLogNorm(logits_dev, (float*)(base + ws.off), (long long)chunk_time * B, C, stream));
+  if (ws.Cs == 0) CTCX_CUDA(LaunchLogNorm(logits_dev, (float*)(base + ws.off), (long long)chunk_time * B, C, stream));
   ctcx::BeamParams bp;
   bp.logits = logits_dev;
   bp.off = (const float*)(base + ws.off);
@@ -877,8 +879,8 @@ int ctcx_stream_step_f32(void* workspace, int T_total, int B, int C, int W, int 
   if (ws.Cs > 0) {
     bp.srt_pl = (const float*)(base + ws.srt_pl);
     bp.srt_cls = (const unsigned short*)(base + ws.srt_cls);
-    CTCX_CUDA(LaunchTopClasses(logits_dev, bp.off, (long long)chunk_time * B, C, blank_index, W,
-                               (float*)(base + ws.srt_pl), (unsigned short*)(base + ws.srt_cls), stream));
+    CTCX_CUDA(LaunchNormTopClasses(logits_dev, (float*)(base + ws.off), (long long)chunk_time * B, C, blank_index, W,
+                                   (float*)(base + ws.srt_pl), (unsigned short*)(base + ws.srt_cls), stream));
   }
   return LaunchBeamFor(bp, stream);
 }

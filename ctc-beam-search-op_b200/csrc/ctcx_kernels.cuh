@@ -161,35 +161,69 @@ __global__ void __launch_bounds__(kLogNormRows) LogNormRowKernel(const float* __
   }
 }
 
-// Pre-pass for wide vocabularies (32 < C <= 2048): per (t,b) row, the `Ke` best non-blank classes
-// ordered by (log-prob x_l - off descending, class ascending) -- the per-frame candidate-class
-// ordering of the north star. The children of a beam entry above ANY threshold are a prefix of this
-// order (fp addition is monotone), so the beam kernel finds them by binary search instead of scoring
-// all C classes; and no entry can place more than beam_width children in the next beam, so the first
-// Kc = 2*beam_width+2 classes (+1 sentinel, Ke = Kc+1) are all it ever needs (ctcx_beam_wide.cuh has
-// the argument and the exact handling of the one tie case that reaches past the cut).
-// One warp per row: keys in registers (NI per lane), the Ke-th largest key by a bitwise search with
-// warp-wide counts, compaction by ballots, final order by rank counting. Runs after LogNorm*Kernel.
+// Pre-pass for wide vocabularies (32 < C <= 2048): the FUSED log-softmax normaliser and per-frame
+// candidate-class top-k of the north star. One warp per (t,b) row reads the row once into registers
+// (coalesced), computes off = max + log(sum exp) exactly as LogNormKernel does, and emits the `Ke` best
+// non-blank classes ordered by (log-prob x_l - off descending, class ascending). The children of a
+// beam entry above ANY threshold are a prefix of this order (fp addition is monotone), so the beam
+// kernel finds them by binary search instead of scoring all C classes; and no entry can place more
+// than beam_width children in the next beam, so the first Kc = 2*beam_width+2 classes (+1 sentinel,
+// Ke = Kc+1) are all it ever needs (ctcx_beam_wide.cuh has the argument and the exact handling of the
+// one tie case that reaches past the cut). Selection: keys in registers (NI per lane), the Ke-th
+// largest key by a bitwise search with warp-wide counts, compaction by ballots, final order by rank
+// counting.
 template <int NI>
-__global__ void __launch_bounds__(256, 4) TopClassesKernel(const float* __restrict__ logits,
-                                                        const float* __restrict__ off, long long rows,
-                                                        int C, int blank, int Ke, int Ks,
-                                                        float* __restrict__ srt_pl,
-                                                        unsigned short* __restrict__ srt_cls) {
-  extern __shared__ __align__(16) unsigned long long tbuf[];  // [warps][Ke]
+__global__ void __launch_bounds__(256, 3) NormTopClassesKernel(const float* __restrict__ logits,
+                                                            float* __restrict__ off, long long rows, int C,
+                                                            int blank, int Ke, int Ks,
+                                                            float* __restrict__ srt_pl,
+                                                            unsigned short* __restrict__ srt_cls) {
+  // dynamic shared memory: [8 warps][NI*32] floats (the exp terms of a row), then [8 warps][Ke] u64
+  extern __shared__ __align__(16) unsigned char nsm[];
+  __shared__ unsigned long long s_tab[32];
+  LoadExpTable(s_tab, threadIdx.x, blockDim.x);
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned long long* buf = tbuf + (size_t)warp * Ke;
+  float* e = reinterpret_cast<float*>(nsm) + (size_t)warp * NI * 32;
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(nsm + (size_t)8 * NI * 32 * sizeof(float)) + (size_t)warp * Ke;
   const unsigned lt = (1u << lane) - 1u;
+  const int C4 = (C + 3) & ~3;
   const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long row = warp_global; row < rows; row += nwarps) {
     const float* x = logits + row * C;
-    const float o = off[row];
-    unsigned k[NI];  // 0 = blank / padding (every real key is > 0)
+    // the row, once, into registers (lane = class mod 32: coalesced)
+    float v[NI];
+    float mx = NegInf();
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
       const int j = i * 32 + lane;
-      k[i] = (j < C && j != blank) ? KeyOf(__fsub_rn(x[j], o)) : 0u;
+      v[i] = (j < C) ? x[j] : NegInf();
+      mx = fmaxf(mx, v[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+    // log-softmax normaliser (decoder.h:71-80): exp terms to shared memory, summed in index order
+    __syncwarp();  // the previous row is done with e and buf
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int j = i * 32 + lane;
+      if (j < C4) e[j] = (j < C) ? ExpfExact(__fsub_rn(v[i], mx), s_tab) : 0.0f;
+    }
+    __syncwarp();
+    float sum = 0.0f;
+    for (int i = 0; i < C4; i += 4) {
+      const float4 q = *reinterpret_cast<const float4*>(e + i);
+      sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, q.x), q.y), q.z), q.w);
+    }
+    const float o = __fadd_rn(mx, LogfExact(sum));
+    if (lane == 0) off[row] = o;
+    // per-frame candidate classes: keys of the log-probs, 0 = blank / padding (every real key is > 0)
+    unsigned k[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int j = i * 32 + lane;
+      k[i] = (j < C && j != blank) ? KeyOf(__fsub_rn(v[i], o)) : 0u;
     }
     // the Ke-th largest key, most significant bit first; stop early once some threshold separates
     // exactly Ke keys (the usual case long before bit 0)
@@ -213,7 +247,6 @@ __global__ void __launch_bounds__(256, 4) TopClassesKernel(const float* __restri
       for (int i = 0; i < NI; ++i) g += (k[i] > kth) ? 1 : 0;
       ties_left = Ke - __reduce_add_sync(kFull, g);
     }
-    __syncwarp();  // the previous row's rank pass is done with buf
     int base = 0;
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
@@ -229,16 +262,16 @@ __global__ void __launch_bounds__(256, 4) TopClassesKernel(const float* __restri
       base += __popc(sm);
     }
     __syncwarp();
-    for (int e = lane; e < Ks; e += 32) {
-      if (e < Ke) {
-        const unsigned long long mine = buf[e];
+    for (int q0 = lane; q0 < Ks; q0 += 32) {
+      if (q0 < Ke) {
+        const unsigned long long mine = buf[q0];
         int rank = 0;
         for (int q = 0; q < Ke; ++q) rank += (buf[q] > mine) ? 1 : 0;
         srt_pl[row * Ks + rank] = UnKey((unsigned)(mine >> 16));
         srt_cls[row * Ks + rank] = (unsigned short)(0xffff - (unsigned)(mine & 0xffffull));
       } else {
-        srt_pl[row * Ks + e] = NegInf();
-        srt_cls[row * Ks + e] = (unsigned short)0xffff;
+        srt_pl[row * Ks + q0] = NegInf();
+        srt_cls[row * Ks + q0] = (unsigned short)0xffff;
       }
     }
   }
