@@ -259,7 +259,7 @@ int LaunchBeamFor(ctcx::BeamParams& bp, cudaStream_t stream) {
   const bool want_generic = (impl != nullptr && std::strcmp(impl, "generic") == 0) || bp.lm != nullptr;
   const bool want_v2 = impl != nullptr && std::strcmp(impl, "v2") == 0 && bp.state == nullptr;
   cudaError_t e;
-  if (bp.srt_pl != nullptr && bp.lm == nullptr) {  // wide-vocabulary fast path (the caller ran TopClassesKernel)
+  if (bp.srt_pl != nullptr && bp.lm == nullptr) {  // wide-vocabulary fast path (the caller ran NormTopClassesKernel)
     bp.Kc = WideKc(W, C);
     bp.cand_cap = W * bp.Kc;
     ctcx::BeamSmemWide layw;

@@ -1,7 +1,7 @@
 // Beam kernel for WIDE vocabularies (32 < num_classes <= 2048: BASELINE's Conformer-BPE shape
 // C=1024, W=16). Derived from BeamKernelV3 (ctcx_beam_v3.cuh): same phases, same total order,
 // bit-identical results as the generic BeamKernel. What differs is how candidates are found: the
-// pre-pass (TopClassesKernel) orders every frame's best classes by log-prob; the children of a row
+// pre-pass (NormTopClassesKernel) orders every frame's best classes by log-prob; the children of a row
 // above ANY threshold are then a PREFIX of that order (fp addition is monotone), whose length an
 // exact binary search finds in ~log2(Kc) steps -- instead of scoring W*C children and issuing W*C
 // shared-memory histogram atomics per pass, as the generic kernel's streaming mode does.
