@@ -569,64 +569,54 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       __syncthreads();
       CTCX_TICK(1)  // PB
 
-      // ---- PD: boundary bin of the W-th item and group offsets (two bins per thread) ----
-      {
-        // suffix sums over bins kBinsV2-1..0: thread `tid` owns bins hi = kBinsV2-1-2*tid and lo = hi-1, so an
-        // inclusive PREFIX scan in thread order is an inclusive SUFFIX scan in bin order
-        const int bin_hi = kBinsV2 - 1 - 2 * tid;
-        unsigned h_hi = 0u, h_lo = 0u;
-        if (bin_hi >= 1) {
-          const uint2 hh = *reinterpret_cast<const uint2*>(&s_hist[bin_hi - 1]);
-          h_lo = hh.x;
-          h_hi = hh.y;
-        }
-        const unsigned h2 = h_hi + h_lo;
-        unsigned incl = h2;
+      // ---- PD: boundary bin of the W-th item and group offsets: ONE warp, 8 bins per lane ----
+      // Lane 0 owns the 8 highest bins, lane 31 the 8 lowest, so an inclusive PREFIX scan in lane order
+      // is a SUFFIX scan in bin order. No barrier inside the phase, the other warps wait at its end.
+      static_assert(kBinsV2 == 256, "8 bins per lane of one warp");
+      if (warp == 0) {
+        const int b0 = kBinsV2 - 8 - 8 * lane;  // this lane's bins are b0 .. b0+7
+        const uint4 ha = *reinterpret_cast<const uint4*>(&s_hist[b0]);
+        const uint4 hb = *reinterpret_cast<const uint4*>(&s_hist[b0 + 4]);
+        const unsigned h[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+        const unsigned loc = (h[0] + h[1]) + (h[2] + h[3]) + (h[4] + h[5]) + (h[6] + h[7]);
+        unsigned incl = loc;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const unsigned v = __shfl_up_sync(kFull, incl, o);
           if (lane >= o) incl += v;
         }
-        const unsigned nz = __ballot_sync(kFull, h2 != 0u);
-        if (lane == 31) s_wsum[warp] = (int)incl;
-        {
-          const int l0 = nz ? (__ffs(nz) - 1) : 0;  // first lane (highest bins) holding anything
-          const unsigned hh = __shfl_sync(kFull, h_hi, l0);
-          const int tb = nz ? ((kBinsV2 - 1 - 2 * (warp * 32 + l0)) - (hh ? 0 : 1)) : -1;
-          if (lane == 0) s_wsum[16 + warp] = tb;
-        }
-        __syncthreads();
-        unsigned before = 0u, total = 0u;
-        int topbin = -1;
+        const unsigned total = __shfl_sync(kFull, incl, 31);
+        const unsigned above = incl - loc;  // items in bins above this lane's
+        // items above each of the 8 bins
+        unsigned ab[8];
+        ab[7] = above;
 #pragma unroll
-        for (int w2 = 0; w2 < NWARP; ++w2) {
-          const unsigned v = (unsigned)s_wsum[w2];
-          total += v;
-          if (w2 < warp) before += v;
-          topbin = max(topbin, s_wsum[16 + w2]);
-        }
+        for (int q = 6; q >= 0; --q) ab[q] = ab[q + 1] + h[q + 1];
+        *reinterpret_cast<uint4*>(&s_offs[b0]) = make_uint4(ab[0], ab[1], ab[2], ab[3]);
+        *reinterpret_cast<uint4*>(&s_offs[b0 + 4]) = make_uint4(ab[4], ab[5], ab[6], ab[7]);
+        *reinterpret_cast<uint4*>(&s_hist[b0]) = make_uint4(0u, 0u, 0u, 0u);  // counters in PE / next attempt
+        *reinterpret_cast<uint4*>(&s_hist[b0 + 4]) = make_uint4(0u, 0u, 0u, 0u);
+        // highest non-empty bin (for the next frame's range prediction)
+        const unsigned nz = __ballot_sync(kFull, loc != 0u);
+        int tb = -1;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (h[q]) tb = b0 + q;
+        const int topbin = nz ? __shfl_sync(kFull, tb, __ffs(nz) - 1) : -1;
         // with a clamped range the cut is valid only if the W-th item lies inside the range
         const bool usable = !clamped || (int)total >= W;
-        if (bin_hi >= 1) {
-          const int K = min(W, (int)total);
-          const unsigned above_hi = before + incl - h2;  // items in bins above bin_hi
-          const unsigned above_lo = above_hi + h_hi;
-          *reinterpret_cast<uint2*>(&s_offs[bin_hi - 1]) = make_uint2(above_lo, above_hi);
-          *reinterpret_cast<uint2*>(&s_hist[bin_hi - 1]) = make_uint2(0u, 0u);  // counters in PE / next attempt
-          if (usable && (int)(above_hi + h_hi) >= K && (int)above_hi < K) {
-            sci[kV2Bstar] = bin_hi;
-            sci[kV2KRem] = K - (int)above_hi;
-            sci[kV2E] = (int)h_hi;
-            sci[kV2NNew] = K;
-            sci[kV2TopBin] = topbin;
-            sci[kV3Found] = 1;
-          } else if (usable && (int)(above_lo + h_lo) >= K && (int)above_lo < K) {
-            sci[kV2Bstar] = bin_hi - 1;
-            sci[kV2KRem] = K - (int)above_lo;
-            sci[kV2E] = (int)h_lo;
-            sci[kV2NNew] = K;
-            sci[kV2TopBin] = topbin;
-            sci[kV3Found] = 1;
+        const int K = min(W, (int)total);
+        if (usable && (int)incl >= K && (int)above < K) {  // the boundary bin is one of this lane's
+#pragma unroll
+          for (int q = 7; q >= 0; --q) {
+            if ((int)(ab[q] + h[q]) >= K && (int)ab[q] < K) {
+              sci[kV2Bstar] = b0 + q;
+              sci[kV2KRem] = K - (int)ab[q];
+              sci[kV2E] = (int)h[q];
+              sci[kV2NNew] = K;
+              sci[kV2TopBin] = topbin;
+              sci[kV3Found] = 1;
+            }
           }
         }
       }
