@@ -538,17 +538,11 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
           const int v = __shfl_up_sync(kFull, incl, o);
           if (lane >= o) incl += v;
         }
-        if (lane == 31) s_wsum[warp] = incl;
-        __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int w2 = 0; w2 < NWARP; ++w2) {
-          const int v = s_wsum[w2];
-          total += v;
-          if (w2 < warp) before += v;
-        }
-        pos0 = before + incl - cnt;
-        n_cand = total;
+        // list positions: one shared-memory atomic per warp (the order of the list does not matter)
+        int base = 0;
+        if (lane == 31 && incl) base = atomicAdd(&sci[kV2NCand], incl);
+        base = __shfl_sync(kFull, base, 31);
+        pos0 = base + incl - cnt;
       }
       CTCX_TICK(18)  // PB: scan
       // PB pass 2: list + histogram
@@ -567,6 +561,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       }
       CTCX_TICK(19)  // PB: list
       __syncthreads();
+      n_cand = sci[kV2NCand];
       CTCX_TICK(1)  // PB
 
       // ---- PD: boundary bin of the W-th item and group offsets: ONE warp, 8 bins per lane ----
@@ -623,6 +618,8 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       __syncthreads();
       CTCX_TICK(3)  // PD
       if (__builtin_expect(sc[kV3Found] != 0, 1)) break;  // otherwise the prediction missed: run again over the full range
+      if (tid == 0) sci[kV2NCand] = 0;  // the list is rebuilt
+      __syncthreads();
     }
     const bool member_in = !clamped || my_key > lo_key;
     const int bstar = sc[kV2Bstar], k_rem = sc[kV2KRem], e_b = sc[kV2E], n_new = sc[kV2NNew];
