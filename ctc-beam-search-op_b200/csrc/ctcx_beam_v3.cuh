@@ -667,9 +667,14 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     CTCX_TICK(4)  // PE
 
     // ---- PF: cut the boundary bin exactly ----
+    // Usual case (at most 32 items in the boundary bin): the LAST warp ranks them with shuffles and
+    // writes the k_rem best straight into their final positions, while the other warps already rank
+    // the groups above the boundary (PG) -- no barrier between the two phases.
+    const bool pf_fast = !bnd_all && e_b <= kBndFast;
+    const int bnd_start = pf_fast ? (int)s_offs[bstar] : 0x7fffffff;  // slots from here on are set by PF
     if (!bnd_all) {
       if (__builtin_expect(e_b <= kBndFast, 1)) {
-        if (warp == 0) {
+        if (warp == NWARP - 1) {
           const unsigned long long mine = (lane < e_b) ? s_bnd[lane] : 0ull;
           const unsigned mlo = (unsigned)mine, mhi = (unsigned)(mine >> 32);
           int rank = 0;
@@ -746,8 +751,8 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
               s_sorted[pos] = ((unsigned long long)key << 32) | (unsigned long long)(~okey);
           }
         });
+        __syncthreads();
       }
-      __syncthreads();
     }
 
     CTCX_TICK(5)  // PF
@@ -765,7 +770,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       for (int i = tid; i < TS; i += NT) s_htab[i] = 0xffffffffu;
       unsigned long long comp = 0ull;
       int r = -1;
-      if (tid < n_new) {
+      if (tid < n_new && tid < bnd_start) {
         comp = s_sorted[tid];
         const int bucket = bucket_of((unsigned)(comp >> 32));
         const int g0 = (int)s_offs[bucket], g1 = g0 + (int)s_hist[bucket];
@@ -775,6 +780,10 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       }
       CTCX_TICK(13)  // PG: rank in group
       __syncthreads();  // table cleared, ranks known; s_hist / scalars no longer needed this frame
+      if (tid < n_new && tid >= bnd_start) {  // boundary items: PF wrote them in final order
+        comp = s_sorted[tid];
+        r = tid;
+      }
       CTCX_TICK(14)  // PG: barrier
       for (int i = tid; i < kBinsV2; i += NT) s_hist[i] = 0u;
       if (tid == 0) {
