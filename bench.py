@@ -231,7 +231,8 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
     # ---- warm-up ----
     for i in range(max(args.warmup, 3)):
         step_device(i)
-    step_e2e(0)
+    for i in range(max(args.warmup, 3)):  # the host path has its own cold costs (pinned result buffers)
+        step_e2e(i)
     barrier()
 
     # ---- device-resident timing (CUDA events per step on the launching stream) ----
