@@ -77,7 +77,9 @@ CASES = [
     ("gauss", 30, 16, 6, 4, 4, True, 3, 1, True),
     ("gauss", 20, 16, 3, 2, 2, False, 1, 9, False),
     ("gauss", 20, 16, 5, 1, 1, True, 0, -1, False),
-    ("gauss", 25, 4, 40, 200, 2, False, 7, -1, False),   # WMAX=256 tier
+    ("gauss", 25, 4, 40, 200, 2, False, 7, -1, False),   # WMAX=256 tier (wide kernel)
+    ("gauss", 30, 3, 29, 140, 2, False, 28, -1, False),  # WMAX=256 tier of the narrow fast kernel
+    ("peaky", 40, 3, 12, 256, 3, True, 0, -1, True),     # beam_width = 256 exactly, narrow fast kernel
     ("gauss", 12, 2, 12, 300, 3, False, 0, -1, False),   # WMAX=1024 tier
 ]
 
