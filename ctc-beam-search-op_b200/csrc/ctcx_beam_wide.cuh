@@ -870,7 +870,8 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       unsigned long long* w_hash = s_hash + nxt * WMAX;
       unsigned long long* w_phash = s_phash + nxt * WMAX;
       // clear the parent look-up table (this frame's look-ups happened in PA) before re-filling it
-      for (int i = tid; i < TS; i += NT) s_htab[i] = 0xffffffffu;
+      for (int i = tid; i < TS / 4; i += NT)  // 16-byte stores
+        reinterpret_cast<uint4*>(s_htab)[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
       unsigned long long comp = 0ull;
       int r = -1;
       if (tid < n_new) {
@@ -878,6 +879,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
         const int bucket = bucket_of((unsigned)(comp >> 32));
         const int g0 = (int)s_offs[bucket], g1 = g0 + (int)s_hist[bucket];
         int rank = 0;
+#pragma unroll 1  // groups hold 1-3 items: an unrolled loop only costs instructions
         for (int j = g0; j < g1; ++j) rank += (s_sorted[j] > comp) ? 1 : 0;
         r = g0 + rank;
       }
