@@ -156,3 +156,29 @@ def test_error_classes_survive_pickling():
     for cls, code in ((m.InvalidArgumentError, 6), (m.FailedPreconditionError, 5), (m.UnsupportedError, 9)):
         e = pickle.loads(pickle.dumps(cls(code, "sequence_length(3) <= 8")))
         assert type(e) is cls and e.code == code and str(e) == "sequence_length(3) <= 8"
+
+
+def test_packed_output_buffer_layout():
+    """All 6*P sparse tensors + log_probability are views of ONE int64 buffer (one D2H copy for host
+    callers): the carve-up must be gap-free, non-overlapping and typed as ops.cc:17-23 says."""
+    import torch
+    from ctc_beam_search_op_b200 import decoder as D
+    for f64 in (False, True):
+        B, P = 5, 3
+        counts = ([7, 0, 12], [40, 40, 33])
+        n = D._pack_elems(B, P, counts, f64)
+        buf = torch.arange(n, dtype=torch.int64)
+        groups, lp = D._carve(buf, B, P, counts, f64)
+        seen = torch.zeros(n, dtype=torch.int32)
+        for g in range(6):
+            for p in range(P):
+                t = groups[g][p]
+                nd = counts[0][p] if g < 3 else counts[1][p]
+                want = {0: (nd, 2), 1: (nd,), 2: (2,)}[g % 3]
+                assert tuple(t.shape) == want and t.dtype == torch.int64 and t.is_contiguous()
+                if t.numel():
+                    seen[t.reshape(-1)] += 1  # values are the buffer offsets themselves
+        assert lp.shape == (B, P) and lp.dtype == (torch.float64 if f64 else torch.float32)
+        lp_words = B * P if f64 else (B * P + 1) // 2
+        assert int(seen.sum()) == n - lp_words and int(seen.max()) == 1
+        assert lp.data_ptr() == buf.data_ptr() + 8 * (n - lp_words)
