@@ -313,7 +313,7 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
                      "note": "algorithmic bytes = 4*C per frame (logits read once); the kernel is "
                              "bound by the T-long serial recurrence per utterance, not by HBM"},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # a reported baseline, measured at N=1 only
         cores = host_threads()
         n_utt = min(B, cores)
         dt, kind = cpu_reference_run(base, n_utt, cores)
