@@ -28,11 +28,17 @@ class CtcxHostResult(ctypes.Structure):
                 ("flags", ctypes.c_int32), ("log_probability_f64", ctypes.POINTER(ctypes.c_double))]
 
 
-# every symbol include/ctcx.h declares (tests check that the library exports all of them)
-EXPORTS = ("ctcx_strerror", "ctcx_last_cuda_error", "ctcx_get_limits", "ctcx_workspace_bytes",
-           "ctcx_decode_f32", "ctcx_decode_f64", "ctcx_decode_scorer_f32", "ctcx_decode_half", "ctcx_pack_f32", "ctcx_pack_f64", "ctcx_decode_host_f32", "ctcx_decode_host_f64", "ctcx_free_host",
-           "ctcx_workspace_views", "ctcx_stream_workspace_bytes", "ctcx_stream_reset",
-           "ctcx_stream_step_f32", "ctcx_stream_top_paths")
+# every symbol include/ctcx.h declares (tests check that the library exports exactly these)
+EXPORTS = ("ctcx_strerror", "ctcx_last_cuda_error", "ctcx_error_batch_index", "ctcx_get_limits",
+           "ctcx_workspace_bytes", "ctcx_decode_f32", "ctcx_decode_f64", "ctcx_decode_scorer_f32",
+           "ctcx_decode_half", "ctcx_decode_view", "ctcx_hostin_staging_bytes", "ctcx_decode_hostin",
+           "ctcx_pack_f32", "ctcx_pack_f64", "ctcx_decode_host_f32", "ctcx_decode_host_f64", "ctcx_free_host",
+           "ctcx_stream_workspace_bytes", "ctcx_stream_reset", "ctcx_stream_step_f32", "ctcx_stream_top_paths",
+           # measurement and test hooks
+           "ctcx_workspace_views", "ctcx_profile_enable", "ctcx_profile_get", "ctcx_debug_set_cycles_buffer",
+           "ctcx_debug_set_beam_impl", "ctcx_debug_math_f32", "ctcx_debug_math_f64")
+
+F32, F16, BF16, F64 = 0, 1, 2, 3  # CTCX_F32 ... (include/ctcx.h)
 
 _lib = None
 
@@ -46,11 +52,11 @@ def load():
     if _build.is_stale():
         try:
             _build.build()
-        except Exception as e:  # no nvcc on this box and no prebuilt library
-            if not os.path.exists(path):
-                raise RuntimeError(
-                    "ctcx: the CUDA library %s is missing and could not be built (%s). "
-                    "There is no CPU fallback." % (path, e))
+        except Exception as e:  # no nvcc on this box and no library built from these sources
+            # never load a library built from OTHER sources silently: bit-exactness is the contract
+            raise RuntimeError(
+                "ctcx: the CUDA library %s is %s and could not be (re)built (%s). "
+                "There is no CPU fallback." % (path, "stale" if os.path.exists(path) else "missing", e))
     lib = ctypes.CDLL(path)
     lib.ctcx_strerror.restype = ctypes.c_char_p
     lib.ctcx_strerror.argtypes = [ctypes.c_int]
@@ -71,6 +77,18 @@ def load():
                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      _vp, ctypes.c_size_t, _vp, ctypes.POINTER(CtcxSizes),
                                      ctypes.POINTER(ctypes.c_int32)]
+    _i = ctypes.c_int
+    lib.ctcx_error_batch_index.argtypes = []
+    lib.ctcx_decode_view.argtypes = [_vp, _i, ctypes.c_int64, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp,
+                                     ctypes.c_size_t, _vp, ctypes.POINTER(CtcxSizes),
+                                     ctypes.POINTER(ctypes.c_int32)]
+    lib.ctcx_hostin_staging_bytes.restype = ctypes.c_size_t
+    lib.ctcx_hostin_staging_bytes.argtypes = [_i] * 4
+    lib.ctcx_decode_hostin.argtypes = [_vp, _i, ctypes.c_int64, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp,
+                                       ctypes.c_size_t, _vp, ctypes.c_size_t, _vp, _vp,
+                                       ctypes.POINTER(CtcxSizes), ctypes.POINTER(ctypes.c_int32)]
+    lib.ctcx_debug_set_beam_impl.argtypes = [_i]
+    lib.ctcx_debug_set_beam_impl.restype = None
     lib.ctcx_pack_f32.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [_vp] * 6 + [_vp, _vp]
     lib.ctcx_pack_f64.argtypes = lib.ctcx_pack_f32.argtypes
     lib.ctcx_decode_host_f32.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,

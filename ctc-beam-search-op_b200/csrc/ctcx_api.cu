@@ -1,25 +1,25 @@
-// C-ABI shim (include/ctcx.h) over the kernels in ctcx_kernels.cuh: validation, workspace carve-up,
-// launches and the host-buffer convenience entry. No global state; no CPU fallback.
+// C-ABI shim (include/ctcx.h): validation, workspace carve-up, stream choreography and the host-buffer
+// entries. The kernels live in their own translation units behind ctcx_launch.h. No CPU fallback.
 //
 // Reference counterparts (tensorflow_ctc_ext_beam_search_decoder/cc/kernels/
 // ctc_ext_beam_search_decoder_kernels.cc): ValidateInputsGenerateOutputs :97-160, Compute :20-95,
 // StoreAllDecodedSequences :163-257.
+// the library is built with -fvisibility=hidden: only what include/ctcx.h declares is exported
+#pragma GCC visibility push(default)
 #include "../../include/ctcx.h"
+#pragma GCC visibility pop
 
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 
-#include "ctcx_kernels.cuh"
-#include "ctcx_beam_v2.cuh"
-#include "ctcx_beam_v3.cuh"
-#include "ctcx_beam_wide.cuh"
+#include "ctcx_launch.h"
 
 namespace {
 
@@ -35,146 +35,99 @@ bool Check(cudaError_t e, const char* what) {
     if (!Check((call), #call)) return CTCX_ERR_CUDA;    \
   } while (0)
 
+// result of a kernel launcher -> CTCX_* code
+int FromLaunch(const ctcx::LaunchStatus& st) {
+  if (st.code == ctcx::kLaunchCuda) Check(st.cuda, st.what);
+  return st.code;
+}
+#define CTCX_LAUNCH(call)                       \
+  do {                                          \
+    const int rc_ = FromLaunch(call);           \
+    if (rc_ != CTCX_OK) return rc_;             \
+  } while (0)
+
 constexpr int kMaxBeamWidth = 1024;
 constexpr int kMaxClasses = 65535;
-constexpr int kListCapMax = 4608;  // candidate-list entries kept in shared memory (8 B each)
-constexpr uint32_t kMagic = 0x43544358u;  // "CTCX"
+constexpr uint32_t kMagic = 0x43544359u;  // "CTCY": workspace layout of this build
+constexpr int kNStats = 16;
 
 size_t Align256(size_t v) { return (v + 255) / 256 * 256; }
 
-struct Tier {
-  int wmax, nt;
-};
-Tier PickTier(int W) {
-  if (W <= 32) return {32, 128};
-  if (W <= 128) return {128, 256};
-  if (W <= 256) return {256, 256};
-  return {1024, 1024};
+// test hook (ctcx_debug_set_beam_impl): 1 = route every decode to the generic beam kernel
+std::atomic<int> g_force_generic{0};
+// measurement hook (ctcx_debug_set_cycles_buffer)
+thread_local long long* g_dbg_cycles = nullptr;
+
+enum Path { kPathNarrow, kPathWide, kPathGeneric };
+Path PathOf(int W, int C, bool scorer) {
+  // a scorer table breaks the fast kernels' monotone-prefix argument: generic kernel only
+  if (scorer || g_force_generic.load(std::memory_order_relaxed)) return kPathGeneric;
+  if (ctcx::NarrowFastShape(W, C)) return kPathNarrow;
+  if (ctcx::WideFastShape(W, C)) return kPathWide;
+  return kPathGeneric;
 }
 
-// Wide-vocabulary fast path (ctcx_beam_wide.cuh): 32 < C <= 2048 and the candidate list of the worst
-// frame (beam_width rows x the Kc = min(C-1, 2*beam_width+2) best classes of the frame) fits in
-// shared memory. WideKc = sorted classes the beam kernel uses, WideKs = row stride of the sorted
-// arrays (Kc + one sentinel when classes are left out, rounded up to 8).
-int WideKc(int W, int C) { return std::min(C - 1, 2 * W + 2); }
-int WideKe(int W, int C) { return std::min(C - 1, WideKc(W, C) + 1); }
-int WideKs(int W, int C) { return (WideKe(W, C) + 7) / 8 * 8; }
-bool UseWide(int W, int C) {
-  if (C <= 32 || C > 2048 || W > 256) return false;
-  const char* impl = std::getenv("CTCX_BEAM_IMPL");
-  if (impl != nullptr && std::strcmp(impl, "generic") == 0) return false;
-  ctcx::BeamSmemWide lay;
-  lay.Init(PickTier(W).wmax, W * WideKc(W, C), C, WideKs(W, C));
-  return lay.bytes <= 200 * 1024;
-}
-
-// Everything a decode leaves behind for pack, at fixed offsets inside the caller's workspace.
+// Everything a decode leaves behind for pack, at fixed offsets inside the caller's workspace. The
+// layout is a pure function of the shape; the first group (up to `ali`) depends on (T, B, P) only, so
+// ctcx_pack_* needs neither the class count nor the beam width, and no look at the device header.
 struct Workspace {
   struct Header {
     uint32_t magic;
     int T, B, C, W, P;
     int real_bytes;  // 4: float32 decode, 8: float64 decode
   };
-  size_t header, off, bp, fin_total, fin_kind, fin_n, flags, dec_len, ali_len, dec, ali, dec_off,
-      ali_off, sizes, ptrs, stats, t_done, state, srt_pl, srt_cls, bytes;
-  int Cs;  // row stride of the sorted-class arrays (0 when the wide fast path does not apply)
-  void Init(int T, int B, int C, int W, int P) {
+  size_t header, result, ctrl, dec_len, ali_len, dec_off, ali_off, ptrs, fin_total, fin_kind, dec, ali,
+      seq, fin_n, flags, t_done, state, off, bp, srt_pl, srt_cls, scratch, bytes;
+  int Cs;         // row stride of the sorted-class arrays (0 when the wide fast path does not apply)
+  int rec_bytes;  // back-pointer record size
+  size_t InitPack(int T, int B, int P) {
     size_t o = 0;
-    const size_t b = (size_t)B, t = (size_t)T, w = (size_t)W, pp = (size_t)P;
-    (void)C;
+    const size_t b = (size_t)B, t = (size_t)T, pp = (size_t)P;
     header = o; o += Align256(sizeof(Header));
-    off = o; o += Align256(t * b * 8);                           // float or double
-    bp = o; o += Align256(b * t * w * 8);
-    fin_total = o; o += Align256(b * pp * 8);                    // float or double
-    fin_kind = o; o += Align256(b * pp * 4);
-    fin_n = o; o += Align256(b * 4);
-    flags = o; o += Align256(b * 4);
+    result = o; o += Align256(4 * pp * 8 + kNStats * 4);         // sizes [4,P] int64, then stats: ONE copy to the host
+    ctrl = o; o += 256;                                          // [0] utterance queue, [1] frames landed
     dec_len = o; o += Align256(b * pp * 4);
     ali_len = o; o += Align256(b * pp * 4);
-    dec = o; o += Align256(b * pp * t * 4);
-    ali = o; o += Align256(b * pp * t * 4);
     dec_off = o; o += Align256(pp * b * 8);
     ali_off = o; o += Align256(pp * b * 8);
-    sizes = o; o += Align256(4 * pp * 8);
     ptrs = o; o += Align256(6 * pp * 8);
-    stats = o; o += Align256(16 * 4);
+    fin_total = o; o += Align256(b * pp * 8);                    // float or double
+    fin_kind = o; o += Align256(b * pp * 4);
+    dec = o; o += Align256(b * pp * t * 4);
+    ali = o; o += Align256(b * pp * t * 4);
+    return o;
+  }
+  void Init(int T, int B, int C, int W, int P) {
+    size_t o = InitPack(T, B, P);
+    const size_t b = (size_t)B, t = (size_t)T, w = (size_t)W;
+    seq = o; o += Align256(b * 4);                               // sequence_length of host-input decodes
+    fin_n = o; o += Align256(b * 4);
+    flags = o; o += Align256(b * 4);
     t_done = o; o += Align256(b * 4);                            // streaming: frames consumed so far
     state = o; o += Align256(b * ctcx::StreamStateBytes(W));     // streaming: beam between chunks
-    Cs = UseWide(W, C) ? WideKs(W, C) : 0;                       // wide fast path: best classes per frame, sorted
+    const bool narrow = ctcx::NarrowFastShape(W, C), wide = ctcx::WideFastShape(W, C);
+    off = o; o += Align256(t * b * 8);                           // float or double (unused by the narrow kernel, which normalises itself)
+    rec_bytes = ctcx::RecBytes(W, C);
+    bp = o; o += Align256(b * t * w * (size_t)rec_bytes);
+    Cs = wide ? ctcx::WideKs(W, C) : 0;                          // wide fast path: best classes per frame, sorted
     srt_pl = o; o += Align256(t * b * (size_t)Cs * 4);
     srt_cls = o; o += Align256(t * b * (size_t)Cs * 2);
+    // shapes served by the generic kernel only: room to upcast half-precision logits (the fast kernels
+    // read them directly)
+    scratch = o; o += (narrow || wide) ? 0 : Align256(t * b * (size_t)C * 4);
     bytes = o;
   }
 };
 
-template <typename R, int WMAX, int NT>
-cudaError_t LaunchBeam(const ctcx::BeamParamsT<R>& p, size_t smem, cudaStream_t stream) {
-  auto kern = ctcx::BeamKernelT<R, WMAX, NT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  kern<<<p.B, NT, smem, stream>>>(p);
-  return cudaGetLastError();
-}
-
-template <int WMAX, int NT>
-cudaError_t LaunchBeamV2(const ctcx::BeamParams& p, size_t smem, cudaStream_t stream) {
-  auto kern = (p.dbg_cycles != nullptr) ? ctcx::BeamKernelV2<WMAX, NT, true> : ctcx::BeamKernelV2<WMAX, NT, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  kern<<<p.B, NT, smem, stream>>>(p);
-  return cudaGetLastError();
-}
-
-template <int WMAX, int NT>
-cudaError_t LaunchBeamV3(const ctcx::BeamParams& p, size_t smem, cudaStream_t stream) {
-  auto kern = (p.dbg_cycles != nullptr) ? ctcx::BeamKernelV3<WMAX, NT, true> : ctcx::BeamKernelV3<WMAX, NT, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  kern<<<p.B, NT, smem, stream>>>(p);
-  return cudaGetLastError();
-}
-
-// Exact upcast of half-precision logits to the float32 the decoder computes in.
-template <typename H>
-__global__ void UpcastKernel(const H* __restrict__ in, float* __restrict__ out, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = (float)in[i];
-}
-
-template <int WMAX, int NT>
-cudaError_t LaunchBeamWide(const ctcx::BeamParams& p, size_t smem, cudaStream_t stream) {
-  auto kern = (p.dbg_cycles != nullptr) ? ctcx::BeamKernelWide<WMAX, NT, true> : ctcx::BeamKernelWide<WMAX, NT, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  kern<<<p.B, NT, smem, stream>>>(p);
-  return cudaGetLastError();
-}
-
-// flag = 1 if any entry is positive or NaN (scorer tables hold log-probabilities)
-__global__ void PositiveKernel(const float* v, long long n, int* flag) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    if (!(v[i] <= 0.0f)) *flag = 1;
-}
-
-// Reduces the per-utterance flags to {anomaly, too_few_leaves, first bad utterance}.
-__global__ void FlagsKernel(const int* flags, const int* seq_len, int B, int T, int* out) {
-  // out[0] = OR of anomaly bits, out[1] = first b with too few leaves (or B), out[2] = first b with
-  // sequence_length out of range (or B), out[3] = first b with negative sequence_length (or B)
-  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
-    const int f = flags ? flags[b] : 0;
-    if (f & 1) atomicOr(&out[0], 1);
-    if (f & 2) atomicMin(&out[1], b);
-    if (seq_len[b] > T) atomicMin(&out[2], b);
-    if (seq_len[b] < 0) atomicMin(&out[3], b);
-    if (f & 4) atomicMin(&out[4], b);  // streaming: more frames fed than the stream was sized for
-  }
-}
+thread_local int g_err_batch = -1;
+thread_local int g_err_max_time = 0;
+thread_local char g_msg[160];
 
 // optional per-kernel timing (ctcx_profile_enable): CUDA events on the launching stream
 thread_local int g_profile = 0;
 thread_local cudaEvent_t g_ev[6];
 thread_local bool g_ev_ready = false;
-thread_local float g_ms[5] = {0, 0, 0, 0, 0};  // lognorm, beam, trace, scan+flags, total
+thread_local float g_ms[5] = {0, 0, 0, 0, 0};  // pre-pass, beam, trace, scan+flags, total
 void ProfRecord(int i, cudaStream_t s) {
   if (!g_profile) return;
   if (!g_ev_ready) {
@@ -184,182 +137,323 @@ void ProfRecord(int i, cudaStream_t s) {
   cudaEventRecord(g_ev[i], s);
 }
 
-thread_local long long* g_dbg_cycles = nullptr;
-int DeviceSmCount() {
-  int sm_count = 148, dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  return sm_count;
-}
+struct DecodeOpts {
+  int in_dtype = ctcx::kInF32;     // float32 decodes: element type of the logits
+  long long tstride = 0;           // elements between frames; 0 = batch * num_classes
+  const int* ready = nullptr;      // device word "frames landed" (narrow path only), or null
+  const void* lm = nullptr;        // scorer table (float32 decodes)
+  // host-input decodes: called after the kernels are enqueued and before the result is awaited
+  int (*feed)(void*) = nullptr;
+  void* feed_arg = nullptr;
+};
 
-// kernel 1: softmax normalisers of `rows` consecutive logit rows
-cudaError_t LaunchLogNorm(const float* logits_dev, float* off_dev, long long rows, int C, cudaStream_t stream) {
-  const int sm_count = DeviceSmCount();
-  if (C <= 64) {  // thread per row, rows staged through shared memory
-    long long blocks = (rows + ctcx::kLogNormRows - 1) / ctcx::kLogNormRows;
-    if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
-    const size_t lsm = (size_t)ctcx::kLogNormRows * (C | 1) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(ctcx::LogNormRowKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
-    if (e != cudaSuccess) return e;
-    ctcx::LogNormRowKernel<<<(unsigned)blocks, ctcx::kLogNormRows, lsm, stream>>>(logits_dev, off_dev, rows, C);
-  } else {  // warp per row
-    long long blocks = (rows + 7) / 8;
-    if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
-    ctcx::LogNormKernel<<<(unsigned)blocks, 256, 0, stream>>>(logits_dev, off_dev, rows, C);
+int ReportSizes(const long long* h_sizes, const int* h_stats, int B, int T, int P, ctcx_sizes* sizes,
+                int32_t* flags_out) {
+  if (h_stats[5] < B) {
+    std::snprintf(g_cuda_err, sizeof(g_cuda_err), "the host->device copy of the logits never delivered the frames of utterance %d",
+                  h_stats[5]);
+    return CTCX_ERR_CUDA;
   }
-  return cudaGetLastError();
+  if (h_stats[2] < B) {  // kernels.cc:134-138
+    g_err_batch = h_stats[2];
+    g_err_max_time = T;
+    return CTCX_ERR_SEQ_LEN_RANGE;
+  }
+  if (h_stats[3] < B) return CTCX_ERR_BAD_ARGUMENT;  // negative sequence_length
+  if (h_stats[4] < B) {  // streaming: an utterance was fed more frames than the stream holds
+    g_err_batch = h_stats[4];
+    g_err_max_time = T;
+    return CTCX_ERR_SEQ_LEN_RANGE;
+  }
+  if (h_stats[1] < B) return CTCX_ERR_TOO_FEW_LEAVES;
+  for (int p = 0; p < P; ++p) {
+    if (sizes->n_decoded) sizes->n_decoded[p] = h_sizes[0 * (size_t)P + p];
+    if (sizes->max_decoded) sizes->max_decoded[p] = h_sizes[1 * (size_t)P + p];
+    if (sizes->n_alignment) sizes->n_alignment[p] = h_sizes[2 * (size_t)P + p];
+    if (sizes->max_alignment) sizes->max_alignment[p] = h_sizes[3 * (size_t)P + p];
+  }
+  if (flags_out) *flags_out = h_stats[0];
+  return CTCX_OK;
 }
 
-cudaError_t LaunchLogNorm(const double* logits_dev, double* off_dev, long long rows, int C, cudaStream_t stream) {
-  long long blocks = (rows + 7) / 8;
-  if (blocks > (long long)DeviceSmCount() * 16) blocks = (long long)DeviceSmCount() * 16;
-  ctcx::LogNormKernelF64<<<(unsigned)blocks, 256, 0, stream>>>(logits_dev, off_dev, rows, C);
-  return cudaGetLastError();
-}
+// header + zeroed sizes + initial stats + control words, staged in one host block -> one H2D copy
+struct InitBlock {
+  std::vector<unsigned char> bytes;
+  InitBlock(const Workspace& ws, const Workspace::Header& hdr, int B, int P) : bytes(ws.dec_len, 0) {
+    std::memcpy(bytes.data() + ws.header, &hdr, sizeof(hdr));
+    int* stats = reinterpret_cast<int*>(bytes.data() + ws.result + 4 * (size_t)P * 8);
+    stats[0] = 0;
+    for (int k = 1; k < 6; ++k) stats[k] = B;
+  }
+};
 
-// kernel 1 for wide vocabularies: fused normaliser + the best classes of every row ordered by log-prob
-template <int NI>
-cudaError_t LaunchNormTopClassesNI(const float* logits_dev, float* off_dev, long long rows, int C, int blank,
-                                   int Ke, int Ks, float* srt_pl, unsigned short* srt_cls, cudaStream_t stream) {
-  auto kern = ctcx::NormTopClassesKernel<NI>;
-  const size_t smem = (size_t)8 * NI * 32 * sizeof(float) + (size_t)8 * Ke * 8;  // exp terms + selection buffer per warp
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  long long blocks = std::min<long long>((rows + 7) / 8, (long long)DeviceSmCount() * 16);
-  kern<<<(unsigned)blocks, 256, smem, stream>>>(logits_dev, off_dev, rows, C, blank, Ke, Ks, srt_pl, srt_cls);
-  return cudaGetLastError();
-}
-cudaError_t LaunchNormTopClasses(const float* logits_dev, float* off_dev, long long rows, int C, int blank,
-                                 int W, float* srt_pl, unsigned short* srt_cls, cudaStream_t stream) {
-  const int Ke = WideKe(W, C), Ks = WideKs(W, C), ni = (C + 31) / 32;
-#define CTCX_TOPC(N) LaunchNormTopClassesNI<N>(logits_dev, off_dev, rows, C, blank, Ke, Ks, srt_pl, srt_cls, stream)
-  if (ni <= 2) return CTCX_TOPC(2);
-  if (ni <= 4) return CTCX_TOPC(4);
-  if (ni <= 8) return CTCX_TOPC(8);
-  if (ni <= 16) return CTCX_TOPC(16);
-  if (ni <= 32) return CTCX_TOPC(32);
-  return CTCX_TOPC(64);
-#undef CTCX_TOPC
-}
+template <typename R>
+int DecodeImpl(const void* logits_dev, int T, int B, int C, const int32_t* seq_len_dev, int W,
+               int P, int merge_repeated, int blank_index, int blank_label, void* workspace,
+               size_t workspace_bytes, void* stream_v, ctcx_sizes* sizes, int32_t* flags_out,
+               const DecodeOpts& opt) {
+  constexpr bool kF32 = (sizeof(R) == 4);
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  // --- validation, in the reference's order (kernels.cc:111-138), then TopPaths' (decoder.h:237) ---
+  if (T == 0) return CTCX_ERR_MAX_TIME_ZERO;
+  if (T < 0 || B < 0 || C <= 0 || W < 1 || P < 1 || blank_index < 0 || blank_index >= C)
+    return CTCX_ERR_BAD_ARGUMENT;
+  if (W > kMaxBeamWidth || C > kMaxClasses) return CTCX_ERR_UNSUPPORTED;
+  if (sizes == nullptr) return CTCX_ERR_BAD_ARGUMENT;
+  const long long tstride = opt.tstride ? opt.tstride : (long long)B * C;
+  if (tstride < (long long)B * C) return CTCX_ERR_BAD_ARGUMENT;
+  Workspace ws;
+  ws.Init(T, B, C, W, P);
+  if (workspace == nullptr || workspace_bytes < ws.bytes || ((uintptr_t)workspace & 255u))
+    return CTCX_ERR_WORKSPACE;
+  unsigned char* base = (unsigned char*)workspace;
+  long long* d_sizes = (long long*)(base + ws.result);
+  int* d_stats = (int*)(base + ws.result + 4 * (size_t)P * 8);
+  int* d_ctrl = (int*)(base + ws.ctrl);
 
-// kernel 2: picks the beam kernel for the shape (fast path for narrow vocabularies, generic
-// otherwise; CTCX_BEAM_IMPL=generic | v2 forces the generic / the previous fast kernel for A/B
-// tests). Returns CTCX_OK, CTCX_ERR_UNSUPPORTED or CTCX_ERR_CUDA.
-int LaunchBeamFor(ctcx::BeamParams& bp, cudaStream_t stream) {
-  const int W = bp.W, C = bp.C;
-  bp.kid_words = (C + 31) / 32;
-  const long long full_list = (long long)W * C;
-  bp.cand_cap = (full_list <= kListCapMax) ? (int)full_list : 0;
-  bp.dbg_totals = nullptr;
-  bp.dbg_n = nullptr;
-  bp.dbg_cycles = g_dbg_cycles;  // test/measurement hook (ctcx_debug_set_cycles_buffer)
-  const Tier tier = PickTier(W);
-  const char* impl = std::getenv("CTCX_BEAM_IMPL");
-  // a scorer table breaks the fast kernels' monotone-prefix argument: generic kernel only
-  const bool want_generic = (impl != nullptr && std::strcmp(impl, "generic") == 0) || bp.lm != nullptr;
-  const bool want_v2 = impl != nullptr && std::strcmp(impl, "v2") == 0 && bp.state == nullptr;
-  cudaError_t e;
-  if (bp.srt_pl != nullptr && bp.lm == nullptr) {  // wide-vocabulary fast path (the caller ran NormTopClassesKernel)
-    bp.Kc = WideKc(W, C);
-    bp.cand_cap = W * bp.Kc;
-    ctcx::BeamSmemWide layw;
-    layw.Init(tier.wmax, bp.cand_cap, C, bp.Cs);
-    switch (tier.wmax) {
-      case 32: e = LaunchBeamWide<32, 256>(bp, layw.bytes, stream); break;
-      case 128: e = LaunchBeamWide<128, 256>(bp, layw.bytes, stream); break;
-      default: e = LaunchBeamWide<256, 256>(bp, layw.bytes, stream); break;
+  // sequence_length lives on the device: its range check (kernels.cc:134-138) is folded into the
+  // flags reduction at the end -- every kernel clamps the lengths it walks -- so that a decode has
+  // ONE host round trip. Only when top_paths > beam_width (an error either way) is it evaluated
+  // first, because the reference reports a bad length before TopPaths' own error (decoder.h:237).
+  Workspace::Header hdr = {kMagic, T, B, C, W, P, (int)sizeof(R)};
+  {
+    // the control words are not part of this copy when a host->device feed owns them (opt.ready)
+    InitBlock init(ws, hdr, B, P);
+    const size_t n = (opt.ready != nullptr) ? ws.ctrl : ws.dec_len;
+    CTCX_CUDA(cudaMemcpyAsync(base, init.bytes.data(), n, cudaMemcpyHostToDevice, stream));
+    if (opt.ready != nullptr) CTCX_CUDA(cudaMemsetAsync(d_ctrl, 0, 4, stream));  // the queue word only
+  }
+  if (B > 0 && P > W) {
+    CTCX_LAUNCH(ctcx::LaunchFlagsOnly(seq_len_dev, B, T, d_stats, stream));
+    int h[kNStats];
+    CTCX_CUDA(cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    CTCX_CUDA(cudaStreamSynchronize(stream));
+    if (h[2] < B) {
+      g_err_batch = h[2];
+      g_err_max_time = T;
+      return CTCX_ERR_SEQ_LEN_RANGE;
     }
-  } else if (!want_generic && C <= 32 && bp.cand_cap > 0 && tier.wmax <= 256) {
-    if (want_v2) {
-      ctcx::BeamSmemV2 lay2;
-      lay2.Init(tier.wmax, bp.cand_cap);
-      if (lay2.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
-      switch (tier.wmax) {
-        case 32: e = LaunchBeamV2<32, 256>(bp, lay2.bytes, stream); break;
-        case 128: e = LaunchBeamV2<128, 256>(bp, lay2.bytes, stream); break;
-        default: e = LaunchBeamV2<256, 256>(bp, lay2.bytes, stream); break;
+    if (h[3] < B) return CTCX_ERR_BAD_ARGUMENT;
+    // TopPaths is reached for utterance 0 only after its frames; for B == 0 it is never reached
+    return CTCX_ERR_TOO_MANY_PATHS;
+  }
+
+  if (B > 0) {
+    ProfRecord(0, stream);
+    ctcx::BeamParamsT<R> bp;
+    std::memset(&bp, 0, sizeof(bp));
+    bp.logits = (const R*)logits_dev;
+    bp.off = (const R*)(base + ws.off);
+    bp.seq_len = seq_len_dev;
+    bp.T = T; bp.B = B; bp.C = C; bp.W = W; bp.P = P;
+    bp.blank_index = blank_index;
+    if (ws.rec_bytes == 4) bp.bp32 = (unsigned*)(base + ws.bp); else bp.bp = (uint2*)(base + ws.bp);
+    bp.fin_total = (R*)(base + ws.fin_total);
+    bp.fin_kind = (int*)(base + ws.fin_kind);
+    bp.fin_n = (int*)(base + ws.fin_n);
+    bp.flags = (int*)(base + ws.flags);
+    bp.Tcap = T;  // one-shot decode: t_done / state stay null
+    bp.lm = (const R*)opt.lm;
+    bp.tstride = tstride;
+    bp.queue = d_ctrl;
+    bp.dbg_cycles = g_dbg_cycles;
+    if constexpr (kF32) {
+      const Path path = PathOf(W, C, opt.lm != nullptr);
+      int in_dtype = opt.in_dtype;
+      if (path == kPathGeneric && in_dtype != ctcx::kInF32) {
+        // half-precision logits on the generic path: exact upcast into the workspace scratch
+        if (ctcx::NarrowFastShape(W, C) || ctcx::WideFastShape(W, C)) return CTCX_ERR_UNSUPPORTED;  // (forced generic: no scratch)
+        CTCX_LAUNCH(ctcx::LaunchUpcast(logits_dev, in_dtype, (float*)(base + ws.scratch), T, B, C, tstride, stream));
+        bp.logits = (const float*)(base + ws.scratch);
+        bp.tstride = (long long)B * C;
+        in_dtype = ctcx::kInF32;
+      }
+      if (path == kPathNarrow) {
+        bp.ready = opt.ready;
+        ProfRecord(1, stream);
+        CTCX_LAUNCH(ctcx::LaunchBeamNarrow(bp, in_dtype, stream));
+      } else if (path == kPathWide) {
+        // wide vocabulary: normaliser and candidate classes in one pass over the logits
+        bp.srt_pl = (const float*)(base + ws.srt_pl);
+        bp.srt_cls = (const unsigned short*)(base + ws.srt_cls);
+        CTCX_LAUNCH(ctcx::LaunchNormTopClasses(logits_dev, in_dtype, (float*)(base + ws.off), (long long)T * B, C,
+                                               blank_index, W, (float*)(base + ws.srt_pl),
+                                               (unsigned short*)(base + ws.srt_cls), B, tstride, stream));
+        ProfRecord(1, stream);
+        CTCX_LAUNCH(ctcx::LaunchBeamWide(bp, in_dtype, stream));
+      } else {
+        CTCX_LAUNCH(ctcx::LaunchLogNorm(bp.logits, (float*)(base + ws.off), (long long)T * B, C, B, bp.tstride, stream));
+        ProfRecord(1, stream);
+        CTCX_LAUNCH(ctcx::LaunchBeamGeneric(bp, stream));
       }
     } else {
-      ctcx::BeamSmemV3 lay3;
-      lay3.Init(tier.wmax, bp.cand_cap);
-      if (lay3.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
-      switch (tier.wmax) {
-        case 32: e = LaunchBeamV3<32, 256>(bp, lay3.bytes, stream); break;
-        case 128: e = LaunchBeamV3<128, 256>(bp, lay3.bytes, stream); break;
-        default: e = LaunchBeamV3<256, 256>(bp, lay3.bytes, stream); break;
-      }
+      CTCX_LAUNCH(ctcx::LaunchLogNorm((const double*)logits_dev, (double*)(base + ws.off), (long long)T * B, C, B,
+                                      tstride, stream));
+      ProfRecord(1, stream);
+      CTCX_LAUNCH(ctcx::LaunchBeamGeneric(bp, stream));
     }
-  } else {
-    ctcx::BeamSmem lay;
-    lay.Init(tier.wmax, tier.nt, C, bp.kid_words, bp.cand_cap, 4, W);
-    if (lay.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;
-    switch (tier.wmax) {
-      case 32: e = LaunchBeam<float, 32, 128>(bp, lay.bytes, stream); break;
-      case 128: e = LaunchBeam<float, 128, 256>(bp, lay.bytes, stream); break;
-      case 256: e = LaunchBeam<float, 256, 256>(bp, lay.bytes, stream); break;
-      default: e = LaunchBeam<float, 1024, 1024>(bp, lay.bytes, stream); break;
+    ProfRecord(2, stream);
+
+    ctcx::TraceParams tp;
+    tp.bp = base + ws.bp; tp.seq_len = seq_len_dev; tp.fin_kind = bp.fin_kind;
+    tp.fin_n = bp.fin_n; tp.T = T; tp.B = B; tp.W = W; tp.P = P;
+    tp.merge_repeated = merge_repeated ? 1 : 0; tp.blank_label = blank_label;
+    tp.dec_len = (int*)(base + ws.dec_len); tp.dec = (int*)(base + ws.dec);
+    tp.ali_len = (int*)(base + ws.ali_len); tp.ali = (int*)(base + ws.ali);
+    ctcx::ScanParams sp;
+    sp.dec_len = tp.dec_len; sp.ali_len = tp.ali_len; sp.B = B; sp.P = P;
+    sp.dec_off = (long long*)(base + ws.dec_off); sp.ali_off = (long long*)(base + ws.ali_off);
+    sp.sizes = d_sizes;
+    CTCX_LAUNCH(ctcx::LaunchTraceScanFlags(tp, ws.rec_bytes, sp, bp.flags, d_stats, stream,
+                                           g_profile ? g_ev[3] : nullptr));
+    ProfRecord(4, stream);
+  }
+
+  if (opt.feed != nullptr) {  // host-input decode: the slab copies go out now, behind the kernel launches
+    const int rc = opt.feed(opt.feed_arg);
+    if (rc != CTCX_OK) {
+      cudaStreamSynchronize(stream);
+      return rc;
     }
   }
-  return Check(e, "beam kernel launch") ? CTCX_OK : CTCX_ERR_CUDA;
-}
 
-// T = double: the generic kernel instantiated for double scores (64-bit keys)
-int LaunchBeamFor(ctcx::BeamParamsT<double>& bp, cudaStream_t stream) {
-  const int W = bp.W, C = bp.C;
-  bp.kid_words = (C + 31) / 32;
-  const long long full_list = (long long)W * C;
-  bp.cand_cap = (full_list <= kListCapMax) ? (int)full_list : 0;
-  bp.dbg_totals = nullptr;
-  bp.dbg_n = nullptr;
-  bp.dbg_cycles = nullptr;
-  // double state is twice as wide: the largest tier that fits in shared memory holds 512 slots
-  Tier tier = PickTier(W);
-  if (tier.wmax > 256) tier = (W <= 512) ? Tier{512, 512} : Tier{1024, 1024};
-  ctcx::BeamSmem lay;
-  lay.Init(tier.wmax, tier.nt, C, bp.kid_words, bp.cand_cap, 8, W);
-  if (lay.bytes > 220 * 1024) return CTCX_ERR_UNSUPPORTED;  // beam_width > 512, or a very wide vocabulary
-  cudaError_t e;
-  switch (tier.wmax) {
-    case 32: e = LaunchBeam<double, 32, 128>(bp, lay.bytes, stream); break;
-    case 128: e = LaunchBeam<double, 128, 256>(bp, lay.bytes, stream); break;
-    case 256: e = LaunchBeam<double, 256, 256>(bp, lay.bytes, stream); break;
-    case 512: e = LaunchBeam<double, 512, 512>(bp, lay.bytes, stream); break;
-    default: return CTCX_ERR_UNSUPPORTED;
+  // ONE copy brings the sparse sizes and the status words to the host
+  std::vector<unsigned char> h_res(4 * (size_t)P * 8 + kNStats * 4);
+  CTCX_CUDA(cudaMemcpyAsync(h_res.data(), base + ws.result, h_res.size(), cudaMemcpyDeviceToHost, stream));
+  CTCX_CUDA(cudaStreamSynchronize(stream));
+  if (g_profile && B > 0) {
+    for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&g_ms[k], g_ev[k], g_ev[k + 1]);
+    cudaEventElapsedTime(&g_ms[4], g_ev[0], g_ev[4]);
   }
-  return Check(e, "beam kernel launch") ? CTCX_OK : CTCX_ERR_CUDA;
+  return ReportSizes((const long long*)h_res.data(), (const int*)(h_res.data() + 4 * (size_t)P * 8), B, T, P, sizes,
+                     flags_out);
 }
 
-// kernels 3 + 4: trace-back of the top paths, per-path offsets and sizes
-cudaError_t LaunchTraceAndScan(const ctcx::TraceParams& tp, const ctcx::ScanParams& sp, cudaStream_t stream,
-                               bool profile) {
-  const int W = tp.W;
-  const long long walks = (long long)tp.B * tp.P;
-  if (walks >= 4096) {
-    // thousands of independent walks hide the latency of the dependent loads by themselves, and
-    // touch one record per frame instead of whole rows
-    ctcx::TraceKernel<<<(unsigned)((walks + 127) / 128), 128, 0, stream>>>(tp);
+int PackImpl(const void* workspace, int T, int B, int P, int64_t* const* decoded_indices,
+             int64_t* const* decoded_values, int64_t* const* decoded_shape,
+             int64_t* const* alignment_indices, int64_t* const* alignment_values,
+             int64_t* const* alignment_shape, void* log_probability, int real_bytes, void* stream_v) {
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  if (workspace == nullptr || T <= 0 || B < 0 || P < 1 || ((uintptr_t)workspace & 255u)) return CTCX_ERR_WORKSPACE;
+  const unsigned char* base = (const unsigned char*)workspace;
+  Workspace ws;
+  ws.InitPack(T, B, P);  // everything pack touches is laid out by (T, B, P) alone: no look at the device
+  // device copy of the 6*P output pointers
+  std::vector<long long*> table(6 * (size_t)P);
+  for (int p = 0; p < P; ++p) {
+    table[0 * (size_t)P + p] = (long long*)decoded_indices[p];
+    table[1 * (size_t)P + p] = (long long*)decoded_values[p];
+    table[2 * (size_t)P + p] = (long long*)decoded_shape[p];
+    table[3 * (size_t)P + p] = (long long*)alignment_indices[p];
+    table[4 * (size_t)P + p] = (long long*)alignment_values[p];
+    table[5 * (size_t)P + p] = (long long*)alignment_shape[p];
+  }
+  unsigned char* wbase = (unsigned char*)workspace;
+  // (a cudaMemcpyAsync from pageable memory returns only after the source has been staged)
+  CTCX_CUDA(cudaMemcpyAsync(wbase + ws.ptrs, table.data(), table.size() * sizeof(void*),
+                            cudaMemcpyHostToDevice, stream));
+  if (B > 0) {
+    ctcx::PackParams pp;
+    pp.dec_len = (const int*)(base + ws.dec_len); pp.dec = (const int*)(base + ws.dec);
+    pp.ali_len = (const int*)(base + ws.ali_len); pp.ali = (const int*)(base + ws.ali);
+    pp.dec_off = (const long long*)(base + ws.dec_off); pp.ali_off = (const long long*)(base + ws.ali_off);
+    pp.sizes = (const long long*)(base + ws.result);
+    pp.fin_total = (const void*)(base + ws.fin_total);
+    pp.ptrs = (long long* const*)(base + ws.ptrs);
+    pp.log_prob = log_probability;
+    pp.real_bytes = real_bytes;
+    pp.T = T; pp.B = B; pp.P = P;
+    CTCX_LAUNCH(ctcx::LaunchPack(pp, stream));
   } else {
-    // one warp per (utterance, path); two blocks of 2^rows_log2 back-pointer rows per warp in
-    // shared memory (about 26 KB per block)
-    constexpr int kTraceWarps = 2;
-    int rows_log2 = 5;
-    while (rows_log2 > 0 && ((size_t)W << rows_log2) * sizeof(uint2) > 26 * 1024) --rows_log2;
-    const size_t tsm = (size_t)kTraceWarps * 2 * ((size_t)W << rows_log2) * sizeof(uint2);
-    auto tk = ctcx::TraceWarpKernel<kTraceWarps>;
-    cudaError_t e = cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
-    if (e != cudaSuccess) return e;
-    tk<<<(unsigned)((walks + kTraceWarps - 1) / kTraceWarps), kTraceWarps * 32, tsm, stream>>>(tp, rows_log2);
+    // empty batch: shapes [0, 0]
+    const long long zeros[2] = {0, 0};
+    for (int p = 0; p < P; ++p) {
+      CTCX_CUDA(cudaMemcpyAsync(decoded_shape[p], zeros, 16, cudaMemcpyHostToDevice, stream));
+      CTCX_CUDA(cudaMemcpyAsync(alignment_shape[p], zeros, 16, cudaMemcpyHostToDevice, stream));
+    }
   }
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  if (profile) ProfRecord(3, stream);
-  ctcx::ScanKernel<<<tp.P, 1024, 0, stream>>>(sp);
-  return cudaGetLastError();
+  return CTCX_OK;
 }
 
-thread_local int g_err_batch = -1;
-thread_local int g_err_max_time = 0;
-thread_local char g_msg[160];
+// Stream-ordered 32-bit store (the driver's cuStreamWriteValue32, resolved at run time so that the
+// library does not link against libcuda): how the copy stream publishes "frames landed". Unlike a
+// 4-byte cudaMemcpyAsync from pageable memory it never synchronises with anything.
+typedef int (*StreamWriteValue32Fn)(cudaStream_t, unsigned long long, unsigned, unsigned);
+StreamWriteValue32Fn StreamWriteValue32() {
+  static StreamWriteValue32Fn fn = []() -> StreamWriteValue32Fn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (StreamWriteValue32Fn)p;
+  }();
+  return fn;
+}
+
+// true if `p` is page-locked host memory (cudaHostAlloc / cudaHostRegister): only then is a
+// cudaMemcpyAsync truly asynchronous
+bool IsPinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// ---- host -> device feed of the logits in time slabs (ctcx_decode_hostin_*) ----
+struct Feed {
+  const unsigned char* src;   // host logits
+  unsigned char* dst;         // device staging [T, B, C]
+  size_t row_bytes;           // B * C * element size
+  size_t src_pitch;           // host bytes between frames
+  int T;
+  int* d_ready;               // device word: frames landed
+  bool flags;                 // publish progress per slab (the narrow kernel consumes it)
+  cudaStream_t copy_stream;
+};
+int RunFeed(void* arg) {
+  Feed& f = *(Feed*)arg;
+  // Slabs grow geometrically: the first frames land after a few microseconds so the beam kernel can
+  // start, the bulk moves in large copies.
+  int t0 = 0, n = f.flags ? 4 : f.T;
+  while (t0 < f.T) {
+    const int t1 = std::min(f.T, t0 + n);
+    cudaError_t e;
+    if (f.src_pitch == f.row_bytes)
+      e = cudaMemcpyAsync(f.dst + (size_t)t0 * f.row_bytes, f.src + (size_t)t0 * f.src_pitch,
+                          (size_t)(t1 - t0) * f.row_bytes, cudaMemcpyHostToDevice, f.copy_stream);
+    else
+      e = cudaMemcpy2DAsync(f.dst + (size_t)t0 * f.row_bytes, f.row_bytes, f.src + (size_t)t0 * f.src_pitch,
+                            f.src_pitch, f.row_bytes, (size_t)(t1 - t0), cudaMemcpyHostToDevice, f.copy_stream);
+    bool ok = Check(e, "host->device copy of the logits");
+    if (ok && f.flags && StreamWriteValue32()(f.copy_stream, (unsigned long long)(uintptr_t)f.d_ready, (unsigned)t1, 0) != 0) {
+      std::snprintf(g_cuda_err, sizeof(g_cuda_err), "cuStreamWriteValue32 failed");
+      ok = false;
+    }
+    if (!ok) {
+      // release the kernel: it must not wait for frames that will never come
+      if (f.flags) StreamWriteValue32()(f.copy_stream, (unsigned long long)(uintptr_t)f.d_ready, (unsigned)INT_MAX, 0);
+      return CTCX_ERR_CUDA;
+    }
+    t0 = t1;
+    n = std::min(128, n * 5 / 2);
+  }
+  return CTCX_OK;
+}
+
+size_t ElemBytes(int dtype) {
+  switch (dtype) {
+    case CTCX_F32: return 4;
+    case CTCX_F16: case CTCX_BF16: return 2;
+    case CTCX_F64: return 8;
+    default: return 0;
+  }
+}
+int InDtypeOf(int dtype) {
+  return dtype == CTCX_F16 ? ctcx::kInF16 : dtype == CTCX_BF16 ? ctcx::kInBF16 : ctcx::kInF32;
+}
 
 }  // namespace
 
@@ -377,15 +471,17 @@ const char* ctcx_strerror(int code) {
       return g_msg;
     case CTCX_ERR_TOO_MANY_PATHS: return "requested more paths than the beam width.";
     case CTCX_ERR_TOO_FEW_LEAVES: return "Less leaves in the beam search than requested.";
-    case CTCX_ERR_BAD_ARGUMENT: return "bad argument (blank_index outside [0, num_classes), negative sequence_length, or beam_width/top_paths < 1)";
+    case CTCX_ERR_BAD_ARGUMENT: return "bad argument (blank_index outside [0, num_classes), negative sequence_length, beam_width/top_paths < 1, or a time stride shorter than a frame)";
     case CTCX_ERR_UNSUPPORTED: return "shape not supported by this build (see ctcx_get_limits)";
-    case CTCX_ERR_WORKSPACE: return "workspace missing, misaligned, too small or not produced by ctcx_decode_f32";
+    case CTCX_ERR_WORKSPACE: return "workspace missing, misaligned or too small";
     case CTCX_ERR_CUDA: return g_cuda_err;
     default: return "unknown error";
   }
 }
 
 const char* ctcx_last_cuda_error(void) { return g_cuda_err; }
+
+int ctcx_error_batch_index(void) { return g_err_batch; }
 
 int ctcx_get_limits(ctcx_limits* out) {
   if (out) {
@@ -402,196 +498,28 @@ size_t ctcx_workspace_bytes(int T, int B, int C, int W, int P) {
   ws.Init(T, B, C, W, P);
   return ws.bytes;
 }
-}  // extern "C"
-
-namespace {
-template <typename R>
-int DecodeImpl(const R* logits_dev, int T, int B, int C, const int32_t* seq_len_dev, int W,
-               int P, int merge_repeated, int blank_index, int blank_label, void* workspace,
-               size_t workspace_bytes, void* stream_v, ctcx_sizes* sizes, int32_t* flags_out,
-               const R* lm_dev = nullptr) {
-  constexpr bool kF32 = (sizeof(R) == 4);
-  cudaStream_t stream = (cudaStream_t)stream_v;
-  // --- validation, in the reference's order (kernels.cc:111-138), then TopPaths' (decoder.h:237) ---
-  if (T == 0) return CTCX_ERR_MAX_TIME_ZERO;
-  if (T < 0 || B < 0 || C <= 0 || W < 1 || P < 1 || blank_index < 0 || blank_index >= C)
-    return CTCX_ERR_BAD_ARGUMENT;
-  if (W > kMaxBeamWidth || C > kMaxClasses) return CTCX_ERR_UNSUPPORTED;
-  if (sizes == nullptr) return CTCX_ERR_BAD_ARGUMENT;
-  Workspace ws;
-  ws.Init(T, B, C, W, P);
-  if (workspace == nullptr || workspace_bytes < ws.bytes || ((uintptr_t)workspace & 255u))
-    return CTCX_ERR_WORKSPACE;
-  unsigned char* base = (unsigned char*)workspace;
-  int* d_stats = (int*)(base + ws.stats);
-
-  // sequence_length lives on the device: its range check (kernels.cc:134-138) is folded into the
-  // flags reduction at the end -- every kernel clamps the lengths it walks -- so that a decode has
-  // ONE host round trip. Only when top_paths > beam_width (an error either way) is it evaluated
-  // first, because the reference reports a bad length before TopPaths' own error (decoder.h:237).
-  {
-    const int init[5] = {0, B, B, B, B};
-    CTCX_CUDA(cudaMemcpyAsync(d_stats, init, sizeof(init), cudaMemcpyHostToDevice, stream));
-  }
-  if (B > 0 && P > W) {
-    FlagsKernel<<<(B + 255) / 256, 256, 0, stream>>>(nullptr, seq_len_dev, B, T, d_stats);
-    CTCX_CUDA(cudaGetLastError());
-    int h[4];
-    CTCX_CUDA(cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, stream));
-    CTCX_CUDA(cudaStreamSynchronize(stream));
-    if (h[2] < B) {
-      g_err_batch = h[2];
-      g_err_max_time = T;
-      return CTCX_ERR_SEQ_LEN_RANGE;
-    }
-    if (h[3] < B) return CTCX_ERR_BAD_ARGUMENT;
-    // TopPaths is reached for utterance 0 only after its frames; for B == 0 it is never reached
-    return CTCX_ERR_TOO_MANY_PATHS;
-  }
-
-  Workspace::Header hdr = {kMagic, T, B, C, W, P, (int)sizeof(R)};
-  CTCX_CUDA(cudaMemcpyAsync(base + ws.header, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, stream));
-
-  if (B > 0) {
-    ProfRecord(0, stream);
-    bool fused_prepass = false;
-    if constexpr (kF32) fused_prepass = (ws.Cs > 0 && lm_dev == nullptr);
-    if (!fused_prepass) CTCX_CUDA(LaunchLogNorm(logits_dev, (R*)(base + ws.off), (long long)T * B, C, stream));
-
-    ctcx::BeamParamsT<R> bp;
-    bp.logits = logits_dev;
-    bp.off = (const R*)(base + ws.off);
-    bp.seq_len = seq_len_dev;
-    bp.T = T; bp.B = B; bp.C = C; bp.W = W; bp.P = P;
-    bp.blank_index = blank_index;
-    bp.bp = (uint2*)(base + ws.bp);
-    bp.fin_total = (R*)(base + ws.fin_total);
-    bp.fin_kind = (int*)(base + ws.fin_kind);
-    bp.fin_n = (int*)(base + ws.fin_n);
-    bp.flags = (int*)(base + ws.flags);
-    bp.Tcap = T; bp.t_done = nullptr; bp.state = nullptr;  // one-shot decode
-    bp.srt_pl = nullptr; bp.srt_cls = nullptr; bp.Cs = ws.Cs; bp.Kc = 0;
-    bp.lm = lm_dev;
-    if constexpr (kF32) {
-      if (fused_prepass) {  // wide vocabulary: normaliser and candidate classes in one pass over the logits
-        bp.srt_pl = (const float*)(base + ws.srt_pl);
-        bp.srt_cls = (const unsigned short*)(base + ws.srt_cls);
-        CTCX_CUDA(LaunchNormTopClasses(logits_dev, (float*)(base + ws.off), (long long)T * B, C, blank_index, W,
-                                       (float*)(base + ws.srt_pl), (unsigned short*)(base + ws.srt_cls), stream));
-      }
-    }
-    ProfRecord(1, stream);
-    const int brc = LaunchBeamFor(bp, stream);
-    if (brc != CTCX_OK) return brc;
-    ProfRecord(2, stream);
-
-    ctcx::TraceParams tp;
-    tp.bp = bp.bp; tp.seq_len = seq_len_dev; tp.fin_kind = bp.fin_kind;
-    tp.fin_n = bp.fin_n; tp.T = T; tp.B = B; tp.W = W; tp.P = P;
-    tp.merge_repeated = merge_repeated ? 1 : 0; tp.blank_label = blank_label;
-    tp.dec_len = (int*)(base + ws.dec_len); tp.dec = (int*)(base + ws.dec);
-    tp.ali_len = (int*)(base + ws.ali_len); tp.ali = (int*)(base + ws.ali);
-    ctcx::ScanParams sp;
-    sp.dec_len = tp.dec_len; sp.ali_len = tp.ali_len; sp.B = B; sp.P = P;
-    sp.dec_off = (long long*)(base + ws.dec_off); sp.ali_off = (long long*)(base + ws.ali_off);
-    sp.sizes = (long long*)(base + ws.sizes);
-    CTCX_CUDA(LaunchTraceAndScan(tp, sp, stream, true));
-
-    FlagsKernel<<<(B + 255) / 256, 256, 0, stream>>>(bp.flags, seq_len_dev, B, T, d_stats);
-    CTCX_CUDA(cudaGetLastError());
-    ProfRecord(4, stream);
-  } else {
-    CTCX_CUDA(cudaMemsetAsync(base + ws.sizes, 0, 4 * (size_t)P * 8, stream));
-  }
-
-  std::vector<long long> h_sizes(4 * (size_t)P);
-  int h_stats[4];
-  CTCX_CUDA(cudaMemcpyAsync(h_sizes.data(), base + ws.sizes, h_sizes.size() * 8, cudaMemcpyDeviceToHost, stream));
-  CTCX_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
-  CTCX_CUDA(cudaStreamSynchronize(stream));
-  if (g_profile && B > 0) {
-    for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&g_ms[k], g_ev[k], g_ev[k + 1]);
-    cudaEventElapsedTime(&g_ms[4], g_ev[0], g_ev[4]);
-  }
-  if (h_stats[2] < B) {  // kernels.cc:134-138
-    g_err_batch = h_stats[2];
-    g_err_max_time = T;
-    return CTCX_ERR_SEQ_LEN_RANGE;
-  }
-  if (h_stats[3] < B) return CTCX_ERR_BAD_ARGUMENT;  // negative sequence_length
-  if (h_stats[1] < B) return CTCX_ERR_TOO_FEW_LEAVES;
-  for (int p = 0; p < P; ++p) {
-    if (sizes->n_decoded) sizes->n_decoded[p] = h_sizes[0 * (size_t)P + p];
-    if (sizes->max_decoded) sizes->max_decoded[p] = h_sizes[1 * (size_t)P + p];
-    if (sizes->n_alignment) sizes->n_alignment[p] = h_sizes[2 * (size_t)P + p];
-    if (sizes->max_alignment) sizes->max_alignment[p] = h_sizes[3 * (size_t)P + p];
-  }
-  if (flags_out) *flags_out = h_stats[0];
-  return CTCX_OK;
-}
-
-int PackImpl(const void* workspace, int T, int B, int P, int64_t* const* decoded_indices,
-             int64_t* const* decoded_values, int64_t* const* decoded_shape,
-             int64_t* const* alignment_indices, int64_t* const* alignment_values,
-             int64_t* const* alignment_shape, void* log_probability, int real_bytes, void* stream_v) {
-  cudaStream_t stream = (cudaStream_t)stream_v;
-  if (workspace == nullptr || T <= 0 || B < 0 || P < 1) return CTCX_ERR_WORKSPACE;
-  const unsigned char* base = (const unsigned char*)workspace;
-  Workspace::Header hdr;
-  CTCX_CUDA(cudaMemcpyAsync(&hdr, base, sizeof(hdr), cudaMemcpyDeviceToHost, stream));
-  CTCX_CUDA(cudaStreamSynchronize(stream));
-  if (hdr.magic != kMagic || hdr.T != T || hdr.B != B || hdr.P != P || hdr.real_bytes != real_bytes)
-    return CTCX_ERR_WORKSPACE;
-  Workspace ws;
-  ws.Init(hdr.T, hdr.B, hdr.C, hdr.W, hdr.P);
-  // device copy of the 6*P output pointers
-  std::vector<long long*> table(6 * (size_t)P);
-  for (int p = 0; p < P; ++p) {
-    table[0 * (size_t)P + p] = (long long*)decoded_indices[p];
-    table[1 * (size_t)P + p] = (long long*)decoded_values[p];
-    table[2 * (size_t)P + p] = (long long*)decoded_shape[p];
-    table[3 * (size_t)P + p] = (long long*)alignment_indices[p];
-    table[4 * (size_t)P + p] = (long long*)alignment_values[p];
-    table[5 * (size_t)P + p] = (long long*)alignment_shape[p];
-  }
-  unsigned char* wbase = (unsigned char*)workspace;
-  CTCX_CUDA(cudaMemcpyAsync(wbase + ws.ptrs, table.data(), table.size() * sizeof(void*),
-                            cudaMemcpyHostToDevice, stream));
-  if (B > 0) {
-    ctcx::PackParams pp;
-    pp.dec_len = (const int*)(base + ws.dec_len); pp.dec = (const int*)(base + ws.dec);
-    pp.ali_len = (const int*)(base + ws.ali_len); pp.ali = (const int*)(base + ws.ali);
-    pp.dec_off = (const long long*)(base + ws.dec_off); pp.ali_off = (const long long*)(base + ws.ali_off);
-    pp.sizes = (const long long*)(base + ws.sizes);
-    pp.fin_total = (const void*)(base + ws.fin_total);
-    pp.ptrs = (long long* const*)(base + ws.ptrs);
-    pp.log_prob = log_probability;
-    pp.real_bytes = real_bytes;
-    pp.T = T; pp.B = B; pp.P = P;
-    dim3 grid((unsigned)B, (unsigned)P);
-    ctcx::PackKernel<<<grid, 128, 0, stream>>>(pp);
-    CTCX_CUDA(cudaGetLastError());
-  } else {
-    // empty batch: shapes [0, 0]
-    const long long zeros[2] = {0, 0};
-    for (int p = 0; p < P; ++p) {
-      CTCX_CUDA(cudaMemcpyAsync(decoded_shape[p], zeros, 16, cudaMemcpyHostToDevice, stream));
-      CTCX_CUDA(cudaMemcpyAsync(alignment_shape[p], zeros, 16, cudaMemcpyHostToDevice, stream));
-    }
-  }
-  // the pointer table lives in a host vector: a cudaMemcpyAsync from pageable memory returns only
-  // after the source has been copied to the driver's staging buffer, so no synchronisation is needed
-  return CTCX_OK;
-}
-}  // namespace
-
-extern "C" {
 
 int ctcx_decode_f32(const float* logits_dev, int T, int B, int C, const int32_t* seq_len_dev, int W,
                     int P, int merge_repeated, int blank_index, int blank_label, void* workspace,
                     size_t workspace_bytes, void* stream_v, ctcx_sizes* sizes, int32_t* flags_out) {
   return DecodeImpl<float>(logits_dev, T, B, C, seq_len_dev, W, P, merge_repeated, blank_index, blank_label,
-                           workspace, workspace_bytes, stream_v, sizes, flags_out);
+                           workspace, workspace_bytes, stream_v, sizes, flags_out, DecodeOpts());
+}
+
+/* A view into a larger tensor / any of the four element types, decoded in place. */
+int ctcx_decode_view(const void* logits_dev, int dtype, int64_t time_stride, int T, int B, int C,
+                     const int32_t* seq_len_dev, int W, int P, int merge_repeated, int blank_index,
+                     int blank_label, void* workspace, size_t workspace_bytes, void* stream_v,
+                     ctcx_sizes* sizes, int32_t* flags_out) {
+  if (ElemBytes(dtype) == 0 || time_stride < 0) return CTCX_ERR_BAD_ARGUMENT;
+  DecodeOpts opt;
+  opt.tstride = time_stride;
+  if (dtype == CTCX_F64)
+    return DecodeImpl<double>(logits_dev, T, B, C, seq_len_dev, W, P, merge_repeated, blank_index, blank_label,
+                              workspace, workspace_bytes, stream_v, sizes, flags_out, opt);
+  opt.in_dtype = InDtypeOf(dtype);
+  return DecodeImpl<float>(logits_dev, T, B, C, seq_len_dev, W, P, merge_repeated, blank_index, blank_label,
+                           workspace, workspace_bytes, stream_v, sizes, flags_out, opt);
 }
 
 /* Decode with a scorer plugged into the reference's extension point (util/ctc_beam_scorer.h:31-65). */
@@ -599,32 +527,127 @@ int ctcx_decode_scorer_f32(const float* logits_dev, int T, int B, int C, const i
                            int P, int merge_repeated, int blank_index, int blank_label,
                            const float* expansion_scores_dev, void* workspace, size_t workspace_bytes,
                            void* stream_v, ctcx_sizes* sizes, int32_t* flags_out) {
+  DecodeOpts opt;
   if (expansion_scores_dev != nullptr && C > 0) {  // expansion scores are log-probabilities: <= 0
     cudaStream_t stream = (cudaStream_t)stream_v;
-    int* d_flag = nullptr;
     if (workspace == nullptr || ((uintptr_t)workspace & 255u)) return CTCX_ERR_WORKSPACE;
     Workspace ws;
     ws.Init(T > 0 ? T : 1, B > 0 ? B : 0, C, W > 0 ? W : 1, P > 0 ? P : 1);
     if (workspace_bytes < ws.bytes) return CTCX_ERR_WORKSPACE;
-    d_flag = (int*)((unsigned char*)workspace + ws.stats) + 8;
+    int* d_flag = (int*)((unsigned char*)workspace + ws.ctrl) + 8;
     CTCX_CUDA(cudaMemsetAsync(d_flag, 0, 4, stream));
-    const long long n = (long long)(C + 1) * C;
-    PositiveKernel<<<(unsigned)std::min<long long>((n + 255) / 256, 1024), 256, 0, stream>>>(expansion_scores_dev, n, d_flag);
-    CTCX_CUDA(cudaGetLastError());
+    CTCX_LAUNCH(ctcx::LaunchPositive(expansion_scores_dev, (long long)(C + 1) * C, d_flag, stream));
     int h_flag = 0;
     CTCX_CUDA(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, stream));
     CTCX_CUDA(cudaStreamSynchronize(stream));
     if (h_flag) return CTCX_ERR_BAD_ARGUMENT;
+    opt.lm = expansion_scores_dev;
   }
   return DecodeImpl<float>(logits_dev, T, B, C, seq_len_dev, W, P, merge_repeated, blank_index, blank_label,
-                           workspace, workspace_bytes, stream_v, sizes, flags_out, expansion_scores_dev);
+                           workspace, workspace_bytes, stream_v, sizes, flags_out, opt);
 }
 
 int ctcx_decode_f64(const double* logits_dev, int T, int B, int C, const int32_t* seq_len_dev, int W,
                     int P, int merge_repeated, int blank_index, int blank_label, void* workspace,
                     size_t workspace_bytes, void* stream_v, ctcx_sizes* sizes, int32_t* flags_out) {
   return DecodeImpl<double>(logits_dev, T, B, C, seq_len_dev, W, P, merge_repeated, blank_index, blank_label,
-                            workspace, workspace_bytes, stream_v, sizes, flags_out);
+                            workspace, workspace_bytes, stream_v, sizes, flags_out, DecodeOpts());
+}
+
+/* fp16 / bf16 logits (what an acoustic model's projection typically emits), read by the kernels as
+ * they are. dtype: 0 = IEEE half, 1 = bfloat16. scratch_dev is ignored (kept for ABI stability). */
+int ctcx_decode_half(const void* logits_dev, int dtype, float* scratch_dev, int T, int B, int C,
+                     const int32_t* seq_len_dev, int W, int P, int merge_repeated, int blank_index,
+                     int blank_label, void* workspace, size_t workspace_bytes, void* stream_v,
+                     ctcx_sizes* sizes, int32_t* flags_out) {
+  (void)scratch_dev;
+  if (dtype != 0 && dtype != 1) return (T == 0) ? CTCX_ERR_MAX_TIME_ZERO : CTCX_ERR_BAD_ARGUMENT;
+  DecodeOpts opt;
+  opt.in_dtype = (dtype == 0) ? ctcx::kInF16 : ctcx::kInBF16;
+  return DecodeImpl<float>(logits_dev, T, B, C, seq_len_dev, W, P, merge_repeated, blank_index, blank_label,
+                           workspace, workspace_bytes, stream_v, sizes, flags_out, opt);
+}
+
+size_t ctcx_hostin_staging_bytes(int dtype, int T, int B, int C) {
+  if (T <= 0 || B < 0 || C <= 0) return 0;
+  return (size_t)T * B * C * ElemBytes(dtype);
+}
+
+/* Host logits in, decode result left in the workspace: the copy to the device runs in time slabs on
+ * `copy_stream` WHILE the beam kernel already consumes the first frames (narrow fast path); other
+ * shapes wait for the copy. */
+int ctcx_decode_hostin(const void* logits_host, int dtype, int64_t host_time_stride, int T, int B, int C,
+                       const int32_t* seq_len_host, int W, int P, int merge_repeated, int blank_index,
+                       int blank_label, void* staging_dev, size_t staging_bytes, void* workspace,
+                       size_t workspace_bytes, void* stream_v, void* copy_stream_v, ctcx_sizes* sizes,
+                       int32_t* flags_out) {
+  cudaStream_t stream = (cudaStream_t)stream_v, copy_stream = (cudaStream_t)copy_stream_v;
+  const size_t es = ElemBytes(dtype);
+  if (T == 0) return CTCX_ERR_MAX_TIME_ZERO;
+  if (es == 0 || T < 0 || B < 0 || C <= 0 || W < 1 || P < 1 || blank_index < 0 || blank_index >= C)
+    return CTCX_ERR_BAD_ARGUMENT;
+  if (W > kMaxBeamWidth || C > kMaxClasses) return CTCX_ERR_UNSUPPORTED;
+  const long long hstride = host_time_stride ? host_time_stride : (long long)B * C;
+  if (hstride < (long long)B * C) return CTCX_ERR_BAD_ARGUMENT;
+  Workspace ws;
+  ws.Init(T, B, C, W, P);
+  if (workspace == nullptr || workspace_bytes < ws.bytes || ((uintptr_t)workspace & 255u))
+    return CTCX_ERR_WORKSPACE;
+  if (B > 0 && (staging_dev == nullptr || staging_bytes < (size_t)T * B * C * es || logits_host == nullptr ||
+                seq_len_host == nullptr))
+    return CTCX_ERR_BAD_ARGUMENT;
+  if (copy_stream == stream) return CTCX_ERR_BAD_ARGUMENT;  // the kernel would wait for a copy queued behind it
+  unsigned char* base = (unsigned char*)workspace;
+  int* d_ctrl = (int*)(base + ws.ctrl);
+  int32_t* d_seq = (int32_t*)(base + ws.seq);
+
+  // overlap needs a truly asynchronous copy (page-locked source) and the stream-ordered flag store;
+  // pageable sources are staged by the driver, which may wait for the kernel that waits for them
+  const bool overlap = (B > 0) && dtype != CTCX_F64 && PathOf(W, C, false) == kPathNarrow && P <= W &&
+                       IsPinned(logits_host) && StreamWriteValue32() != nullptr;
+  Feed feed = {(const unsigned char*)logits_host, (unsigned char*)staging_dev, (size_t)B * C * es,
+               (size_t)hstride * es, T, d_ctrl + 1, overlap, copy_stream};
+  cudaEvent_t ev = nullptr;
+  int rc = CTCX_OK;
+  DecodeOpts opt;
+  opt.in_dtype = InDtypeOf(dtype);
+  if (B > 0) {
+    CTCX_CUDA(cudaMemcpyAsync(d_seq, seq_len_host, (size_t)B * 4, cudaMemcpyHostToDevice, stream));
+    CTCX_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (overlap) {
+      // frames landed = 0, then the copy stream may start once everything queued on `stream` so far
+      // (earlier users of the staging memory included) is done
+      CTCX_CUDA(cudaMemsetAsync(d_ctrl + 1, 0, 4, stream));
+      CTCX_CUDA(cudaEventRecord(ev, stream));
+      CTCX_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
+      opt.ready = d_ctrl + 1;
+      opt.feed = RunFeed;
+      opt.feed_arg = &feed;
+    } else {
+      // copy first (on the copy stream, so that it can still overlap other work of the caller), then decode
+      CTCX_CUDA(cudaEventRecord(ev, stream));
+      CTCX_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
+      rc = RunFeed(&feed);
+      if (rc == CTCX_OK) {
+        if (!Check(cudaEventRecord(ev, copy_stream), "cudaEventRecord") ||
+            !Check(cudaStreamWaitEvent(stream, ev, 0), "cudaStreamWaitEvent"))
+          rc = CTCX_ERR_CUDA;
+      }
+    }
+  }
+  if (rc == CTCX_OK) {
+    if (dtype == CTCX_F64)
+      rc = DecodeImpl<double>(staging_dev, T, B, C, d_seq, W, P, merge_repeated, blank_index, blank_label, workspace,
+                              workspace_bytes, stream_v, sizes, flags_out, opt);
+    else
+      rc = DecodeImpl<float>(staging_dev, T, B, C, d_seq, W, P, merge_repeated, blank_index, blank_label, workspace,
+                             workspace_bytes, stream_v, sizes, flags_out, opt);
+  }
+  if (ev != nullptr) {
+    if (rc != CTCX_OK) cudaStreamSynchronize(copy_stream);  // nothing of this call stays in flight after an error
+    cudaEventDestroy(ev);
+  }
+  return rc;
 }
 
 int ctcx_pack_f32(const void* workspace, int T, int B, int P, int64_t* const* decoded_indices,
@@ -653,7 +676,7 @@ int ctcx_workspace_views(const void* workspace, int T, int B, int P, const int32
   if (hdr.magic != kMagic || hdr.T != T || hdr.B != B || hdr.P != P) return CTCX_ERR_WORKSPACE;
   if (logp != nullptr && hdr.real_bytes != 4) return CTCX_ERR_BAD_ARGUMENT;  // float32 decodes only
   Workspace ws;
-  ws.Init(hdr.T, hdr.B, hdr.C, hdr.W, hdr.P);
+  ws.InitPack(T, B, P);
   if (dec_len) *dec_len = (const int32_t*)(base + ws.dec_len);
   if (dec) *dec = (const int32_t*)(base + ws.dec);
   if (ali_len) *ali_len = (const int32_t*)(base + ws.ali_len);
@@ -682,20 +705,19 @@ void ctcx_free_host(ctcx_host_result* r) {
   std::free(r);
 }
 
-static int DecodeHostImpl(const void* logits_host, int rb, int T, int B, int C, const int32_t* seq_len_host,
+static int DecodeHostImpl(const void* logits_host, int dtype, int T, int B, int C, const int32_t* seq_len_host,
                           int W, int P, int merge_repeated, int blank_index, int blank_label,
                           int device, ctcx_host_result** result) {
   if (result == nullptr) return CTCX_ERR_BAD_ARGUMENT;
   *result = nullptr;
   if (T == 0) return CTCX_ERR_MAX_TIME_ZERO;
   if (T < 0 || B < 0 || C <= 0 || W < 1 || P < 1) return CTCX_ERR_BAD_ARGUMENT;
+  const int rb = (dtype == CTCX_F64) ? 8 : 4;
   CTCX_CUDA(cudaSetDevice(device));
-  cudaStream_t stream;
-  CTCX_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  const size_t n_logits = (size_t)T * B * C;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  const size_t staging_bytes = ctcx_hostin_staging_bytes(dtype, T, B, C);
   const size_t ws_bytes = ctcx_workspace_bytes(T, B, C, W, P);
   void* d_logits = nullptr;
-  int32_t* d_seq = nullptr;
   void* d_ws = nullptr;
   unsigned char* d_out = nullptr;
   int rc = CTCX_OK;
@@ -709,19 +731,16 @@ static int DecodeHostImpl(const void* logits_host, int rb, int T, int B, int C, 
   do {                                                        \
     if (!Check((call), #call)) { rc = CTCX_ERR_CUDA; goto done; } \
   } while (0)
-  CTCX_TRY(cudaMalloc(&d_logits, n_logits * rb + 8));
-  CTCX_TRY(cudaMalloc(&d_seq, (size_t)B * 4 + 4));
+  CTCX_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  CTCX_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  CTCX_TRY(cudaMalloc(&d_logits, staging_bytes + 8));
   CTCX_TRY(cudaMalloc(&d_ws, ws_bytes));
-  CTCX_TRY(cudaMemcpyAsync(d_logits, logits_host, n_logits * rb, cudaMemcpyHostToDevice, stream));
-  CTCX_TRY(cudaMemcpyAsync(d_seq, seq_len_host, (size_t)B * 4, cudaMemcpyHostToDevice, stream));
-  rc = (rb == 8) ? ctcx_decode_f64((const double*)d_logits, T, B, C, d_seq, W, P, merge_repeated, blank_index,
-                                   blank_label, d_ws, ws_bytes, stream, &sizes, &flags)
-                 : ctcx_decode_f32((const float*)d_logits, T, B, C, d_seq, W, P, merge_repeated, blank_index,
-                                   blank_label, d_ws, ws_bytes, stream, &sizes, &flags);
+  rc = ctcx_decode_hostin(logits_host, dtype, 0, T, B, C, seq_len_host, W, P, merge_repeated, blank_index,
+                          blank_label, d_logits, staging_bytes + 8, d_ws, ws_bytes, stream, copy_stream, &sizes,
+                          &flags);
   if (rc != CTCX_OK) goto done;
   {
     // one device block for all outputs, then one D2H copy
-    std::vector<size_t> offs;
     size_t o = 0;
     auto take = [&](size_t n64) { size_t at = o; o += Align256(n64 * 8); return at; };
     std::vector<size_t> o_di(P), o_dv(P), o_ds(P), o_ai(P), o_av(P), o_as(P);
@@ -775,50 +794,28 @@ static int DecodeHostImpl(const void* logits_host, int rb, int T, int B, int C, 
   }
 done:
 #undef CTCX_TRY
+  if (stream) cudaStreamSynchronize(stream);
+  if (copy_stream) cudaStreamSynchronize(copy_stream);
   cudaFree(d_logits);
-  cudaFree(d_seq);
   cudaFree(d_ws);
   cudaFree(d_out);
-  cudaStreamDestroy(stream);
+  if (stream) cudaStreamDestroy(stream);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
   return rc;
 }
 
 int ctcx_decode_host_f32(const float* logits_host, int T, int B, int C, const int32_t* seq_len_host,
                          int W, int P, int merge_repeated, int blank_index, int blank_label,
                          int device, ctcx_host_result** result) {
-  return DecodeHostImpl(logits_host, 4, T, B, C, seq_len_host, W, P, merge_repeated, blank_index, blank_label,
+  return DecodeHostImpl(logits_host, CTCX_F32, T, B, C, seq_len_host, W, P, merge_repeated, blank_index, blank_label,
                         device, result);
 }
 
 int ctcx_decode_host_f64(const double* logits_host, int T, int B, int C, const int32_t* seq_len_host,
                          int W, int P, int merge_repeated, int blank_index, int blank_label,
                          int device, ctcx_host_result** result) {
-  return DecodeHostImpl(logits_host, 8, T, B, C, seq_len_host, W, P, merge_repeated, blank_index, blank_label,
+  return DecodeHostImpl(logits_host, CTCX_F64, T, B, C, seq_len_host, W, P, merge_repeated, blank_index, blank_label,
                         device, result);
-}
-
-/* fp16 / bf16 logits (what an acoustic model's projection typically emits): upcast exactly to
- * float32 into `scratch_dev` ([T*B*C] float32, caller-allocated device memory), then decode as
- * ctcx_decode_f32 does. dtype: 0 = IEEE half, 1 = bfloat16. */
-int ctcx_decode_half(const void* logits_dev, int dtype, float* scratch_dev, int T, int B, int C,
-                     const int32_t* seq_len_dev, int W, int P, int merge_repeated, int blank_index,
-                     int blank_label, void* workspace, size_t workspace_bytes, void* stream_v,
-                     ctcx_sizes* sizes, int32_t* flags_out) {
-  cudaStream_t stream = (cudaStream_t)stream_v;
-  if (T == 0) return CTCX_ERR_MAX_TIME_ZERO;
-  if (T < 0 || B < 0 || C <= 0 || (dtype != 0 && dtype != 1) || (scratch_dev == nullptr && B > 0))
-    return CTCX_ERR_BAD_ARGUMENT;
-  const long long n = (long long)T * B * C;
-  if (n > 0) {
-    const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, 148LL * 32);
-    if (dtype == 0)
-      UpcastKernel<__half><<<blocks, 256, 0, stream>>>((const __half*)logits_dev, scratch_dev, n);
-    else
-      UpcastKernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)logits_dev, scratch_dev, n);
-    CTCX_CUDA(cudaGetLastError());
-  }
-  return ctcx_decode_f32(scratch_dev, T, B, C, seq_len_dev, W, P, merge_repeated, blank_index, blank_label,
-                         workspace, workspace_bytes, stream_v, sizes, flags_out);
 }
 
 /* ---- streaming: Step / TopPaths / Reset of the reference decoder (decoder.h:39-53) ---- */
@@ -839,35 +836,42 @@ int ctcx_stream_reset(void* workspace, size_t workspace_bytes, int T_total, int 
     return CTCX_ERR_WORKSPACE;
   unsigned char* base = (unsigned char*)workspace;
   Workspace::Header hdr = {kMagic, T_total, B, C, W, P, 4};
-  CTCX_CUDA(cudaMemcpyAsync(base + ws.header, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, stream));
+  InitBlock init(ws, hdr, B, P);
+  CTCX_CUDA(cudaMemcpyAsync(base, init.bytes.data(), ws.dec_len, cudaMemcpyHostToDevice, stream));
   if (B > 0) {
-    // decoder.h:212-227: with zero frames consumed the kernels start from the root
+    // decoder.h:212-227: with zero frames consumed the kernels start from the root; TopPaths before
+    // the first Step() sees the root itself: one leaf, log-probability 0 (ln 1), empty sequences
     CTCX_CUDA(cudaMemsetAsync(base + ws.t_done, 0, (size_t)B * 4, stream));
-    CTCX_CUDA(cudaMemsetAsync(base + ws.flags, 0, (size_t)B * 4, stream));
     CTCX_CUDA(cudaMemsetAsync(base + ws.state, 0, (size_t)B * ctcx::StreamStateBytes(W), stream));
+    CTCX_CUDA(cudaMemsetAsync(base + ws.fin_total, 0, (size_t)B * P * 8, stream));
+    CTCX_CUDA(cudaMemsetAsync(base + ws.fin_kind, 0, (size_t)B * P * 4, stream));
+    std::vector<int> ones((size_t)B, 1), fl((size_t)B, (P > 1) ? 2 : 0);  // fewer leaves than top_paths
+    CTCX_CUDA(cudaMemcpyAsync(base + ws.fin_n, ones.data(), (size_t)B * 4, cudaMemcpyHostToDevice, stream));
+    CTCX_CUDA(cudaMemcpyAsync(base + ws.flags, fl.data(), (size_t)B * 4, cudaMemcpyHostToDevice, stream));
   }
-  CTCX_CUDA(cudaStreamSynchronize(stream));  // the header was staged from the stack
-  return CTCX_OK;
+  return CTCX_OK;  // (copies from pageable memory are staged before the calls return)
 }
 
 int ctcx_stream_step_f32(void* workspace, int T_total, int B, int C, int W, int P, const float* logits_dev,
                          int chunk_time, const int32_t* chunk_len_dev, int blank_index, void* stream_v) {
   cudaStream_t stream = (cudaStream_t)stream_v;
-  if (workspace == nullptr) return CTCX_ERR_WORKSPACE;
-  if (chunk_time <= 0 || chunk_time > T_total || chunk_len_dev == nullptr || blank_index < 0 || blank_index >= C)
+  if (workspace == nullptr || ((uintptr_t)workspace & 255u)) return CTCX_ERR_WORKSPACE;
+  if (T_total <= 0 || B < 0 || C <= 0 || W < 1 || P < 1 || W > kMaxBeamWidth || C > kMaxClasses || P > W ||
+      chunk_time <= 0 || chunk_time > T_total || chunk_len_dev == nullptr || blank_index < 0 || blank_index >= C)
     return CTCX_ERR_BAD_ARGUMENT;
   if (B == 0) return CTCX_OK;
   Workspace ws;
   ws.Init(T_total, B, C, W, P);
   unsigned char* base = (unsigned char*)workspace;
-  if (ws.Cs == 0) CTCX_CUDA(LaunchLogNorm(logits_dev, (float*)(base + ws.off), (long long)chunk_time * B, C, stream));
+  int* d_ctrl = (int*)(base + ws.ctrl);
   ctcx::BeamParams bp;
+  std::memset(&bp, 0, sizeof(bp));
   bp.logits = logits_dev;
   bp.off = (const float*)(base + ws.off);
   bp.seq_len = chunk_len_dev;  // frames of THIS chunk to consume, per utterance
   bp.T = chunk_time; bp.B = B; bp.C = C; bp.W = W; bp.P = P;
   bp.blank_index = blank_index;
-  bp.bp = (uint2*)(base + ws.bp);
+  if (ws.rec_bytes == 4) bp.bp32 = (unsigned*)(base + ws.bp); else bp.bp = (uint2*)(base + ws.bp);
   bp.fin_total = (float*)(base + ws.fin_total);
   bp.fin_kind = (int*)(base + ws.fin_kind);
   bp.fin_n = (int*)(base + ws.fin_n);
@@ -875,30 +879,44 @@ int ctcx_stream_step_f32(void* workspace, int T_total, int B, int C, int W, int 
   bp.Tcap = T_total;
   bp.t_done = (int*)(base + ws.t_done);
   bp.state = base + ws.state;
-  bp.srt_pl = nullptr; bp.srt_cls = nullptr; bp.Cs = ws.Cs; bp.Kc = 0; bp.lm = nullptr;
-  if (ws.Cs > 0) {
+  bp.tstride = (long long)B * C;
+  bp.queue = d_ctrl;
+  bp.dbg_cycles = nullptr;
+  const Path path = PathOf(W, C, false);
+  if (path == kPathNarrow) {
+    CTCX_CUDA(cudaMemsetAsync(d_ctrl, 0, 4, stream));
+    CTCX_LAUNCH(ctcx::LaunchBeamNarrow(bp, ctcx::kInF32, stream));
+  } else if (path == kPathWide) {
     bp.srt_pl = (const float*)(base + ws.srt_pl);
     bp.srt_cls = (const unsigned short*)(base + ws.srt_cls);
-    CTCX_CUDA(LaunchNormTopClasses(logits_dev, (float*)(base + ws.off), (long long)chunk_time * B, C, blank_index, W,
-                                   (float*)(base + ws.srt_pl), (unsigned short*)(base + ws.srt_cls), stream));
+    CTCX_LAUNCH(ctcx::LaunchNormTopClasses(logits_dev, ctcx::kInF32, (float*)(base + ws.off), (long long)chunk_time * B,
+                                           C, blank_index, W, (float*)(base + ws.srt_pl),
+                                           (unsigned short*)(base + ws.srt_cls), B, bp.tstride, stream));
+    CTCX_LAUNCH(ctcx::LaunchBeamWide(bp, ctcx::kInF32, stream));
+  } else {
+    CTCX_LAUNCH(ctcx::LaunchLogNorm(logits_dev, (float*)(base + ws.off), (long long)chunk_time * B, C, B, bp.tstride, stream));
+    CTCX_LAUNCH(ctcx::LaunchBeamGeneric(bp, stream));
   }
-  return LaunchBeamFor(bp, stream);
+  return CTCX_OK;
 }
 
 int ctcx_stream_top_paths(void* workspace, int T_total, int B, int C, int W, int P, int merge_repeated,
                           int blank_label, void* stream_v, ctcx_sizes* sizes, int32_t* flags_out) {
   cudaStream_t stream = (cudaStream_t)stream_v;
-  if (workspace == nullptr || sizes == nullptr) return CTCX_ERR_WORKSPACE;
+  if (workspace == nullptr || sizes == nullptr || ((uintptr_t)workspace & 255u)) return CTCX_ERR_WORKSPACE;
+  if (T_total <= 0 || B < 0 || C <= 0 || W < 1 || P < 1 || W > kMaxBeamWidth || C > kMaxClasses)
+    return CTCX_ERR_BAD_ARGUMENT;
   Workspace ws;
   ws.Init(T_total, B, C, W, P);
   unsigned char* base = (unsigned char*)workspace;
-  int* d_stats = (int*)(base + ws.stats);
-  std::vector<long long> h_sizes(4 * (size_t)P, 0);
-  int h_stats[5] = {0, B, B, B, B};
+  std::vector<unsigned char> h_res(4 * (size_t)P * 8 + kNStats * 4, 0);
+  int* h_stats = (int*)(h_res.data() + 4 * (size_t)P * 8);
+  h_stats[0] = 0;
+  for (int k = 1; k < 6; ++k) h_stats[k] = B;
   if (B > 0) {
-    CTCX_CUDA(cudaMemcpyAsync(d_stats, h_stats, sizeof(h_stats), cudaMemcpyHostToDevice, stream));
+    CTCX_CUDA(cudaMemcpyAsync(base + ws.result, h_res.data(), h_res.size(), cudaMemcpyHostToDevice, stream));
     ctcx::TraceParams tp;
-    tp.bp = (const uint2*)(base + ws.bp);
+    tp.bp = base + ws.bp;
     tp.seq_len = (const int*)(base + ws.t_done);  // frames consumed so far
     tp.fin_kind = (const int*)(base + ws.fin_kind);
     tp.fin_n = (const int*)(base + ws.fin_n);
@@ -909,57 +927,43 @@ int ctcx_stream_top_paths(void* workspace, int T_total, int B, int C, int W, int
     ctcx::ScanParams sp;
     sp.dec_len = tp.dec_len; sp.ali_len = tp.ali_len; sp.B = B; sp.P = P;
     sp.dec_off = (long long*)(base + ws.dec_off); sp.ali_off = (long long*)(base + ws.ali_off);
-    sp.sizes = (long long*)(base + ws.sizes);
-    CTCX_CUDA(LaunchTraceAndScan(tp, sp, stream, false));
-    FlagsKernel<<<(B + 255) / 256, 256, 0, stream>>>((const int*)(base + ws.flags), tp.seq_len, B, T_total, d_stats);
-    CTCX_CUDA(cudaGetLastError());
-    CTCX_CUDA(cudaMemcpyAsync(h_sizes.data(), base + ws.sizes, h_sizes.size() * 8, cudaMemcpyDeviceToHost, stream));
-    CTCX_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
+    sp.sizes = (long long*)(base + ws.result);
+    CTCX_LAUNCH(ctcx::LaunchTraceScanFlags(tp, ws.rec_bytes, sp, (const int*)(base + ws.flags),
+                                           (int*)(base + ws.result + 4 * (size_t)P * 8), stream, nullptr));
+    CTCX_CUDA(cudaMemcpyAsync(h_res.data(), base + ws.result, h_res.size(), cudaMemcpyDeviceToHost, stream));
     CTCX_CUDA(cudaStreamSynchronize(stream));
   }
-  if (h_stats[4] < B) {  // an utterance was fed more frames than the stream holds
-    g_err_batch = h_stats[4];
-    g_err_max_time = T_total;
-    return CTCX_ERR_SEQ_LEN_RANGE;
-  }
-  if (h_stats[1] < B) return CTCX_ERR_TOO_FEW_LEAVES;
-  for (int p = 0; p < P; ++p) {
-    if (sizes->n_decoded) sizes->n_decoded[p] = h_sizes[0 * (size_t)P + p];
-    if (sizes->max_decoded) sizes->max_decoded[p] = h_sizes[1 * (size_t)P + p];
-    if (sizes->n_alignment) sizes->n_alignment[p] = h_sizes[2 * (size_t)P + p];
-    if (sizes->max_alignment) sizes->max_alignment[p] = h_sizes[3 * (size_t)P + p];
-  }
-  if (flags_out) *flags_out = h_stats[0];
-  return CTCX_OK;
+  return ReportSizes((const long long*)h_res.data(), h_stats, B, T_total, P, sizes, flags_out);
 }
 
-/* measurement hook (bench.py): per-kernel device times of this thread's last ctcx_decode_f32, from
- * CUDA events recorded on the launching stream. out_ms = {lognorm, beam, trace, scan, total}. */
+/* ---- measurement and test hooks (declared at the end of include/ctcx.h) ---- */
+
+/* per-kernel device times of this thread's last decode, from CUDA events recorded on the launching
+ * stream. out_ms = {pre-pass, beam, trace, scan + flags, total}. */
 void ctcx_profile_enable(int on) { g_profile = on; }
 void ctcx_profile_get(float* out_ms) {
   for (int k = 0; k < 5; ++k) out_ms[k] = g_ms[k];
 }
 
-/* measurement hook: device buffer [B,16] int64 receiving per-phase clock64 cycles of the fast beam
- * kernel (thread 0 of every CTA, summed over frames); NULL switches it off. */
+/* device buffer [B,24] int64 receiving per-phase clock64 cycles of the fast beam kernels (thread 0
+ * of every CTA, summed over frames) for this thread's decodes; NULL switches it off. */
 void ctcx_debug_set_cycles_buffer(long long* dev_buf) { g_dbg_cycles = dev_buf; }
 
-/* test hook: y = f(x) element-wise with the exact device math; op 0 expf, 1 log1pf, 2 logf */
+/* 0 = dispatch by shape (default); 1 = route every decode of the process to the generic beam kernel,
+ * the independent second implementation the parity tests compare with the fast ones. */
+void ctcx_debug_set_beam_impl(int impl) { g_force_generic.store(impl == 1 ? 1 : 0); }
+
+/* y = f(x) element-wise with the exact device math; op 0 expf, 1 log1pf, 2 logf */
 int ctcx_debug_math_f32(int op, const float* x_dev, float* y_dev, int n, void* stream_v) {
-  cudaStream_t stream = (cudaStream_t)stream_v;
   if (n <= 0) return CTCX_OK;
-  ctcx::MathTestKernel<<<(n + 255) / 256, 256, 0, stream>>>(op, x_dev, y_dev, n);
-  CTCX_CUDA(cudaGetLastError());
+  CTCX_LAUNCH(ctcx::LaunchMathTest(op, x_dev, y_dev, n, (cudaStream_t)stream_v));
   return CTCX_OK;
 }
 
-
 /* the double-precision twin: op 0 exp (x <= 0), 1 log (x >= 1), 2 LogSumExp(x, 0) */
 int ctcx_debug_math_f64(int op, const double* x_dev, double* y_dev, int n, void* stream_v) {
-  cudaStream_t stream = (cudaStream_t)stream_v;
   if (n <= 0) return CTCX_OK;
-  ctcx::MathTestKernelF64<<<(n + 255) / 256, 256, 0, stream>>>(op, x_dev, y_dev, n);
-  CTCX_CUDA(cudaGetLastError());
+  CTCX_LAUNCH(ctcx::LaunchMathTest(op, x_dev, y_dev, n, (cudaStream_t)stream_v));
   return CTCX_OK;
 }
 

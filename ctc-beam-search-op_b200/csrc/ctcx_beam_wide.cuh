@@ -21,7 +21,7 @@
 // revisit-wipe counts saturate at W, and a capped row alone contributes >= W+2, so they are exact
 // as well (the own-row part falls back to the raw row when capped).
 #pragma once
-#include "ctcx_beam_v3.cuh"
+#include "ctcx_beam_common.cuh"
 
 namespace ctcx {
 
@@ -96,7 +96,7 @@ struct BeamSmemWide {
 
 enum { kWNKid = 23, kWCapped = 24, kWBest = 25 };  // scalar slots in addition to the kV2* / kV3* ones
 
-template <int WMAX, int NT, bool TIMING>
+template <typename IN, int WMAX, int NT, bool TIMING>
 __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKernelWide(BeamParams p) {
   static_assert(NT >= WMAX && 2 * NT >= kBinsV2, "one thread per beam slot and per two histogram bins");
   extern __shared__ __align__(16) unsigned char smem[];
@@ -190,8 +190,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
   // thread -> (row, class slice) mapping of the candidate pass
   for (int i = tid; i < WMAX * KW; i += NT) s_kid[i] = 0u;
   if (L > 0) {  // frame 0: raw row, normaliser, sorted classes
-    const float* g = p.logits + (size_t)b * C;
-    for (int l = tid; l < C; l += NT) s_x[l] = g[l];
+    for (int l = tid; l < C; l += NT) s_x[l] = LoadLogit<IN>(p.logits, (size_t)b * C + l);
     const float* gp = p.srt_pl + (size_t)b * Cs;
     const unsigned short* gc = p.srt_cls + (size_t)b * Cs;
     for (int j = tid; j < Cs; j += NT) {
@@ -254,16 +253,23 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     // consumed after the barrier that ends this frame
     if (warp == NWARP - 1 && t + 1 < L) {
       const size_t r1 = (size_t)(t + 1) * B + b;
-      const float* g = p.logits + r1 * C;
-      if ((C & 3) == 0) {  // rows 16-byte aligned
-        for (int l = lane * 4; l < C; l += 128) {
-          const unsigned sa = (unsigned)__cvta_generic_to_shared(s_x + nxt * Cx + l);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g + l));
-        }
+      const size_t g0 = (size_t)(t + 1) * (size_t)p.tstride + (size_t)b * C;
+      if (sizeof(IN) != 4) {
+        // half-precision logits: upcast in registers on the way to shared memory (the loads of the whole
+        // row are issued back to back; this warp is idle during PA anyway)
+        for (int l = lane; l < C; l += 32) s_x[nxt * Cx + l] = LoadLogit<IN>(p.logits, g0 + l);
       } else {
-        for (int l = lane; l < C; l += 32) {
-          const unsigned sa = (unsigned)__cvta_generic_to_shared(s_x + nxt * Cx + l);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(g + l));
+        const float* g = reinterpret_cast<const float*>(p.logits) + g0;
+        if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15u) == 0) {  // rows 16-byte aligned
+          for (int l = lane * 4; l < C; l += 128) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(s_x + nxt * Cx + l);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g + l));
+          }
+        } else {
+          for (int l = lane; l < C; l += 32) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(s_x + nxt * Cx + l);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(g + l));
+          }
         }
       }
       const float* gp = p.srt_pl + r1 * Cs;            // rows are 16-byte aligned (Cs % 8 == 0)
@@ -946,7 +952,10 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
         w_label[r] = lbl;
         w_hash[r] = hsh;
         s_row[r] = make_uint4(__float_as_uint(nt_), __float_as_uint(nb_), (unsigned)lbl, 0u);
-        p.bp[((size_t)b * p.Tcap + (t_done + t)) * W + r] = make_uint2(rec, (unsigned)lbl);
+        if (p.bp32 != nullptr)
+          p.bp32[((size_t)b * p.Tcap + (t_done + t)) * W + r] = Rec64To32(rec, (unsigned)lbl);
+        else
+          p.bp[((size_t)b * p.Tcap + (t_done + t)) * W + r] = make_uint2(rec, (unsigned)lbl);
         if (p.dbg_totals) p.dbg_totals[((size_t)b * T + t) * W + r] = nt_;
         unsigned h = (unsigned)hsh & (TS - 1);
         const unsigned entry = ((unsigned)(hsh >> 42) << 10) | (unsigned)r;

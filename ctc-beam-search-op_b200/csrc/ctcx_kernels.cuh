@@ -1,5 +1,9 @@
 // Hand-written sm_100a kernels for the CTC "extended" beam-search decode.
 //
+// The sections of this header are compiled by different translation units: define CTCX_WITH_NORM
+// (normaliser kernels), CTCX_WITH_GENERIC (the generic beam kernel) and / or CTCX_WITH_POST (trace-back,
+// scan, pack) before including it; the common helpers at the top are always available.
+//
 // What each kernel replaces in the reference (paths relative to
 // tensorflow_ctc_ext_beam_search_decoder/cc/):
 //   LogNormKernel   util/ctc_ext_beam_search_decoder.h:71-80   softmax normaliser of Step()
@@ -21,7 +25,11 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "ctcx_math.cuh"
+#include "ctcx_params.h"
 
 namespace ctcx {
 
@@ -58,6 +66,37 @@ __device__ __forceinline__ unsigned long long HashChild(unsigned long long h, in
   return z;
 }
 
+// element i of the caller's logits tensor as the decoder's score type (exact: float16 / bfloat16 ->
+// float32 is a widening). The loads bypass L1: the narrow fast kernel may run while a host->device
+// copy of later frames is still in flight (BeamParamsT::ready).
+template <typename IN>
+__device__ __forceinline__ float LoadLogit(const void* base, size_t i);
+template <>
+__device__ __forceinline__ float LoadLogit<float>(const void* base, size_t i) {
+  return __ldcg(reinterpret_cast<const float*>(base) + i);
+}
+template <>
+__device__ __forceinline__ float LoadLogit<__half>(const void* base, size_t i) {
+  return __half2float(__ldcg(reinterpret_cast<const __half*>(base) + i));
+}
+template <>
+__device__ __forceinline__ float LoadLogit<__nv_bfloat16>(const void* base, size_t i) {
+  return __bfloat162float(__ldcg(reinterpret_cast<const __nv_bfloat16*>(base) + i));
+}
+
+// 4-byte back-pointer record (beam_width <= 256 and num_classes <= 256): [0,8) prev_self slot |
+// [8,16) an_src slot | [16] ab_kind | [17,19) an_kind | [24,32) label. A fresh child has no previous
+// self (0xff, never followed).
+__device__ __forceinline__ unsigned PackRec32(unsigned prev_self, unsigned an_src, unsigned ab_kind,
+                                              unsigned an_kind, unsigned label) {
+  return (prev_self & 0xffu) | ((an_src & 0xffu) << 8) | (ab_kind << 16) | (an_kind << 17) | (label << 24);
+}
+// 8-byte form (PackRec word + label) -> 4-byte form
+__device__ __forceinline__ unsigned Rec64To32(unsigned rec, unsigned label) {
+  return PackRec32(rec & 0x7ffu, (rec >> 11) & 0x7ffu, (rec >> 22) & 1u, (rec >> 23) & 3u, label & 0xffu);
+}
+
+#ifdef CTCX_WITH_NORM
 // ---------------------------------------------------------------------------------------------
 // Kernel 1: per-row softmax normaliser off[t,b] = max_j x_j + logf(sum_{j in index order} expf(x_j - max))
 // (decoder.h:71-80). One warp per row; lanes evaluate expf in parallel into a per-warp shared-memory
@@ -65,9 +104,16 @@ __device__ __forceinline__ unsigned long long HashChild(unsigned long long h, in
 // sum is bit-identical) with 16-byte broadcast loads -- 4x fewer issue slots than passing the terms
 // around with shuffles, which is what bounded the first version of this kernel.
 // ---------------------------------------------------------------------------------------------
+// element offset of logits row `row` = t * B + b in a tensor whose time stride is `tstride` elements
+__device__ __forceinline__ long long RowOffset(long long row, int B, int C, long long tstride) {
+  const long long t = row / B;
+  return t * tstride + (row - t * B) * C;
+}
+
 constexpr int kLogNormChunk = 1024;  // floats per warp per pass
-__global__ void __launch_bounds__(256) LogNormKernel(const float* __restrict__ logits,
-                                                     float* __restrict__ off, long long rows, int C) {
+static __global__ void __launch_bounds__(256) LogNormKernel(const float* __restrict__ logits,
+                                                     float* __restrict__ off, long long rows, int C,
+                                                     int B, long long tstride) {
   __shared__ unsigned long long s_tab[32];
   __shared__ __align__(16) float s_e[8][kLogNormChunk];
   LoadExpTable(s_tab, threadIdx.x, blockDim.x);
@@ -77,7 +123,7 @@ __global__ void __launch_bounds__(256) LogNormKernel(const float* __restrict__ l
   const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long row = warp_global; row < rows; row += nwarps) {
-    const float* x = logits + row * C;
+    const float* x = logits + RowOffset(row, B, C, tstride);
     float mx = NegInf();
     for (int j = lane; j < C; j += 32) mx = fmaxf(mx, x[j]);
 #pragma unroll
@@ -101,8 +147,9 @@ __global__ void __launch_bounds__(256) LogNormKernel(const float* __restrict__ l
 }
 
 // T = double (kernels.cc:275): the same normaliser through the double-precision exp()/log().
-__global__ void __launch_bounds__(256) LogNormKernelF64(const double* __restrict__ logits,
-                                                        double* __restrict__ off, long long rows, int C) {
+static __global__ void __launch_bounds__(256) LogNormKernelF64(const double* __restrict__ logits,
+                                                        double* __restrict__ off, long long rows, int C,
+                                                        int B, long long tstride) {
   __shared__ unsigned long long s_tab[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = kCtcxExpTab[i];
   __syncthreads();
@@ -110,7 +157,7 @@ __global__ void __launch_bounds__(256) LogNormKernelF64(const double* __restrict
   const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long row = warp_global; row < rows; row += nwarps) {
-    const double* x = logits + row * C;
+    const double* x = logits + RowOffset(row, B, C, tstride);
     double mx = __longlong_as_double((long long)0xfff0000000000000ull);
     for (int j = lane; j < C; j += 32) mx = fmax(mx, x[j]);
 #pragma unroll
@@ -132,9 +179,9 @@ __global__ void __launch_bounds__(256) LogNormKernelF64(const double* __restrict
 // issued instructions per row than the warp-per-row form, which is what keeps this kernel off the
 // HBM roofline (the exact expf is ~25 instructions, half of them fp64).
 constexpr int kLogNormRows = 256;
-__global__ void __launch_bounds__(kLogNormRows) LogNormRowKernel(const float* __restrict__ logits,
+static __global__ void __launch_bounds__(kLogNormRows) LogNormRowKernel(const float* __restrict__ logits,
                                                                   float* __restrict__ off, long long rows,
-                                                                  int C) {
+                                                                  int C, int B, long long tstride) {
   extern __shared__ __align__(16) float lsm[];
   __shared__ unsigned long long s_tab[32];
   LoadExpTable(s_tab, threadIdx.x, blockDim.x);
@@ -142,12 +189,12 @@ __global__ void __launch_bounds__(kLogNormRows) LogNormRowKernel(const float* __
   for (long long row0 = (long long)blockIdx.x * kLogNormRows; row0 < rows;
        row0 += (long long)gridDim.x * kLogNormRows) {
     const int nrow = (int)min((long long)kLogNormRows, rows - row0);
-    const float* src = logits + row0 * C;
     const int total = nrow * C;
+    const bool dense = (tstride == (long long)B * C);
     __syncthreads();  // previous tile fully consumed (and the table is loaded)
     for (int i = threadIdx.x; i < total; i += kLogNormRows) {
       const int r = i / C, c = i - r * C;
-      lsm[r * stride + c] = src[i];
+      lsm[r * stride + c] = dense ? logits[row0 * C + i] : logits[RowOffset(row0 + r, B, C, tstride) + c];
     }
     __syncthreads();
     if ((int)threadIdx.x < nrow) {
@@ -172,12 +219,13 @@ __global__ void __launch_bounds__(kLogNormRows) LogNormRowKernel(const float* __
 // one tie case that reaches past the cut). Selection: keys in registers (NI per lane), the Ke-th
 // largest key by a bitwise search with warp-wide counts, compaction by ballots, final order by rank
 // counting.
-template <int NI>
-__global__ void __launch_bounds__(256, 3) NormTopClassesKernel(const float* __restrict__ logits,
+template <typename IN, int NI>
+__global__ void __launch_bounds__(256, 3) NormTopClassesKernel(const IN* __restrict__ logits,
                                                             float* __restrict__ off, long long rows, int C,
                                                             int blank, int Ke, int Ks,
                                                             float* __restrict__ srt_pl,
-                                                            unsigned short* __restrict__ srt_cls) {
+                                                            unsigned short* __restrict__ srt_cls, int B,
+                                                            long long tstride) {
   // dynamic shared memory: [8 warps][NI*32] floats (the exp terms of a row), then [8 warps][Ke] u64
   extern __shared__ __align__(16) unsigned char nsm[];
   __shared__ unsigned long long s_tab[32];
@@ -191,14 +239,14 @@ __global__ void __launch_bounds__(256, 3) NormTopClassesKernel(const float* __re
   const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long row = warp_global; row < rows; row += nwarps) {
-    const float* x = logits + row * C;
+    const size_t x0 = (size_t)RowOffset(row, B, C, tstride);
     // the row, once, into registers (lane = class mod 32: coalesced)
     float v[NI];
     float mx = NegInf();
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
       const int j = i * 32 + lane;
-      v[i] = (j < C) ? x[j] : NegInf();
+      v[i] = (j < C) ? LoadLogit<IN>(logits, x0 + j) : NegInf();
       mx = fmaxf(mx, v[i]);
     }
 #pragma unroll
@@ -277,6 +325,9 @@ __global__ void __launch_bounds__(256, 3) NormTopClassesKernel(const float* __re
   }
 }
 
+#endif  // CTCX_WITH_NORM
+
+#ifdef CTCX_WITH_GENERIC
 // ---------------------------------------------------------------------------------------------
 // Kernel 2: the beam kernel.
 // ---------------------------------------------------------------------------------------------
@@ -331,64 +382,6 @@ struct RealOps<double> {
   __device__ static __forceinline__ unsigned CompNotOrder(Comp c) { return (unsigned)c.y; }
 };
 
-template <typename R>
-struct BeamParamsT {
-  const R* logits;  // [T,B,C] time-major raw logits
-  const R* off;     // [T,B]   normaliser from LogNormKernel
-  const int* seq_len;   // [B]
-  int T, B, C, W, P;
-  int blank_index;
-  int cand_cap;   // capacity of the shared-memory candidate list; 0 = streaming mode
-  int kid_words;  // ceil(C/32)
-  uint2* bp;      // [B,T,W] back-pointer records {packed, label}
-  R* fin_total;      // [B,P]
-  int* fin_kind;     // [B,P] 1 = best alignment ends in blank
-  int* fin_n;        // [B]   members in the final beam
-  int* flags;        // [B]   bit0 rounding anomaly, bit1 fewer leaves than top_paths
-  R* dbg_totals;      // optional [B,T,W]
-  int* dbg_n;         // optional [B,T]
-  long long* dbg_cycles;  // optional [B,24]: clock64 cycles per phase (thread 0), summed over frames
-  // streaming (Step / TopPaths / Reset, decoder.h:39-53); all null / T for a one-shot decode
-  int Tcap;               // frames per utterance the back-pointer array can hold (its row stride)
-  int* t_done;            // [B] frames already consumed per utterance (updated by the kernel), or null
-  unsigned char* state;   // [B] x StreamStateBytes(W): beam state carried between chunks, or null
-  // wide-vocabulary fast path (ctcx_beam_wide.cuh): per frame, the classes sorted by log-prob
-  const R* srt_pl;               // [T,B,Cs] x_l - off of the best classes, descending (padding = -inf)
-  const unsigned short* srt_cls; // [T,B,Cs] class index at each sorted position
-  int Cs;                        // row stride of the two arrays (a multiple of 8)
-  int Kc;                        // sorted classes per frame the kernel may use (entry Kc, if < C-1
-                                 // classes are listed, is a sentinel: the best class left out)
-  // scorer extension point (util/ctc_beam_scorer.h:31-65), generic kernel only: null = the default
-  // scorer; otherwise a [C+1, C] table of expansion scores (<= 0), row = label of the expanded
-  // entry + 1 (row 0: the root), column = new label: GetStateExpansionScore(state, s) = s + entry
-  const R* lm;
-};
-using BeamParams = BeamParamsT<float>;
-
-// Beam state of one utterance between two chunks of a streamed decode.
-struct StreamHdr {
-  int n;         // members in the beam
-  unsigned gap;  // score-range prediction of the fast kernel
-  int flags;     // bit0 rounding anomaly, bit2 more frames than the stream was sized for
-  int pad;
-};
-__host__ __device__ inline size_t StreamStateBytes(int W) {
-  return (sizeof(StreamHdr) + (size_t)W * 40 + 15) / 16 * 16;  // 5 x f32 + label + 2 x u64 per slot
-}
-struct StreamView {
-  StreamHdr* hdr;
-  float *total, *blk, *lab, *ab, *an;
-  int* label;
-  unsigned long long *hash, *phash;
-  __device__ StreamView(unsigned char* base, int W) {
-    hdr = reinterpret_cast<StreamHdr*>(base);
-    total = reinterpret_cast<float*>(base + sizeof(StreamHdr));
-    blk = total + W; lab = blk + W; ab = lab + W; an = ab + W;
-    label = reinterpret_cast<int*>(an + W);
-    hash = reinterpret_cast<unsigned long long*>(label + W);
-    phash = hash + W;
-  }
-};
 
 // Shared-memory carve-up, computed identically on host and device.
 struct BeamSmem {
@@ -575,7 +568,7 @@ __global__ void __launch_bounds__(NT) BeamKernelT(BeamParamsT<R> p) {
 
     // prefetch the next frame's row (consumed after the barrier that ends this frame)
     if (t + 1 < L) {
-      const R* g = p.logits + ((size_t)(t + 1) * B + b) * C;
+      const R* g = p.logits + (size_t)(t + 1) * (size_t)p.tstride + (size_t)b * C;
       R* dst = s_x + nxt * cpad;
       for (int l = tid; l < C; l += NT) {
         const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + l);
@@ -986,7 +979,10 @@ __global__ void __launch_bounds__(NT) BeamKernelT(BeamParamsT<R> p) {
         }
         w_label[r] = lbl;
         w_hash[r] = hsh;
-        p.bp[((size_t)b * p.Tcap + (t_done + t)) * W + r] = make_uint2(rec, (unsigned)lbl);
+        if (p.bp32 != nullptr)
+          p.bp32[((size_t)b * p.Tcap + (t_done + t)) * W + r] = Rec64To32(rec, (unsigned)lbl);
+        else
+          p.bp[((size_t)b * p.Tcap + (t_done + t)) * W + r] = make_uint2(rec, (unsigned)lbl);
         if (p.dbg_totals) p.dbg_totals[((size_t)b * T + t) * W + r] = w_total[r];
         // next frame's parent look-up table
         unsigned h = (unsigned)hsh & (TS - 1);
@@ -1042,24 +1038,29 @@ __global__ void __launch_bounds__(NT) BeamKernelT(BeamParamsT<R> p) {
   }
 }
 
+#endif  // CTCX_WITH_GENERIC
+
+#ifdef CTCX_WITH_POST
 // ---------------------------------------------------------------------------------------------
 // Kernel 3: trace-back. One thread per (utterance, path) walks the back-pointer records from the
 // last frame to the first, emitting the alignment (entry.h:137-152) and the decoded labels
 // (entry.h:123-136, with optional repeat merging).
 // ---------------------------------------------------------------------------------------------
-struct TraceParams {
-  const uint2* bp;
-  const int* seq_len;
-  const int* fin_kind;
-  const int* fin_n;
-  int T, B, W, P;
-  int merge_repeated, blank_label;
-  int* dec_len;  // [B,P]
-  int* dec;      // [B,P,T]
-  int* ali_len;  // [B,P]
-  int* ali;      // [B,P,T]
+// Back-pointer record formats: the generic / wide kernels write 8-byte records {packed word, label}
+// (PackRec), the narrow fast kernel 4-byte ones (PackRec32, ctcx_beam_v4.cuh).
+struct RecFields {
+  unsigned prev_self, an_src, ab_kind, an_kind;
+  int label;
 };
+__device__ __forceinline__ RecFields UnpackRec(const uint2 r) {
+  return {r.x & 0x7ffu, (r.x >> 11) & 0x7ffu, (r.x >> 22) & 1u, (r.x >> 23) & 3u, (int)r.y};
+}
+__device__ __forceinline__ RecFields UnpackRec(const unsigned r) {
+  return {r & 0xffu, (r >> 8) & 0xffu, (r >> 16) & 1u, (r >> 17) & 3u, (int)(r >> 24)};
+}
 
+
+template <typename REC>
 __global__ void __launch_bounds__(128) TraceKernel(TraceParams p) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p.B * p.P) return;
@@ -1074,25 +1075,23 @@ __global__ void __launch_bounds__(128) TraceKernel(TraceParams p) {
   }
   int slot = path;
   int kind_ab = p.fin_kind[idx];
-  const uint2* bp = p.bp + (size_t)b * p.T * p.W;
+  const REC* bp = reinterpret_cast<const REC*>(p.bp) + (size_t)b * p.T * p.W;
   for (int t = L - 1; t >= 0; --t) {
-    const uint2 r = bp[(size_t)t * p.W + slot];
-    const unsigned prev_self = r.x & 0x7ffu, an_src = (r.x >> 11) & 0x7ffu;
-    const unsigned ab_kind = (r.x >> 22) & 1u, an_kind = (r.x >> 23) & 3u;
+    const RecFields r = UnpackRec(bp[(size_t)t * p.W + min(slot, p.W - 1)]);
     if (kind_ab) {
       ali[t] = p.blank_label;
       dec[t] = -1;
-      kind_ab = (ab_kind == kAbFromAb) ? 1 : 0;
-      slot = (int)prev_self;
+      kind_ab = (r.ab_kind == kAbFromAb) ? 1 : 0;
+      slot = (int)r.prev_self;
     } else {
-      ali[t] = (int)r.y;
-      if (an_kind == kAnSelfAn) {
+      ali[t] = r.label;
+      if (r.an_kind == kAnSelfAn) {
         dec[t] = -1;
-        slot = (int)prev_self;
+        slot = (int)r.prev_self;
       } else {
-        dec[t] = (int)r.y;  // a new label was emitted at this frame
-        slot = (int)an_src;
-        kind_ab = (an_kind == kAnParAb) ? 1 : 0;
+        dec[t] = r.label;  // a new label was emitted at this frame
+        slot = (int)r.an_src;
+        kind_ab = (r.an_kind == kAnParAb) ? 1 : 0;
       }
     }
   }
@@ -1116,7 +1115,7 @@ __global__ void __launch_bounds__(128) TraceKernel(TraceParams p) {
 // walk, so a step is one shared-memory broadcast read plus a few ALU operations instead of a
 // dependent trip to L2/HBM. Symbols are collected 32 frames at a time in registers and written as
 // coalesced rows; the decoded labels are compacted with warp ballots.
-template <int WARPS>
+template <typename REC, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) TraceWarpKernel(TraceParams p, int rows_log2) {
   extern __shared__ __align__(16) unsigned char tsm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1135,17 +1134,18 @@ __global__ void __launch_bounds__(WARPS * 32) TraceWarpKernel(TraceParams p, int
   }
   const int W = p.W;
   const int R = 1 << rows_log2;
-  uint2* buf = reinterpret_cast<uint2*>(tsm) + (size_t)warp * 2 * R * W;
-  const uint2* bp = p.bp + (size_t)b * p.T * W;
+  REC* buf = reinterpret_cast<REC*>(tsm) + (size_t)warp * 2 * R * W;
+  const REC* bp = reinterpret_cast<const REC*>(p.bp) + (size_t)b * p.T * W;
   // block k holds frames [k*R, min(L, (k+1)*R)); blocks are walked from the last one down
   auto fetch_block = [&](int k) {
     if (k >= 0) {
       const int t0 = k << rows_log2;
       const int nrec = (min(L, t0 + R) - t0) * W;
-      const uint2* src = bp + (size_t)t0 * W;
+      const REC* src = bp + (size_t)t0 * W;
       const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + (size_t)(k & 1) * R * W);
       for (int i = lane; i < nrec; i += 32)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst + 8u * (unsigned)i), "l"(src + i));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(dst + (unsigned)sizeof(REC) * (unsigned)i),
+                     "l"(src + i), "n"(sizeof(REC)));
     }
     asm volatile("cp.async.commit_group;\n" ::);
   };
@@ -1158,25 +1158,23 @@ __global__ void __launch_bounds__(WARPS * 32) TraceWarpKernel(TraceParams p, int
     fetch_block(k - 1);                               // next block in flight while this one is walked
     asm volatile("cp.async.wait_group 1;\n" ::);     // block k has landed
     __syncwarp();
-    const uint2* blk = buf + (size_t)(k & 1) * R * W;
+    const REC* blk = buf + (size_t)(k & 1) * R * W;
     const int t_lo = k << rows_log2;
     for (int t = min(L, t_lo + R) - 1; t >= t_lo; --t) {
-      const uint2 r = blk[(t - t_lo) * W + slot];
-      const unsigned prev_self = r.x & 0x7ffu, an_src = (r.x >> 11) & 0x7ffu;
-      const unsigned ab_kind = (r.x >> 22) & 1u, an_kind = (r.x >> 23) & 3u;
+      const RecFields r = UnpackRec(blk[(t - t_lo) * W + min(slot, W - 1)]);
       int sym_a, sym_d = -1;
       if (kind_ab) {  // entry.h:133-136: a blank frame
         sym_a = p.blank_label;
-        kind_ab = (ab_kind == kAbFromAb) ? 1 : 0;
-        slot = (int)prev_self;
+        kind_ab = (r.ab_kind == kAbFromAb) ? 1 : 0;
+        slot = (int)r.prev_self;
       } else {
-        sym_a = (int)r.y;
-        if (an_kind == kAnSelfAn) {
-          slot = (int)prev_self;
+        sym_a = r.label;
+        if (r.an_kind == kAnSelfAn) {
+          slot = (int)r.prev_self;
         } else {
-          sym_d = (int)r.y;  // a new label was emitted at this frame
-          slot = (int)an_src;
-          kind_ab = (an_kind == kAnParAb) ? 1 : 0;
+          sym_d = r.label;  // a new label was emitted at this frame
+          slot = (int)r.an_src;
+          kind_ab = (r.an_kind == kAnParAb) ? 1 : 0;
         }
       }
       if (lane == (t & 31)) {
@@ -1221,16 +1219,8 @@ __global__ void __launch_bounds__(WARPS * 32) TraceWarpKernel(TraceParams p, int
 // Kernels 4/5: sparse packing (kernels.cc:163-257). ScanKernel: per path, exclusive prefix sums of
 // the lengths over the batch + totals + maxima. PackKernel: indices [b,pos], values, shapes.
 // ---------------------------------------------------------------------------------------------
-struct ScanParams {
-  const int* dec_len;  // [B,P]
-  const int* ali_len;  // [B,P]
-  int B, P;
-  long long* dec_off;  // [P,B]
-  long long* ali_off;  // [P,B]
-  long long* sizes;    // [4,P]: n_dec, max_dec, n_ali, max_ali
-};
 
-__global__ void __launch_bounds__(1024) ScanKernel(ScanParams p) {
+static __global__ void __launch_bounds__(1024) ScanKernel(ScanParams p) {
   __shared__ long long s_sum[2][32];
   __shared__ int s_max[2][32];
   const int path = blockIdx.x;
@@ -1290,18 +1280,8 @@ __global__ void __launch_bounds__(1024) ScanKernel(ScanParams p) {
   }
 }
 
-struct PackParams {
-  const int* dec_len; const int* dec; const int* ali_len; const int* ali;  // dense rows
-  const long long* dec_off; const long long* ali_off;                      // [P,B]
-  const long long* sizes;                                                   // [4,P]
-  const void* fin_total;                                                    // [B,P] float or double
-  long long* const* ptrs;  // device table [6,P]: dec_idx, dec_val, dec_shape, ali_idx, ali_val, ali_shape
-  void* log_prob;          // [B,P] float or double
-  int real_bytes;          // 4 or 8
-  int T, B, P;
-};
 
-__global__ void __launch_bounds__(128) PackKernel(PackParams p) {
+static __global__ void __launch_bounds__(128) PackKernel(PackParams p) {
   const int b = blockIdx.x, path = blockIdx.y;
   const size_t row = (size_t)b * p.P + path;
   {
@@ -1343,7 +1323,7 @@ __global__ void __launch_bounds__(128) PackKernel(PackParams p) {
 }
 
 // Test hook: element-wise evaluation of the exact math functions.
-__global__ void MathTestKernel(int op, const float* x, float* y, int n) {
+static __global__ void MathTestKernel(int op, const float* x, float* y, int n) {
   __shared__ unsigned long long s_tab[32];
   LoadExpTable(s_tab, threadIdx.x, blockDim.x);
   __syncthreads();
@@ -1354,7 +1334,7 @@ __global__ void MathTestKernel(int op, const float* x, float* y, int n) {
 }
 
 // op 0: exp (x <= 0), 1: log (x >= 1), 2: LogSumExp(x, 0) of the double path
-__global__ void MathTestKernelF64(int op, const double* x, double* y, int n) {
+static __global__ void MathTestKernelF64(int op, const double* x, double* y, int n) {
   __shared__ unsigned long long s_tab[256];
   __shared__ unsigned long long s_tabf[32];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = kCtcxExpTab[i];
@@ -1365,5 +1345,7 @@ __global__ void MathTestKernelF64(int op, const double* x, double* y, int n) {
   const double v = x[i];
   y[i] = (op == 0) ? ExpExactD(v, s_tab) : (op == 1) ? LogExactD(v) : LogSumExp(v, 0.0, s_tabf);
 }
+
+#endif  // CTCX_WITH_POST
 
 }  // namespace ctcx

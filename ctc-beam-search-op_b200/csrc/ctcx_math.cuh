@@ -15,7 +15,7 @@
 namespace ctcx {
 
 // bits of 2^(i/32) - (i << 47)
-__device__ __constant__ unsigned long long kExp2fTabConst[32] = {
+static __device__ __constant__ unsigned long long kExp2fTabConst[32] = {
     0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
     0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
     0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
@@ -27,7 +27,7 @@ __device__ __constant__ unsigned long long kExp2fTabConst[32] = {
 };
 
 // (1/c, log c) pairs of the logf table
-__device__ __constant__ unsigned long long kLogfTabConst[32] = {
+static __device__ __constant__ unsigned long long kLogfTabConst[32] = {
     0x3ff661ec79f8f3beull, 0xbfd57bf7808caadeull, 0x3ff571ed4aaf883dull, 0xbfd2bef0a7c06ddbull,
     0x3ff49539f0f010b0ull, 0xbfd01eae7f513a67ull, 0x3ff3c995b0b80385ull, 0xbfcb31d8a68224e9ull,
     0x3ff30d190c8864a5ull, 0xbfc6574f0ac07758ull, 0x3ff25e227b0b8ea0ull, 0xbfc1aa2bc79c8100ull,
@@ -181,7 +181,7 @@ __device__ __forceinline__ float LogSumExp(float a, float b, const unsigned long
 // double (util/ctc_loss_util.h:39-40).
 // ---------------------------------------------------------------------------------------------
 }  // namespace ctcx
-#define CTCX_TAB_QUAL __device__ __constant__
+#define CTCX_TAB_QUAL static __device__ __constant__
 #include "ctcx_libm_f64_tables.h"
 #undef CTCX_TAB_QUAL
 namespace ctcx {

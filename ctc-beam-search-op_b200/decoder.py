@@ -23,10 +23,21 @@ from . import _lib
 SparseTensor = collections.namedtuple("SparseTensor", ["indices", "values", "dense_shape"])
 
 # Same field order as the raw op's outputs (ops.cc:17-23); indexable like the generated TF wrapper.
-CTCExtBeamSearchDecoder = collections.namedtuple(
+_RawBase = collections.namedtuple(
     "CTCExtBeamSearchDecoder",
     ["decoded_indices", "decoded_values", "decoded_shape", "alignment_indices", "alignment_values",
      "alignment_shape", "log_probability"])
+
+
+class CTCExtBeamSearchDecoder(_RawBase):
+    """The raw op's 7 output groups (indexable [0..6] like the generated TF wrapper). `.flags` carries
+    this decode's diagnostic bits (FLAG_ROUNDING_ANOMALY) -- an attribute, not an eighth output."""
+    flags = 0
+
+
+class DecodeResult(tuple):
+    """`(decoded, alignment, log_probability)` (README.md:19-31) plus a `.flags` attribute."""
+    flags = 0
 
 
 class CtcxError(ValueError):
@@ -58,13 +69,37 @@ _ERR_CLASS = {1: InvalidArgumentError, 2: InvalidArgumentError, 3: InvalidArgume
 
 FLAG_ROUNDING_ANOMALY = 1  # see DESIGN.md "Known deviation"
 
-last_flags = 0  # flags of the most recent decode in this process (diagnostics only)
+_DTYPE_CODE = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16,
+               torch.float64: _lib.F64}
+_copy_streams = {}
 
 
-def _raise(lib, rc):
+def set_beam_impl(name):
+    """Test hook: None / "fast" = dispatch by shape; "generic" = route every decode of this process to
+    the generic beam kernel (the independent second implementation the parity tests compare with)."""
+    if name not in (None, "fast", "generic"):
+        raise ValueError("unknown beam implementation %r" % (name,))
+    _lib.load().ctcx_debug_set_beam_impl(1 if name == "generic" else 0)
+
+
+def _copy_stream(device):
+    """One side stream per device for the host->device feed of host-input decodes."""
+    key = (device.type, device.index)
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device=device)
+    return _copy_streams[key]
+
+
+def _raise(lib, rc, batch_offset=0):
     msg = lib.ctcx_strerror(rc).decode()
+    if rc == 5 and batch_offset:  # kernels.cc:134-138 names the utterance: report its index in the WHOLE batch
+        b = lib.ctcx_error_batch_index()
+        msg = msg.replace("sequence_length(%d)" % b, "sequence_length(%d)" % (b + batch_offset), 1)
     if rc in _ERR_CLASS:
-        raise _ERR_CLASS[rc](rc, msg)
+        exc = _ERR_CLASS[rc](rc, msg)
+        if rc == 5:
+            exc.batch_index = lib.ctcx_error_batch_index() + int(batch_offset)
+        raise exc
     raise RuntimeError("ctcx: %s (code %d)" % (msg, rc))
 
 
@@ -126,20 +161,33 @@ def _pack(lib, ws, T, B, P, counts, device, stream, f64=False, host_out=False):
         hbuf = torch.empty((n,), dtype=torch.int64, pin_memory=True)
         hbuf.copy_(buf, non_blocking=True)
         torch.cuda.current_stream(device).synchronize()
+        buf = hbuf
         groups, logp = _carve(hbuf, B, P, counts, f64)
-    return groups, logp
+    return groups, logp, buf
+
+
+def _frame_strided(x):
+    """True if x[t, b, c] sits at t * stride + b * C + c, i.e. x is a contiguous tensor or a batch
+    shard [:, b0:b1, :] of one -- what the kernels decode in place (ctcx_decode_view)."""
+    T, B, C = x.shape
+    st = x.stride()
+    return (C == 1 or st[2] == 1) and (B == 1 or st[1] == C) and (T == 1 or st[0] >= B * C)
 
 
 def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_paths,
                                     merge_repeated=False, blank_index=0, blank_label=-1,
-                                    name=None, device=None, expansion_scores=None):
+                                    name=None, device=None, expansion_scores=None, batch_offset=0,
+                                    outputs="auto"):
     """The raw op: returns a 7-field namedtuple of (lists of) tensors, exactly the op's outputs.
 
     inputs            [max_time, batch, num_classes] float32 or float64 (the reference registers both,
                       kernels.cc:269-275; float64 is computed in float64 by the double instantiation
-                      of the generic kernel and log_probability is float64); torch float16 / bfloat16
-                      are accepted and upcast exactly on the device; numpy array or torch tensor on
-                      any device
+                      of the generic kernel and log_probability is float64); float16 / bfloat16 are
+                      read by the kernels as they are (widened exactly in registers); numpy array or
+                      torch tensor on any device. A batch shard `x[:, b0:b1, :]` of a contiguous
+                      tensor is decoded in place (device) / copied with a pitched copy (host) -- no
+                      repack. Host inputs are copied to the device in time slabs on a side stream
+                      while the beam kernel already runs (ctcx_decode_hostin).
     sequence_length   [batch] int32
     beam_width >= 1, top_paths >= 1, merge_repeated=False, blank_index=0, blank_label=-1
     expansion_scores  optional [num_classes + 1, num_classes] float32 table (entries <= 0) for the
@@ -147,7 +195,10 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
                       whose last label is f (row f + 1; row 0 = empty prefix) by label l adds
                       table[f + 1, l] to the score carried over -- a bigram LM / insertion penalty.
                       float32 inputs only; None = the op's default scorer.
-    Outputs live where the inputs live (numpy in -> numpy out).
+    batch_offset      index of utterance 0 in the caller's whole batch (error messages of a shard)
+    outputs           "auto": outputs live where the inputs live (numpy in -> numpy out); "device" /
+                      "host" force the placement (torch tensors)
+    `.flags` = diagnostic bits; `.packed` = the one int64 buffer all outputs are views of.
     """
     del name
     if int(beam_width) < 1:
@@ -155,7 +206,16 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
     if int(top_paths) < 1:
         raise ValueError("Attr top_paths has value %d less than minimum 1" % int(top_paths))
     lib = _lib.load()
-    x, x_np = _as_tensor(inputs)
+    x_np = not isinstance(inputs, torch.Tensor)
+    if x_np:
+        xa = np.asarray(inputs)
+        if xa.dtype.kind != "f":
+            raise TypeError("inputs must be a floating-point array, got %s" % xa.dtype)
+        if not xa.flags.writeable:  # torch.from_numpy wants a writable array
+            xa = xa.copy()
+        x = torch.from_numpy(xa)
+    else:
+        x = inputs
     seq, _ = _as_tensor(np.asarray(sequence_length, dtype=np.int32)
                         if not isinstance(sequence_length, torch.Tensor) else sequence_length)
     # kernels.cc:111-130, in order
@@ -175,57 +235,80 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
     if not torch.cuda.is_available():
         raise RuntimeError("ctcx: no CUDA device available and there is no CPU fallback")
 
-    f64 = x.dtype == torch.float64
     if device is None:
         device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
     device = torch.device(device)
-    host_out = not x.is_cuda
-    half = x.dtype in (torch.float16, torch.bfloat16) and expansion_scores is None
+    host_in = not x.is_cuda
+    if x.dtype not in _DTYPE_CODE or expansion_scores is not None:
+        if expansion_scores is not None and x.dtype == torch.float64:
+            raise TypeError("expansion_scores is supported for float32 inputs only")
+        x = x.to(torch.float32)
+    f64 = x.dtype == torch.float64
+    if not _frame_strided(x):
+        x = x.contiguous()
+    tstride = int(x.stride(0)) if T > 1 else B * C
+    W, P = int(beam_width), int(top_paths)
+    attrs = (W, P, int(bool(merge_repeated)), int(blank_index), int(blank_label))
     with torch.cuda.device(device):
-        # fp16 / bf16 logits cross the bus as they are and are upcast (exactly) on the device
-        xd = x.to(device=device, dtype=(x.dtype if (half or f64) else torch.float32),
-                  non_blocking=True).contiguous()
-        sd = seq.to(device=device, dtype=torch.int32, non_blocking=True).contiguous()
-        stream = torch.cuda.current_stream(device).cuda_stream
-        P = int(top_paths)
-        ws_bytes = lib.ctcx_workspace_bytes(T, B, C, int(beam_width), P)
+        cur = torch.cuda.current_stream(device)
+        stream = cur.cuda_stream
+        ws_bytes = lib.ctcx_workspace_bytes(T, B, C, W, P)
         ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=device)
         arr = ctypes.c_int64 * P
         n_dec, max_dec, n_ali, max_ali = arr(), arr(), arr(), arr()
         sizes = _lib.CtcxSizes(n_dec, max_dec, n_ali, max_ali)
         flags = ctypes.c_int32(0)
-        if half:
-            scratch = torch.empty((T, B, C), dtype=torch.float32, device=device)
-            rc = lib.ctcx_decode_half(xd.data_ptr(), 0 if x.dtype == torch.float16 else 1,
-                                      scratch.data_ptr(), T, B, C, sd.data_ptr(), int(beam_width), P,
-                                      int(bool(merge_repeated)), int(blank_index), int(blank_label),
-                                      ws.data_ptr(), ws_bytes, stream, ctypes.byref(sizes),
-                                      ctypes.byref(flags))
-        elif expansion_scores is not None:
-            if f64:
-                raise TypeError("expansion_scores is supported for float32 inputs only")
-            es, _ = _as_tensor(expansion_scores)
-            if tuple(es.shape) != (C + 1, C):
-                raise InvalidArgumentError(8, "expansion_scores must have shape [num_classes + 1, num_classes]")
-            esd = es.to(device=device, dtype=torch.float32).contiguous()
-            rc = lib.ctcx_decode_scorer_f32(xd.data_ptr(), T, B, C, sd.data_ptr(), int(beam_width), P,
-                                            int(bool(merge_repeated)), int(blank_index), int(blank_label),
-                                            esd.data_ptr(), ws.data_ptr(), ws_bytes, stream,
-                                            ctypes.byref(sizes), ctypes.byref(flags))
+        if host_in and expansion_scores is None:
+            # host logits: copied in time slabs on a side stream while the beam kernel already runs
+            sh = seq.to(dtype=torch.int32).contiguous()
+            n_stage = lib.ctcx_hostin_staging_bytes(_DTYPE_CODE[x.dtype], T, B, C)
+            staging = torch.empty(max(n_stage, 16), dtype=torch.uint8, device=device)
+            side = _copy_stream(device)
+            rc = lib.ctcx_decode_hostin(x.data_ptr(), _DTYPE_CODE[x.dtype], tstride, T, B, C, sh.data_ptr(),
+                                        *attrs, staging.data_ptr(), n_stage, ws.data_ptr(), ws_bytes, stream,
+                                        side.cuda_stream, ctypes.byref(sizes), ctypes.byref(flags))
+            if rc == 9 and x.dtype in (torch.float16, torch.bfloat16):  # (test hook only, see below)
+                x = x.float().contiguous()
+                n_stage = lib.ctcx_hostin_staging_bytes(_lib.F32, T, B, C)
+                staging = torch.empty(max(n_stage, 16), dtype=torch.uint8, device=device)
+                rc = lib.ctcx_decode_hostin(x.data_ptr(), _lib.F32, 0, T, B, C, sh.data_ptr(), *attrs,
+                                            staging.data_ptr(), n_stage, ws.data_ptr(), ws_bytes, stream,
+                                            side.cuda_stream, ctypes.byref(sizes), ctypes.byref(flags))
+            staging.record_stream(side)
         else:
-            decode = lib.ctcx_decode_f64 if f64 else lib.ctcx_decode_f32
-            rc = decode(xd.data_ptr(), T, B, C, sd.data_ptr(), int(beam_width), P,
-                        int(bool(merge_repeated)), int(blank_index), int(blank_label),
-                        ws.data_ptr(), ws_bytes, stream, ctypes.byref(sizes), ctypes.byref(flags))
+            xd = x.to(device=device, non_blocking=True)
+            sd = seq.to(device=device, dtype=torch.int32, non_blocking=True).contiguous()
+            if expansion_scores is not None:
+                es, _ = _as_tensor(expansion_scores)
+                if tuple(es.shape) != (C + 1, C):
+                    raise InvalidArgumentError(8, "expansion_scores must have shape [num_classes + 1, num_classes]")
+                esd = es.to(device=device, dtype=torch.float32).contiguous()
+                xd = xd.contiguous()
+                rc = lib.ctcx_decode_scorer_f32(xd.data_ptr(), T, B, C, sd.data_ptr(), *attrs, esd.data_ptr(),
+                                                ws.data_ptr(), ws_bytes, stream, ctypes.byref(sizes),
+                                                ctypes.byref(flags))
+            else:
+                rc = lib.ctcx_decode_view(xd.data_ptr(), _DTYPE_CODE[xd.dtype], tstride, T, B, C, sd.data_ptr(),
+                                          *attrs, ws.data_ptr(), ws_bytes, stream, ctypes.byref(sizes),
+                                          ctypes.byref(flags))
+                if rc == 9 and xd.dtype in (torch.float16, torch.bfloat16):
+                    # (test hook only: the generic kernel forced onto a fast-path shape has no room to widen
+                    # half-precision logits in the workspace)
+                    xd = xd.float().contiguous()
+                    rc = lib.ctcx_decode_view(xd.data_ptr(), _lib.F32, 0, T, B, C, sd.data_ptr(), *attrs,
+                                              ws.data_ptr(), ws_bytes, stream, ctypes.byref(sizes),
+                                              ctypes.byref(flags))
         if rc != 0:
-            _raise(lib, rc)
-        global last_flags
-        last_flags = int(flags.value)
-        groups, logp = _pack(lib, ws, T, B, P, (n_dec, n_ali), device, stream, f64, host_out)
-        if host_out and x_np:
+            _raise(lib, rc, int(batch_offset))
+        host_out = host_in if outputs == "auto" else (outputs == "host")
+        groups, logp, packed = _pack(lib, ws, T, B, P, (n_dec, n_ali), device, stream, f64, host_out)
+        if host_out and x_np and outputs == "auto":
             groups = [[t.numpy() for t in g] for g in groups]
             logp = logp.numpy()
-    return CTCExtBeamSearchDecoder(*groups, logp)
+    res = CTCExtBeamSearchDecoder(*groups, logp)
+    res.flags = int(flags.value)
+    res.packed = packed
+    return res
 
 
 def ctc_ext_beam_search_decoder(inputs, sequence_length, beam_width, top_paths,
@@ -239,14 +322,17 @@ def ctc_ext_beam_search_decoder(inputs, sequence_length, beam_width, top_paths,
                                           expansion_scores)
     decoded = [SparseTensor(i, v, s) for i, v, s in zip(raw[0], raw[1], raw[2])]
     alignment = [SparseTensor(i, v, s) for i, v, s in zip(raw[3], raw[4], raw[5])]
-    return decoded, alignment, raw[6]
+    out = DecodeResult((decoded, alignment, raw[6]))
+    out.flags = raw.flags
+    return out
 
 
 class CTCExtBeamSearchDecoderStream:
     """Streaming form of the decoder: the reference's `Step / TopPaths / Reset`
     (cc/util/ctc_ext_beam_search_decoder.h:39-53) for a whole batch, with the beam kept on the
     device between calls. Feeding the frames of an utterance in any chunking gives bit-identical
-    results to one `ctc_ext_beam_search_decoder` call on the concatenation.
+    results to one `ctc_ext_beam_search_decoder` call on the concatenation. float32 scores only
+    (float16 / bfloat16 chunks are widened; float64 chunks are refused).
 
         dec = CTCExtBeamSearchDecoderStream(batch_size=B, num_classes=C, beam_width=100, top_paths=1,
                                             max_time=3000, merge_repeated=True, blank_index=C - 1)
@@ -293,6 +379,9 @@ class CTCExtBeamSearchDecoderStream:
         x, _ = _as_tensor(inputs)
         if x.dim() != 3:
             raise InvalidArgumentError(1, self._lib.ctcx_strerror(1).decode())
+        if x.dtype == torch.float64:
+            raise TypeError("the streaming decoder computes in float32; float64 chunks would not be "
+                            "bit-identical to a one-shot float64 decode -- cast explicitly if that is intended")
         Tc, B, C = (int(v) for v in x.shape)
         if B != self.B or C != self.C:
             raise InvalidArgumentError(8, "chunk shape %s does not match the stream (batch %d, classes %d)"
@@ -353,15 +442,19 @@ class CTCExtBeamSearchDecoderStream:
                                                  ctypes.byref(sizes), ctypes.byref(flags))
             if rc != 0:
                 _raise(self._lib, rc)
-            groups, logp = _pack(self._lib, self._ws, self.T, self.B, P, (n_dec, n_ali), self.device,
-                                 self._stream())
-        return CTCExtBeamSearchDecoder(*groups, logp)
+            groups, logp, _ = _pack(self._lib, self._ws, self.T, self.B, P, (n_dec, n_ali), self.device,
+                                    self._stream())
+        res = CTCExtBeamSearchDecoder(*groups, logp)
+        res.flags = int(flags.value)
+        return res
 
     def top_paths(self):
         raw = self.top_paths_raw()
         decoded = [SparseTensor(i, v, s) for i, v, s in zip(raw[0], raw[1], raw[2])]
         alignment = [SparseTensor(i, v, s) for i, v, s in zip(raw[3], raw[4], raw[5])]
-        return decoded, alignment, raw[6]
+        out = DecodeResult((decoded, alignment, raw[6]))
+        out.flags = raw.flags
+        return out
 
 
 def decode_host_cabi(inputs, sequence_length, beam_width, top_paths, merge_repeated=False,

@@ -1,17 +1,22 @@
 """Multi-GPU host logic: utterances are independent (the reference never shares state across the
 batch -- cc/kernels/ctc_ext_beam_search_decoder_kernels.cc:68-90 merely re-uses one decoder after
-Reset()), so the batch is cut into contiguous blocks, one per GPU, and the sparse outputs are
-concatenated on the host. There is NO collective on the decode path.
+Reset()), so the batch is cut into contiguous blocks, one per GPU, each block is decoded IN PLACE from
+a view `inputs[:, b0:b1, :]` of the time-major tensor (no repack: the kernels take a time stride, a
+host view is copied with a pitched copy), and the sparse outputs are concatenated. There is NO
+collective on the decode path; the only exchange is the gather of the (small) sparse outputs.
 
-  * shard_bounds / merge_raw        pure host logic (numpy), used by both drivers below
+  * shard_bounds / merge_raw        pure host logic, used by both drivers below
   * decode_multi_device             one process, several GPUs (a host thread + stream per device)
-  * decode_distributed              one process per GPU under torch.distributed (NCCL or gloo): each
-                                    rank decodes its block; rank `dst` receives the merged result
+  * decode_distributed              one process per GPU under torch.distributed: each rank decodes its
+                                    block; rank `dst` receives the merged result. Under NCCL the packed
+                                    outputs travel GPU -> GPU (NVLink) and are merged on the device;
+                                    under gloo (CPU tests) they are gathered as host objects.
 """
 import threading
 
 import numpy as np
 
+from . import decoder as _dec
 from .decoder import CTCExtBeamSearchDecoder, ctc_ext_beam_search_decoder_raw
 
 
@@ -49,7 +54,39 @@ def merge_raw(shards, bounds, batch):
             groups[base + 1].append(np.concatenate(val, axis=0))
             groups[base + 2].append(np.asarray([batch, mx], np.int64))
     logp = np.concatenate([_np(sh[6]).reshape(-1, P) for sh in shards], axis=0)
+    res = CTCExtBeamSearchDecoder(*groups, logp)
+    res.flags = 0
+    for sh in shards:
+        res.flags |= int(getattr(sh, "flags", 0))
+    return res
+
+
+def _merge_device(shards, bounds, batch):
+    """merge_raw for torch tensors that live on one device (no host round trip)."""
+    import torch
+    P = len(shards[0][0])
+    groups = [[], [], [], [], [], []]
+    dev = shards[0][6].device
+    for p in range(P):
+        for base in (0, 3):
+            idx, val, mx = [], [], 0
+            for sh, (b0, _) in zip(shards, bounds):
+                i = sh[base][p]
+                if b0:
+                    i[:, 0] += b0  # in place: the gathered buffer is ours
+                idx.append(i)
+                val.append(sh[base + 1][p])
+                mx = max(mx, int(sh[base + 2][p][1]))
+            groups[base].append(torch.cat(idx, dim=0))
+            groups[base + 1].append(torch.cat(val, dim=0))
+            groups[base + 2].append(torch.tensor([batch, mx], dtype=torch.int64, device=dev))
+    logp = torch.cat([sh[6].reshape(-1, P) for sh in shards], dim=0)
     return CTCExtBeamSearchDecoder(*groups, logp)
+
+
+def _view(x, b0, b1):
+    """Block [b0, b1) of the batch axis as a VIEW (numpy or torch): no copy."""
+    return x[:, b0:b1, :]
 
 
 def decode_multi_device(inputs, sequence_length, beam_width, top_paths, merge_repeated=False,
@@ -57,7 +94,7 @@ def decode_multi_device(inputs, sequence_length, beam_width, top_paths, merge_re
     """Single process, several GPUs: block r of the batch goes to devices[r]. Host arrays in, merged
     host (numpy) result out."""
     import torch
-    x = _np(inputs)
+    x = inputs if isinstance(inputs, (np.ndarray, torch.Tensor)) else np.asarray(inputs)
     sl = _np(sequence_length).astype(np.int32)
     B = x.shape[1]
     if devices is None:
@@ -69,9 +106,8 @@ def decode_multi_device(inputs, sequence_length, beam_width, top_paths, merge_re
     def work(r):
         b0, b1 = bounds[r]
         try:
-            xs = np.ascontiguousarray(x[:, b0:b1, :])
-            kw = {} if decode_fn else {"device": "cuda:%d" % devices[r]}
-            results[r] = fn(xs, sl[b0:b1], beam_width, top_paths, merge_repeated, blank_index,
+            kw = {} if decode_fn else {"device": "cuda:%d" % devices[r], "batch_offset": b0}
+            results[r] = fn(_view(x, b0, b1), sl[b0:b1], beam_width, top_paths, merge_repeated, blank_index,
                             blank_label, **kw)
         except Exception as e:  # re-raised below, first failing shard first (reference order)
             errors[r] = e
@@ -87,26 +123,108 @@ def decode_multi_device(inputs, sequence_length, beam_width, top_paths, merge_re
     return merge_raw(results, bounds, B)
 
 
+def _gather_packed_nccl(raw, err, bounds, B, P, f64, rank, world, dst, group, to_host, max_time):
+    """Gather of the packed outputs GPU -> GPU. Every decode leaves its 6*P + 1 outputs as views of ONE
+    int64 buffer (`raw.packed`); the buffers (padded to the longest) are gathered on `dst` with one
+    NCCL call, carved up there and merged on the device."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", torch.cuda.current_device())
+    # header: [error code, error batch index, flags, n_dec[P], n_ali[P], packed length]
+    hdr = torch.zeros(4 + 2 * P, dtype=torch.int64)
+    if err is not None:
+        hdr[0] = int(getattr(err, "code", -1)) or -1
+        hdr[1] = int(getattr(err, "batch_index", -1))
+    else:
+        hdr[2] = int(raw.flags)
+        for p in range(P):
+            hdr[3 + p] = raw[0][p].shape[0]
+            hdr[3 + P + p] = raw[3][p].shape[0]
+        hdr[3 + 2 * P] = raw.packed.numel()
+    hdr = hdr.to(dev)
+    all_hdr = torch.empty((world, hdr.numel()), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_hdr, hdr, group=group)
+    all_hdr = all_hdr.cpu()
+    failed = [r for r in range(world) if int(all_hdr[r, 0]) != 0]
+    if failed:  # every rank learns of the failure; the reference aborts at the first failing utterance
+        if err is not None and (rank != dst or failed[0] == rank):
+            raise err
+        r0 = failed[0]
+        if rank == dst:
+            code, b = int(all_hdr[r0, 0]), int(all_hdr[r0, 1])
+            lib = _dec._lib.load()
+            if code == 5:  # kernels.cc:134-138, with the index in the whole batch
+                raise _dec.FailedPreconditionError(5, "sequence_length(%d) <= %d" % (b, max_time))
+            if code in _dec._ERR_CLASS:
+                raise _dec._ERR_CLASS[code](code, lib.ctcx_strerror(code).decode())
+            raise RuntimeError("ctcx: rank %d failed (code %d)" % (r0, code))
+        return None
+    n_max = int(all_hdr[:, 3 + 2 * P].max())
+    mine = raw.packed
+    if mine.numel() < n_max:
+        padded = torch.empty(n_max, dtype=torch.int64, device=dev)
+        padded[:mine.numel()] = mine
+        mine = padded
+    if rank == dst:
+        recv = [torch.empty(n_max, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.gather(mine, recv, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+    else:
+        dist.gather(mine, None, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+        return None
+    shards = []
+    for r in range(world):
+        b0, b1 = bounds[r]
+        counts = ([int(v) for v in all_hdr[r, 3:3 + P]], [int(v) for v in all_hdr[r, 3 + P:3 + 2 * P]])
+        groups, logp = _dec._carve(recv[r], b1 - b0, P, counts, f64)
+        shards.append(CTCExtBeamSearchDecoder(*groups, logp))
+    out = _merge_device(shards, bounds, B)
+    flags = 0
+    for r in range(world):
+        flags |= int(all_hdr[r, 2])
+    if to_host:
+        out = CTCExtBeamSearchDecoder(*[[t.cpu().numpy() for t in g] for g in out[:6]], out[6].cpu().numpy())
+    out.flags = flags
+    return out
+
+
 def decode_distributed(inputs, sequence_length, beam_width, top_paths, merge_repeated=False,
                        blank_index=0, blank_label=-1, dst=0, group=None, decode_fn=None):
-    """One process per GPU: every rank holds the full (host) batch description, decodes its own
-    contiguous block, and the raw outputs are gathered on rank `dst` (host-side gather of small
-    sparse tensors; returns None elsewhere)."""
+    """One process per GPU: every rank holds the full batch description (or at least its own block of
+    it -- only `inputs[:, b0:b1, :]` of this rank's block is touched), decodes its contiguous block in
+    place, and the raw outputs are gathered on rank `dst` (returns None elsewhere). Outputs live where
+    the inputs live (device tensors in -> device tensors on `dst`)."""
+    import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    x = _np(inputs)
-    sl = _np(sequence_length).astype(np.int32)
-    B = x.shape[1]
+    x = inputs if isinstance(inputs, (np.ndarray, torch.Tensor)) else np.asarray(inputs)
+    sl = sequence_length if isinstance(sequence_length, torch.Tensor) else np.asarray(sequence_length, np.int32)
+    B = int(x.shape[1]) if x.ndim == 3 else 0
     bounds = shard_bounds(B, world)
     b0, b1 = bounds[rank]
-    fn = decode_fn or ctc_ext_beam_search_decoder_raw
-    err, mine = None, None
+    device_gather = decode_fn is None and dist.get_backend(group) == "nccl" and x.ndim == 3
+    err, raw = None, None
     try:
-        raw = fn(np.ascontiguousarray(x[:, b0:b1, :]), sl[b0:b1], beam_width, top_paths,
-                 merge_repeated, blank_index, blank_label)
-        mine = tuple([_np(t) for t in g] for g in raw[:6]) + (_np(raw[6]),)
+        if decode_fn is not None:
+            raw = decode_fn(np.ascontiguousarray(_np(x)[:, b0:b1, :]), _np(sl)[b0:b1].astype(np.int32), beam_width,
+                            top_paths, merge_repeated, blank_index, blank_label)
+        else:
+            raw = ctc_ext_beam_search_decoder_raw(_view(x, b0, b1), sl[b0:b1], beam_width, top_paths,
+                                                  merge_repeated, blank_index, blank_label, batch_offset=b0,
+                                                  outputs="device" if device_gather else "auto")
     except Exception as e:
         err = e
+    if device_gather:
+        f64 = (x.dtype == torch.float64) if isinstance(x, torch.Tensor) else (x.dtype == np.float64)
+        to_host = not (isinstance(x, torch.Tensor) and x.is_cuda)
+        out = _gather_packed_nccl(raw, err, bounds, B, int(top_paths), f64, rank, world, dst, group, to_host,
+                                  int(x.shape[0]))
+        if out is not None and to_host and isinstance(x, torch.Tensor):
+            out = CTCExtBeamSearchDecoder(*[[torch.from_numpy(t) for t in g] for g in out[:6]],
+                                          torch.from_numpy(out[6]))
+        return out
+    mine = None
+    if raw is not None:
+        mine = tuple([_np(t) for t in g] for g in raw[:6]) + (_np(raw[6]), int(getattr(raw, "flags", 0)))
     gathered = [None] * world if rank == dst else None
     dist.gather_object((mine, err), gathered, dst=dst, group=group)
     if rank != dst:
@@ -116,4 +234,9 @@ def decode_distributed(inputs, sequence_length, beam_width, top_paths, merge_rep
     for res, e in gathered:  # the reference aborts at the first failing utterance
         if e is not None:
             raise e
-    return merge_raw([g[0] for g in gathered], bounds, B)
+    shards = []
+    for g, _ in gathered:
+        sh = CTCExtBeamSearchDecoder(*g[:7])
+        sh.flags = g[7]
+        shards.append(sh)
+    return merge_raw(shards, bounds, B)

@@ -40,13 +40,17 @@ enum {
   CTCX_ERR_BAD_ARGUMENT = 8,        /* not validated by the reference (UB there): blank_index outside
                                        [0,C), negative sequence_length, beam_width/top_paths < 1 */
   CTCX_ERR_UNSUPPORTED = 9,         /* shape outside what this build supports (see ctcx_limits) */
-  CTCX_ERR_WORKSPACE = 10,          /* workspace too small / NULL */
+  CTCX_ERR_WORKSPACE = 10,          /* workspace too small / NULL / not 256-byte aligned */
   CTCX_ERR_CUDA = 11                /* a CUDA runtime call failed; ctcx_last_cuda_error() has it */
 };
 
-/* Human-readable text of a return code; for 1-7 the reference's own message. `detail` (may be NULL)
- * receives e.g. the offending batch index for CTCX_ERR_SEQ_LEN_RANGE. */
+/* Human-readable text of a return code; for 1-7 the reference's own message (for
+ * CTCX_ERR_SEQ_LEN_RANGE with the offending batch index of this thread's last decode filled in). */
 const char* ctcx_strerror(int code);
+
+/* Batch index of this thread's last CTCX_ERR_SEQ_LEN_RANGE (kernels.cc:134-138 reports it in the
+ * message); a caller that decodes a shard [b0, b1) of a batch adds b0 before reporting. */
+int ctcx_error_batch_index(void);
 
 /* Last CUDA error string seen by this thread ("" if none). */
 const char* ctcx_last_cuda_error(void);
@@ -85,6 +89,40 @@ int ctcx_decode_f32(const float* logits_dev, int max_time, int batch, int num_cl
                     int blank_index, int blank_label, void* workspace, size_t workspace_bytes,
                     void* stream, ctcx_sizes* sizes, int32_t* flags_out);
 
+/* Element types of a logits tensor. The reference registers float and double (kernels.cc:269-275);
+ * half and bfloat16 are what an acoustic model's projection emits -- they are read by the kernels as
+ * they are (widened exactly to float32 in registers), so the result equals the reference op run on
+ * the widened values. */
+enum { CTCX_F32 = 0, CTCX_F16 = 1, CTCX_BF16 = 2, CTCX_F64 = 3 };
+
+/* Decode a VIEW: logits_dev points at element (t = 0, b = 0, c = 0) of a [max_time, batch, num_classes]
+ * view whose frames are `time_stride` ELEMENTS apart (0 = batch * num_classes, i.e. contiguous) -- e.g.
+ * the batch shard inputs[:, b0:b1, :] of a wider time-major tensor (pointer = &inputs[0, b0, 0], stride
+ * = total_batch * num_classes) is decoded in place, without a repack. Utterances are independent
+ * (kernels.cc:67-89), so a shard's result is the corresponding slice of the whole batch's. dtype is
+ * one of CTCX_F32 / F16 / BF16 / F64 (F64: pack with ctcx_pack_f64). Everything else as
+ * ctcx_decode_f32. */
+int ctcx_decode_view(const void* logits_dev, int dtype, int64_t time_stride, int max_time, int batch,
+                     int num_classes, const int32_t* seq_len_dev, int beam_width, int top_paths,
+                     int merge_repeated, int blank_index, int blank_label, void* workspace,
+                     size_t workspace_bytes, void* stream, ctcx_sizes* sizes, int32_t* flags_out);
+
+/* Decode HOST logits, with the host->device copy off the critical path. logits_host is a
+ * [max_time, batch, num_classes] view in host memory (frames host_time_stride elements apart, 0 =
+ * contiguous; pinned memory copies asynchronously, pageable memory works too), seq_len_host [batch]
+ * int32 in host memory. The logits are copied into staging_dev (device memory, at least
+ * ctcx_hostin_staging_bytes(...) bytes) in time slabs on `copy_stream` while, for the char-CTC shapes
+ * (num_classes <= 32), the beam kernel on `stream` already consumes the frames that have landed; other
+ * shapes start after the copy. copy_stream must be a different stream from `stream`. The decode result
+ * is left in the workspace exactly as by ctcx_decode_f32 (follow with ctcx_pack_f32 / _f64).
+ * Synchronises `stream` once. */
+size_t ctcx_hostin_staging_bytes(int dtype, int max_time, int batch, int num_classes);
+int ctcx_decode_hostin(const void* logits_host, int dtype, int64_t host_time_stride, int max_time,
+                       int batch, int num_classes, const int32_t* seq_len_host, int beam_width,
+                       int top_paths, int merge_repeated, int blank_index, int blank_label,
+                       void* staging_dev, size_t staging_bytes, void* workspace, size_t workspace_bytes,
+                       void* stream, void* copy_stream, ctcx_sizes* sizes, int32_t* flags_out);
+
 /* Pack: replaces StoreAllDecodedSequences (kernels.cc:163-257) and the log-prob copy (:87-89).
  * All pointers are DEVICE memory; arrays of `top_paths` device pointers are HOST arrays.
  *   decoded_indices[p]   int64 [n_decoded[p], 2]   rows [b, position], row-major over b then position
@@ -92,8 +130,9 @@ int ctcx_decode_f32(const float* logits_dev, int max_time, int batch, int num_cl
  *   decoded_shape[p]     int64 [2] = [batch, max_decoded[p]]
  *   alignment_*          likewise
  *   log_probability      float32 [batch, top_paths]
- * Synchronises `stream` once at entry (it validates the workspace header); the pack kernel itself is
- * only enqueued. */
+ * Does not synchronise: the pack kernel is only enqueued on `stream` (the part of the workspace it
+ * reads is laid out by max_time, batch and top_paths alone). A workspace decoded as float64 must be
+ * packed with ctcx_pack_f64. */
 int ctcx_pack_f32(const void* workspace, int max_time, int batch, int top_paths,
                   int64_t* const* decoded_indices, int64_t* const* decoded_values,
                   int64_t* const* decoded_shape, int64_t* const* alignment_indices,
@@ -134,9 +173,10 @@ int ctcx_decode_host_f64(const double* logits_host, int max_time, int batch, int
 void ctcx_free_host(ctcx_host_result* result);
 
 /* Half-precision logits: logits_dev is [max_time, batch, num_classes] IEEE half (dtype 0) or bfloat16
- * (dtype 1) in DEVICE memory. They are upcast exactly to float32 into scratch_dev (caller-allocated
- * device memory, max_time*batch*num_classes floats) and decoded like ctcx_decode_f32, i.e. the result
- * equals the reference op run on the upcast values. Everything else as ctcx_decode_f32. */
+ * (dtype 1) in DEVICE memory. The kernels read them directly and widen them exactly to float32 in
+ * registers, i.e. the result equals the reference op run on the widened values. scratch_dev is
+ * IGNORED (the first version of this entry upcast into it; the argument stays for ABI stability and
+ * may be NULL). Everything else as ctcx_decode_f32. */
 int ctcx_decode_half(const void* logits_dev, int dtype, float* scratch_dev, int max_time, int batch,
                      int num_classes, const int32_t* seq_len_dev, int beam_width, int top_paths,
                      int merge_repeated, int blank_index, int blank_label, void* workspace,
@@ -147,7 +187,7 @@ int ctcx_decode_half(const void* logits_dev, int dtype, float* scratch_dev, int 
  * are computed in float64 exactly as the reference does (LogSumExp still through the float
  * functions, util/ctc_loss_util.h:39-40); ctcx_pack_f64 writes log_probability as float64 [batch,
  * top_paths]. Same workspace size, same error codes. A workspace decoded with one dtype must be
- * packed with the same one (CTCX_ERR_WORKSPACE otherwise). */
+ * packed with the same one. */
 int ctcx_decode_f64(const double* logits_dev, int max_time, int batch, int num_classes,
                     const int32_t* seq_len_dev, int beam_width, int top_paths, int merge_repeated,
                     int blank_index, int blank_label, void* workspace, size_t workspace_bytes,
@@ -201,11 +241,34 @@ int ctcx_stream_top_paths(void* workspace, int max_time_total, int batch, int nu
                           int beam_width, int top_paths, int merge_repeated, int blank_label,
                           void* stream, ctcx_sizes* sizes, int32_t* flags_out);
 
-/* Debug/test hook: dense per-(b,p) rows as left in the workspace by ctcx_decode_f32 (device
- * pointers into the workspace; stride max_time per row). Any output pointer may be NULL. */
+/* ---- Measurement and test hooks (not part of the operator's contract) ---- */
+
+/* Dense per-(b,p) rows as left in the workspace by a decode (device pointers into the workspace;
+ * stride max_time per row). Any output pointer may be NULL. Synchronises the device (it validates
+ * the workspace header). */
 int ctcx_workspace_views(const void* workspace, int max_time, int batch, int top_paths,
                          const int32_t** dec_len, const int32_t** dec, const int32_t** ali_len,
                          const int32_t** ali, const float** logp);
+
+/* Per-kernel device times of the calling thread's last decode, from CUDA events recorded on the
+ * launching stream (bench.py's roofline line): out_ms[5] = {pre-pass, beam kernel, trace-back,
+ * scan + flags, whole decode}. */
+void ctcx_profile_enable(int on);
+void ctcx_profile_get(float* out_ms);
+
+/* Device buffer [batch, 24] int64 receiving per-phase clock64 cycles of the fast beam kernels (thread
+ * 0 of every CTA, summed over frames; a separately compiled timing build of the kernel is launched
+ * while it is set) for the calling thread's decodes; NULL switches it off. tools/phase_cycles.py. */
+void ctcx_debug_set_cycles_buffer(long long* dev_buf);
+
+/* 0 = dispatch by shape (default); 1 = route every decode of the process to the generic beam kernel,
+ * the independently written second implementation the parity tests compare with the fast kernels. */
+void ctcx_debug_set_beam_impl(int impl);
+
+/* y = f(x) element-wise with the exact device math (bit-identical to glibc 2.39):
+ * f32 op 0 expf (x <= 0), 1 log1pf (0 <= x <= 1), 2 logf (x >= 1); f64 op 0 exp, 1 log, 2 LogSumExp(x, 0). */
+int ctcx_debug_math_f32(int op, const float* x_dev, float* y_dev, int n, void* stream);
+int ctcx_debug_math_f64(int op, const double* x_dev, double* y_dev, int n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -252,6 +252,106 @@ def pack_sparse(res, P=None):
     return out + (res.logp.copy(),)
 
 
+def pack_sparse_fast(res, P=None):
+    """pack_sparse, vectorised (same arrays; for batches of thousands of utterances)."""
+    P = res.P if P is None else P
+    B = res.B
+    out = ([], [], [], [], [], [])
+    for lens, rows, (o_idx, o_val, o_shape) in ((res.dec_len, res.dec, out[0:3]),
+                                               (res.ali_len, res.ali, out[3:6])):
+        for p in range(P):
+            n = np.asarray(lens[:, p], np.int64)
+            mask = np.arange(rows.shape[2])[None, :] < n[:, None]
+            o_idx.append(np.argwhere(mask).astype(np.int64).reshape(-1, 2))
+            o_val.append(np.asarray(rows[:, p, :])[mask].astype(np.int64))
+            o_shape.append(np.asarray([B, int(n.max()) if B else 0], np.int64))
+    return out + (res.logp.copy(),)
+
+
+def host_threads(cap=64):
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, cap))
+
+
+def _sharded(fn, x, sl, P, threads, dtype):
+    """Runs fn(b0, b1) -> DenseResult over contiguous utterance blocks on host threads (the C
+    checkers release the GIL) and concatenates the blocks."""
+    from concurrent.futures import ThreadPoolExecutor
+    T, B, _ = x.shape
+    n = max(1, min(threads or host_threads(), B))
+    bounds = [(B * i // n, B * (i + 1) // n) for i in range(n)]
+    with ThreadPoolExecutor(n) as ex:
+        parts = list(ex.map(lambda bb: fn(*bb), bounds))
+    r = DenseResult.__new__(DenseResult)
+    r.B, r.P, r.T = B, P, T
+    r.dec_len = np.concatenate([q.dec_len for q in parts], axis=0)
+    r.ali_len = np.concatenate([q.ali_len for q in parts], axis=0)
+    r.dec = np.concatenate([q.dec for q in parts], axis=0)
+    r.ali = np.concatenate([q.ali for q in parts], axis=0)
+    r.logp = np.concatenate([q.logp for q in parts], axis=0)
+    return r
+
+
+def oracle_decode_threaded(x, sl, W, P, merge=False, blank=0, blank_label=-1, lm=None, threads=None):
+    """oracle_decode over host threads, one contiguous block of utterances per thread."""
+    x = np.asarray(x)
+    sl = np.asarray(sl, np.int32)
+    return _sharded(lambda b0, b1: oracle_decode(np.ascontiguousarray(x[:, b0:b1]), sl[b0:b1], W, P, merge,
+                                                 blank, blank_label, lm=lm),
+                    x, sl, P, threads, x.dtype)
+
+
+def ref_decode_threaded(x, sl, W, P, merge=False, blank=0, blank_label=-1, threads=None):
+    """The compiled reference over host threads. It keeps ~0.5 GB of trie per in-flight utterance at
+    T=500, W=100, so the number of threads is what bounds the memory."""
+    x = np.ascontiguousarray(x)
+    sl = np.asarray(sl, np.int32)
+
+    def block(b0, b1):
+        r = ref_decode(x, sl, W, P, merge, blank, blank_label, b_range=(b0, b1))
+        q = DenseResult.__new__(DenseResult)
+        q.B, q.P, q.T = b1 - b0, P, r.T
+        q.dec_len, q.ali_len = r.dec_len[b0:b1], r.ali_len[b0:b1]
+        q.dec, q.ali, q.logp = r.dec[b0:b1], r.ali[b0:b1], r.logp[b0:b1]
+        return q
+    return _sharded(block, x, sl, P, threads, x.dtype)
+
+
+def raw_mismatches(raw, want):
+    """Utterances whose raw op outputs (7 groups, device or host tensors) differ from a DenseResult:
+    compared array-for-array per path against the vectorised restatement of the reference's packing,
+    log_probability by its IEEE bits. Returns the sorted list of differing utterance indices."""
+    def npy(a):
+        return a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
+    packed = pack_sparse_fast(want)
+    B, P = want.B, want.P
+    bad = set()
+    for base, lens, rows in ((0, want.dec_len, want.dec), (3, want.ali_len, want.ali)):
+        for p in range(P):
+            idx, val, shape = npy(raw[base][p]), npy(raw[base + 1][p]), npy(raw[base + 2][p])
+            if idx.shape == packed[base][p].shape and np.array_equal(idx, packed[base][p]) and \
+                    np.array_equal(val, packed[base + 1][p]) and np.array_equal(shape, packed[base + 2][p]):
+                continue
+            # locate the utterances: compare per-utterance segments
+            got = [[] for _ in range(B)]
+            for (b, _), v in zip(idx.tolist(), val.tolist()):
+                if 0 <= b < B:
+                    got[b].append(v)
+            for b in range(B):
+                if got[b] != rows[b, p, :lens[b, p]].tolist():
+                    bad.add(b)
+            if not np.array_equal(shape, packed[base + 2][p]):
+                bad.add(-1)
+    lp = npy(raw[6])
+    view = np.uint64 if lp.dtype == np.float64 else np.uint32
+    neq = np.argwhere(lp.view(view) != np.asarray(want.logp, lp.dtype).view(view))
+    bad.update(int(b) for b, _ in neq)
+    return sorted(bad)
+
+
 # ----------------------------------------------------------------------------------------------
 # Synthetic inputs (SURVEY.md section 8d): identical tensors for the CPU checkers and the GPU path.
 def make_logits(kind, T, B, C, blank_index, seed, sigma=1.0, spike=8.0):
