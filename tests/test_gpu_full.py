@@ -149,4 +149,6 @@ def test_gpu_against_the_compiled_reference_directly(op):
         assert not bad, "%s %s: utterances %s differ from the compiled reference" % (name, kind, bad)
         # exact ties are frequent at these lengths (adjacent beam entries with equal float32 totals) but
         # they almost never reach a returned path: nearly every utterance is identical, tied or not
-        assert tie_free.sum() >= 1 and len(differ) <= max(1, n_utt // 8), (name, kind, differ, int(tie_free.sum()))
+        # (on Gaussian logits at T=500 every utterance has SOME exact tie; ~1 in 16 has one that matters)
+        assert len(differ) <= max(1, n_utt // 8), (name, kind, differ, int(tie_free.sum()))
+        assert kind != "peaky" or tie_free.sum() >= n_utt // 4
