@@ -39,85 +39,61 @@
 
 namespace ctcx {
 
+// Shared-memory layout. Every offset is a compile-time constant of the tier (WMAX): the candidate list,
+// the only array whose size depends on the shape, comes last -- so the kernel addresses all arrays as
+// "base + immediate" and spends no registers on array pointers.
+template <int WMAX>
 struct BeamSmemV4 {
-  size_t hash, phash;              // u64 [2][WMAX]
-  size_t sorted;                   // u64 [WMAX]   score-grouped survivors
-  size_t fin;                      // u64 [WMAX]   survivors at their final slot
-  size_t bnd;                      // u64 [32]     boundary-bin items (fast path)
-  size_t exptab;                   // u64 [32]
-  size_t row;                      // uint4 [WMAX] {old total, old blank, label, member-children mask}
-  size_t list;                     // uint2 [cand_cap] {score key, (row<<16)|label}
-  size_t total, blk, lab, ab, an;  // f32 [2][WMAX]
-  size_t label;                    // i32 [2][WMAX]
-  size_t m_nt, m_nb, m_nl, m_nab, m_nan;  // f32 [WMAX]
-  size_t m_key, m_rec;             // u32 [WMAX]
-  size_t m_pslot;                  // i32 [WMAX]
-  size_t risk, risk_new;           // i32 [WMAX]
-  size_t wiped;                    // u32 [WMAX]
-  size_t htab;                     // u32 [8*WMAX]  (hash tag << 10 | slot), 0xffffffff = empty
-  size_t hist, offs;               // u32 [kBinsV2] each
-  size_t bins2;                    // u32 [256]
-  size_t wtot;                     // u32 [16]     per-warp histogram totals + top bins (PD)
-  size_t x;                        // f32 [2][32]  raw logits of the frame
-  size_t pl;                       // f32 [2][32]  x[l] - off
-  size_t pls;                      // f32 [2][32]  class log-probs sorted descending (-inf padding)
-  size_t plh;                      // f32 [2][8]   pls[0,4,8,...]: heads of the groups of four
-  size_t pref;                     // u32 [2][36]  pref[j] = classes at sorted positions < j
-  size_t fsc;                      // f32 [2][4]   {off, lp_max, lp_min, -}
-  size_t bits;                     // u32 [32]     class bit at each sorted position (S warp scratch)
-  size_t e;                        // f32 [32]     exp terms of the normaliser (S warp scratch)
-  size_t scal;                     // 32 x 4 B
-  size_t bytes;
-  __host__ __device__ void Init(int wmax, int cand_cap) {
-    size_t o = 0;
-    const size_t w = (size_t)wmax;
-    hash = o; o += 2 * w * 8;
-    phash = o; o += 2 * w * 8;
-    sorted = o; o += w * 8;
-    fin = o; o += w * 8;
-    bnd = o; o += kBndFast * 8;
-    exptab = o; o += 32 * 8;
-    row = o; o += w * 16;
-    list = o; o += ((size_t)cand_cap * 8 + 15) / 16 * 16;  // keep the following arrays 16-byte aligned
-    total = o; o += 2 * w * 4;
-    blk = o; o += 2 * w * 4;
-    lab = o; o += 2 * w * 4;
-    ab = o; o += 2 * w * 4;
-    an = o; o += 2 * w * 4;
-    label = o; o += 2 * w * 4;
-    m_nt = o; o += w * 4;
-    m_nb = o; o += w * 4;
-    m_nl = o; o += w * 4;
-    m_nab = o; o += w * 4;
-    m_nan = o; o += w * 4;
-    m_key = o; o += w * 4;
-    m_rec = o; o += w * 4;
-    m_pslot = o; o += w * 4;
-    risk = o; o += w * 4;
-    risk_new = o; o += w * 4;
-    wiped = o; o += w * 4;
-    htab = o; o += 8 * w * 4;
-    hist = o; o += kBinsV2 * 4;
-    offs = o; o += kBinsV2 * 4;
-    bins2 = o; o += 256 * 4;
-    wtot = o; o += 16 * 4;
-    x = o; o += 2 * 32 * 4;
-    pl = o; o += 2 * 32 * 4;
-    pls = o; o += 2 * 32 * 4;
-    plh = o; o += 2 * 8 * 4;
-    pref = o; o += 2 * 36 * 4;
-    fsc = o; o += 2 * 4 * 4;
-    bits = o; o += 32 * 4;
-    e = o; o += 32 * 4;
-    scal = o; o += 32 * 4;
-    bytes = (o + 15) / 16 * 16;
-  }
+  static constexpr size_t w = (size_t)WMAX;
+  static constexpr size_t hash = 0;                       // u64 [2][WMAX]
+  static constexpr size_t phash = hash + 2 * w * 8;       // u64 [2][WMAX]
+  static constexpr size_t sorted = phash + 2 * w * 8;     // u64 [WMAX]   score-grouped survivors
+  static constexpr size_t fin = sorted + w * 8;           // u64 [WMAX]   survivors at their final slot
+  static constexpr size_t bnd = fin + w * 8;              // u64 [32]     boundary-bin items (fast path)
+  static constexpr size_t exptab = bnd + kBndFast * 8;    // u64 [32]
+  static constexpr size_t row = exptab + 32 * 8;          // uint4 [WMAX] {old total, old blank, label, member-children mask}
+  static constexpr size_t total = row + w * 16;           // f32 [2][WMAX]
+  static constexpr size_t blk = total + 2 * w * 4;
+  static constexpr size_t lab = blk + 2 * w * 4;
+  static constexpr size_t ab = lab + 2 * w * 4;
+  static constexpr size_t an = ab + 2 * w * 4;
+  static constexpr size_t label = an + 2 * w * 4;         // i32 [2][WMAX]
+  static constexpr size_t m_nt = label + 2 * w * 4;       // f32 [WMAX] x 5: the members' new values
+  static constexpr size_t m_nb = m_nt + w * 4;
+  static constexpr size_t m_nl = m_nb + w * 4;
+  static constexpr size_t m_nab = m_nl + w * 4;
+  static constexpr size_t m_nan = m_nab + w * 4;
+  static constexpr size_t m_key = m_nan + w * 4;          // u32 [WMAX]
+  static constexpr size_t m_rec = m_key + w * 4;          // u32 [WMAX]
+  static constexpr size_t m_pslot = m_rec + w * 4;        // i32 [WMAX]
+  static constexpr size_t risk = m_pslot + w * 4;         // i32 [WMAX]
+  static constexpr size_t risk_new = risk + w * 4;        // i32 [WMAX]
+  static constexpr size_t wiped = risk_new + w * 4;       // u32 [WMAX]
+  static constexpr size_t htab = wiped + w * 4;           // u32 [8*WMAX]  (hash tag << 10 | slot), 0xffffffff = empty
+  static constexpr size_t hist = htab + 8 * w * 4;        // u32 [kBinsV2]
+  static constexpr size_t offs = hist + kBinsV2 * 4;      // u32 [kBinsV2]
+  static constexpr size_t bins2 = offs + kBinsV2 * 4;     // u32 [256]
+  static constexpr size_t wtot = bins2 + 256 * 4;         // u32 [16]     per-warp histogram totals + top bins (PD)
+  static constexpr size_t x = wtot + 16 * 4;              // f32 [2][32]  raw logits of the frame
+  static constexpr size_t pl = x + 2 * 32 * 4;            // f32 [2][32]  x[l] - off
+  static constexpr size_t pls = pl + 2 * 32 * 4;          // f32 [2][32]  class log-probs sorted descending (-inf padding)
+  static constexpr size_t plh = pls + 2 * 32 * 4;         // f32 [2][8]   pls[0,4,8,...]: heads of the groups of four
+  static constexpr size_t pref = plh + 2 * 8 * 4;         // u32 [2][36]  pref[j] = classes at sorted positions < j
+  static constexpr size_t fsc = pref + 2 * 36 * 4;        // f32 [2][4]   {off, lp_max, lp_min, -}
+  static constexpr size_t bits = fsc + 2 * 4 * 4;         // u32 [32]     S warp scratch: sort keys, then class bits
+  static constexpr size_t e = bits + 32 * 4;              // f32 [32]     S warp scratch: exp terms of the normaliser
+  static constexpr size_t scal = e + 32 * 4;              // 32 x 4 B
+  static constexpr size_t list = (scal + 32 * 4 + 15) / 16 * 16;  // uint2 [cand_cap] {score key, (row<<16)|label}
+  static constexpr size_t Bytes(int cand_cap) { return (list + (size_t)cand_cap * 8 + 15) / 16 * 16; }
 };
 
 enum { kV4Utt = 23, kV4Abort = 24 };  // scalar slots in addition to the kV2* / kV3* ones
 
-template <typename IN, int WMAX, int NT, bool TIMING>
-__global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKernelV4(BeamParams p) {
+// MINB = resident CTAs per SM the register allocation is tuned for: 4 (64 registers) for batches that
+// fill the machine, 2 (128 registers: more loads in flight, no re-materialisation) for the latency
+// regime of at most two utterances per SM.
+template <typename IN, int WMAX, int NT, bool TIMING, int MINB>
+__global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamParams p) {
   static_assert(NT >= WMAX && NT >= kBinsV2, "one thread per beam slot and per histogram bin");
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int NWARP = NT / 32;
@@ -126,49 +102,48 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
   const int W = p.W, C = p.C, T = p.T, B = p.B, blank = p.blank_index;
   const bool s_warp = (warp == NWARP - 1);
 
-  BeamSmemV4 lay;
-  lay.Init(WMAX, p.cand_cap);
-  unsigned long long* s_hash = (unsigned long long*)(smem + lay.hash);
-  unsigned long long* s_phash = (unsigned long long*)(smem + lay.phash);
-  unsigned long long* s_sorted = (unsigned long long*)(smem + lay.sorted);
-  unsigned long long* s_fin = (unsigned long long*)(smem + lay.fin);
-  unsigned long long* s_bnd = (unsigned long long*)(smem + lay.bnd);
-  unsigned long long* s_exptab = (unsigned long long*)(smem + lay.exptab);
-  uint4* s_row = (uint4*)(smem + lay.row);
-  uint2* c_list = (uint2*)(smem + lay.list);
-  float* s_total = (float*)(smem + lay.total);
-  float* s_blk = (float*)(smem + lay.blk);
-  float* s_lab = (float*)(smem + lay.lab);
-  float* s_ab = (float*)(smem + lay.ab);
-  float* s_an = (float*)(smem + lay.an);
-  int* s_label = (int*)(smem + lay.label);
-  float* m_nt = (float*)(smem + lay.m_nt);
-  float* m_nb = (float*)(smem + lay.m_nb);
-  float* m_nl = (float*)(smem + lay.m_nl);
-  float* m_nab = (float*)(smem + lay.m_nab);
-  float* m_nan = (float*)(smem + lay.m_nan);
-  unsigned* m_key = (unsigned*)(smem + lay.m_key);
-  unsigned* m_rec = (unsigned*)(smem + lay.m_rec);
-  int* m_pslot = (int*)(smem + lay.m_pslot);
-  int* s_risk = (int*)(smem + lay.risk);
-  int* s_risk_new = (int*)(smem + lay.risk_new);
-  unsigned* s_wiped = (unsigned*)(smem + lay.wiped);
-  unsigned* s_htab = (unsigned*)(smem + lay.htab);
-  unsigned* s_hist = (unsigned*)(smem + lay.hist);
-  unsigned* s_offs = (unsigned*)(smem + lay.offs);
-  unsigned* s_bins2 = (unsigned*)(smem + lay.bins2);
-  unsigned* s_wtot = (unsigned*)(smem + lay.wtot);
-  float* s_xb = (float*)(smem + lay.x);
-  float* s_plb = (float*)(smem + lay.pl);
-  float* s_plSb = (float*)(smem + lay.pls);
-  float* s_plHb = (float*)(smem + lay.plh);
-  unsigned* s_prefb = (unsigned*)(smem + lay.pref);
-  float* s_fsc = (float*)(smem + lay.fsc);
-  unsigned* s_bits = (unsigned*)(smem + lay.bits);
-  float* s_e = (float*)(smem + lay.e);
-  volatile int* sc = (volatile int*)(smem + lay.scal);
-  int* sci = (int*)(smem + lay.scal);
-  unsigned* scu = (unsigned*)(smem + lay.scal);
+  using lay = BeamSmemV4<WMAX>;
+  unsigned long long* s_hash = (unsigned long long*)(smem + lay::hash);
+  unsigned long long* s_phash = (unsigned long long*)(smem + lay::phash);
+  unsigned long long* s_sorted = (unsigned long long*)(smem + lay::sorted);
+  unsigned long long* s_fin = (unsigned long long*)(smem + lay::fin);
+  unsigned long long* s_bnd = (unsigned long long*)(smem + lay::bnd);
+  unsigned long long* s_exptab = (unsigned long long*)(smem + lay::exptab);
+  uint4* s_row = (uint4*)(smem + lay::row);
+  uint2* c_list = (uint2*)(smem + lay::list);
+  float* s_total = (float*)(smem + lay::total);
+  float* s_blk = (float*)(smem + lay::blk);
+  float* s_lab = (float*)(smem + lay::lab);
+  float* s_ab = (float*)(smem + lay::ab);
+  float* s_an = (float*)(smem + lay::an);
+  int* s_label = (int*)(smem + lay::label);
+  float* m_nt = (float*)(smem + lay::m_nt);
+  float* m_nb = (float*)(smem + lay::m_nb);
+  float* m_nl = (float*)(smem + lay::m_nl);
+  float* m_nab = (float*)(smem + lay::m_nab);
+  float* m_nan = (float*)(smem + lay::m_nan);
+  unsigned* m_key = (unsigned*)(smem + lay::m_key);
+  unsigned* m_rec = (unsigned*)(smem + lay::m_rec);
+  int* m_pslot = (int*)(smem + lay::m_pslot);
+  int* s_risk = (int*)(smem + lay::risk);
+  int* s_risk_new = (int*)(smem + lay::risk_new);
+  unsigned* s_wiped = (unsigned*)(smem + lay::wiped);
+  unsigned* s_htab = (unsigned*)(smem + lay::htab);
+  unsigned* s_hist = (unsigned*)(smem + lay::hist);
+  unsigned* s_offs = (unsigned*)(smem + lay::offs);
+  unsigned* s_bins2 = (unsigned*)(smem + lay::bins2);
+  unsigned* s_wtot = (unsigned*)(smem + lay::wtot);
+  float* s_xb = (float*)(smem + lay::x);
+  float* s_plb = (float*)(smem + lay::pl);
+  float* s_plSb = (float*)(smem + lay::pls);
+  float* s_plHb = (float*)(smem + lay::plh);
+  unsigned* s_prefb = (unsigned*)(smem + lay::pref);
+  float* s_fsc = (float*)(smem + lay::fsc);
+  unsigned* s_bits = (unsigned*)(smem + lay::bits);
+  float* s_e = (float*)(smem + lay::e);
+  volatile int* sc = (volatile int*)(smem + lay::scal);
+  int* sci = (int*)(smem + lay::scal);
+  unsigned* scu = (unsigned*)(smem + lay::scal);
 
   LoadExpTable(s_exptab, tid, NT);
 
@@ -224,8 +199,9 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       }
       return (lane < C) ? LoadLogit<IN>(p.logits, (size_t)t * (size_t)p.tstride + row0 + lane) : 0.0f;
     };
-    // S warp: everything the frame needs from its row, into buffer `buf` (decoder.h:71-80 + class order)
-    auto prepare = [&](float xr, int buf) {
+    // S warp, part 1 (runs while the other warps are in PA): the softmax normaliser of the row
+    // (decoder.h:71-80) and the per-class log-probs, into buffer `buf`. Returns the lane's sort key.
+    auto prepare1 = [&](float xr, int buf) -> unsigned {
       const bool in_row = lane < C;
       const float mx = UnKey(__reduce_max_sync(kFull, in_row ? KeyOf(xr) : 0u));
       s_e[lane] = in_row ? ExpfExact(__fsub_rn(xr, mx), s_exptab) : 0.0f;
@@ -237,24 +213,38 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
         sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, v.x), v.y), v.z), v.w);
       }
       const float off = __fadd_rn(mx, LogfExact(sum));
-      float* bx = s_xb + buf * 32;
-      float* bpl = s_plb + buf * 32;
+      const bool lane_ok = in_row && (lane != blank);
+      const float pl_lane = lane_ok ? __fsub_rn(xr, off) : 0.0f;
+      s_xb[buf * 32 + lane] = xr;
+      s_plb[buf * 32 + lane] = pl_lane;
+      const unsigned key = lane_ok ? KeyOf(pl_lane) : 0u;  // blank / padding sort last
+      s_bits[lane] = key;  // the keys of the row, read back as broadcasts by part 2
+      if (lane == 0) s_fsc[buf * 4 + 0] = off;
+      return key;
+    };
+    // S warp, part 2 (runs while the other warps list the candidates, PB): classes ranked by log-prob,
+    // sorted log-probs, prefix masks. Equal keys keep lane order; the order inside a tie never matters
+    // (a prefix of the sorted classes never ends inside a group of equal scores).
+    auto prepare2 = [&](unsigned key, int buf) {
+      __syncwarp();
+      int rank = 0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const uint4 k = *reinterpret_cast<const uint4*>(s_bits + i);
+        rank += (k.x > key) ? 1 : 0;
+        rank += (k.y > key) ? 1 : 0;
+        rank += (k.z > key) ? 1 : 0;
+        rank += (k.w > key) ? 1 : 0;
+      }
+      rank += __popc(__match_any_sync(kFull, key) & ((1u << lane) - 1u));
+      const bool lane_ok = (lane < C) && (lane != blank);
+      const float pl_lane = s_plb[buf * 32 + lane];
       float* bplS = s_plSb + buf * 32;
       float* bplH = s_plHb + buf * 8;
       unsigned* bpref = s_prefb + buf * 36;
-      bx[lane] = xr;
-      const bool lane_ok = in_row && (lane != blank);
-      const float pl_lane = lane_ok ? __fsub_rn(xr, off) : 0.0f;
-      bpl[lane] = pl_lane;
-      const unsigned kl = lane_ok ? KeyOf(pl_lane) : 0u;  // blank / padding sort last
-      int rank = 0;
-#pragma unroll 4  // code size: the frame loop must stay inside the instruction cache
-      for (int j = 0; j < 32; ++j) {
-        const unsigned kj = __shfl_sync(kFull, kl, j);
-        rank += (kj > kl || (kj == kl && j < lane)) ? 1 : 0;
-      }
       bplS[rank] = lane_ok ? pl_lane : NegInf();
       if ((rank & 3) == 0) bplH[rank >> 2] = lane_ok ? pl_lane : NegInf();
+      __syncwarp();  // every lane has read the keys
       s_bits[rank] = lane_ok ? (1u << lane) : 0u;
       __syncwarp();
       unsigned incl = s_bits[lane];
@@ -268,7 +258,6 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       __syncwarp();
       if (lane == 0) {
         bpref[0] = 0u;
-        s_fsc[buf * 4 + 0] = off;
         s_fsc[buf * 4 + 1] = (cv > 0) ? bplS[0] : NegInf();
         s_fsc[buf * 4 + 2] = (cv > 0) ? bplS[cv - 1] : 0.0f;
       }
@@ -305,10 +294,11 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     }
     int n = 1;
     float xr_next = 0.0f;  // S warp: raw row of the frame after the one being prepared
+    unsigned s_key = 0u;   // S warp: sort key of the row being prepared (between its two parts)
     if (s_warp && L > 0) {
       const float x0 = load_row(0);
       if (L > 1) xr_next = load_row(1);
-      prepare(x0, 0);
+      prepare2(prepare1(x0, 0), 0);
     }
     __syncthreads();
     if (resume) {  // beam as the previous chunk left it (buffer 0: local frame 0 reads buffer 0)
@@ -357,7 +347,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       if (s_warp && t + 1 < L) {
         const float xr = xr_next;
         if (t + 2 < L) xr_next = load_row(t + 2);
-        prepare(xr, nxt);
+        s_key = prepare1(xr, nxt);
       }
       const float xb = x[blank];
       const float pb = __fsub_rn(xb, off);
@@ -548,6 +538,9 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
         }
       }
       CTCX_TICK(2)  // PC
+
+      // ---- S, second part: ranks and prefix masks of frame t+1, while the others list the candidates ----
+      if (s_warp && t + 1 < L) prepare2(s_key, nxt);
 
       // ---- PB / PD: list + histogram of the items in the score range, boundary bin ----
       const unsigned minkey_m = scu[kV2MinKey];

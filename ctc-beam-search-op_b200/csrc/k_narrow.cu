@@ -9,18 +9,45 @@ constexpr int kListCapMax = 4608;  // candidate-list entries kept in shared memo
 
 int TierOf(int W) { return (W <= 32) ? 32 : (W <= 128) ? 128 : 256; }
 
-template <typename IN, int WMAX, bool TIMING>
-LaunchStatus LaunchOne(const BeamParams& p, size_t smem, cudaStream_t stream) {
-  auto kern = BeamKernelV4<IN, WMAX, 256, TIMING>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return LaunchFrom(e, "cudaFuncSetAttribute(BeamKernelV4)");
-  // persistent CTAs: as many as the device keeps resident, each pulls utterances from p.queue
-  int dev = 0, sms = 148, per_sm = 1;
+int SmCount() {
+  static int cached[64] = {0};
+  int dev = 0, sms = 148;
   cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
-  if (e != cudaSuccess) return LaunchFrom(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(BeamKernelV4)");
-  const long long resident = (long long)sms * (per_sm > 0 ? per_sm : 1);
+  if (dev >= 0 && dev < 64) cached[dev] = sms;
+  return sms;
+}
+
+// Launch configuration of one kernel instantiation on one device, computed once: the attribute and
+// occupancy queries cost tens of microseconds of host time that would otherwise sit between the
+// kernels of every decode. (A cache of immutable facts about the device, not decoder state.)
+struct LaunchCfg {
+  size_t smem = 0;   // dynamic shared memory the attribute was raised to
+  int resident = 0;  // CTAs the device keeps resident at that size
+};
+constexpr int kMaxDevices = 64;
+
+template <typename IN, int WMAX, bool TIMING, int MINB>
+LaunchStatus LaunchOne(const BeamParams& p, size_t smem, cudaStream_t stream) {
+  auto kern = BeamKernelV4<IN, WMAX, 256, TIMING, MINB>;
+  static LaunchCfg cfgs[kMaxDevices];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  LaunchCfg local;
+  LaunchCfg& cfg = (dev >= 0 && dev < kMaxDevices) ? cfgs[dev] : local;
+  if (cfg.resident == 0 || cfg.smem != smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return LaunchFrom(e, "cudaFuncSetAttribute(BeamKernelV4)");
+    // persistent CTAs: as many as the device keeps resident, each pulls utterances from p.queue
+    int per_sm = 1, sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+    if (e != cudaSuccess) return LaunchFrom(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(BeamKernelV4)");
+    cfg.smem = smem;
+    cfg.resident = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  const long long resident = cfg.resident;
   const unsigned grid = (unsigned)(p.B < resident ? p.B : resident);
   kern<<<grid, 256, smem, stream>>>(p);
   return LaunchFrom(cudaGetLastError(), "BeamKernelV4 launch");
@@ -31,25 +58,38 @@ LaunchStatus LaunchTyped(const BeamParams& p, int wmax, size_t smem, cudaStream_
   if constexpr (sizeof(IN) == 4) {
     if (p.dbg_cycles != nullptr) {  // timing build: float32 inputs only
       switch (wmax) {
-        case 32: return LaunchOne<IN, 32, true>(p, smem, stream);
-        case 128: return LaunchOne<IN, 128, true>(p, smem, stream);
-        default: return LaunchOne<IN, 256, true>(p, smem, stream);
+        case 32: return LaunchOne<IN, 32, true, 1>(p, smem, stream);
+        case 128: return LaunchOne<IN, 128, true, 1>(p, smem, stream);
+        default: return LaunchOne<IN, 256, true, 1>(p, smem, stream);
       }
     }
   }
+  if (p.B <= 2 * SmCount()) {  // latency regime: at most two utterances per SM, 128 registers per thread
+    switch (wmax) {
+      case 32: return LaunchOne<IN, 32, false, 2>(p, smem, stream);
+      case 128: return LaunchOne<IN, 128, false, 2>(p, smem, stream);
+      default: return LaunchOne<IN, 256, false, 2>(p, smem, stream);
+    }
+  }
   switch (wmax) {
-    case 32: return LaunchOne<IN, 32, false>(p, smem, stream);
-    case 128: return LaunchOne<IN, 128, false>(p, smem, stream);
-    default: return LaunchOne<IN, 256, false>(p, smem, stream);
+    case 32: return LaunchOne<IN, 32, false, 4>(p, smem, stream);
+    case 128: return LaunchOne<IN, 128, false, 4>(p, smem, stream);
+    default: return LaunchOne<IN, 256, false, 4>(p, smem, stream);
+  }
+}
+
+size_t SmemBytes(int wmax, int cand_cap) {
+  switch (wmax) {
+    case 32: return BeamSmemV4<32>::Bytes(cand_cap);
+    case 128: return BeamSmemV4<128>::Bytes(cand_cap);
+    default: return BeamSmemV4<256>::Bytes(cand_cap);
   }
 }
 }  // namespace
 
 bool NarrowFastShape(int W, int C) {
   if (C > 32 || W > 256 || (long long)W * C > kListCapMax) return false;
-  BeamSmemV4 lay;
-  lay.Init(TierOf(W), W * C);
-  return lay.bytes <= 220 * 1024;
+  return SmemBytes(TierOf(W), W * C) <= 220 * 1024;
 }
 
 LaunchStatus LaunchBeamNarrow(BeamParams& p, int in_dtype, cudaStream_t stream) {
@@ -57,12 +97,11 @@ LaunchStatus LaunchBeamNarrow(BeamParams& p, int in_dtype, cudaStream_t stream) 
   p.cand_cap = p.W * p.C;
   p.kid_words = 1;
   const int wmax = TierOf(p.W);
-  BeamSmemV4 lay;
-  lay.Init(wmax, p.cand_cap);
+  const size_t smem = SmemBytes(wmax, p.cand_cap);
   switch (in_dtype) {
-    case kInF32: return LaunchTyped<float>(p, wmax, lay.bytes, stream);
-    case kInF16: return LaunchTyped<__half>(p, wmax, lay.bytes, stream);
-    case kInBF16: return LaunchTyped<__nv_bfloat16>(p, wmax, lay.bytes, stream);
+    case kInF32: return LaunchTyped<float>(p, wmax, smem, stream);
+    case kInF16: return LaunchTyped<__half>(p, wmax, smem, stream);
+    case kInBF16: return LaunchTyped<__nv_bfloat16>(p, wmax, smem, stream);
     default: return {kLaunchUnsupported, cudaSuccess, ""};
   }
 }

@@ -1,4 +1,4 @@
-"""Per-phase instruction/sample split of a BeamKernelV2 ncu report (phases = '// ---- Px' markers).
+"""Per-phase instruction/sample split of a narrow beam kernel ncu report (phases = '// ---- Px' markers).
    python tools/ncu_phases.py report.ncu-rep frames_per_launch"""
 import csv
 import re
@@ -6,14 +6,22 @@ import subprocess
 import sys
 
 rep, frames = sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else 128000.0
-src = open(__file__.rsplit("/tools/", 1)[0] + "/ctc-beam-search-op_b200/csrc/" + (sys.argv[3] if len(sys.argv) > 3 else "ctcx_beam_v3.cuh")).read().splitlines()
+src = open(__file__.rsplit("/tools/", 1)[0] + "/ctc-beam-search-op_b200/csrc/" + (sys.argv[3] if len(sys.argv) > 3 else "ctcx_beam_v4.cuh")).read().splitlines()
 bounds = [(1, "init")]
 for i, ln in enumerate(src, 1):
     m = re.search(r"// ---- (P[A-G])", ln)
     if m:
         bounds.append((i, m.group(1)))
-    elif "prefetch the next frame" in ln:
-        bounds.append((i, "frame-setup"))
+    elif "auto load_row" in ln:
+        bounds.append((i, "S:load_row"))
+    elif "auto prepare1" in ln:
+        bounds.append((i, "S:part1"))
+    elif "auto prepare2" in ln:
+        bounds.append((i, "S:part2"))
+    elif "---- initial state" in ln:
+        bounds.append((i, "init"))
+    elif "// ---- S" in ln:
+        bounds.append((i, "S:call"))
     elif "---- final beam" in ln:
         bounds.append((i, "final"))
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
@@ -55,7 +63,7 @@ def phase(line):
 
 agg, cur, tot, tots = {}, "init", 0, 0
 for a, f, l, i, s in items:
-    if f == (sys.argv[3] if len(sys.argv) > 3 else "ctcx_beam_v3.cuh") and l:
+    if f == (sys.argv[3] if len(sys.argv) > 3 else "ctcx_beam_v4.cuh") and l:
         cur = phase(l)
     agg.setdefault(cur, [0, 0])
     agg[cur][0] += i
