@@ -257,6 +257,8 @@ int DecodeImpl(const void* logits_dev, int T, int B, int C, const int32_t* seq_l
     bp.tstride = tstride;
     bp.queue = d_ctrl;
     bp.dbg_cycles = g_dbg_cycles;
+    bp.n_slices = 1;
+    bp.slice_frames = T;
     if constexpr (kF32) {
       const Path path = PathOf(W, C, opt.lm != nullptr);
       int in_dtype = opt.in_dtype;
@@ -270,6 +272,11 @@ int DecodeImpl(const void* logits_dev, int T, int B, int C, const int32_t* seq_l
       }
       if (path == kPathNarrow) {
         bp.ready = opt.ready;
+        // time-sliced work queue (large batches): per-utterance state block + progress words (the regions
+        // the streaming entries use for the same purpose between calls)
+        bp.state = base + ws.state;
+        bp.progress = (int*)(base + ws.t_done);
+        CTCX_CUDA(cudaMemsetAsync(bp.progress, 0, (size_t)B * 4, stream));
         ProfRecord(1, stream);
         CTCX_LAUNCH(ctcx::LaunchBeamNarrow(bp, in_dtype, stream));
       } else if (path == kPathWide) {
@@ -882,6 +889,8 @@ int ctcx_stream_step_f32(void* workspace, int T_total, int B, int C, int W, int 
   bp.tstride = (long long)B * C;
   bp.queue = d_ctrl;
   bp.dbg_cycles = nullptr;
+  bp.n_slices = 1;
+  bp.slice_frames = chunk_time;
   const Path path = PathOf(W, C, false);
   if (path == kPathNarrow) {
     CTCX_CUDA(cudaMemsetAsync(d_ctrl, 0, 4, stream));

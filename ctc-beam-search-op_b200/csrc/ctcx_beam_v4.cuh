@@ -169,17 +169,44 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
 
   int ready_known = (p.ready != nullptr) ? 0 : 0x7fffffff;  // S warp: frames known to have landed
 
-  for (;;) {  // ---- persistent loop: one utterance per iteration ----
+  // Tasks: (time slice, utterance), slice-major -- task q is slice q / B of utterance q % B. With one slice
+  // per utterance (batches that fit the resident CTAs, streaming) a task is a whole utterance. Larger
+  // batches are cut into p.n_slices slices of p.slice_frames frames so that the CTAs stay evenly loaded
+  // to the end (no tail wave, ragged lengths balance): the beam is handed from slice to slice through
+  // the per-utterance state block in HBM, and a slice waits for its predecessor's release of
+  // p.progress[b]. Every predecessor has a smaller task number, i.e. it is already owned by a resident
+  // CTA that waits for nothing later: the wait cannot deadlock.
+  const int n_tasks = B * p.n_slices;
+  for (;;) {  // ---- persistent loop: one task per iteration ----
     if (tid == 0) sci[kV4Utt] = atomicAdd(p.queue, 1);
     __syncthreads();
-    const int b = sci[kV4Utt];
-    if (b >= B) break;
+    const int task = sci[kV4Utt];
+    if (task >= n_tasks) break;
+    const int slice = task / B, b = task - slice * B;
 
-    // streaming: frames already consumed by earlier chunks; this chunk contributes L more
+    // streaming: frames already consumed by earlier calls; this call contributes up to Lall more
     const int t_done = (p.t_done != nullptr) ? p.t_done[b] : 0;
-    const int L = max(0, min(p.seq_len[b], p.Tcap - t_done));
-    const bool resume = (p.state != nullptr) && t_done > 0;
+    const int Lall = max(0, min(p.seq_len[b], p.Tcap - t_done));
+    const int t0 = slice * p.slice_frames;  // first frame of this task (within this call's logits)
+    if (slice > 0 && t0 >= Lall) {  // the utterance ended in an earlier slice
+      __syncthreads();
+      continue;
+    }
+    const int L = min(Lall, t0 + p.slice_frames) - t0;  // frames of this task
+    const bool last_slice = (t0 + L == Lall);
+    const bool resume = (p.state != nullptr) && (t_done > 0 || slice > 0);
     const size_t row0 = (size_t)b * C;  // element offset of (t = 0, b) in the logits tensor
+    if (slice > 0) {  // wait for the previous slice of this utterance (acquire), then read its state
+      if (tid == 0) {
+        int done = 0;
+        for (;;) {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(done) : "l"(p.progress + b) : "memory");
+          if (done >= slice) break;
+          __nanosleep(100);
+        }
+      }
+      __syncthreads();
+    }
 
     // S warp: raw logit (lane = class) of frame t, as float. Frames arrive in order; wait for the copy
     // that is still in flight (p.ready counts the frames that have landed).
@@ -296,22 +323,24 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
     float xr_next = 0.0f;  // S warp: raw row of the frame after the one being prepared
     unsigned s_key = 0u;   // S warp: sort key of the row being prepared (between its two parts)
     if (s_warp && L > 0) {
-      const float x0 = load_row(0);
-      if (L > 1) xr_next = load_row(1);
+      const float x0 = load_row(t0);
+      if (L > 1) xr_next = load_row(t0 + 1);
       prepare2(prepare1(x0, 0), 0);
     }
     __syncthreads();
-    if (resume) {  // beam as the previous chunk left it (buffer 0: local frame 0 reads buffer 0)
+    int carried = 0;  // flag bits handed on from the previous slice / call
+    if (resume) {  // beam as the previous slice left it (buffer 0: local frame 0 reads buffer 0)
       StreamView sv(p.state + (size_t)b * StreamStateBytes(W), W);
-      n = sv.hdr->n;
-      for (int i = tid; i < n; i += NT) {
-        s_total[i] = sv.total[i]; s_blk[i] = sv.blk[i]; s_lab[i] = sv.lab[i];
-        s_ab[i] = sv.ab[i]; s_an[i] = sv.an[i]; s_label[i] = sv.label[i];
-        s_hash[i] = sv.hash[i]; s_phash[i] = sv.phash[i];
+      n = __ldcg(&sv.hdr->n);
+      carried = __ldcg(&sv.hdr->flags);
+      for (int i = tid; i < n; i += NT) {  // (L2 loads: another SM wrote the block)
+        s_total[i] = __ldcg(sv.total + i); s_blk[i] = __ldcg(sv.blk + i); s_lab[i] = __ldcg(sv.lab + i);
+        s_ab[i] = __ldcg(sv.ab + i); s_an[i] = __ldcg(sv.an + i); s_label[i] = __ldcg(sv.label + i);
+        s_hash[i] = __ldcg(sv.hash + i); s_phash[i] = __ldcg(sv.phash + i);
       }
       if (tid == 0) {
-        scu[kV2Gap] = sv.hdr->gap;
-        sci[kV2Anomaly] = sv.hdr->flags & 1;
+        scu[kV2Gap] = __ldcg(&sv.hdr->gap);
+        sci[kV2Anomaly] = carried & 1;
       }
       __syncthreads();
     }
@@ -346,7 +375,7 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
       // ---- S: the last warp prepares frame t+1 (and puts row t+2 in flight) while the others run PA ----
       if (s_warp && t + 1 < L) {
         const float xr = xr_next;
-        if (t + 2 < L) xr_next = load_row(t + 2);
+        if (t + 2 < L) xr_next = load_row(t0 + t + 2);
         s_key = prepare1(xr, nxt);
       }
       const float xb = x[blank];
@@ -893,8 +922,8 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
               rec = PackRec32(0xffu, (unsigned)src, kAbFromAb, an_kind, (unsigned)lbl);
             }
             w_label[r] = lbl;
-            p.bp32[((size_t)b * p.Tcap + (t_done + t)) * W + r] = rec;
-            if (p.dbg_totals) p.dbg_totals[((size_t)b * T + t) * W + r] = w_total[r];
+            p.bp32[((size_t)b * p.Tcap + (t_done + t0 + t)) * W + r] = rec;
+            if (p.dbg_totals) p.dbg_totals[((size_t)b * T + t0 + t) * W + r] = w_total[r];
           }
           if (PGS == 1 || pg_role == 1) {  // prefix hash, row info of the next frame, parent look-up table
             unsigned long long hsh;
@@ -917,7 +946,7 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
             while (atomicCAS(&s_htab[h], 0xffffffffu, entry) != 0xffffffffu) h = (h + 1) & (TS - 1);
           }
         }
-        if (p.dbg_n && tid == 0) p.dbg_n[(size_t)b * T + t] = n_new;
+        if (p.dbg_n && tid == 0) p.dbg_n[(size_t)b * T + t0 + t] = n_new;
         CTCX_TICK(15)  // PG: state write
       }
       __syncthreads();
@@ -930,29 +959,32 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
     }
     if (TIMING && timing)
       for (int i = 0; i < (TIMING ? 24 : 1); ++i) {
-        p.dbg_cycles[(size_t)b * 24 + i] = cyc[i];
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg_cycles + (size_t)b * 24 + i), (unsigned long long)cyc[i]);
         cyc[TIMING ? i : 0] = 0;
       }
 
-    // ---- final beam (decoder.h:229-261): sorted, the first P slots are the top paths ----
     {
       const int cur = t_end & 1;
-      for (int q = tid; q < p.P; q += NT) {
-        if (q < n) {
-          p.fin_total[(size_t)b * p.P + q] = s_total[cur * WMAX + q];
-          p.fin_kind[(size_t)b * p.P + q] = (s_ab[cur * WMAX + q] > s_an[cur * WMAX + q]) ? 1 : 0;
-        } else {
-          p.fin_total[(size_t)b * p.P + q] = 0.0f;
-          p.fin_kind[(size_t)b * p.P + q] = 0;
+      const int overflow = (p.seq_len[b] > p.Tcap - t_done) ? 4 : 0;
+      const int lost = ((t_end != L) ? 8 : 0) | (carried & 8);  // an input frame never arrived (this slice or before)
+      // ---- final beam (decoder.h:229-261): sorted, the first P slots are the top paths ----
+      if (last_slice || lost) {
+        for (int q = tid; q < p.P; q += NT) {
+          if (q < n) {
+            p.fin_total[(size_t)b * p.P + q] = s_total[cur * WMAX + q];
+            p.fin_kind[(size_t)b * p.P + q] = (s_ab[cur * WMAX + q] > s_an[cur * WMAX + q]) ? 1 : 0;
+          } else {
+            p.fin_total[(size_t)b * p.P + q] = 0.0f;
+            p.fin_kind[(size_t)b * p.P + q] = 0;
+          }
+        }
+        if (tid == 0) {
+          p.fin_n[b] = n;
+          p.flags[b] = (sci[kV2Anomaly] ? 1 : 0) | ((p.P > n) ? 2 : 0) | overflow | lost;
         }
       }
-      const int overflow = (p.seq_len[b] > p.Tcap - t_done) ? 4 : 0;
-      const int lost = (t_end != L) ? 8 : 0;
-      if (tid == 0) {
-        p.fin_n[b] = n;
-        p.flags[b] = (sci[kV2Anomaly] ? 1 : 0) | ((p.P > n) ? 2 : 0) | overflow | lost;
-      }
-      if (p.state != nullptr) {  // carry the beam (and the score-range prediction) to the next chunk
+      // ---- carry the beam (and the score-range prediction) to the next slice / the next call ----
+      if (p.state != nullptr && (!last_slice || p.t_done != nullptr)) {
         StreamView sv(p.state + (size_t)b * StreamStateBytes(W), W);
         for (int i = tid; i < n; i += NT) {
           sv.total[i] = s_total[cur * WMAX + i]; sv.blk[i] = s_blk[cur * WMAX + i];
@@ -963,12 +995,17 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         if (tid == 0) {
           sv.hdr->n = n;
           sv.hdr->gap = scu[kV2Gap];
-          sv.hdr->flags = (sci[kV2Anomaly] ? 1 : 0) | overflow | (resume ? (sv.hdr->flags & 4) : 0);
+          sv.hdr->flags = (sci[kV2Anomaly] ? 1 : 0) | overflow | lost | (carried & 4);
         }
       }
       if (p.t_done != nullptr && tid == 0) p.t_done[b] = t_done + t_end;
+      if (p.n_slices > 1 && !last_slice) {  // release the next slice of this utterance
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p.progress + b), "r"(slice + 1) : "memory");
+      }
     }
-    __syncthreads();  // the next utterance re-initialises the shared state
+    __syncthreads();  // the next task re-initialises the shared state
   }
 #undef CTCX_TICK
 }

@@ -47,6 +47,10 @@ struct BeamParamsT {
                        // in time slabs may still be in flight); null = everything is there
   int* queue;          // device word, zero at launch: next utterance for the persistent CTAs
   unsigned* bp32;      // [B,Tcap,W] 4-byte back-pointer records (instead of `bp`)
+  // time slicing of the narrow kernel's work queue (set by its launcher): an utterance is cut into
+  // n_slices tasks of slice_frames frames; progress[b] = slices of utterance b finished so far
+  int n_slices, slice_frames;
+  int* progress;       // [B] device words, zero at launch (needed when n_slices > 1)
 };
 using BeamParams = BeamParamsT<float>;
 

@@ -27,9 +27,10 @@ struct LaunchCfg {
   int resident = 0;  // CTAs the device keeps resident at that size
 };
 constexpr int kMaxDevices = 64;
+constexpr int kMinSliceFrames = 32;  // shorter slices would not amortise the hand-over
 
 template <typename IN, int WMAX, bool TIMING, int MINB>
-LaunchStatus LaunchOne(const BeamParams& p, size_t smem, cudaStream_t stream) {
+LaunchStatus LaunchOne(BeamParams& p, size_t smem, cudaStream_t stream) {
   auto kern = BeamKernelV4<IN, WMAX, 256, TIMING, MINB>;
   static LaunchCfg cfgs[kMaxDevices];
   int dev = 0;
@@ -49,12 +50,20 @@ LaunchStatus LaunchOne(const BeamParams& p, size_t smem, cudaStream_t stream) {
   }
   const long long resident = cfg.resident;
   const unsigned grid = (unsigned)(p.B < resident ? p.B : resident);
+  // Batches beyond the resident CTAs: cut every utterance into time slices so that the queue keeps all
+  // CTAs busy to the end (the beam travels between slices through the state block in HBM, ~4 KB).
+  p.n_slices = 1;
+  p.slice_frames = p.T > 0 ? p.T : 1;
+  if (p.B > resident && p.t_done == nullptr && p.state != nullptr && p.progress != nullptr && p.T >= 4 * kMinSliceFrames) {
+    p.n_slices = 4;
+    p.slice_frames = (p.T + p.n_slices - 1) / p.n_slices;
+  }
   kern<<<grid, 256, smem, stream>>>(p);
   return LaunchFrom(cudaGetLastError(), "BeamKernelV4 launch");
 }
 
 template <typename IN>
-LaunchStatus LaunchTyped(const BeamParams& p, int wmax, size_t smem, cudaStream_t stream) {
+LaunchStatus LaunchTyped(BeamParams& p, int wmax, size_t smem, cudaStream_t stream) {
   if constexpr (sizeof(IN) == 4) {
     if (p.dbg_cycles != nullptr) {  // timing build: float32 inputs only
       switch (wmax) {

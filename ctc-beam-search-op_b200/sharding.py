@@ -61,12 +61,18 @@ def merge_raw(shards, bounds, batch):
     return res
 
 
-def _merge_device(shards, bounds, batch):
-    """merge_raw for torch tensors that live on one device (no host round trip)."""
+def _merge_device(shards, counts, bounds, batch, f64):
+    """merge_raw for torch tensors that live on one device (no host round trip): the merged outputs are
+    written straight into ONE packed int64 buffer (the layout of decoder._carve), so a host caller gets
+    them with a single copy into page-locked memory."""
     import torch
     P = len(shards[0][0])
-    groups = [[], [], [], [], [], []]
     dev = shards[0][6].device
+    n_dec = [sum(c[0][p] for c in counts) for p in range(P)]
+    n_ali = [sum(c[1][p] for c in counts) for p in range(P)]
+    n = _dec._pack_elems(batch, P, (n_dec, n_ali), f64)
+    buf = torch.empty((n,), dtype=torch.int64, device=dev)
+    groups, logp = _dec._carve(buf, batch, P, (n_dec, n_ali), f64)
     for p in range(P):
         for base in (0, 3):
             idx, val, mx = [], [], 0
@@ -77,11 +83,15 @@ def _merge_device(shards, bounds, batch):
                 idx.append(i)
                 val.append(sh[base + 1][p])
                 mx = max(mx, int(sh[base + 2][p][1]))
-            groups[base].append(torch.cat(idx, dim=0))
-            groups[base + 1].append(torch.cat(val, dim=0))
-            groups[base + 2].append(torch.tensor([batch, mx], dtype=torch.int64, device=dev))
-    logp = torch.cat([sh[6].reshape(-1, P) for sh in shards], dim=0)
-    return CTCExtBeamSearchDecoder(*groups, logp)
+            if groups[base][p].numel():
+                torch.cat(idx, dim=0, out=groups[base][p])
+                torch.cat(val, dim=0, out=groups[base + 1][p])
+            groups[base + 2][p].copy_(torch.tensor([batch, mx], dtype=torch.int64))
+    if logp.numel():
+        torch.cat([sh[6].reshape(-1, P) for sh in shards], dim=0, out=logp)
+    res = CTCExtBeamSearchDecoder(*groups, logp)
+    res.packed = buf
+    return res, (n_dec, n_ali)
 
 
 def _view(x, b0, b1):
@@ -171,44 +181,60 @@ def _gather_packed_nccl(raw, err, bounds, B, P, f64, rank, world, dst, group, to
     else:
         dist.gather(mine, None, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
         return None
-    shards = []
+    shards, all_counts = [], []
     for r in range(world):
         b0, b1 = bounds[r]
         counts = ([int(v) for v in all_hdr[r, 3:3 + P]], [int(v) for v in all_hdr[r, 3 + P:3 + 2 * P]])
         groups, logp = _dec._carve(recv[r], b1 - b0, P, counts, f64)
         shards.append(CTCExtBeamSearchDecoder(*groups, logp))
-    out = _merge_device(shards, bounds, B)
+        all_counts.append(counts)
+    out, merged_counts = _merge_device(shards, all_counts, bounds, B, f64)
     flags = 0
     for r in range(world):
         flags |= int(all_hdr[r, 2])
-    if to_host:
-        out = CTCExtBeamSearchDecoder(*[[t.cpu().numpy() for t in g] for g in out[:6]], out[6].cpu().numpy())
+    if to_host:  # one copy of the packed result into page-locked memory, carved up there
+        hbuf = torch.empty(out.packed.shape, dtype=torch.int64, pin_memory=True)
+        hbuf.copy_(out.packed, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        groups, logp = _dec._carve(hbuf, B, P, merged_counts, f64)
+        out = CTCExtBeamSearchDecoder(*groups, logp)
+        out.packed = hbuf
     out.flags = flags
     return out
 
 
 def decode_distributed(inputs, sequence_length, beam_width, top_paths, merge_repeated=False,
-                       blank_index=0, blank_label=-1, dst=0, group=None, decode_fn=None):
-    """One process per GPU: every rank holds the full batch description (or at least its own block of
-    it -- only `inputs[:, b0:b1, :]` of this rank's block is touched), decodes its contiguous block in
-    place, and the raw outputs are gathered on rank `dst` (returns None elsewhere). Outputs live where
-    the inputs live (device tensors in -> device tensors on `dst`)."""
+                       blank_index=0, blank_label=-1, dst=0, group=None, decode_fn=None, global_batch=None):
+    """One process per GPU: each rank decodes its contiguous block of the batch and the raw outputs are
+    gathered on rank `dst` (returns None elsewhere). Outputs live where the inputs live (device tensors
+    in -> device tensors on `dst`).
+
+    global_batch=None   every rank passes the WHOLE batch ([T, B, C], [B]); only the view
+                        `inputs[:, b0:b1, :]` of its own block is read -- in place, no repack.
+    global_batch=B      every rank passes only ITS block ([T, b1-b0, C], [b1-b0]) of a batch of B
+                        utterances cut by `shard_bounds(B, world_size)` -- the usual layout of a
+                        multi-process job."""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     x = inputs if isinstance(inputs, (np.ndarray, torch.Tensor)) else np.asarray(inputs)
     sl = sequence_length if isinstance(sequence_length, torch.Tensor) else np.asarray(sequence_length, np.int32)
-    B = int(x.shape[1]) if x.ndim == 3 else 0
+    local = global_batch is not None
+    B = int(global_batch) if local else (int(x.shape[1]) if x.ndim == 3 else 0)
     bounds = shard_bounds(B, world)
     b0, b1 = bounds[rank]
+    if local and x.ndim == 3 and int(x.shape[1]) != b1 - b0:
+        raise ValueError("rank %d holds %d utterances, its block of a batch of %d over %d ranks has %d"
+                         % (rank, int(x.shape[1]), B, world, b1 - b0))
     device_gather = decode_fn is None and dist.get_backend(group) == "nccl" and x.ndim == 3
     err, raw = None, None
     try:
+        xb, slb = (x, sl) if local else (_view(x, b0, b1), sl[b0:b1])
         if decode_fn is not None:
-            raw = decode_fn(np.ascontiguousarray(_np(x)[:, b0:b1, :]), _np(sl)[b0:b1].astype(np.int32), beam_width,
+            raw = decode_fn(np.ascontiguousarray(_np(xb)), _np(slb).astype(np.int32), beam_width,
                             top_paths, merge_repeated, blank_index, blank_label)
         else:
-            raw = ctc_ext_beam_search_decoder_raw(_view(x, b0, b1), sl[b0:b1], beam_width, top_paths,
+            raw = ctc_ext_beam_search_decoder_raw(xb, slb, beam_width, top_paths,
                                                   merge_repeated, blank_index, blank_label, batch_offset=b0,
                                                   outputs="device" if device_gather else "auto")
     except Exception as e:
@@ -218,9 +244,10 @@ def decode_distributed(inputs, sequence_length, beam_width, top_paths, merge_rep
         to_host = not (isinstance(x, torch.Tensor) and x.is_cuda)
         out = _gather_packed_nccl(raw, err, bounds, B, int(top_paths), f64, rank, world, dst, group, to_host,
                                   int(x.shape[0]))
-        if out is not None and to_host and isinstance(x, torch.Tensor):
-            out = CTCExtBeamSearchDecoder(*[[torch.from_numpy(t) for t in g] for g in out[:6]],
-                                          torch.from_numpy(out[6]))
+        if out is not None and to_host and not isinstance(x, torch.Tensor):  # numpy in -> numpy out
+            flags = out.flags
+            out = CTCExtBeamSearchDecoder(*[[t.numpy() for t in g] for g in out[:6]], out[6].numpy())
+            out.flags = flags
         return out
     mine = None
     if raw is not None:

@@ -36,14 +36,36 @@ def main():
         ok &= int(np.array_equal(np.asarray(got[6]).view(np.uint32), want[6].view(np.uint32)))
     else:
         assert got is None
+    # device tensors in -> the packed outputs travel GPU to GPU and the merged result stays on rank 0's GPU;
+    # here every rank passes only ITS block (the usual layout of a multi-process job)
+    b0, b1 = op.shard_bounds(B, world)[rank]
+    xd = torch.from_numpy(x[:, b0:b1]).cuda().contiguous()
+    sd = torch.from_numpy(sl[b0:b1]).cuda()
+    got2 = op.decode_distributed(xd, sd, beam_width=W, top_paths=P, merge_repeated=True, blank_index=28,
+                                 global_batch=B)
+    if rank == 0:
+        assert got2[6].is_cuda and got2[0][0].is_cuda
+        for g in range(6):
+            for p in range(P):
+                ok &= int(np.array_equal(got2[g][p].cpu().numpy(), want[g][p]))
+        ok &= int(np.array_equal(got2[6].cpu().numpy().view(np.uint32), want[6].view(np.uint32)))
+    else:
+        assert got2 is None
+    # ... and the whole tensor on every GPU, each rank decoding a strided view of it in place
+    got3 = op.decode_distributed(torch.from_numpy(x).cuda(), torch.from_numpy(sl).cuda(), beam_width=W, top_paths=P,
+                                 merge_repeated=True, blank_index=28)
+    if rank == 0:
+        for g in range(6):
+            for p in range(P):
+                ok &= int(np.array_equal(got3[g][p].cpu().numpy(), want[g][p]))
     # an error in any block is raised where the result is gathered
     bad = sl.copy()
     bad[B - 1] = T + 3
     try:
         op.decode_distributed(x, bad, beam_width=W, top_paths=P, blank_index=28)
         raised = False
-    except op.FailedPreconditionError:
-        raised = True
+    except op.FailedPreconditionError as e:
+        raised = ("sequence_length(%d) <= %d" % (B - 1, T)) in str(e)  # the index in the WHOLE batch
     if rank == 0 or rank == world - 1:
         ok &= int(raised)
     t = torch.tensor([ok], device="cuda")

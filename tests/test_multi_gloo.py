@@ -22,9 +22,14 @@ def _worker(rank, world, port, case, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import ctc_beam_search_op_b200 as op
-        x, sl, W, P, merge, blank, bl = case
+        x, sl, W, P, merge, blank, bl = case[:7]
         try:
-            out = op.decode_distributed(x, sl, W, P, merge, blank, bl, dst=0, decode_fn=_oracle_raw)
+            if len(case) > 7 and case[7] == "local":  # every rank holds only its block of the batch
+                b0, b1 = op.shard_bounds(x.shape[1], world)[rank]
+                out = op.decode_distributed(np.ascontiguousarray(x[:, b0:b1]), sl[b0:b1], W, P, merge, blank, bl, dst=0,
+                                            decode_fn=_oracle_raw, global_batch=x.shape[1])
+            else:
+                out = op.decode_distributed(x, sl, W, P, merge, blank, bl, dst=0, decode_fn=_oracle_raw)
             if rank == 0:
                 q.put(("ok", [[np.asarray(t) for t in g] for g in out[:6]] + [np.asarray(out[6])]))
         except Exception as e:
@@ -65,6 +70,18 @@ def test_two_ranks_equal_single_process():
     want = _oracle_raw(x, sl, 6, 3, True, 7, -1)
     for g in range(6):
         for p in range(3):
+            np.testing.assert_array_equal(got[g][p], want[g][p])
+    np.testing.assert_array_equal(got[6], want[6])
+
+
+def test_two_ranks_each_holding_its_own_block():
+    x = L.make_logits("gauss", 20, 7, 6, 5, 12)
+    sl = L.ragged_lengths(20, 7, 12)
+    status, got = _run((x, sl, 5, 2, False, 5, -1, "local"))
+    assert status == "ok"
+    want = _oracle_raw(x, sl, 5, 2, False, 5, -1)
+    for g in range(6):
+        for p in range(2):
             np.testing.assert_array_equal(got[g][p], want[g][p])
     np.testing.assert_array_equal(got[6], want[6])
 
