@@ -226,9 +226,9 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
       }
       return (lane < C) ? LoadLogit<IN>(p.logits, (size_t)t * (size_t)p.tstride + row0 + lane) : 0.0f;
     };
-    // S warp, part 1 (runs while the other warps are in PA): the softmax normaliser of the row
-    // (decoder.h:71-80) and the per-class log-probs, into buffer `buf`. Returns the lane's sort key.
-    auto prepare1 = [&](float xr, int buf) -> unsigned {
+    // The S warp prepares frame t+1 in three stages, each placed where the warp has nothing else to do:
+    // S1 (while the other warps are in PA): max and the exp-sum of the softmax normaliser (decoder.h:71-80)
+    auto prepare1 = [&](float xr, float& mx_out) -> float {
       const bool in_row = lane < C;
       const float mx = UnKey(__reduce_max_sync(kFull, in_row ? KeyOf(xr) : 0u));
       s_e[lane] = in_row ? ExpfExact(__fsub_rn(xr, mx), s_exptab) : 0.0f;
@@ -239,20 +239,21 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         const float4 v = *reinterpret_cast<const float4*>(s_e + i);
         sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, v.x), v.y), v.z), v.w);
       }
+      mx_out = mx;
+      return sum;
+    };
+    // S2 (while the other warps list the candidates, PB): the normaliser, per-class log-probs, classes
+    // ranked by log-prob. Equal keys keep lane order; the order inside a tie never matters (a prefix of
+    // the sorted classes never ends inside a group of equal scores). Returns the lane's rank.
+    auto prepare2 = [&](float xr, float mx, float sum, int buf) -> int {
       const float off = __fadd_rn(mx, LogfExact(sum));
-      const bool lane_ok = in_row && (lane != blank);
+      const bool lane_ok = (lane < C) && (lane != blank);
       const float pl_lane = lane_ok ? __fsub_rn(xr, off) : 0.0f;
       s_xb[buf * 32 + lane] = xr;
       s_plb[buf * 32 + lane] = pl_lane;
       const unsigned key = lane_ok ? KeyOf(pl_lane) : 0u;  // blank / padding sort last
-      s_bits[lane] = key;  // the keys of the row, read back as broadcasts by part 2
+      s_bits[lane] = key;  // the keys of the row, read back as broadcasts
       if (lane == 0) s_fsc[buf * 4 + 0] = off;
-      return key;
-    };
-    // S warp, part 2 (runs while the other warps list the candidates, PB): classes ranked by log-prob,
-    // sorted log-probs, prefix masks. Equal keys keep lane order; the order inside a tie never matters
-    // (a prefix of the sorted classes never ends inside a group of equal scores).
-    auto prepare2 = [&](unsigned key, int buf) {
       __syncwarp();
       int rank = 0;
 #pragma unroll
@@ -264,14 +265,15 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         rank += (k.w > key) ? 1 : 0;
       }
       rank += __popc(__match_any_sync(kFull, key) & ((1u << lane) - 1u));
+      s_plSb[buf * 32 + rank] = lane_ok ? pl_lane : NegInf();
+      if ((rank & 3) == 0) s_plHb[buf * 8 + (rank >> 2)] = lane_ok ? pl_lane : NegInf();
+      return rank;
+    };
+    // S3 (while the other warps write the next beam, PG): prefix masks of the sorted classes
+    auto prepare3 = [&](int rank, int buf) {
       const bool lane_ok = (lane < C) && (lane != blank);
-      const float pl_lane = s_plb[buf * 32 + lane];
-      float* bplS = s_plSb + buf * 32;
-      float* bplH = s_plHb + buf * 8;
       unsigned* bpref = s_prefb + buf * 36;
-      bplS[rank] = lane_ok ? pl_lane : NegInf();
-      if ((rank & 3) == 0) bplH[rank >> 2] = lane_ok ? pl_lane : NegInf();
-      __syncwarp();  // every lane has read the keys
+      __syncwarp();
       s_bits[rank] = lane_ok ? (1u << lane) : 0u;
       __syncwarp();
       unsigned incl = s_bits[lane];
@@ -285,8 +287,8 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
       __syncwarp();
       if (lane == 0) {
         bpref[0] = 0u;
-        s_fsc[buf * 4 + 1] = (cv > 0) ? bplS[0] : NegInf();
-        s_fsc[buf * 4 + 2] = (cv > 0) ? bplS[cv - 1] : 0.0f;
+        s_fsc[buf * 4 + 1] = (cv > 0) ? s_plSb[buf * 32] : NegInf();
+        s_fsc[buf * 4 + 2] = (cv > 0) ? s_plSb[buf * 32 + cv - 1] : 0.0f;
       }
     };
 
@@ -321,11 +323,13 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
     }
     int n = 1;
     float xr_next = 0.0f;  // S warp: raw row of the frame after the one being prepared
-    unsigned s_key = 0u;   // S warp: sort key of the row being prepared (between its two parts)
+    float s_xr = 0.0f, s_mx = 0.0f, s_sum = 0.0f;  // S warp: the row being prepared, between the stages
+    int s_rank = 0;
     if (s_warp && L > 0) {
       const float x0 = load_row(t0);
       if (L > 1) xr_next = load_row(t0 + 1);
-      prepare2(prepare1(x0, 0), 0);
+      const float sum0 = prepare1(x0, s_mx);
+      prepare3(prepare2(x0, s_mx, sum0, 0), 0);
     }
     __syncthreads();
     int carried = 0;  // flag bits handed on from the previous slice / call
@@ -374,9 +378,9 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
 
       // ---- S: the last warp prepares frame t+1 (and puts row t+2 in flight) while the others run PA ----
       if (s_warp && t + 1 < L) {
-        const float xr = xr_next;
+        s_xr = xr_next;
         if (t + 2 < L) xr_next = load_row(t0 + t + 2);
-        s_key = prepare1(xr, nxt);
+        s_sum = prepare1(s_xr, s_mx);
       }
       const float xb = x[blank];
       const float pb = __fsub_rn(xb, off);
@@ -468,7 +472,6 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
       }
       __syncthreads();
       CTCX_TICK(0)  // PA
-
       const int n_risk = sci[kV2NRisk];
 
       // Candidates of one row above a threshold, as a class bitmask. The classes are sorted by
@@ -568,8 +571,12 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
       }
       CTCX_TICK(2)  // PC
 
-      // ---- S, second part: ranks and prefix masks of frame t+1, while the others list the candidates ----
-      if (s_warp && t + 1 < L) prepare2(s_key, nxt);
+      // ---- S, second and third part: normaliser, log-probs, class ranks and prefix masks of frame t+1,
+      // while the others list the candidates ----
+      if (s_warp && t + 1 < L) {
+        s_rank = prepare2(s_xr, s_mx, s_sum, nxt);
+        prepare3(s_rank, nxt);
+      }
 
       // ---- PB / PD: list + histogram of the items in the score range, boundary bin ----
       const unsigned minkey_m = scu[kV2MinKey];
@@ -608,7 +615,9 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         const bool member_in = !clamped || my_key > lo_key;
         CTCX_TICK(16)  // PB: range
 
-        // PB pass 1: admissible classes of this thread's (row, class slice)
+        // PB pass 1: admissible classes of this thread's (row, class slice). A warp whose rows all lie
+        // beyond the beam (the S warp at beam widths up to 112, for one) has nothing to list.
+        const bool warp_has_rows = ((warp * 32) / PARTS) < n;
         unsigned mymask = 0u;
         float r_ot = 0.0f, r_ob = 0.0f;
         int r_label = -1;
@@ -623,8 +632,8 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
           }
         }
         CTCX_TICK(17)  // PB: masks
-        int pos0;
-        {
+        int pos0 = 0;
+        if (warp_has_rows) {
           const int cnt = __popc(mymask);
           int incl = cnt;
 #pragma unroll
@@ -881,7 +890,7 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         if (tid == 0) {
           sci[kV2NCand] = 0;
           sci[kV2NRisk] = 0;
-          scu[kV2MinKey] = 0xffffffffu;
+              scu[kV2MinKey] = 0xffffffffu;
           scu[kV2MaxKey] = 0u;
           sci[kV2NBnd] = 0;
           scu[kV2MinBase] = 0xffffffffu;
