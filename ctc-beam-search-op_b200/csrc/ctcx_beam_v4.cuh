@@ -148,7 +148,9 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
   LoadExpTable(s_exptab, tid, NT);
 
   // thread -> (row, class slice) mapping of the candidate pass
-  constexpr int PARTS = NT / WMAX;  // threads per row
+  // (latency regime: all threads share the rows, two per row at the 128-slot tier; throughput regime:
+  // one thread per row -- the candidate search runs on half as many warps, fewer instructions in total)
+  constexpr int PARTS = (MINB >= 4 && !TIMING) ? 1 : NT / WMAX;  // threads per row
   constexpr int CP = 32 / PARTS;    // classes per thread
   static_assert(NT % WMAX == 0 && 32 % PARTS == 0, "row/class tiling");
   const int prow = tid / PARTS, pbase = (tid % PARTS) * CP;
@@ -633,7 +635,7 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         }
         CTCX_TICK(17)  // PB: masks
         int pos0 = 0;
-        if (warp_has_rows) {
+        if (warp_has_rows && __any_sync(kFull, mymask != 0u)) {  // (warp-uniform) somebody has something to list
           const int cnt = __popc(mymask);
           int incl = cnt;
 #pragma unroll
