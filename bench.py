@@ -281,7 +281,7 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
     if args.workload == "cfg2" and not args.no_sharded:
         del dev_batches, host_batches
         torch.cuda.empty_cache()
-        sharded = run_sharded_cfg5(rank, world, local_rank, steps=max(3, min(args.steps, 10)), warmup=2)
+        sharded = run_sharded_cfg5(rank, world, local_rank, steps=max(3, min(args.steps, 10)), warmup=3)
     if rank != 0:
         return
 
@@ -330,7 +330,7 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
         cores = host_threads()
         n_utt = min(B, cores)
         dt, kind = cpu_reference_run(base, n_utt, cores)
-        n1 = 2 if T * W >= 20000 else 8
+        n1 = 8 if T * W >= 20000 else 32
         dt1, _ = cpu_reference_run(base, n1, 1)
         # the op as it really runs is single-threaded (kernels.cc:68-90): that is the primary figure; the
         # batch sharded over all host threads (memory-bound: ~0.5 GB of trie per utterance in flight) beside it

@@ -54,8 +54,12 @@ LaunchStatus LaunchOne(BeamParams& p, size_t smem, cudaStream_t stream) {
   // CTAs busy to the end (the beam travels between slices through the state block in HBM, ~4 KB).
   p.n_slices = 1;
   p.slice_frames = p.T > 0 ? p.T : 1;
-  if (p.B > resident && p.t_done == nullptr && p.state != nullptr && p.progress != nullptr && p.T >= 4 * kMinSliceFrames) {
-    p.n_slices = 4;
+  if (p.B > resident && p.t_done == nullptr && p.state != nullptr && p.progress != nullptr && p.T >= 2 * kMinSliceFrames) {
+    // enough tasks that the last round of the queue is a small part of the whole: ~12 per CTA
+    long long want = (12 * resident + p.B - 1) / p.B;
+    want = want < 2 ? 2 : (want > 16 ? 16 : want);
+    const long long most = p.T / kMinSliceFrames;
+    p.n_slices = (int)(want < most ? want : most);
     p.slice_frames = (p.T + p.n_slices - 1) / p.n_slices;
   }
   kern<<<grid, 256, smem, stream>>>(p);

@@ -68,13 +68,15 @@ def test_every_utterance_of_the_baseline_shapes(op, name, kind):
     assert raw.flags == 0  # no utterance met the re-score anomaly
 
 
-def test_cfg5_size_batch_on_one_gpu(op):
+@pytest.mark.parametrize("B", [8192, 1000])
+def test_cfg5_size_batch_on_one_gpu(op, B):
     """BASELINE configs[4]: T=500, C=29, beam 100, B=8192 on ONE GPU. Device tensors in (the 475 MB
     of logits are generated from 512 distinct utterances), every utterance compared with its twin in
-    a permuted re-run (order independence across CTA waves / queue positions), and the 512 distinct
-    ones with the oracle."""
+    a permuted re-run (order independence across CTA waves / queue positions / time slices), and the
+    512 distinct ones with the oracle. B=1000 is the regime of many time slices per utterance (the
+    work queue cuts utterances finer the closer the batch is to the number of resident CTAs)."""
     import torch
-    T, B, C, W, P, merge, blank = 500, 8192, 29, 100, 1, True, 28
+    T, C, W, P, merge, blank = 500, 29, 100, 1, True, 28
     n_distinct = 512
     base = np.concatenate([L.make_logits("gauss", T, n_distinct // 2, C, blank, 4),
                            L.make_logits("peaky", T, n_distinct // 2, C, blank, 104)], axis=1)
