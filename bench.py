@@ -236,8 +236,10 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
     # ---- warm-up ----
     for i in range(max(args.warmup, 3)):
         step_device(i)
+    out = None
     for i in range(max(args.warmup, 3, n_rot)):  # the host path has its own cold costs (side stream, pinned
-        step_e2e(i)                              # result buffers per batch size): once over every rotating batch
+        out = step_e2e(i)                        # result buffers): once over every rotating batch, holding the
+    del out                                      # previous result while the next is produced, as the timed loop does
     barrier()
 
     # ---- device-resident timing (CUDA events per step on the launching stream) ----
@@ -263,11 +265,16 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
     barrier()
     t0 = time.perf_counter()
     d2h = 0
+    step_s = []
     for i in range(args.steps):
+        ts = time.perf_counter()
         out = step_e2e(i)
         d2h = sum(t.numel() * t.element_size() for g in out[:6] for t in g) + out[6].numel() * 4
+        step_s.append(time.perf_counter() - ts)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if os.environ.get("CTCX_BENCH_VERBOSE"):
+        sys.stderr.write("e2e per-step ms: %s\n" % " ".join("%.2f" % (1e3 * v) for v in step_s))
     barrier()
     clocks = sampler.stop()
 

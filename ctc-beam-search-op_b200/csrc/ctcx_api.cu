@@ -424,7 +424,7 @@ int RunFeed(void* arg) {
   Feed& f = *(Feed*)arg;
   // Slabs grow geometrically: the first frames land after a few microseconds so the beam kernel can
   // start, the bulk moves in large copies.
-  int t0 = 0, n = f.flags ? 4 : f.T;
+  int t0 = 0, n = f.flags ? 6 : f.T;
   while (t0 < f.T) {
     const int t1 = std::min(f.T, t0 + n);
     cudaError_t e;
@@ -445,7 +445,7 @@ int RunFeed(void* arg) {
       return CTCX_ERR_CUDA;
     }
     t0 = t1;
-    n = std::min(128, n * 5 / 2);
+    n = std::min(192, n * 4);
   }
   return CTCX_OK;
 }

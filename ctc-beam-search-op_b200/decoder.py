@@ -308,6 +308,7 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
     res = CTCExtBeamSearchDecoder(*groups, logp)
     res.flags = int(flags.value)
     res.packed = packed
+    res.max_lengths = ([int(v) for v in max_dec], [int(v) for v in max_ali])  # dense_shape[1] per path, on the host
     return res
 
 

@@ -61,7 +61,7 @@ def merge_raw(shards, bounds, batch):
     return res
 
 
-def _merge_device(shards, counts, bounds, batch, f64):
+def _merge_device(shards, counts, maxima, bounds, batch, f64):
     """merge_raw for torch tensors that live on one device (no host round trip): the merged outputs are
     written straight into ONE packed int64 buffer (the layout of decoder._carve), so a host caller gets
     them with a single copy into page-locked memory."""
@@ -73,20 +73,25 @@ def _merge_device(shards, counts, bounds, batch, f64):
     n = _dec._pack_elems(batch, P, (n_dec, n_ali), f64)
     buf = torch.empty((n,), dtype=torch.int64, device=dev)
     groups, logp = _dec._carve(buf, batch, P, (n_dec, n_ali), f64)
+    shapes = torch.empty((2 * P, 2), dtype=torch.int64)
     for p in range(P):
-        for base in (0, 3):
-            idx, val, mx = [], [], 0
+        for k, base in enumerate((0, 3)):
+            idx, val = [], []
             for sh, (b0, _) in zip(shards, bounds):
                 i = sh[base][p]
                 if b0:
                     i[:, 0] += b0  # in place: the gathered buffer is ours
                 idx.append(i)
                 val.append(sh[base + 1][p])
-                mx = max(mx, int(sh[base + 2][p][1]))
             if groups[base][p].numel():
                 torch.cat(idx, dim=0, out=groups[base][p])
                 torch.cat(val, dim=0, out=groups[base + 1][p])
-            groups[base + 2][p].copy_(torch.tensor([batch, mx], dtype=torch.int64))
+            shapes[2 * p + k, 0] = batch
+            shapes[2 * p + k, 1] = max(m[k][p] for m in maxima)  # the longest sequence over all shards (host values)
+    shapes = shapes.to(dev, non_blocking=True)
+    for p in range(P):
+        groups[2][p].copy_(shapes[2 * p])
+        groups[5][p].copy_(shapes[2 * p + 1])
     if logp.numel():
         torch.cat([sh[6].reshape(-1, P) for sh in shards], dim=0, out=logp)
     res = CTCExtBeamSearchDecoder(*groups, logp)
@@ -140,8 +145,8 @@ def _gather_packed_nccl(raw, err, bounds, B, P, f64, rank, world, dst, group, to
     import torch
     import torch.distributed as dist
     dev = torch.device("cuda", torch.cuda.current_device())
-    # header: [error code, error batch index, flags, n_dec[P], n_ali[P], packed length]
-    hdr = torch.zeros(4 + 2 * P, dtype=torch.int64)
+    # header: [error code, error batch index, flags, n_dec[P], n_ali[P], packed length, max_dec[P], max_ali[P]]
+    hdr = torch.zeros(4 + 4 * P, dtype=torch.int64)
     if err is not None:
         hdr[0] = int(getattr(err, "code", -1)) or -1
         hdr[1] = int(getattr(err, "batch_index", -1))
@@ -151,6 +156,9 @@ def _gather_packed_nccl(raw, err, bounds, B, P, f64, rank, world, dst, group, to
             hdr[3 + p] = raw[0][p].shape[0]
             hdr[3 + P + p] = raw[3][p].shape[0]
         hdr[3 + 2 * P] = raw.packed.numel()
+        for p in range(P):
+            hdr[4 + 2 * P + p] = raw.max_lengths[0][p]
+            hdr[4 + 3 * P + p] = raw.max_lengths[1][p]
     hdr = hdr.to(dev)
     all_hdr = torch.empty((world, hdr.numel()), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(all_hdr, hdr, group=group)
@@ -181,14 +189,16 @@ def _gather_packed_nccl(raw, err, bounds, B, P, f64, rank, world, dst, group, to
     else:
         dist.gather(mine, None, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
         return None
-    shards, all_counts = [], []
+    shards, all_counts, maxima = [], [], []
+    rows = all_hdr.tolist()
     for r in range(world):
         b0, b1 = bounds[r]
-        counts = ([int(v) for v in all_hdr[r, 3:3 + P]], [int(v) for v in all_hdr[r, 3 + P:3 + 2 * P]])
+        counts = (rows[r][3:3 + P], rows[r][3 + P:3 + 2 * P])
         groups, logp = _dec._carve(recv[r], b1 - b0, P, counts, f64)
         shards.append(CTCExtBeamSearchDecoder(*groups, logp))
         all_counts.append(counts)
-    out, merged_counts = _merge_device(shards, all_counts, bounds, B, f64)
+        maxima.append((rows[r][4 + 2 * P:4 + 3 * P], rows[r][4 + 3 * P:4 + 4 * P]))
+    out, merged_counts = _merge_device(shards, all_counts, maxima, bounds, B, f64)
     flags = 0
     for r in range(world):
         flags |= int(all_hdr[r, 2])
