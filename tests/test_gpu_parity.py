@@ -866,3 +866,29 @@ def test_shard_errors_name_the_utterance_in_the_whole_batch(op):
     sl[4] = 23
     with pytest.raises(op.FailedPreconditionError, match=r"sequence_length\(4\) <= 20"):
         op.decode_multi_device(x, sl, 4, 1, False, 7, -1, devices=[0, 0, 0])
+
+
+def test_rescore_acceptance_cases_are_flagged(op):
+    """The utterances of tests/golden/rescore_cases.npz make the reference accept the re-score of an
+    evicted member (decoder.h:189-199) -- possible only at an exact tie with the beam bottom, see
+    tests/test_oracle.py. The kernels do not model the event; they must REPORT it: the result's flags
+    carry FLAG_ROUNDING_ANOMALY, so a caller can tell that this utterance left the bit-exact contract
+    (it is a tie case, where the reference's own answer depends on heap order)."""
+    import os
+    arr = np.load(os.path.join(L.ROOT, "tests", "golden", "rescore_cases.npz"))
+    n = int(arr["n"][0])
+    flagged = same = 0
+    for k in range(n):
+        W, P, merge, blank = (int(v) for v in arr["c%d/attrs" % k])
+        x = arr["c%d/x" % k][:, None, :]
+        sl = np.asarray([x.shape[0]], np.int32)
+        raw = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=W, top_paths=P, merge_repeated=bool(merge),
+                                                 blank_index=blank, blank_label=-1)
+        flagged += int(bool(raw.flags & op.FLAG_ROUNDING_ANOMALY))
+        same += int(not L.raw_mismatches(raw, L.oracle_decode(x, sl, W, P, bool(merge), blank, -1)))
+    assert flagged == n, (flagged, n)   # every one of them is reported
+    assert same >= 0                    # (most still decode like the oracle; not required)
+    # ... and ordinary inputs never raise the flag
+    x = L.make_logits("gauss", 120, 8, 29, 28, 77)
+    raw = op.ctc_ext_beam_search_decoder_raw(x, np.full(8, 120, np.int32), beam_width=100, top_paths=1, blank_index=28)
+    assert raw.flags == 0

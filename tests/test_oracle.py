@@ -240,3 +240,55 @@ def test_minus_infinity_logits_oracle_equals_reference():
         got, margin = L.oracle_decode(x, sl, W, P, merge, blank, -1, want_margin=True)
         assert not [bp for bp in L.same_result(ref, got) if margin[bp[0]].min() > 0]
         assert not L.same_result(got, L.model_decode(x, sl, W, P, merge, blank, -1))
+
+
+# --- the re-score acceptance (decoder.h:167-199), the one event the kernels flag instead of modelling
+def _rescore_cases():
+    arr = np.load(os.path.join(L.ROOT, "tests", "golden", "rescore_cases.npz"))
+    for k in range(int(arr["n"][0])):
+        W, P, merge, blank = (int(v) for v in arr["c%d/attrs" % k])
+        yield k, arr, arr["c%d/x" % k], W, P, bool(merge), blank
+
+
+def test_rescore_acceptance_happens_only_at_an_exact_tie():
+    """A member that was evicted during the grow phase and is re-scored by its parent (decoder.h:167-187)
+    is accepted again (decoder.h:189-199) only if the re-score s exceeds the beam bottom, and the bottom
+    is >= the member's own total at that moment: s > bottom >= total(member), where s and total(member)
+    are the same quantity up to rounding. So the event needs the beam bottom to TIE with the evicted
+    member's total (exactly, or inside the rounding gap): an utterance in which it happens always has an
+    order-deciding comparison with zero margin -- the regime where the reference's own result depends on
+    libstdc++ heap order and which the parity contract excuses. The fixture holds
+    utterances found by tools/anomaly_search.py (350 M frames of adversarial inputs: 4 039 acceptances,
+    every one in a label-symmetric input where permuted prefixes tie exactly)."""
+    n = 0
+    for k, arr, x, W, P, merge, blank in _rescore_cases():
+        r, margin, st = L.oracle_decode(x[:, None, :], [x.shape[0]], W, P, merge, blank, -1, want_margin=True,
+                                        want_stats=True)
+        assert st.revisit_accepts > 0 and st.revisit_above_former >= st.revisit_accepts
+        assert margin[0, [1, 2]].min() == 0.0, (k, margin)  # an exact tie at the beam bottom / in the visiting order
+        n += 1
+    assert n >= 16
+
+
+@pytest.mark.skipif(not L.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+def test_rescore_acceptance_search_on_tie_free_inputs_finds_nothing():
+    """The complement: on inputs WITHOUT exact ties (continuous logits) the necessary condition
+    (re-score above the member's former total) does occur -- one in ~800 revisits in the offline search
+    -- but the acceptance never: 0 in the sample here, 0 in 2e8 frames offline (tools/anomaly_search.py),
+    and on those inputs the oracle equals the compiled reference wherever the margins are positive."""
+    rng = np.random.default_rng(7)
+    above = accepts = 0
+    for _ in range(60):
+        C = int(rng.integers(3, 9)); W = int(rng.integers(2, 9)); T = int(rng.integers(10, 50)); B = 32
+        blank = int(rng.integers(0, C))
+        x = rng.standard_normal((T, B, C)).astype(np.float32)
+        idx = rng.integers(0, C, (T, B))
+        np.put_along_axis(x, idx[..., None], np.float32(x.max() + rng.choice([10, 20, 40])), axis=2)
+        sl = np.full(B, T, np.int32)
+        r, margin, st = L.oracle_decode(x, sl, W, 1, False, blank, -1, want_margin=True, want_stats=True)
+        above += st.revisit_above_former
+        accepts += st.revisit_accepts
+        ref = L.ref_decode(x, sl, W, 1, False, blank, -1)
+        tie_free = margin[:, [1, 2, 4]].min(axis=1) > 0
+        assert not [bp for bp in L.same_result(ref, r) if tie_free[bp[0]]]
+    assert accepts == 0, (accepts, above)
