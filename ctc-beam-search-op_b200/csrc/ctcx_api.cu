@@ -142,9 +142,6 @@ struct DecodeOpts {
   long long tstride = 0;           // elements between frames; 0 = batch * num_classes
   const int* ready = nullptr;      // device word "frames landed" (narrow path only), or null
   const void* lm = nullptr;        // scorer table (float32 decodes)
-  // host-input decodes: called after the kernels are enqueued and before the result is awaited
-  int (*feed)(void*) = nullptr;
-  void* feed_arg = nullptr;
 };
 
 int ReportSizes(const long long* h_sizes, const int* h_stats, int B, int T, int P, ctcx_sizes* sizes,
@@ -314,14 +311,6 @@ int DecodeImpl(const void* logits_dev, int T, int B, int C, const int32_t* seq_l
     CTCX_LAUNCH(ctcx::LaunchTraceScanFlags(tp, ws.rec_bytes, sp, bp.flags, d_stats, stream,
                                            g_profile ? g_ev[3] : nullptr));
     ProfRecord(4, stream);
-  }
-
-  if (opt.feed != nullptr) {  // host-input decode: the slab copies go out now, behind the kernel launches
-    const int rc = opt.feed(opt.feed_arg);
-    if (rc != CTCX_OK) {
-      cudaStreamSynchronize(stream);
-      return rc;
-    }
   }
 
   // ONE copy brings the sparse sizes and the status words to the host
@@ -628,8 +617,10 @@ int ctcx_decode_hostin(const void* logits_host, int dtype, int64_t host_time_str
       CTCX_CUDA(cudaEventRecord(ev, stream));
       CTCX_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
       opt.ready = d_ctrl + 1;
-      opt.feed = RunFeed;
-      opt.feed_arg = &feed;
+      // The slab copies (page-locked source: the calls only enqueue) go out BEFORE the kernels: whatever
+      // serialises launches -- a profiler, CUDA_LAUNCH_BLOCKING -- then finds the data already landed
+      // instead of a kernel waiting for copies its own launch is holding back.
+      rc = RunFeed(&feed);
     } else {
       // copy first (on the copy stream, so that it can still overlap other work of the caller), then decode
       CTCX_CUDA(cudaEventRecord(ev, stream));

@@ -389,11 +389,13 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
       CTCX_TICK(7)  // frame setup
       // ---- PA: update the existing members (decoder.h:95-143) ----
       unsigned my_key = 0u;
+      bool suspect = false;
       if (tid < n) {
         const int i = tid;
         const int lbl = o_label[i];
         int pslot = -1;
         float v_nl = o_lab[i], v_an = NegInf();
+        float rescore = NegInf();  // what the parent's re-score of this member would be (decoder.h:172-182)
         unsigned an_kind = kAnNone, an_src = 0xffu;
         if (lbl >= 0) {
           const unsigned long long ph = o_phash[i];
@@ -415,6 +417,7 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
             const bool same = (lbl == o_label[pslot]);
             const float base = same ? o_blk[pslot] : o_total[pslot];
             v_nl = __fsub_rn(__fadd_rn(LogSumExp(o_lab[i], base, s_exptab), xl), off);
+            rescore = __fadd_rn(pl, base);
             v_an = __fadd_rn(o_ab[pslot], pl);
             an_kind = kAnParAb;
             an_src = (unsigned)pslot;
@@ -445,6 +448,12 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         m_key[i] = my_key;
         m_rec[i] = PackRec32((unsigned)i, an_src, ab_kind, an_kind, (unsigned)(lbl & 0xff));
         m_pslot[i] = pslot;
+        // Precondition of the one event that is reported instead of modelled (DESIGN.md "Known deviation"):
+        // were this member evicted and then re-scored by its parent, rounding would put the re-score ABOVE
+        // the member's own total, so the reference could accept it again (decoder.h:189-199; it does so only
+        // when the beam bottom ties with that total). Mathematically total >= re-score always. The utterance
+        // is flagged if such a member then drops out of the beam (after the selection, below).
+        suspect = KeyOf(rescore) > my_key;
         if (pslot >= 0) {
           atomicOr(&s_row[pslot].w, 1u << lbl);
           if (pslot < i) {
@@ -559,16 +568,6 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
           // a query only counts rows up to its parent's: if every wiped row lies beyond every parent
           // row, no count (and no parent) is affected and the verdicts are final
           if (min_wiped > max_parent) break;
-        }
-        // documented rounding anomaly: flag, do not model
-        for (int q = tid; q < n_risk; q += NT) {
-          const int m = s_risk[q];
-          if (s_wiped[m]) {
-            const int pslot = m_pslot[m];
-            const int lbl = o_label[m];
-            const float base = (lbl == o_label[pslot]) ? o_blk[pslot] : o_total[pslot];
-            if (KeyOf(__fadd_rn(__fsub_rn(x[lbl], off), base)) > m_key[m]) sci[kV2Anomaly] = 1;
-          }
         }
       }
       CTCX_TICK(2)  // PC
@@ -740,6 +739,8 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         cyc[TIMING ? 22 : 0] += wiped;
         cyc[TIMING ? 23 : 0] += (n_risk > 0) ? 1 : 0;
       }
+      // a suspect member (see PA) that is not certain to stay in the beam: report the utterance
+      if (__builtin_expect(suspect, 0) && (!member_in || bucket_of(my_key) <= bstar)) sci[kV2Anomaly] = 1;
       const bool bnd_all = (e_b == k_rem);
       // next frame's range prediction: the measured top-to-threshold gap
       const unsigned gap_next = (unsigned)(sc[kV2TopBin] - bstar + 1) << shift;

@@ -298,11 +298,13 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     CTCX_TICK(7)  // frame setup
     // ---- PA: update the existing members (decoder.h:95-143) ----
     unsigned my_key = 0u;
+    bool suspect = false;
     if (tid < n) {
       const int i = tid;
       const int lbl = o_label[i];
       int pslot = -1;
       float v_nl = o_lab[i], v_an = NegInf();
+      float rescore = NegInf();  // what the parent's re-score of this member would be (decoder.h:172-182)
       unsigned an_kind = kAnNone, an_src = kInvalidSlot;
       if (lbl >= 0) {
         const unsigned long long ph = o_phash[i];
@@ -324,6 +326,7 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
           const bool same = (lbl == o_label[pslot]);
           const float base = same ? o_blk[pslot] : o_total[pslot];
           v_nl = __fsub_rn(__fadd_rn(LogSumExp(o_lab[i], base, s_exptab), xl), off);
+          rescore = __fadd_rn(pl, base);
           v_an = __fadd_rn(o_ab[pslot], pl);
           an_kind = kAnParAb;
           an_src = (unsigned)pslot;
@@ -354,6 +357,9 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       m_key[i] = my_key;
       m_rec[i] = PackRec((unsigned)i, an_src, ab_kind, an_kind);
       m_pslot[i] = pslot;
+      // precondition of the reference's re-acceptance of an evicted member (decoder.h:189-199): rounding puts
+      // the parent's re-score above the member's own total -- reported, not modelled (DESIGN.md "Known deviation")
+      suspect = KeyOf(rescore) > my_key;
       if (pslot >= 0) {
         atomicOr(&s_kid[pslot * KW + (lbl >> 5)], 1u << (lbl & 31));
         s_kids[atomicAdd(&sci[kWNKid], 1)] = ((unsigned)pslot << 16) | (unsigned)lbl;
@@ -536,16 +542,6 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
         // row, no count (and no parent) is affected and the verdicts are final
         if (min_wiped > max_parent) break;
       }
-      // documented rounding anomaly: flag, do not model
-      for (int q = tid; q < n_risk; q += NT) {
-        const int m = s_risk[q];
-        if (s_wiped[m]) {
-          const int pslot = m_pslot[m];
-          const int lbl = o_label[m];
-          const float base = (lbl == o_label[pslot]) ? o_blk[pslot] : o_total[pslot];
-          if (KeyOf(__fadd_rn(__fsub_rn(x[lbl], off), base)) > m_key[m]) sci[kV2Anomaly] = 1;
-        }
-      }
     }
     CTCX_TICK(2)  // PC
 
@@ -696,6 +692,8 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
     }
     const bool member_in = !clamped || my_key > lo_key;
     const int bstar = sc[kV2Bstar], k_rem = sc[kV2KRem], e_b = sc[kV2E], n_new = sc[kV2NNew];
+    // a suspect member (see PA) that is not certain to stay in the beam: report the utterance
+    if (__builtin_expect(suspect, 0) && (!member_in || bucket_of(my_key) <= bstar)) sci[kV2Anomaly] = 1;
     const bool bnd_all = (e_b == k_rem);
     // next frame's range prediction: the measured top-to-threshold gap
     const unsigned gap_next = (unsigned)(sc[kV2TopBin] - bstar + 1) << shift;

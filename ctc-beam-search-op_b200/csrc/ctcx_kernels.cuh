@@ -594,11 +594,13 @@ __global__ void __launch_bounds__(NT) BeamKernelT(BeamParamsT<R> p) {
     const R xb = x[blank];
     const R pb = Ops::Sub(xb, off);
     Key my_key = (Key)0;
+    bool suspect = false;
     if (tid < n) {
       const int i = tid;
       const int lbl = o_label[i];
       int pslot = -1;
       R v_nl = o_lab[i], v_an = Ops::NegInf();
+      R rescore = Ops::NegInf();  // what the parent's re-score of this member would be (decoder.h:172-182)
       unsigned an_kind = kAnNone, an_src = kInvalidSlot;
       if (lbl >= 0) {
         const unsigned long long ph = o_phash[i];
@@ -618,6 +620,7 @@ __global__ void __launch_bounds__(NT) BeamKernelT(BeamParamsT<R> p) {
           if (p.lm != nullptr)  // GetStateExpansionScore(b->state, .), decoder.h:103,114
             base = Ops::Add(base, p.lm[(size_t)(o_label[pslot] + 1) * C + lbl]);
           v_nl = Ops::Sub(Ops::Add(LogSumExp(o_lab[i], base, s_exptab), xl), off);  // :102-104,:113-115
+          rescore = Ops::Add(pl, base);
           v_an = Ops::Add(o_ab[pslot], pl);
           an_kind = kAnParAb;
           an_src = (unsigned)pslot;
@@ -646,6 +649,12 @@ __global__ void __launch_bounds__(NT) BeamKernelT(BeamParamsT<R> p) {
       m_key[i] = my_key;
       m_rec[i] = PackRec((unsigned)i, an_src, ab_kind, an_kind);
       m_pslot[i] = pslot;
+      // Precondition of the one event that is reported instead of modelled (DESIGN.md "Known deviation"):
+      // were this member evicted and then re-scored by its parent, rounding would put the re-score ABOVE
+      // the member's own total, so the reference could accept it again (decoder.h:189-199; it does so only
+      // when the beam bottom ties with that total). Mathematically total >= re-score always. The utterance
+      // is flagged if such a member then drops out of the beam (survivor collection, below).
+      suspect = Ops::KeyOf(rescore) > my_key;
       if (pslot >= 0) {
         atomicOr(&s_kid[pslot * KW + (lbl >> 5)], 1u << (lbl & 31));
         if (pslot < i) {  // the parent's turn comes first: candidate for the revisit-wipe
@@ -782,17 +791,9 @@ __global__ void __launch_bounds__(NT) BeamKernelT(BeamParamsT<R> p) {
         __syncthreads();  // everyone has read the flag before it is written again
         if (!changed) break;
       }
-      // documented rounding anomaly: a wiped member whose re-scored value would beat its own
-      // former total (never observed). Flag the utterance instead of modelling it.
       for (int q = tid; q < n_risk; q += NT) {
         const int m = s_risk[q];
         if (s_wiped[m]) {
-          const int pslot = m_pslot[m];
-          const int lbl = o_label[m];
-          const R pl = Ops::Sub(x[lbl], off);
-          R base = (lbl == o_label[pslot]) ? o_blk[pslot] : o_total[pslot];
-          if (p.lm != nullptr) base = Ops::Add(base, p.lm[(size_t)(o_label[pslot] + 1) * C + lbl]);
-          if (Ops::KeyOf(Ops::Add(pl, base)) > m_key[m]) sci[kScAnomaly] = 1;
           sci[kScChanged] = 2;  // "some member is wiped"
         }
       }
@@ -907,6 +908,8 @@ __global__ void __launch_bounds__(NT) BeamKernelT(BeamParamsT<R> p) {
       if (take_all || d > cut_d || (d == cut_d && ~okey >= cut_o)) {
         const int pos = atomicAdd(&sci[kScNSurv], 1);
         if (pos < WMAX) s_surv[pos] = Ops::MakeComp(skey, ~okey);
+      } else if (okey == (unsigned)tid && suspect) {
+        sci[kScAnomaly] = 1;  // a suspect member (see (A)) drops out of the beam: report the utterance
       }
     });
     __syncthreads();
