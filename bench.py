@@ -204,9 +204,12 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
     base = make_batch(args.kind, 1 + rank, T, B, C, CFG["blank_index"])
     host_batches, dev_batches = [], []
     rng = np.random.default_rng(77 + rank)
+    in_dt = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}[args.dtype]
+    bytes_per_batch = T * B * C * (4 if args.dtype == "f32" else 2)
+    n_rot = L2_BYTES // bytes_per_batch + 2
     for r in range(n_rot):
         xb = base if r == 0 else np.ascontiguousarray(base[:, rng.permutation(B), :])
-        hb = torch.from_numpy(xb).pin_memory()
+        hb = torch.from_numpy(xb).to(in_dt).pin_memory()
         host_batches.append(hb)
         dev_batches.append(hb.to(dev))
     seq_host = torch.full((B,), T, dtype=torch.int32).pin_memory()
@@ -285,7 +288,7 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
     else:
         e2e_ms = e2e_s * 1e3
     sharded = None
-    if args.workload == "cfg2" and not args.no_sharded:
+    if args.workload == "cfg2" and args.dtype == "f32" and not args.no_sharded:
         del dev_batches, host_batches
         torch.cuda.empty_cache()
         sharded = run_sharded_cfg5(rank, world, local_rank, steps=max(3, min(args.steps, 10)), warmup=3)
@@ -301,7 +304,7 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     beam_ms = float(kern_ms[:, 1].mean())
-    algo_bytes = 4.0 * C * frames_per_step  # per beam-kernel launch
+    algo_bytes = (4.0 if args.dtype == "f32" else 2.0) * C * frames_per_step  # per beam-kernel launch
     achieved = algo_bytes / (beam_ms * 1e-3) / 1e9
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "beam_kernel_traffic.json")
@@ -313,7 +316,7 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (%s logits, seed 1+rank)" % args.kind,
-        "config": dict(CFG, n_gpus=world, kind=args.kind, global_batch=B * world,
+        "config": dict(CFG, n_gpus=world, kind=args.kind, global_batch=B * world, input_dtype=args.dtype,
                        l2="inputs rotate over %d distinct batches (%.0f MB > 126 MB L2)"
                           % (n_rot, n_rot * bytes_per_batch / 1e6)),
         "clocks": clocks,
@@ -423,6 +426,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="skip the B=8192 strong-scaling leg")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f16", "bf16"],
+                    help="element type of the logits (scores are float32 either way)")
     args = ap.parse_args()
     CFG.clear()
     CFG.update(WORKLOADS[args.workload])

@@ -82,6 +82,6 @@ for seed, kind in [(21 + 100 * k, kd) for k in range(NSEEDS) for kd in ("gauss",
             total_bad += bad
             print("seed %4d %-5s %-5s %-10s T=%4d B=%3d C=%4d W=%3d P=%d: %6d frames, mismatching (utterance,path) pairs: %d"
                   "   [gpu call %.3f s, oracle %.1f s, flags %d]"
-                  % (seed, kind, name, vname, T, B, C, W, P, int(sl.sum()), bad, t_gpu, t_cpu, op.decoder.last_flags))
+                  % (seed, kind, name, vname, T, B, C, W, P, int(sl.sum()), bad, t_gpu, t_cpu, raw.flags))
 print("TOTAL %d utterances, %d frames, %d mismatches" % (total_utt, total_frames, total_bad))
 sys.exit(1 if total_bad else 0)
