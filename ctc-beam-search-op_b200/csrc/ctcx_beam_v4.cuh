@@ -881,9 +881,16 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
           const int bucket = bucket_of((unsigned)(comp >> 32));
           const int g0 = (int)s_offs[bucket];
           const int g1 = (bucket == bstar && !bnd_all) ? n_new : g0 + (int)s_hist[bucket];
-          int rank = 0;
-#pragma unroll 1  // groups hold 1-3 items: an unrolled loop only costs instructions
-          for (int j = g0; j < g1; ++j) rank += (s_sorted[j] > comp) ? 1 : 0;
+          // Groups usually hold 1-3 items; quantised logits (bfloat16 inputs) make exact ties, i.e. groups of
+          // dozens: four independent loads per round keep the count off the shared-memory latency.
+          int rank = 0, j = g0;
+#pragma unroll 1
+          for (; j + 4 <= g1; j += 4) {
+            const unsigned long long a = s_sorted[j], b2 = s_sorted[j + 1], c2 = s_sorted[j + 2], d2 = s_sorted[j + 3];
+            rank += ((a > comp) ? 1 : 0) + ((b2 > comp) ? 1 : 0) + ((c2 > comp) ? 1 : 0) + ((d2 > comp) ? 1 : 0);
+          }
+#pragma unroll 1
+          for (; j < g1; ++j) rank += (s_sorted[j] > comp) ? 1 : 0;
           s_fin[g0 + rank] = comp;
         }
         CTCX_TICK(13)  // PG: rank in group

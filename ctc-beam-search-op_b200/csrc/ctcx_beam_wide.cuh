@@ -255,9 +255,22 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
       const size_t r1 = (size_t)(t + 1) * B + b;
       const size_t g0 = (size_t)(t + 1) * (size_t)p.tstride + (size_t)b * C;
       if (sizeof(IN) != 4) {
-        // half-precision logits: upcast in registers on the way to shared memory (the loads of the whole
-        // row are issued back to back; this warp is idle during PA anyway)
-        for (int l = lane; l < C; l += 32) s_x[nxt * Cx + l] = LoadLogit<IN>(p.logits, g0 + l);
+        // half-precision logits: widened in registers on the way to shared memory. 16-byte loads (eight
+        // elements per lane, all in flight together) where the row is aligned; this warp is idle during PA.
+        const IN* g = reinterpret_cast<const IN*>(p.logits) + g0;
+        if ((C & 7) == 0 && (reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
+#pragma unroll 4
+          for (int l = lane * 8; l < C; l += 256) {
+            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(g + l));
+            const float2 a = Unpack2<IN>(v.x), b2 = Unpack2<IN>(v.y), c2 = Unpack2<IN>(v.z), d2 = Unpack2<IN>(v.w);
+            float* dst = s_x + nxt * Cx + l;
+            *reinterpret_cast<float4*>(dst) = make_float4(a.x, a.y, b2.x, b2.y);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(c2.x, c2.y, d2.x, d2.y);
+          }
+        } else {
+#pragma unroll 4
+          for (int l = lane; l < C; l += 32) s_x[nxt * Cx + l] = LoadLogit<IN>(p.logits, g0 + l);
+        }
       } else {
         const float* g = reinterpret_cast<const float*>(p.logits) + g0;
         if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15u) == 0) {  // rows 16-byte aligned
@@ -882,9 +895,16 @@ __global__ void __launch_bounds__(NT, ((NT <= 256 && !TIMING) ? 4 : 1)) BeamKern
         comp = s_sorted[tid];
         const int bucket = bucket_of((unsigned)(comp >> 32));
         const int g0 = (int)s_offs[bucket], g1 = g0 + (int)s_hist[bucket];
-        int rank = 0;
-#pragma unroll 1  // groups hold 1-3 items: an unrolled loop only costs instructions
-        for (int j = g0; j < g1; ++j) rank += (s_sorted[j] > comp) ? 1 : 0;
+        // groups usually hold 1-3 items; quantised logits (bfloat16 inputs) make exact ties, i.e. large
+        // groups: four independent loads per round keep the count off the shared-memory latency
+        int rank = 0, j = g0;
+#pragma unroll 1
+        for (; j + 4 <= g1; j += 4) {
+          const unsigned long long a = s_sorted[j], b2 = s_sorted[j + 1], c2 = s_sorted[j + 2], d2 = s_sorted[j + 3];
+          rank += ((a > comp) ? 1 : 0) + ((b2 > comp) ? 1 : 0) + ((c2 > comp) ? 1 : 0) + ((d2 > comp) ? 1 : 0);
+        }
+#pragma unroll 1
+        for (; j < g1; ++j) rank += (s_sorted[j] > comp) ? 1 : 0;
         r = g0 + rank;
       }
       CTCX_TICK(13)  // PG: rank in group

@@ -84,6 +84,22 @@ __device__ __forceinline__ float LoadLogit<__nv_bfloat16>(const void* base, size
   return __bfloat162float(__ldcg(reinterpret_cast<const __nv_bfloat16*>(base) + i));
 }
 
+// two packed half-precision elements -> two floats
+template <typename IN>
+__device__ __forceinline__ float2 Unpack2(unsigned v);
+template <>
+__device__ __forceinline__ float2 Unpack2<__half>(unsigned v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+template <>
+__device__ __forceinline__ float2 Unpack2<__nv_bfloat16>(unsigned v) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+}
+template <>
+__device__ __forceinline__ float2 Unpack2<float>(unsigned v) {  // (never used: float rows take the cp.async path)
+  return make_float2(__uint_as_float(v), 0.0f);
+}
+
 // 4-byte back-pointer record (beam_width <= 256 and num_classes <= 256): [0,8) prev_self slot |
 // [8,16) an_src slot | [16] ab_kind | [17,19) an_kind | [24,32) label. A fresh child has no previous
 // self (0xff, never followed).

@@ -1,5 +1,5 @@
 """Per-phase latency (clock64, thread 0 of each CTA) of the fast beam kernels:
-python tools/phase_cycles.py [B] [kind] [cfg2|cfg4]"""
+python tools/phase_cycles.py [B] [kind] [cfg2|cfg4] [bf16]"""
 import os
 import sys
 
@@ -19,6 +19,8 @@ cfg = sys.argv[3] if len(sys.argv) > 3 else "cfg2"
 T, C, W, BLANK, MERGE = (500, 29, 100, 28, True) if cfg == "cfg2" else (400, 1024, 16, 1023, False)
 lib = _lib.load()
 x = torch.from_numpy(L.make_logits(kind, T, B, C, BLANK, 1)).cuda()
+if len(sys.argv) > 4 and sys.argv[4] == "bf16":  # bfloat16-rounded values (many exact ties), float32 kernel
+    x = x.bfloat16().float()
 sl = torch.full((B,), T, dtype=torch.int32).cuda()
 buf = torch.zeros((B, 24), dtype=torch.int64, device="cuda")
 kw = dict(beam_width=W, top_paths=1, merge_repeated=MERGE, blank_index=BLANK)
