@@ -892,3 +892,60 @@ def test_rescore_acceptance_cases_are_flagged(op):
     x = L.make_logits("gauss", 120, 8, 29, 28, 77)
     raw = op.ctc_ext_beam_search_decoder_raw(x, np.full(8, 120, np.int32), beam_width=100, top_paths=1, blank_index=28)
     assert raw.flags == 0
+
+
+def test_host_input_and_view_entries_reject_bad_arguments(op):
+    """Error behaviour of the two round-2 C-ABI entries, straight through ctypes."""
+    import ctypes
+    import torch
+    from ctc_beam_search_op_b200 import _lib
+    lib = _lib.load()
+    T, B, C, W, P = 12, 3, 8, 4, 2
+    x = torch.from_numpy(L.make_logits("gauss", T, B, C, 7, 1)).pin_memory()
+    sl = torch.tensor([12, 5, 3], dtype=torch.int32)
+    ws_bytes = lib.ctcx_workspace_bytes(T, B, C, W, W + 1)  # (room for the top_paths > beam_width call below)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    staging = torch.empty(lib.ctcx_hostin_staging_bytes(_lib.F32, T, B, C), dtype=torch.uint8, device="cuda")
+    side = torch.cuda.Stream()
+    main = torch.cuda.Stream()
+    arr = ctypes.c_int64 * (W + 1)
+    sizes = _lib.CtcxSizes(arr(), arr(), arr(), arr())
+    flags = ctypes.c_int32(0)
+
+    def hostin(**kw):
+        a = dict(x=x.data_ptr(), dtype=_lib.F32, stride=0, T=T, B=B, C=C, sl=sl.data_ptr(), W=W, P=P, blank=7,
+                 staging=staging.data_ptr(), st_bytes=staging.numel(), ws=ws.data_ptr(), ws_bytes=ws_bytes,
+                 stream=main.cuda_stream, copy=side.cuda_stream)
+        a.update(kw)
+        return lib.ctcx_decode_hostin(a["x"], a["dtype"], a["stride"], a["T"], a["B"], a["C"], a["sl"], a["W"], a["P"], 0,
+                                      a["blank"], -1, a["staging"], a["st_bytes"], a["ws"], a["ws_bytes"], a["stream"],
+                                      a["copy"], ctypes.byref(sizes), ctypes.byref(flags))
+
+    assert hostin() == 0 and sizes.n_alignment[0] == 20                      # 12 + 5 + 3 frames
+    assert hostin(T=0) == 2                                                   # "max_time is 0"
+    assert hostin(copy=main.cuda_stream) == 8                                 # the copy stream must differ
+    assert hostin(st_bytes=16) == 8 and hostin(ws_bytes=256) == 10
+    assert hostin(stride=B * C - 1) == 8 and hostin(dtype=9) == 8 and hostin(blank=C) == 8
+    assert hostin(P=W + 1) == 6                                               # more paths than the beam width
+    bad = torch.tensor([12, 13, 3], dtype=torch.int32)
+    assert hostin(sl=bad.data_ptr()) == 5 and lib.ctcx_error_batch_index() == 1
+    assert b"sequence_length(1) <= 12" in lib.ctcx_strerror(5)
+    assert hostin(B=0) == 0 and sizes.n_alignment[0] == 0                     # empty batch
+    torch.cuda.synchronize()
+    xd = x.cuda()
+    sd = sl.cuda()
+
+    def view(dtype=_lib.F32, stride=0):
+        return lib.ctcx_decode_view(xd.data_ptr(), dtype, stride, T, B, C, sd.data_ptr(), W, P, 0, 7, -1, ws.data_ptr(),
+                                    ws_bytes, None, ctypes.byref(sizes), ctypes.byref(flags))
+
+    assert view() == 0 and view(stride=B * C) == 0
+    assert view(stride=B * C - 1) == 8 and view(stride=-5) == 8 and view(dtype=4) == 8
+    # the Python host: empty batch and zero-length utterances through the host-input path
+    raw = op.ctc_ext_beam_search_decoder_raw(np.zeros((5, 0, 4), np.float32), np.zeros((0,), np.int32), beam_width=4, top_paths=1)
+    assert raw[0][0].shape == (0, 2) and raw[6].shape == (0, 1)
+    sl0 = torch.tensor([12, 0, 3], dtype=torch.int32)  # a zero-length utterance: the root, one path only
+    raw = op.ctc_ext_beam_search_decoder_raw(x, sl0, beam_width=W, top_paths=1, blank_index=7)
+    assert not L.raw_mismatches(raw, L.oracle_decode(x.numpy(), sl0.numpy(), W, 1, False, 7, -1))
+    with pytest.raises(op.InvalidArgumentError, match="Less leaves"):
+        op.ctc_ext_beam_search_decoder_raw(x, sl0, beam_width=W, top_paths=2, blank_index=7)
