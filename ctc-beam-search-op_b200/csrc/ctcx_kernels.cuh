@@ -1134,9 +1134,14 @@ __global__ void __launch_bounds__(128) TraceKernel(TraceParams p) {
 // walk, so a step is one shared-memory broadcast read plus a few ALU operations instead of a
 // dependent trip to L2/HBM. Symbols are collected 32 frames at a time in registers and written as
 // coalesced rows; the decoded labels are compacted with warp ballots.
+// When a row of records is a multiple of 16 bytes (beam 100 with 4-byte records: 400 B) a block of rows is
+// ONE contiguous, 16-byte aligned span of HBM: it is fetched by a single bulk-copy instruction
+// (cp.async.bulk, the TMA unit's 1-D form) issued by one lane and signalled on an mbarrier, instead
+// of one 4-byte cp.async per record (3 200 per block).
 template <typename REC, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) TraceWarpKernel(TraceParams p, int rows_log2) {
+__global__ void __launch_bounds__(WARPS * 32) TraceWarpKernel(TraceParams p, int rows_log2, int use_bulk) {
   extern __shared__ __align__(16) unsigned char tsm[];
+  __shared__ __align__(8) unsigned long long s_mbar[WARPS][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int idx = blockIdx.x * WARPS + warp;
   if (idx >= p.B * p.P) return;
@@ -1155,6 +1160,15 @@ __global__ void __launch_bounds__(WARPS * 32) TraceWarpKernel(TraceParams p, int
   const int R = 1 << rows_log2;
   REC* buf = reinterpret_cast<REC*>(tsm) + (size_t)warp * 2 * R * W;
   const REC* bp = reinterpret_cast<const REC*>(p.bp) + (size_t)b * p.T * W;
+  const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(&s_mbar[warp][0]);
+  if (use_bulk) {
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar0));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar0 + 8u));
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
+  }
   // block k holds frames [k*R, min(L, (k+1)*R)); blocks are walked from the last one down
   auto fetch_block = [&](int k) {
     if (k >= 0) {
@@ -1162,20 +1176,51 @@ __global__ void __launch_bounds__(WARPS * 32) TraceWarpKernel(TraceParams p, int
       const int nrec = (min(L, t0 + R) - t0) * W;
       const REC* src = bp + (size_t)t0 * W;
       const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + (size_t)(k & 1) * R * W);
-      for (int i = lane; i < nrec; i += 32)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(dst + (unsigned)sizeof(REC) * (unsigned)i),
-                     "l"(src + i), "n"(sizeof(REC)));
+      if (use_bulk) {
+        if (lane == 0) {
+          const unsigned bytes = (unsigned)nrec * (unsigned)sizeof(REC);
+          const unsigned mbar = mbar0 + 8u * (unsigned)(k & 1);
+          // the buffer was last read through ordinary loads (two blocks ago): order them before the
+          // asynchronous-proxy write
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                       "l"(src), "r"(bytes), "r"(mbar)
+                       : "memory");
+        }
+      } else {
+        for (int i = lane; i < nrec; i += 32)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(dst + (unsigned)sizeof(REC) * (unsigned)i),
+                       "l"(src + i), "n"(sizeof(REC)));
+      }
     }
-    asm volatile("cp.async.commit_group;\n" ::);
+    if (!use_bulk) asm volatile("cp.async.commit_group;\n" ::);
   };
+  // wait until block k has landed (bulk path: the k-th use of its buffer flips the barrier's phase)
   const int last_block = (L - 1) >> rows_log2;
+  auto wait_block = [&](int k) {
+    if (use_bulk) {
+      const unsigned mbar = mbar0 + 8u * (unsigned)(k & 1);
+      const unsigned parity = (unsigned)(((last_block - k) >> 1) & 1);
+      unsigned done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+      }
+    } else {
+      asm volatile("cp.async.wait_group 1;\n" ::);
+    }
+  };
   fetch_block(last_block);
   int slot = path;
   int kind_ab = p.fin_kind[idx];
   int a_val = 0, d_val = -1;  // this lane's symbols of the current 32-frame store block
   for (int k = last_block; k >= 0; --k) {
-    fetch_block(k - 1);                               // next block in flight while this one is walked
-    asm volatile("cp.async.wait_group 1;\n" ::);     // block k has landed
+    fetch_block(k - 1);  // next block in flight while this one is walked
+    wait_block(k);       // block k has landed
     __syncwarp();
     const REC* blk = buf + (size_t)(k & 1) * R * W;
     const int t_lo = k << rows_log2;

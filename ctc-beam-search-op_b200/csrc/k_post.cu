@@ -5,6 +5,7 @@
 #include "ctcx_launch.h"
 
 #include <algorithm>
+#include <cstdint>
 
 namespace ctcx {
 
@@ -48,7 +49,9 @@ LaunchStatus LaunchTrace(const TraceParams& tp, cudaStream_t stream) {
     auto tk = TraceWarpKernel<REC, kTraceWarps>;
     cudaError_t e = cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
     if (e != cudaSuccess) return LaunchFrom(e, "cudaFuncSetAttribute(TraceWarpKernel)");
-    tk<<<(unsigned)((walks + kTraceWarps - 1) / kTraceWarps), kTraceWarps * 32, tsm, stream>>>(tp, rows_log2);
+    // a row of records that is a multiple of 16 bytes makes every block of rows one aligned span: bulk copies
+    const int use_bulk = (((size_t)W * sizeof(REC)) % 16 == 0 && (reinterpret_cast<uintptr_t>(tp.bp) & 15u) == 0) ? 1 : 0;
+    tk<<<(unsigned)((walks + kTraceWarps - 1) / kTraceWarps), kTraceWarps * 32, tsm, stream>>>(tp, rows_log2, use_bulk);
   }
   return LaunchFrom(cudaGetLastError(), "trace kernel launch");
 }
