@@ -204,8 +204,10 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
     base = make_batch(args.kind, 1 + rank, T, B, C, CFG["blank_index"])
     host_batches, dev_batches = [], []
     rng = np.random.default_rng(77 + rank)
-    in_dt = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}[args.dtype]
-    bytes_per_batch = T * B * C * (4 if args.dtype == "f32" else 2)
+    in_dt = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16, "f64": torch.float64}[args.dtype]
+    bytes_per_batch = T * B * C * {"f32": 4, "f16": 2, "bf16": 2, "f64": 8}[args.dtype]
+    if args.scorer:  # the reference's scorer extension point: a random label-bigram table (log-probabilities)
+        kw["expansion_scores"] = -np.abs(np.random.default_rng(5).standard_normal((C + 1, C))).astype(np.float32)
     n_rot = L2_BYTES // bytes_per_batch + 2
     for r in range(n_rot):
         xb = base if r == 0 else np.ascontiguousarray(base[:, rng.permutation(B), :])
@@ -288,7 +290,7 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
     else:
         e2e_ms = e2e_s * 1e3
     sharded = None
-    if args.workload == "cfg2" and args.dtype == "f32" and not args.no_sharded:
+    if args.workload == "cfg2" and args.dtype == "f32" and not args.scorer and not args.no_sharded:
         del dev_batches, host_batches
         torch.cuda.empty_cache()
         sharded = run_sharded_cfg5(rank, world, local_rank, steps=max(3, min(args.steps, 10)), warmup=3)
@@ -304,7 +306,7 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     beam_ms = float(kern_ms[:, 1].mean())
-    algo_bytes = (4.0 if args.dtype == "f32" else 2.0) * C * frames_per_step  # per beam-kernel launch
+    algo_bytes = float(bytes_per_batch)  # per beam-kernel launch: the logits, read once
     achieved = algo_bytes / (beam_ms * 1e-3) / 1e9
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "beam_kernel_traffic.json")
@@ -315,21 +317,24 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
         "metric": "utterance_frames_per_s_beam100", "value": value, "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic (%s logits, seed 1+rank)" % args.kind,
+        "vs_baseline": None, "dtype": "f64" if args.dtype == "f64" else "f32",
+        "data": "synthetic (%s logits, seed 1+rank)" % args.kind,
         "config": dict(CFG, n_gpus=world, kind=args.kind, global_batch=B * world, input_dtype=args.dtype,
+                       scorer="bigram table" if args.scorer else None,
                        l2="inputs rotate over %d distinct batches (%.0f MB > 126 MB L2)"
                           % (n_rot, n_rot * bytes_per_batch / 1e6)),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": bytes_per_batch + B * 4,
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
         # per step: [normaliser + class selection pre-pass (wide vocabularies only)], beam, trace, scan, flags, pack
-        "gpu_launches": (6 if C > 32 else 5) * args.steps,
+        "gpu_launches": (6 if (C > 32 or args.dtype == "f64" or args.scorer) else 5) * args.steps,
         "kernel_ms": {"lognorm": float(kern_ms[:, 0].mean()), "beam": beam_ms,
                       "trace": float(kern_ms[:, 2].mean()), "scan": float(kern_ms[:, 3].mean()),
                       "wall_ms_per_step": 1e3 * wall_dev / args.steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic if args.workload == "cfg2" else None,
-                     "kernel": "BeamKernelWide" if (32 < C <= 2048) else "BeamKernelV4",
+                     "kernel": ("BeamKernelT (generic)" if (args.dtype == "f64" or args.scorer) else
+                                "BeamKernelWide" if (32 < C <= 2048) else "BeamKernelV4"),
                      "peak_source": peak_src,
                      "note": "algorithmic bytes = 4*C per frame (logits read once); the kernel is "
                              "bound by the T-long serial recurrence per utterance, not by HBM"},
@@ -426,8 +431,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="skip the B=8192 strong-scaling leg")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--dtype", default="f32", choices=["f32", "f16", "bf16"],
-                    help="element type of the logits (scores are float32 either way)")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f16", "bf16", "f64"],
+                    help="element type of the logits (scores are float32; float64 for f64, the op's T = double)")
+    ap.add_argument("--scorer", action="store_true", help="decode with a label-bigram expansion-score table")
     args = ap.parse_args()
     CFG.clear()
     CFG.update(WORKLOADS[args.workload])
