@@ -411,8 +411,8 @@ struct Feed {
 };
 int RunFeed(void* arg) {
   Feed& f = *(Feed*)arg;
-  // Slabs grow geometrically: the first frames land after a few microseconds so the beam kernel can
-  // start, the bulk moves in large copies.
+  // Slabs grow geometrically (6, 12, 24, ... 192 frames): the first frames land after a few microseconds so
+  // the beam kernel can start, the bulk moves in large copies.
   int t0 = 0, n = f.flags ? 6 : f.T;
   while (t0 < f.T) {
     const int t1 = std::min(f.T, t0 + n);
@@ -434,7 +434,7 @@ int RunFeed(void* arg) {
       return CTCX_ERR_CUDA;
     }
     t0 = t1;
-    n = std::min(192, n * 4);
+    n = std::min(192, n * 2);  // doubling: a slab lands before the previous one is consumed at any copy rate >= 2x the kernel's
   }
   return CTCX_OK;
 }
