@@ -60,9 +60,10 @@ thread_local long long* g_dbg_cycles = nullptr;
 
 enum Path { kPathNarrow, kPathWide, kPathGeneric };
 Path PathOf(int W, int C, bool scorer) {
-  // a scorer table breaks the fast kernels' monotone-prefix argument: generic kernel only
-  if (scorer || g_force_generic.load(std::memory_order_relaxed)) return kPathGeneric;
-  if (ctcx::NarrowFastShape(W, C)) return kPathNarrow;
+  if (g_force_generic.load(std::memory_order_relaxed)) return kPathGeneric;
+  if (ctcx::NarrowFastShape(W, C)) return kPathNarrow;  // (has a scorer variant: all 32 classes tested per row)
+  // a scorer table breaks the wide kernel's monotone-prefix argument: generic kernel
+  if (scorer) return kPathGeneric;
   if (ctcx::WideFastShape(W, C)) return kPathWide;
   return kPathGeneric;
 }

@@ -42,7 +42,7 @@ namespace ctcx {
 // Shared-memory layout. Every offset is a compile-time constant of the tier (WMAX): the candidate list,
 // the only array whose size depends on the shape, comes last -- so the kernel addresses all arrays as
 // "base + immediate" and spends no registers on array pointers.
-template <int WMAX>
+template <int WMAX, bool LM = false>
 struct BeamSmemV4 {
   static constexpr size_t w = (size_t)WMAX;
   static constexpr size_t hash = 0;                       // u64 [2][WMAX]
@@ -83,7 +83,8 @@ struct BeamSmemV4 {
   static constexpr size_t bits = fsc + 2 * 4 * 4;         // u32 [32]     S warp scratch: sort keys, then class bits
   static constexpr size_t e = bits + 32 * 4;              // f32 [32]     S warp scratch: exp terms of the normaliser
   static constexpr size_t scal = e + 32 * 4;              // 32 x 4 B
-  static constexpr size_t list = (scal + 32 * 4 + 15) / 16 * 16;  // uint2 [cand_cap] {score key, (row<<16)|label}
+  static constexpr size_t lm = (scal + 32 * 4 + 15) / 16 * 16;  // f32 [33][32]  scorer table (LM kernels only), row = previous label + 1
+  static constexpr size_t list = lm + (LM ? 33 * 32 * 4 : 0);     // uint2 [cand_cap] {score key, (row<<16)|label}
   static constexpr size_t Bytes(int cand_cap) { return (list + (size_t)cand_cap * 8 + 15) / 16 * 16; }
 };
 
@@ -92,7 +93,11 @@ enum { kV4Utt = 23, kV4Abort = 24 };  // scalar slots in addition to the kV2* / 
 // MINB = resident CTAs per SM the register allocation is tuned for: 4 (64 registers) for batches that
 // fill the machine, 2 (128 registers: more loads in flight, no re-materialisation) for the latency
 // regime of at most two utterances per SM.
-template <typename IN, int WMAX, int NT, bool TIMING, int MINB>
+// LM = a scorer table is plugged in (util/ctc_beam_scorer.h:31-65 as a [C+1, C] table of expansion
+// log-probabilities <= 0): a child's base is old total (or old blank) + lm[previous label + 1][label],
+// which breaks the "prefix of the sorted classes" shortcut -- the candidate mask of a row is then built
+// by testing all 32 classes.
+template <typename IN, int WMAX, int NT, bool TIMING, int MINB, bool LM = false>
 __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamParams p) {
   static_assert(NT >= WMAX && NT >= kBinsV2, "one thread per beam slot and per histogram bin");
   extern __shared__ __align__(16) unsigned char smem[];
@@ -102,7 +107,7 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
   const int W = p.W, C = p.C, T = p.T, B = p.B, blank = p.blank_index;
   const bool s_warp = (warp == NWARP - 1);
 
-  using lay = BeamSmemV4<WMAX>;
+  using lay = BeamSmemV4<WMAX, LM>;
   unsigned long long* s_hash = (unsigned long long*)(smem + lay::hash);
   unsigned long long* s_phash = (unsigned long long*)(smem + lay::phash);
   unsigned long long* s_sorted = (unsigned long long*)(smem + lay::sorted);
@@ -146,6 +151,16 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
   unsigned* scu = (unsigned*)(smem + lay::scal);
 
   LoadExpTable(s_exptab, tid, NT);
+  const float* s_lm = (const float*)(smem + lay::lm);
+  unsigned valid_mask = 0u;  // LM: the non-blank classes
+  if constexpr (LM) {
+    float* w_lm = (float*)(smem + lay::lm);
+    for (int i = tid; i < 33 * 32; i += NT) {
+      const int r = i >> 5, l = i & 31;
+      w_lm[i] = (r <= C && l < C) ? p.lm[(size_t)r * C + l] : 0.0f;
+    }
+    valid_mask = ((C >= 32) ? 0xffffffffu : ((1u << C) - 1u)) & ~(1u << blank);
+  }
 
   // thread -> (row, class slice) mapping of the candidate pass
   // (latency regime: all threads share the rows, two per row at the 128-slot tier; throughput regime:
@@ -415,7 +430,8 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
           const float self_an = __fadd_rn(o_an[i], pl);
           if (pslot >= 0) {
             const bool same = (lbl == o_label[pslot]);
-            const float base = same ? o_blk[pslot] : o_total[pslot];
+            float base = same ? o_blk[pslot] : o_total[pslot];
+            if constexpr (LM) base = __fadd_rn(base, s_lm[(o_label[pslot] + 1) * 32 + lbl]);  // decoder.h:103,114
             v_nl = __fsub_rn(__fadd_rn(LogSumExp(o_lab[i], base, s_exptab), xl), off);
             rescore = __fadd_rn(pl, base);
             v_an = __fadd_rn(o_ab[pslot], pl);
@@ -490,8 +506,24 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
       // prefix of the sorted order: 2-round exact search, then drop the classes that are already
       // members (decoder.h:168) and re-test the repeated label, whose base is the old blank
       // probability (decoder.h:172-177).
-      auto cand_mask = [&](const uint4 ri, const float thr) -> unsigned {
+      auto cand_mask = [&](const uint4 ri, const float thr, const int c_lo = 0, const int c_n = 32) -> unsigned {
         const float ot = __uint_as_float(ri.x);
+        if constexpr (LM) {  // every class of [c_lo, c_lo + c_n) on its own: score = pl + (base + lm)  (decoder.h:171-182)
+          const float ob = __uint_as_float(ri.y);
+          const int lb = (int)ri.z;
+          const float* lmrow = s_lm + (lb + 1) * 32;
+          unsigned m = 0u;
+#pragma unroll 2
+          for (int g = c_lo; g < c_lo + c_n; g += 4) {
+            const float4 q = *reinterpret_cast<const float4*>(s_pl + g);
+            const float4 e = *reinterpret_cast<const float4*>(lmrow + g);
+            m |= (__fadd_rn(q.x, __fadd_rn((g == lb) ? ob : ot, e.x)) > thr) ? (1u << g) : 0u;
+            m |= (__fadd_rn(q.y, __fadd_rn((g + 1 == lb) ? ob : ot, e.y)) > thr) ? (2u << g) : 0u;
+            m |= (__fadd_rn(q.z, __fadd_rn((g + 2 == lb) ? ob : ot, e.z)) > thr) ? (4u << g) : 0u;
+            m |= (__fadd_rn(q.w, __fadd_rn((g + 3 == lb) ? ob : ot, e.w)) > thr) ? (8u << g) : 0u;
+          }
+          return m & valid_mask & ~ri.w;
+        }
         // prefix length = number of sorted scores above thr (the predicate is monotone): first the
         // heads of the 8 groups of 4, then the group itself. -inf padding never passes.
         const float4 ha = *reinterpret_cast<const float4*>(s_plH), hb = *reinterpret_cast<const float4*>(s_plH + 4);
@@ -628,7 +660,7 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
           r_ob = __uint_as_float(ri.y);
           r_label = (int)ri.z;
           if (__fadd_rn(lp_max, r_ot) > thr) {
-            const unsigned m = cand_mask(ri, thr) >> pbase;
+            const unsigned m = cand_mask(ri, thr, pbase, CP) >> pbase;
             mymask = (CP == 32) ? m : (m & ((1u << (CP & 31)) - 1u));
           }
         }
@@ -657,7 +689,9 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
             const int k = __ffs(m) - 1;
             m &= m - 1u;
             const int l = pbase + k;
-            const unsigned key = KeyOf(__fadd_rn(s_pl[l], (l == r_label) ? r_ob : r_ot));  // :172-182
+            float cbase = (l == r_label) ? r_ob : r_ot;
+            if constexpr (LM) cbase = __fadd_rn(cbase, s_lm[(r_label + 1) * 32 + l]);
+            const unsigned key = KeyOf(__fadd_rn(s_pl[l], cbase));  // :172-182
             c_list[pos++] = make_uint2(key, ((unsigned)prow << 16) | (unsigned)l);
             atomicAdd(&s_hist[bucket_of(key)], 1u);
           }

@@ -29,9 +29,9 @@ struct LaunchCfg {
 constexpr int kMaxDevices = 64;
 constexpr int kMinSliceFrames = 32;  // shorter slices would not amortise the hand-over
 
-template <typename IN, int WMAX, bool TIMING, int MINB>
+template <typename IN, int WMAX, bool TIMING, int MINB, bool LM = false>
 LaunchStatus LaunchOne(BeamParams& p, size_t smem, cudaStream_t stream) {
-  auto kern = BeamKernelV4<IN, WMAX, 256, TIMING, MINB>;
+  auto kern = BeamKernelV4<IN, WMAX, 256, TIMING, MINB, LM>;
   static LaunchCfg cfgs[kMaxDevices];
   int dev = 0;
   cudaGetDevice(&dev);
@@ -69,6 +69,15 @@ LaunchStatus LaunchOne(BeamParams& p, size_t smem, cudaStream_t stream) {
 template <typename IN>
 LaunchStatus LaunchTyped(BeamParams& p, int wmax, size_t smem, cudaStream_t stream) {
   if constexpr (sizeof(IN) == 4) {
+    if (p.lm != nullptr && p.dbg_cycles != nullptr && wmax == 128) return LaunchOne<IN, 128, true, 1, true>(p, smem, stream);
+    if (p.lm != nullptr) {  // scorer table plugged in: float32 inputs only
+      const bool latency = p.B <= 2 * SmCount();
+      switch (wmax) {
+        case 32: return latency ? LaunchOne<IN, 32, false, 2, true>(p, smem, stream) : LaunchOne<IN, 32, false, 4, true>(p, smem, stream);
+        case 128: return latency ? LaunchOne<IN, 128, false, 2, true>(p, smem, stream) : LaunchOne<IN, 128, false, 4, true>(p, smem, stream);
+        default: return latency ? LaunchOne<IN, 256, false, 2, true>(p, smem, stream) : LaunchOne<IN, 256, false, 4, true>(p, smem, stream);
+      }
+    }
     if (p.dbg_cycles != nullptr) {  // timing build: float32 inputs only
       switch (wmax) {
         case 32: return LaunchOne<IN, 32, true, 1>(p, smem, stream);
@@ -91,18 +100,19 @@ LaunchStatus LaunchTyped(BeamParams& p, int wmax, size_t smem, cudaStream_t stre
   }
 }
 
-size_t SmemBytes(int wmax, int cand_cap) {
+size_t SmemBytes(int wmax, int cand_cap, bool lm) {  // (the scorer table adds a constant)
+  const size_t extra = lm ? (BeamSmemV4<32, true>::list - BeamSmemV4<32, false>::list) : 0;
   switch (wmax) {
-    case 32: return BeamSmemV4<32>::Bytes(cand_cap);
-    case 128: return BeamSmemV4<128>::Bytes(cand_cap);
-    default: return BeamSmemV4<256>::Bytes(cand_cap);
+    case 32: return BeamSmemV4<32>::Bytes(cand_cap) + extra;
+    case 128: return BeamSmemV4<128>::Bytes(cand_cap) + extra;
+    default: return BeamSmemV4<256>::Bytes(cand_cap) + extra;
   }
 }
 }  // namespace
 
 bool NarrowFastShape(int W, int C) {
   if (C > 32 || W > 256 || (long long)W * C > kListCapMax) return false;
-  return SmemBytes(TierOf(W), W * C) <= 220 * 1024;
+  return SmemBytes(TierOf(W), W * C, true) <= 220 * 1024;
 }
 
 LaunchStatus LaunchBeamNarrow(BeamParams& p, int in_dtype, cudaStream_t stream) {
@@ -110,7 +120,8 @@ LaunchStatus LaunchBeamNarrow(BeamParams& p, int in_dtype, cudaStream_t stream) 
   p.cand_cap = p.W * p.C;
   p.kid_words = 1;
   const int wmax = TierOf(p.W);
-  const size_t smem = SmemBytes(wmax, p.cand_cap);
+  if (p.lm != nullptr && in_dtype != kInF32) return {kLaunchUnsupported, cudaSuccess, ""};
+  const size_t smem = SmemBytes(wmax, p.cand_cap, p.lm != nullptr);
   switch (in_dtype) {
     case kInF32: return LaunchTyped<float>(p, wmax, smem, stream);
     case kInF16: return LaunchTyped<__half>(p, wmax, smem, stream);

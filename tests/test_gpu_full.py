@@ -68,6 +68,20 @@ def test_every_utterance_of_the_baseline_shapes(op, name, kind):
     assert raw.flags == 0  # no utterance met the re-score anomaly
 
 
+def test_scorer_table_at_cfg2_size(op):
+    """The scorer extension point (ctcx_decode_scorer_f32, util/ctc_beam_scorer.h:31-65) at cfg2's
+    full length and beam: 64 utterances, a random bigram table, against the oracle."""
+    T, B, C, W, P, merge, blank = FULL["cfg2"]
+    x, sl = _inputs("cfg2", "gauss")
+    x, sl = np.ascontiguousarray(x[:, :64]), sl[:64]
+    table = (-np.abs(np.random.default_rng(5).standard_normal((C + 1, C))) * 1.5).astype(np.float32)
+    want = L.oracle_decode_threaded(x, sl, W, P, merge, blank, -1, lm=table)
+    raw = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=W, top_paths=P, merge_repeated=merge,
+                                             blank_index=blank, blank_label=-1, expansion_scores=table)
+    bad = L.raw_mismatches(raw, want)
+    assert not bad, "scorer: %d of 64 utterances differ from the oracle, first %s" % (len(bad), bad[:8])
+
+
 @pytest.mark.parametrize("B", [8192, 1000])
 def test_cfg5_size_batch_on_one_gpu(op, B):
     """BASELINE configs[4]: T=500, C=29, beam 100, B=8192 on ONE GPU. Device tensors in (the 475 MB

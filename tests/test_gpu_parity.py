@@ -646,7 +646,11 @@ def test_scorer_extension_point(op):
     tests/test_oracle.py."""
     rng = np.random.default_rng(77)
     for (kind, T, B, C, W, P, merge, blank) in [("gauss", 50, 5, 29, 10, 3, False, 28), ("peaky", 60, 4, 29, 100, 2, True, 28),
-                                                ("peaky", 30, 3, 120, 6, 2, False, 0), ("gauss", 25, 2, 40, 200, 2, False, 7)]:
+                                                ("peaky", 30, 3, 120, 6, 2, False, 0), ("gauss", 25, 2, 40, 200, 2, False, 7),
+                                                # the narrow kernel's scorer variant: every beam tier, a full
+                                                # 32-class row, blank in the middle, a batch that is time-sliced
+                                                ("gauss", 40, 3, 32, 32, 2, True, 31), ("peaky", 80, 4, 12, 256, 1, False, 5),
+                                                ("gauss", 45, 3, 17, 130, 2, False, 0), ("gauss", 64, 640, 10, 8, 1, True, 3)]:
         x = L.make_logits(kind, T, B, C, blank, 13)
         sl = L.ragged_lengths(T, B, 13)
         for table in (-np.abs(rng.standard_normal((C + 1, C))).astype(np.float32) * 2,

@@ -1,5 +1,5 @@
 """Per-phase latency (clock64, thread 0 of each CTA) of the fast beam kernels:
-python tools/phase_cycles.py [B] [kind] [cfg2|cfg4] [bf16]"""
+python tools/phase_cycles.py [B] [kind] [cfg2|cfg4] [bf16|scorer]"""
 import os
 import sys
 
@@ -24,6 +24,9 @@ if len(sys.argv) > 4 and sys.argv[4] == "bf16":  # bfloat16-rounded values (many
 sl = torch.full((B,), T, dtype=torch.int32).cuda()
 buf = torch.zeros((B, 24), dtype=torch.int64, device="cuda")
 kw = dict(beam_width=W, top_paths=1, merge_repeated=MERGE, blank_index=BLANK)
+if len(sys.argv) > 4 and sys.argv[4] == "scorer":  # the bench's random label-bigram table
+    kw["expansion_scores"] = torch.from_numpy(
+        -np.abs(np.random.default_rng(5).standard_normal((C + 1, C))).astype(np.float32)).cuda()
 op.ctc_ext_beam_search_decoder_raw(x, sl, **kw)
 import ctypes
 lib.ctcx_profile_enable(1)
