@@ -192,6 +192,8 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = _lib.load()
+    # one process per GPU: sit on the cores (and allocate the pinned buffers on the memory) next to it
+    near_cpus = None if args.no_numa_bind else op.bind_host_to_device(local_rank)
     T, B, C = CFG["T"], CFG["B"], CFG["C"]
     W, P = CFG["beam_width"], CFG["top_paths"]
     kw = dict(beam_width=W, top_paths=P, merge_repeated=CFG["merge_repeated"],
@@ -321,6 +323,7 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
         "data": "synthetic (%s logits, seed 1+rank)" % args.kind,
         "config": dict(CFG, n_gpus=world, kind=args.kind, global_batch=B * world, input_dtype=args.dtype,
                        scorer="bigram table" if args.scorer else None,
+                       host_cores_near_gpu=(len(near_cpus) if near_cpus else None),
                        l2="inputs rotate over %d distinct batches (%.0f MB > 126 MB L2)"
                           % (n_rot, n_rot * bytes_per_batch / 1e6)),
         "clocks": clocks,
@@ -435,6 +438,8 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "f16", "bf16", "f64"],
                     help="element type of the logits (scores are float32; float64 for f64, the op's T = double)")
     ap.add_argument("--scorer", action="store_true", help="decode with a label-bigram expansion-score table")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="do not move the process next to its GPU (bind_host_to_device) before allocating host buffers")
     args = ap.parse_args()
     CFG.clear()
     CFG.update(WORKLOADS[args.workload])

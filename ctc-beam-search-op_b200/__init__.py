@@ -14,8 +14,8 @@ from .decoder import (CTCExtBeamSearchDecoder, CTCExtBeamSearchDecoderStream, Ct
                       decode_host_cabi)
 
 from . import torch_op  # noqa: F401,E402  (registers torch.ops.ctcx.ctc_ext_beam_search_decoder)
-from .sharding import decode_distributed, decode_multi_device, merge_raw, shard_bounds  # noqa: F401,E402
+from .sharding import bind_host_to_device, decode_distributed, decode_multi_device, merge_raw, shard_bounds  # noqa: F401,E402
 
-__all__ = ["CTCExtBeamSearchDecoderStream", "DecodeResult", "FLAG_ROUNDING_ANOMALY", "set_beam_impl", "decode_multi_device", "decode_distributed", "shard_bounds", "merge_raw","ctc_ext_beam_search_decoder", "ctc_ext_beam_search_decoder_raw", "decode_host_cabi",
+__all__ = ["CTCExtBeamSearchDecoderStream", "DecodeResult", "FLAG_ROUNDING_ANOMALY", "set_beam_impl", "decode_multi_device", "decode_distributed", "bind_host_to_device", "shard_bounds", "merge_raw","ctc_ext_beam_search_decoder", "ctc_ext_beam_search_decoder_raw", "decode_host_cabi",
            "SparseTensor", "CTCExtBeamSearchDecoder", "CtcxError", "InvalidArgumentError",
            "FailedPreconditionError", "UnsupportedError"]

@@ -20,6 +20,34 @@ from . import decoder as _dec
 from .decoder import CTCExtBeamSearchDecoder, ctc_ext_beam_search_decoder_raw
 
 
+def bind_host_to_device(device=None):
+    """One process per GPU: run this process (and, by first touch, the pinned buffers it allocates from
+    now on) on the CPU cores next to `device` -- /sys/bus/pci/devices/<bdf>/local_cpulist. On a
+    two-socket box the host->device feed of the decode otherwise crosses the socket link for half of the
+    ranks. Returns the cpu list, or None when the topology cannot be read (nothing is changed then)."""
+    import os
+
+    import torch
+    try:
+        idx = torch.device("cuda", torch.cuda.current_device() if device is None else device).index \
+            if not isinstance(device, int) else device
+        pr = torch.cuda.get_device_properties(idx)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as fh:
+            text = fh.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)  # stay inside what the container allows
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
 def shard_bounds(batch, parts):
     """Contiguous, balanced blocks: [(b0, b1)] * parts (empty blocks allowed when batch < parts)."""
     base, extra = divmod(int(batch), int(parts))
