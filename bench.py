@@ -330,15 +330,16 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": bytes_per_batch + B * 4,
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
         # per step: [normaliser + class selection pre-pass (wide vocabularies only)], beam, trace, scan, flags, pack
-        "gpu_launches": ((6 if C <= 32 else 7) if args.scorer else 6 if (C > 32 or args.dtype == "f64") else 5) * args.steps,
+        "gpu_launches": ((6 if C <= 32 else 7) if args.scorer else 6 if C > 32 else 5) * args.steps,
         "kernel_ms": {"lognorm": float(kern_ms[:, 0].mean()), "beam": beam_ms,
                       "trace": float(kern_ms[:, 2].mean()), "scan": float(kern_ms[:, 3].mean()),
                       "wall_ms_per_step": 1e3 * wall_dev / args.steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic if args.workload == "cfg2" else None,
-                     "kernel": ("BeamKernelT (generic)" if (args.dtype == "f64" or (args.scorer and C > 32)) else
+                     "kernel": ("BeamKernelT (generic)" if ((args.dtype == "f64" or args.scorer) and C > 32) else
                                 "BeamKernelWide" if (32 < C <= 2048) else
-                                "BeamKernelV4 (scorer variant)" if args.scorer else "BeamKernelV4"),
+                                "BeamKernelV4 (scorer variant)" if args.scorer else
+                                "BeamKernelV4 (double)" if args.dtype == "f64" else "BeamKernelV4"),
                      "peak_source": peak_src,
                      "note": "algorithmic bytes = 4*C per frame (logits read once); the kernel is "
                              "bound by the T-long serial recurrence per utterance, not by HBM"},

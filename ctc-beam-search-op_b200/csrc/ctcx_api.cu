@@ -291,6 +291,10 @@ int DecodeImpl(const void* logits_dev, int T, int B, int C, const int32_t* seq_l
         ProfRecord(1, stream);
         CTCX_LAUNCH(ctcx::LaunchBeamGeneric(bp, stream));
       }
+    } else if (PathOf(W, C, false) == kPathNarrow) {
+      // float64 logits, narrow vocabulary: the fast kernel computing in double (normaliser inside)
+      ProfRecord(1, stream);
+      CTCX_LAUNCH(ctcx::LaunchBeamNarrow(bp, stream));
     } else {
       CTCX_LAUNCH(ctcx::LaunchLogNorm((const double*)logits_dev, (double*)(base + ws.off), (long long)T * B, C, B,
                                       tstride, stream));

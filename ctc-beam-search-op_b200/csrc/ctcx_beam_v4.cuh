@@ -42,29 +42,33 @@ namespace ctcx {
 // Shared-memory layout. Every offset is a compile-time constant of the tier (WMAX): the candidate list,
 // the only array whose size depends on the shape, comes last -- so the kernel addresses all arrays as
 // "base + immediate" and spends no registers on array pointers.
-template <int WMAX, bool LM = false>
+// RB = bytes of the score type R (4: float, 8: double). Keys are as wide as scores; a (key, ~order)
+// composite, a row-info record and a list item are 2 / 4 / 2 scores wide.
+template <int WMAX, bool LM = false, int RB = 4>
 struct BeamSmemV4 {
   static constexpr size_t w = (size_t)WMAX;
+  static constexpr size_t rb = (size_t)RB;
   static constexpr size_t hash = 0;                       // u64 [2][WMAX]
   static constexpr size_t phash = hash + 2 * w * 8;       // u64 [2][WMAX]
-  static constexpr size_t sorted = phash + 2 * w * 8;     // u64 [WMAX]   score-grouped survivors
-  static constexpr size_t fin = sorted + w * 8;           // u64 [WMAX]   survivors at their final slot
-  static constexpr size_t bnd = fin + w * 8;              // u64 [32]     boundary-bin items (fast path)
-  static constexpr size_t exptab = bnd + kBndFast * 8;    // u64 [32]
-  static constexpr size_t row = exptab + 32 * 8;          // uint4 [WMAX] {old total, old blank, label, member-children mask}
-  static constexpr size_t total = row + w * 16;           // f32 [2][WMAX]
-  static constexpr size_t blk = total + 2 * w * 4;
-  static constexpr size_t lab = blk + 2 * w * 4;
-  static constexpr size_t ab = lab + 2 * w * 4;
-  static constexpr size_t an = ab + 2 * w * 4;
-  static constexpr size_t label = an + 2 * w * 4;         // i32 [2][WMAX]
-  static constexpr size_t m_nt = label + 2 * w * 4;       // f32 [WMAX] x 5: the members' new values
-  static constexpr size_t m_nb = m_nt + w * 4;
-  static constexpr size_t m_nl = m_nb + w * 4;
-  static constexpr size_t m_nab = m_nl + w * 4;
-  static constexpr size_t m_nan = m_nab + w * 4;
-  static constexpr size_t m_key = m_nan + w * 4;          // u32 [WMAX]
-  static constexpr size_t m_rec = m_key + w * 4;          // u32 [WMAX]
+  static constexpr size_t sorted = phash + 2 * w * 8;     // Comp [WMAX]  score-grouped survivors
+  static constexpr size_t fin = sorted + w * 2 * rb;      // Comp [WMAX]  survivors at their final slot
+  static constexpr size_t bnd = fin + w * 2 * rb;         // Comp [32]    boundary-bin items (fast path)
+  static constexpr size_t exptab = bnd + kBndFast * 2 * rb;  // u64 [32]  expf table
+  static constexpr size_t exptabd = exptab + 32 * 8;      // u64 [256]    exp table of the double normaliser (R = double only)
+  static constexpr size_t row = exptabd + (RB == 8 ? 256 * 8 : 0);  // Row [WMAX] {old total, old blank, label, member-children mask}
+  static constexpr size_t total = row + w * 4 * rb;       // R [2][WMAX]
+  static constexpr size_t blk = total + 2 * w * rb;
+  static constexpr size_t lab = blk + 2 * w * rb;
+  static constexpr size_t ab = lab + 2 * w * rb;
+  static constexpr size_t an = ab + 2 * w * rb;
+  static constexpr size_t label = an + 2 * w * rb;        // i32 [2][WMAX]
+  static constexpr size_t m_nt = label + 2 * w * 4;       // R [WMAX] x 5: the members' new values
+  static constexpr size_t m_nb = m_nt + w * rb;
+  static constexpr size_t m_nl = m_nb + w * rb;
+  static constexpr size_t m_nab = m_nl + w * rb;
+  static constexpr size_t m_nan = m_nab + w * rb;
+  static constexpr size_t m_key = m_nan + w * rb;         // Key [WMAX]
+  static constexpr size_t m_rec = m_key + w * rb;         // u32 [WMAX]
   static constexpr size_t m_pslot = m_rec + w * 4;        // i32 [WMAX]
   static constexpr size_t risk = m_pslot + w * 4;         // i32 [WMAX]
   static constexpr size_t risk_new = risk + w * 4;        // i32 [WMAX]
@@ -74,19 +78,123 @@ struct BeamSmemV4 {
   static constexpr size_t offs = hist + kBinsV2 * 4;      // u32 [kBinsV2]
   static constexpr size_t bins2 = offs + kBinsV2 * 4;     // u32 [256]
   static constexpr size_t wtot = bins2 + 256 * 4;         // u32 [16]     per-warp histogram totals + top bins (PD)
-  static constexpr size_t x = wtot + 16 * 4;              // f32 [2][32]  raw logits of the frame
-  static constexpr size_t pl = x + 2 * 32 * 4;            // f32 [2][32]  x[l] - off
-  static constexpr size_t pls = pl + 2 * 32 * 4;          // f32 [2][32]  class log-probs sorted descending (-inf padding)
-  static constexpr size_t plh = pls + 2 * 32 * 4;         // f32 [2][8]   pls[0,4,8,...]: heads of the groups of four
-  static constexpr size_t pref = plh + 2 * 8 * 4;         // u32 [2][36]  pref[j] = classes at sorted positions < j
-  static constexpr size_t fsc = pref + 2 * 36 * 4;        // f32 [2][4]   {off, lp_max, lp_min, -}
-  static constexpr size_t bits = fsc + 2 * 4 * 4;         // u32 [32]     S warp scratch: sort keys, then class bits
-  static constexpr size_t e = bits + 32 * 4;              // f32 [32]     S warp scratch: exp terms of the normaliser
-  static constexpr size_t scal = e + 32 * 4;              // 32 x 4 B
-  static constexpr size_t lm = (scal + 32 * 4 + 15) / 16 * 16;  // f32 [33][32]  scorer table (LM kernels only), row = previous label + 1
-  static constexpr size_t list = lm + (LM ? 33 * 32 * 4 : 0);     // uint2 [cand_cap] {score key, (row<<16)|label}
-  static constexpr size_t Bytes(int cand_cap) { return (list + (size_t)cand_cap * 8 + 15) / 16 * 16; }
+  static constexpr size_t x = wtot + 16 * 4;              // R [2][32]    raw logits of the frame
+  static constexpr size_t pl = x + 2 * 32 * rb;           // R [2][32]    x[l] - off
+  static constexpr size_t pls = pl + 2 * 32 * rb;         // R [2][32]    class log-probs sorted descending (-inf padding)
+  static constexpr size_t plh = pls + 2 * 32 * rb;        // R [2][8]     pls[0,4,8,...]: heads of the groups of four
+  static constexpr size_t pref = plh + 2 * 8 * rb;        // u32 [2][36]  pref[j] = classes at sorted positions < j
+  static constexpr size_t fsc = pref + 2 * 36 * 4;        // R [2][4]     {off, lp_max, lp_min, -}
+  static constexpr size_t bits = fsc + 2 * 4 * rb;        // Key [32]     S warp scratch: sort keys, then class bits (u32)
+  static constexpr size_t e = bits + 32 * rb;             // R [32]       S warp scratch: exp terms of the normaliser
+  static constexpr size_t scal = e + 32 * rb;             // 32 x 4 B
+  static constexpr size_t keys = scal + 32 * 4;           // Key [8]      min / max member key, min base, range prediction
+  static constexpr size_t prefix = keys + 8 * rb;         // Comp [1] (+ pad) radix-select prefix of the slow boundary cut
+  static constexpr size_t lm = (prefix + 32 + 15) / 16 * 16;      // f32 [33][32]  scorer table (LM kernels only), row = previous label + 1
+  static constexpr size_t list = lm + (LM ? 33 * 32 * 4 : 0);     // Item [cand_cap] {score key, (row<<16)|label}
+  static constexpr size_t Bytes(int cand_cap) { return (list + (size_t)cand_cap * 2 * rb + 15) / 16 * 16; }
 };
+
+// Key-typed scalars (shared-memory block `keys`)
+enum { kV4KMin = 0, kV4KMax = 1, kV4KMinBase = 2, kV4KGap = 3 };
+
+// The score type a kernel instantiation computes in: double for float64 logits (the reference's
+// T = double registration, kernels.cc:275), float for float32 / float16 / bfloat16 logits.
+template <typename IN> struct ScoreOf { using type = float; };
+template <> struct ScoreOf<double> { using type = double; };
+
+template <typename IN>
+__device__ __forceinline__ typename ScoreOf<IN>::type LoadRaw(const void* base, size_t i) {
+  if constexpr (sizeof(IN) == 8) return __ldcg(reinterpret_cast<const double*>(base) + i);
+  else return LoadLogit<IN>(base, i);
+}
+
+// Layout-dependent records of the two score types. float keeps the packed 16-byte row record and the
+// 8-byte list item of the single-precision kernel; double doubles both.
+template <typename R> struct V4Rec;
+template <> struct V4Rec<float> {
+  using Row = uint4;   // {old total, old blank, label, member-children mask}
+  using Item = uint2;  // {score key, (row << 16) | label}
+  __device__ static __forceinline__ Row MakeRow(float ot, float ob, int label) {
+    return make_uint4(__float_as_uint(ot), __float_as_uint(ob), (unsigned)label, 0u);
+  }
+  __device__ static __forceinline__ float Ot(const Row& r) { return __uint_as_float(r.x); }
+  __device__ static __forceinline__ float Ob(const Row& r) { return __uint_as_float(r.y); }
+  __device__ static __forceinline__ int Label(const Row& r) { return (int)r.z; }
+  __device__ static __forceinline__ unsigned Mask(const Row& r) { return r.w; }
+  __device__ static __forceinline__ unsigned* MaskPtr(Row* r) { return &r->w; }
+  __device__ static __forceinline__ Item MakeItem(unsigned key, unsigned id) { return make_uint2(key, id); }
+  __device__ static __forceinline__ Item NoItem() { return make_uint2(0u, 0u); }
+  __device__ static __forceinline__ unsigned ItemKey(const Item& e) { return e.x; }
+  __device__ static __forceinline__ unsigned ItemId(const Item& e) { return e.y; }
+};
+template <> struct V4Rec<double> {
+  struct __align__(16) Row { double ot, ob; int label; unsigned mask; unsigned long long pad; };
+  struct __align__(16) Item { unsigned long long key; unsigned id, pad; };
+  __device__ static __forceinline__ Row MakeRow(double ot, double ob, int label) { return Row{ot, ob, label, 0u, 0ull}; }
+  __device__ static __forceinline__ double Ot(const Row& r) { return r.ot; }
+  __device__ static __forceinline__ double Ob(const Row& r) { return r.ob; }
+  __device__ static __forceinline__ int Label(const Row& r) { return r.label; }
+  __device__ static __forceinline__ unsigned Mask(const Row& r) { return r.mask; }
+  __device__ static __forceinline__ unsigned* MaskPtr(Row* r) { return &r->mask; }
+  __device__ static __forceinline__ Item MakeItem(unsigned long long key, unsigned id) { return Item{key, id, 0u}; }
+  __device__ static __forceinline__ Item NoItem() { return Item{0ull, 0u, 0u}; }
+  __device__ static __forceinline__ unsigned long long ItemKey(const Item& e) { return e.key; }
+  __device__ static __forceinline__ unsigned ItemId(const Item& e) { return e.id; }
+};
+
+// warp-wide min / max of keys, and a composite taken from another lane
+__device__ __forceinline__ unsigned WarpMinKey(unsigned k) { return __reduce_min_sync(kFull, k); }
+__device__ __forceinline__ unsigned WarpMaxKey(unsigned k) { return __reduce_max_sync(kFull, k); }
+__device__ __forceinline__ unsigned long long WarpMinKey(unsigned long long k) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) k = min(k, __shfl_xor_sync(kFull, k, o));
+  return k;
+}
+__device__ __forceinline__ unsigned long long WarpMaxKey(unsigned long long k) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) k = max(k, __shfl_xor_sync(kFull, k, o));
+  return k;
+}
+__device__ __forceinline__ unsigned long long ShflComp(unsigned long long c, int src) {
+  const unsigned lo = __shfl_sync(kFull, (unsigned)c, src), hi = __shfl_sync(kFull, (unsigned)(c >> 32), src);
+  return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ ulonglong2 ShflComp(ulonglong2 c, int src) {
+  return make_ulonglong2(__shfl_sync(kFull, c.x, src), (unsigned long long)__shfl_sync(kFull, (unsigned)c.y, src));
+}
+// The radix select of the slow boundary cut walks the bytes of a composite from the top: byte `pass`
+// (0 = least significant), the bytes above it as a "prefix", and a prefix extended by one byte. The
+// 64-bit composite keeps its prefix right-aligned (shifted down), the 96-bit one in place (lower bytes
+// zero); either way the prefix after pass 0 is the whole composite.
+__device__ __forceinline__ unsigned CompByte(unsigned long long c, int pass) { return (unsigned)(c >> (pass * 8)) & 255u; }
+__device__ __forceinline__ unsigned long long CompAbove(unsigned long long c, int pass) {
+  return (pass >= 7) ? 0ull : (c >> (pass * 8 + 8));
+}
+__device__ __forceinline__ unsigned long long CompWithByte(unsigned long long prefix, int, unsigned byte) {
+  return (prefix << 8) | (unsigned long long)byte;
+}
+__device__ __forceinline__ unsigned CompByte(ulonglong2 c, int pass) {  // bytes 0-3: ~order, 4-11: key
+  return (pass < 4) ? ((unsigned)c.y >> (pass * 8)) & 255u : (unsigned)(c.x >> ((pass - 4) * 8)) & 255u;
+}
+__device__ __forceinline__ ulonglong2 CompAbove(ulonglong2 c, int pass) {
+  if (pass < 3) return make_ulonglong2(c.x, (unsigned long long)(((unsigned)c.y >> (pass * 8 + 8)) << (pass * 8 + 8)));
+  if (pass == 3) return make_ulonglong2(c.x, 0ull);
+  const int kp = pass - 4;
+  return make_ulonglong2((kp >= 7) ? 0ull : (c.x >> (kp * 8 + 8)) << (kp * 8 + 8), 0ull);
+}
+__device__ __forceinline__ ulonglong2 CompWithByte(ulonglong2 prefix, int pass, unsigned byte) {
+  if (pass < 4) return make_ulonglong2(prefix.x, prefix.y | ((unsigned long long)byte << (pass * 8)));
+  return make_ulonglong2(prefix.x | ((unsigned long long)byte << ((pass - 4) * 8)), prefix.y);
+}
+__device__ __forceinline__ bool CompEq(unsigned long long a, unsigned long long b) { return a == b; }
+__device__ __forceinline__ bool CompEq(ulonglong2 a, ulonglong2 b) { return a.x == b.x && a.y == b.y; }
+__device__ __forceinline__ bool CompGe(unsigned long long a, unsigned long long b) { return a >= b; }
+__device__ __forceinline__ bool CompGe(ulonglong2 a, ulonglong2 b) { return a.x > b.x || (a.x == b.x && a.y >= b.y); }
+// width of the predicted score range from the previous frame's top-to-threshold gap (in key units)
+__device__ __forceinline__ unsigned long long ReachOf(unsigned gap) { return (5ull * gap) / 4ull + 64ull; }
+__device__ __forceinline__ unsigned long long ReachOf(unsigned long long gap) {
+  return (gap > (1ull << 62)) ? ~0ull : gap + gap / 4ull + 64ull;
+}
 
 enum { kV4Utt = 23, kV4Abort = 24 };  // scalar slots in addition to the kV2* / kV3* ones
 
@@ -98,7 +206,16 @@ enum { kV4Utt = 23, kV4Abort = 24 };  // scalar slots in addition to the kV2* / 
 // which breaks the "prefix of the sorted classes" shortcut -- the candidate mask of a row is then built
 // by testing all 32 classes.
 template <typename IN, int WMAX, int NT, bool TIMING, int MINB, bool LM = false>
-__global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamParams p) {
+__global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamParamsT<typename ScoreOf<IN>::type> p) {
+  using R = typename ScoreOf<IN>::type;
+  using Ops = RealOps<R>;
+  using Key = typename Ops::Key;
+  using Comp = typename Ops::Comp;
+  using Rec = V4Rec<R>;
+  using Row = typename Rec::Row;
+  using Item = typename Rec::Item;
+  constexpr bool kF64 = (sizeof(R) == 8);
+  static_assert(!kF64 || (!TIMING && !LM), "the double kernel has no timing / scorer variant");
   static_assert(NT >= WMAX && NT >= kBinsV2, "one thread per beam slot and per histogram bin");
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int NWARP = NT / 32;
@@ -107,27 +224,28 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
   const int W = p.W, C = p.C, T = p.T, B = p.B, blank = p.blank_index;
   const bool s_warp = (warp == NWARP - 1);
 
-  using lay = BeamSmemV4<WMAX, LM>;
+  using lay = BeamSmemV4<WMAX, LM, (int)sizeof(R)>;
   unsigned long long* s_hash = (unsigned long long*)(smem + lay::hash);
   unsigned long long* s_phash = (unsigned long long*)(smem + lay::phash);
-  unsigned long long* s_sorted = (unsigned long long*)(smem + lay::sorted);
-  unsigned long long* s_fin = (unsigned long long*)(smem + lay::fin);
-  unsigned long long* s_bnd = (unsigned long long*)(smem + lay::bnd);
+  Comp* s_sorted = (Comp*)(smem + lay::sorted);
+  Comp* s_fin = (Comp*)(smem + lay::fin);
+  Comp* s_bnd = (Comp*)(smem + lay::bnd);
   unsigned long long* s_exptab = (unsigned long long*)(smem + lay::exptab);
-  uint4* s_row = (uint4*)(smem + lay::row);
-  uint2* c_list = (uint2*)(smem + lay::list);
-  float* s_total = (float*)(smem + lay::total);
-  float* s_blk = (float*)(smem + lay::blk);
-  float* s_lab = (float*)(smem + lay::lab);
-  float* s_ab = (float*)(smem + lay::ab);
-  float* s_an = (float*)(smem + lay::an);
+  unsigned long long* s_exptabd = (unsigned long long*)(smem + lay::exptabd);
+  Row* s_row = (Row*)(smem + lay::row);
+  Item* c_list = (Item*)(smem + lay::list);
+  R* s_total = (R*)(smem + lay::total);
+  R* s_blk = (R*)(smem + lay::blk);
+  R* s_lab = (R*)(smem + lay::lab);
+  R* s_ab = (R*)(smem + lay::ab);
+  R* s_an = (R*)(smem + lay::an);
   int* s_label = (int*)(smem + lay::label);
-  float* m_nt = (float*)(smem + lay::m_nt);
-  float* m_nb = (float*)(smem + lay::m_nb);
-  float* m_nl = (float*)(smem + lay::m_nl);
-  float* m_nab = (float*)(smem + lay::m_nab);
-  float* m_nan = (float*)(smem + lay::m_nan);
-  unsigned* m_key = (unsigned*)(smem + lay::m_key);
+  R* m_nt = (R*)(smem + lay::m_nt);
+  R* m_nb = (R*)(smem + lay::m_nb);
+  R* m_nl = (R*)(smem + lay::m_nl);
+  R* m_nab = (R*)(smem + lay::m_nab);
+  R* m_nan = (R*)(smem + lay::m_nan);
+  Key* m_key = (Key*)(smem + lay::m_key);
   unsigned* m_rec = (unsigned*)(smem + lay::m_rec);
   int* m_pslot = (int*)(smem + lay::m_pslot);
   int* s_risk = (int*)(smem + lay::risk);
@@ -138,19 +256,23 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
   unsigned* s_offs = (unsigned*)(smem + lay::offs);
   unsigned* s_bins2 = (unsigned*)(smem + lay::bins2);
   unsigned* s_wtot = (unsigned*)(smem + lay::wtot);
-  float* s_xb = (float*)(smem + lay::x);
-  float* s_plb = (float*)(smem + lay::pl);
-  float* s_plSb = (float*)(smem + lay::pls);
-  float* s_plHb = (float*)(smem + lay::plh);
+  R* s_xb = (R*)(smem + lay::x);
+  R* s_plb = (R*)(smem + lay::pl);
+  R* s_plSb = (R*)(smem + lay::pls);
+  R* s_plHb = (R*)(smem + lay::plh);
   unsigned* s_prefb = (unsigned*)(smem + lay::pref);
-  float* s_fsc = (float*)(smem + lay::fsc);
-  unsigned* s_bits = (unsigned*)(smem + lay::bits);
-  float* s_e = (float*)(smem + lay::e);
+  R* s_fsc = (R*)(smem + lay::fsc);
+  Key* s_bits = (Key*)(smem + lay::bits);
+  R* s_e = (R*)(smem + lay::e);
   volatile int* sc = (volatile int*)(smem + lay::scal);
   int* sci = (int*)(smem + lay::scal);
   unsigned* scu = (unsigned*)(smem + lay::scal);
+  Key* s_keys = (Key*)(smem + lay::keys);
+  Comp* s_prefix = (Comp*)(smem + lay::prefix);
 
   LoadExpTable(s_exptab, tid, NT);
+  if constexpr (kF64)
+    for (int i = tid; i < 256; i += NT) s_exptabd[i] = kCtcxExpTab[i];
   const float* s_lm = (const float*)(smem + lay::lm);
   unsigned valid_mask = 0u;  // LM: the non-blank classes
   if constexpr (LM) {
@@ -227,7 +349,7 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
 
     // S warp: raw logit (lane = class) of frame t, as float. Frames arrive in order; wait for the copy
     // that is still in flight (p.ready counts the frames that have landed).
-    auto load_row = [&](int t) -> float {
+    auto load_row = [&](int t) -> R {
       if (t >= ready_known) {
         int r = 0;
         if (lane == 0) {
@@ -241,20 +363,29 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         }
         ready_known = __shfl_sync(kFull, r, 0);
       }
-      return (lane < C) ? LoadLogit<IN>(p.logits, (size_t)t * (size_t)p.tstride + row0 + lane) : 0.0f;
+      return (lane < C) ? LoadRaw<IN>(p.logits, (size_t)t * (size_t)p.tstride + row0 + lane) : (R)0;
     };
     // The S warp prepares frame t+1 in three stages, each placed where the warp has nothing else to do:
     // S1 (while the other warps are in PA): max and the exp-sum of the softmax normaliser (decoder.h:71-80)
-    auto prepare1 = [&](float xr, float& mx_out) -> float {
+    auto prepare1 = [&](R xr, R& mx_out) -> R {
       const bool in_row = lane < C;
-      const float mx = UnKey(__reduce_max_sync(kFull, in_row ? KeyOf(xr) : 0u));
-      s_e[lane] = in_row ? ExpfExact(__fsub_rn(xr, mx), s_exptab) : 0.0f;
+      const R mx = Ops::UnKey(WarpMaxKey(in_row ? Ops::KeyOf(xr) : (Key)0));
+      if constexpr (kF64) s_e[lane] = in_row ? ExpExactD(Ops::Sub(xr, mx), s_exptabd) : 0.0;
+      else s_e[lane] = in_row ? ExpfExact(Ops::Sub(xr, mx), s_exptab) : 0.0f;
       __syncwarp();
-      float sum = 0.0f;  // index order, as the reference sums (trailing +0 terms leave it unchanged)
+      R sum = (R)0;  // index order, as the reference sums (trailing +0 terms leave it unchanged)
+      if constexpr (kF64) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(s_e + i);
-        sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, v.x), v.y), v.z), v.w);
+        for (int i = 0; i < 32; i += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(s_e + i);
+          sum = Ops::Add(Ops::Add(sum, v.x), v.y);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(s_e + i);
+          sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, v.x), v.y), v.z), v.w);
+        }
       }
       mx_out = mx;
       return sum;
@@ -262,38 +393,50 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
     // S2 (while the other warps list the candidates, PB): the normaliser, per-class log-probs, classes
     // ranked by log-prob. Equal keys keep lane order; the order inside a tie never matters (a prefix of
     // the sorted classes never ends inside a group of equal scores). Returns the lane's rank.
-    auto prepare2 = [&](float xr, float mx, float sum, int buf) -> int {
-      const float off = __fadd_rn(mx, LogfExact(sum));
+    auto prepare2 = [&](R xr, R mx, R sum, int buf) -> int {
+      R logsum;
+      if constexpr (kF64) logsum = LogExactD(sum); else logsum = LogfExact(sum);
+      const R off = Ops::Add(mx, logsum);
       const bool lane_ok = (lane < C) && (lane != blank);
-      const float pl_lane = lane_ok ? __fsub_rn(xr, off) : 0.0f;
+      const R pl_lane = lane_ok ? Ops::Sub(xr, off) : (R)0;
       s_xb[buf * 32 + lane] = xr;
       s_plb[buf * 32 + lane] = pl_lane;
-      const unsigned key = lane_ok ? KeyOf(pl_lane) : 0u;  // blank / padding sort last
+      const Key key = lane_ok ? Ops::KeyOf(pl_lane) : (Key)0;  // blank / padding sort last
       s_bits[lane] = key;  // the keys of the row, read back as broadcasts
       if (lane == 0) s_fsc[buf * 4 + 0] = off;
       __syncwarp();
       int rank = 0;
+      if constexpr (kF64) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const uint4 k = *reinterpret_cast<const uint4*>(s_bits + i);
-        rank += (k.x > key) ? 1 : 0;
-        rank += (k.y > key) ? 1 : 0;
-        rank += (k.z > key) ? 1 : 0;
-        rank += (k.w > key) ? 1 : 0;
+        for (int i = 0; i < 32; i += 2) {
+          const ulonglong2 k = *reinterpret_cast<const ulonglong2*>(s_bits + i);
+          rank += (k.x > key) ? 1 : 0;
+          rank += (k.y > key) ? 1 : 0;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const uint4 k = *reinterpret_cast<const uint4*>(s_bits + i);
+          rank += (k.x > key) ? 1 : 0;
+          rank += (k.y > key) ? 1 : 0;
+          rank += (k.z > key) ? 1 : 0;
+          rank += (k.w > key) ? 1 : 0;
+        }
       }
       rank += __popc(__match_any_sync(kFull, key) & ((1u << lane) - 1u));
-      s_plSb[buf * 32 + rank] = lane_ok ? pl_lane : NegInf();
-      if ((rank & 3) == 0) s_plHb[buf * 8 + (rank >> 2)] = lane_ok ? pl_lane : NegInf();
+      s_plSb[buf * 32 + rank] = lane_ok ? pl_lane : Ops::NegInf();
+      if ((rank & 3) == 0) s_plHb[buf * 8 + (rank >> 2)] = lane_ok ? pl_lane : Ops::NegInf();
       return rank;
     };
     // S3 (while the other warps write the next beam, PG): prefix masks of the sorted classes
     auto prepare3 = [&](int rank, int buf) {
       const bool lane_ok = (lane < C) && (lane != blank);
       unsigned* bpref = s_prefb + buf * 36;
+      unsigned* cbits = reinterpret_cast<unsigned*>(s_bits);  // (the sort keys are no longer needed)
       __syncwarp();
-      s_bits[rank] = lane_ok ? (1u << lane) : 0u;
+      cbits[rank] = lane_ok ? (1u << lane) : 0u;
       __syncwarp();
-      unsigned incl = s_bits[lane];
+      unsigned incl = cbits[lane];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const unsigned v = __shfl_up_sync(kFull, incl, o);
@@ -304,8 +447,8 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
       __syncwarp();
       if (lane == 0) {
         bpref[0] = 0u;
-        s_fsc[buf * 4 + 1] = (cv > 0) ? s_plSb[buf * 32] : NegInf();
-        s_fsc[buf * 4 + 2] = (cv > 0) ? s_plSb[buf * 32 + cv - 1] : 0.0f;
+        s_fsc[buf * 4 + 1] = (cv > 0) ? s_plSb[buf * 32] : Ops::NegInf();
+        s_fsc[buf * 4 + 2] = (cv > 0) ? s_plSb[buf * 32 + cv - 1] : (R)0;
       }
     };
 
@@ -313,16 +456,16 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
     for (int i = tid; i < TS; i += NT) s_htab[i] = 0xffffffffu;
     for (int i = tid; i < WMAX; i += NT) {
       s_wiped[i] = 0u;
-      s_row[i] = make_uint4(0u, 0u, 0u, 0u);
+      s_row[i] = Rec::MakeRow((R)0, (R)0, 0);
     }
     for (int i = tid; i < kBinsV2; i += NT) s_hist[i] = 0u;
     if (tid == 0) {
       if (!resume) {
-        s_total[0] = 0.0f;
-        s_blk[0] = 0.0f;
-        s_lab[0] = NegInf();
-        s_ab[0] = 0.0f;  // empty alignment with probability 1 (entry.h:204-209)
-        s_an[0] = NegInf();
+        s_total[0] = (R)0;
+        s_blk[0] = (R)0;
+        s_lab[0] = Ops::NegInf();
+        s_ab[0] = (R)0;  // empty alignment with probability 1 (entry.h:204-209)
+        s_an[0] = Ops::NegInf();
         s_label[0] = -1;
         s_hash[0] = kRootHash;
         s_phash[0] = 0ull;
@@ -330,27 +473,27 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
       sci[kV2Anomaly] = 0;
       sci[kV2NCand] = 0;
       sci[kV2NRisk] = 0;
-      scu[kV2MinKey] = 0xffffffffu;
-      scu[kV2MaxKey] = 0u;
+      s_keys[kV4KMin] = Ops::kKeyMax;
+      s_keys[kV4KMax] = (Key)0;
       sci[kV2NBnd] = 0;
-      scu[kV2MinBase] = 0xffffffffu;
-      scu[kV2Gap] = 0u;
+      s_keys[kV4KMinBase] = Ops::kKeyMax;
+      s_keys[kV4KGap] = (Key)0;
       sci[kV3Found] = 0;
       sci[kV4Abort] = 0;
     }
     int n = 1;
-    float xr_next = 0.0f;  // S warp: raw row of the frame after the one being prepared
-    float s_xr = 0.0f, s_mx = 0.0f, s_sum = 0.0f;  // S warp: the row being prepared, between the stages
+    R xr_next = (R)0;  // S warp: raw row of the frame after the one being prepared
+    R s_xr = (R)0, s_mx = (R)0, s_sum = (R)0;  // S warp: the row being prepared, between the stages
     int s_rank = 0;
     if (s_warp && L > 0) {
-      const float x0 = load_row(t0);
+      const R x0 = load_row(t0);
       if (L > 1) xr_next = load_row(t0 + 1);
-      const float sum0 = prepare1(x0, s_mx);
+      const R sum0 = prepare1(x0, s_mx);
       prepare3(prepare2(x0, s_mx, sum0, 0), 0);
     }
     __syncthreads();
     int carried = 0;  // flag bits handed on from the previous slice / call
-    if (resume) {  // beam as the previous slice left it (buffer 0: local frame 0 reads buffer 0)
+    if constexpr (!kF64) if (resume) {  // beam as the previous slice left it (buffer 0: local frame 0 reads buffer 0)
       StreamView sv(p.state + (size_t)b * StreamStateBytes(W), W);
       n = __ldcg(&sv.hdr->n);
       carried = __ldcg(&sv.hdr->flags);
@@ -360,13 +503,13 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         s_hash[i] = __ldcg(sv.hash + i); s_phash[i] = __ldcg(sv.phash + i);
       }
       if (tid == 0) {
-        scu[kV2Gap] = __ldcg(&sv.hdr->gap);
+        s_keys[kV4KGap] = __ldcg(&sv.hdr->gap);
         sci[kV2Anomaly] = carried & 1;
       }
       __syncthreads();
     }
     for (int i = tid; i < n; i += NT) {  // row info + parent look-up table of the initial beam
-      s_row[i] = make_uint4(__float_as_uint(s_total[i]), __float_as_uint(s_blk[i]), (unsigned)s_label[i], 0u);
+      s_row[i] = Rec::MakeRow(s_total[i], s_blk[i], s_label[i]);
       const unsigned long long hsh = s_hash[i];
       unsigned h = (unsigned)hsh & (TS - 1);
       const unsigned entry = ((unsigned)(hsh >> 42) << 10) | (unsigned)i;
@@ -378,17 +521,17 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
     int t_end = L;  // frames actually consumed (smaller only if the input copy was lost)
     for (int t = 0; t < L; ++t) {
       const int cur = t & 1, nxt = cur ^ 1;
-      const float* x = s_xb + cur * 32;
-      const float* s_pl = s_plb + cur * 32;
-      const float* s_plS = s_plSb + cur * 32;
-      const float* s_plH = s_plHb + cur * 8;
+      const R* x = s_xb + cur * 32;
+      const R* s_pl = s_plb + cur * 32;
+      const R* s_plS = s_plSb + cur * 32;
+      const R* s_plH = s_plHb + cur * 8;
       const unsigned* s_pref = s_prefb + cur * 36;
-      const float off = s_fsc[cur * 4 + 0];
-      const float* o_total = s_total + cur * WMAX;
-      const float* o_blk = s_blk + cur * WMAX;
-      const float* o_lab = s_lab + cur * WMAX;
-      const float* o_ab = s_ab + cur * WMAX;
-      const float* o_an = s_an + cur * WMAX;
+      const R off = s_fsc[cur * 4 + 0];
+      const R* o_total = s_total + cur * WMAX;
+      const R* o_blk = s_blk + cur * WMAX;
+      const R* o_lab = s_lab + cur * WMAX;
+      const R* o_ab = s_ab + cur * WMAX;
+      const R* o_an = s_an + cur * WMAX;
       const int* o_label = s_label + cur * WMAX;
       const unsigned long long* o_hash = s_hash + cur * WMAX;
       const unsigned long long* o_phash = s_phash + cur * WMAX;
@@ -399,18 +542,18 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         if (t + 2 < L) xr_next = load_row(t0 + t + 2);
         s_sum = prepare1(s_xr, s_mx);
       }
-      const float xb = x[blank];
-      const float pb = __fsub_rn(xb, off);
+      const R xb = x[blank];
+      const R pb = Ops::Sub(xb, off);
       CTCX_TICK(7)  // frame setup
       // ---- PA: update the existing members (decoder.h:95-143) ----
-      unsigned my_key = 0u;
+      Key my_key = (Key)0;
       bool suspect = false;
       if (tid < n) {
         const int i = tid;
         const int lbl = o_label[i];
         int pslot = -1;
-        float v_nl = o_lab[i], v_an = NegInf();
-        float rescore = NegInf();  // what the parent's re-score of this member would be (decoder.h:172-182)
+        R v_nl = o_lab[i], v_an = Ops::NegInf();
+        R rescore = Ops::NegInf();  // what the parent's re-score of this member would be (decoder.h:172-182)
         unsigned an_kind = kAnNone, an_src = 0xffu;
         if (lbl >= 0) {
           const unsigned long long ph = o_phash[i];
@@ -425,42 +568,42 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
             h = (h + 2) & (TS - 1);
           }
           CTCX_TICK(8)  // parent look-up
-          const float xl = x[lbl];
-          const float pl = __fsub_rn(xl, off);
-          const float self_an = __fadd_rn(o_an[i], pl);
+          const R xl = x[lbl];
+          const R pl = Ops::Sub(xl, off);
+          const R self_an = Ops::Add(o_an[i], pl);
           if (pslot >= 0) {
             const bool same = (lbl == o_label[pslot]);
-            float base = same ? o_blk[pslot] : o_total[pslot];
-            if constexpr (LM) base = __fadd_rn(base, s_lm[(o_label[pslot] + 1) * 32 + lbl]);  // decoder.h:103,114
-            v_nl = __fsub_rn(__fadd_rn(LogSumExp(o_lab[i], base, s_exptab), xl), off);
-            rescore = __fadd_rn(pl, base);
-            v_an = __fadd_rn(o_ab[pslot], pl);
+            R base = same ? o_blk[pslot] : o_total[pslot];
+            if constexpr (LM) base = Ops::Add(base, s_lm[(o_label[pslot] + 1) * 32 + lbl]);  // decoder.h:103,114
+            v_nl = Ops::Sub(Ops::Add(LogSumExp(o_lab[i], base, s_exptab), xl), off);
+            rescore = Ops::Add(pl, base);
+            v_an = Ops::Add(o_ab[pslot], pl);
             an_kind = kAnParAb;
             an_src = (unsigned)pslot;
             if (!same) {
-              const float c2 = __fadd_rn(o_an[pslot], pl);
+              const R c2 = Ops::Add(o_an[pslot], pl);
               if (c2 > v_an) { v_an = c2; an_kind = kAnParAn; }
             }
             if (self_an > v_an) { v_an = self_an; an_kind = kAnSelfAn; an_src = (unsigned)i; }
           } else {
-            v_nl = __fadd_rn(o_lab[i], pl);
+            v_nl = Ops::Add(o_lab[i], pl);
             v_an = self_an;
             an_kind = kAnSelfAn;
             an_src = (unsigned)i;
           }
         }
         CTCX_TICK(9)  // first LSE + alignment candidates
-        const float v_nb = __fsub_rn(__fadd_rn(o_total[i], xb), off);
-        const float c1 = __fadd_rn(o_ab[i], pb), c2 = __fadd_rn(o_an[i], pb);
+        const R v_nb = Ops::Sub(Ops::Add(o_total[i], xb), off);
+        const R c1 = Ops::Add(o_ab[i], pb), c2 = Ops::Add(o_an[i], pb);
         const unsigned ab_kind = (c2 > c1) ? kAbFromAn : kAbFromAb;
-        const float v_nt = LogSumExp(v_nb, v_nl, s_exptab);
+        const R v_nt = LogSumExp(v_nb, v_nl, s_exptab);
         CTCX_TICK(10)  // second LSE
         m_nt[i] = v_nt;
         m_nb[i] = v_nb;
         m_nl[i] = v_nl;
         m_nab[i] = (c2 > c1) ? c2 : c1;
         m_nan[i] = v_an;
-        my_key = KeyOf(v_nt);
+        my_key = Ops::KeyOf(v_nt);
         m_key[i] = my_key;
         m_rec[i] = PackRec32((unsigned)i, an_src, ab_kind, an_kind, (unsigned)(lbl & 0xff));
         m_pslot[i] = pslot;
@@ -469,9 +612,9 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         // the member's own total, so the reference could accept it again (decoder.h:189-199; it does so only
         // when the beam bottom ties with that total). Mathematically total >= re-score always. The utterance
         // is flagged if such a member then drops out of the beam (after the selection, below).
-        suspect = KeyOf(rescore) > my_key;
+        suspect = Ops::KeyOf(rescore) > my_key;
         if (pslot >= 0) {
-          atomicOr(&s_row[pslot].w, 1u << lbl);
+          atomicOr(Rec::MaskPtr(&s_row[pslot]), 1u << lbl);
           if (pslot < i) {
             const int q = atomicAdd(&sci[kV2NRisk], 1);
             s_risk[q] = i;
@@ -480,22 +623,22 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
       }
       CTCX_TICK(11)  // stores + atomics
       {
-        const unsigned kmin = __reduce_min_sync(kFull, (tid < n) ? my_key : 0xffffffffu);
-        const unsigned kmax = __reduce_max_sync(kFull, (tid < n) ? my_key : 0u);
+        const Key kmin = WarpMinKey((tid < n) ? my_key : Ops::kKeyMax);
+        const Key kmax = WarpMaxKey((tid < n) ? my_key : (Key)0);
         if (lane == 0 && warp * 32 < n) {
-          atomicMin(&scu[kV2MinKey], kmin);
-          atomicMax(&scu[kV2MaxKey], kmax);
+          atomicMin(&s_keys[kV4KMin], kmin);
+          atomicMax(&s_keys[kV4KMax], kmax);
         }
       }
       CTCX_TICK(12)  // min/max reduction
       if (__builtin_expect(n < W, 0)) {  // beam not full: every finite child is admissible; bound the score range
-        unsigned kb = 0xffffffffu;
+        Key kb = Ops::kKeyMax;
         if (tid < n) {
-          const float ob = o_blk[tid], ot = o_total[tid];
-          if (ot > NegInf()) kb = KeyOf((ob > NegInf()) ? fminf(ot, ob) : ot);
+          const R ob = o_blk[tid], ot = o_total[tid];
+          if (ot > Ops::NegInf()) kb = Ops::KeyOf((ob > Ops::NegInf()) ? fmin(ot, ob) : ot);
         }
-        kb = __reduce_min_sync(kFull, kb);
-        if (lane == 0 && warp * 32 < n) atomicMin(&scu[kV2MinBase], kb);
+        kb = WarpMinKey(kb);
+        if (lane == 0 && warp * 32 < n) atomicMin(&s_keys[kV4KMinBase], kb);
       }
       __syncthreads();
       CTCX_TICK(0)  // PA
@@ -506,11 +649,11 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
       // prefix of the sorted order: 2-round exact search, then drop the classes that are already
       // members (decoder.h:168) and re-test the repeated label, whose base is the old blank
       // probability (decoder.h:172-177).
-      auto cand_mask = [&](const uint4 ri, const float thr, const int c_lo = 0, const int c_n = 32) -> unsigned {
-        const float ot = __uint_as_float(ri.x);
+      auto cand_mask = [&](const Row ri, const R thr, const int c_lo = 0, const int c_n = 32) -> unsigned {
+        const R ot = Rec::Ot(ri);
         if constexpr (LM) {  // every class of [c_lo, c_lo + c_n) on its own: score = pl + (base + lm)  (decoder.h:171-182)
-          const float ob = __uint_as_float(ri.y);
-          const int lb = (int)ri.z;
+          const float ob = Rec::Ob(ri);
+          const int lb = Rec::Label(ri);
           const float* lmrow = s_lm + (lb + 1) * 32;
           unsigned m = 0u;
 #pragma unroll 2
@@ -522,31 +665,47 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
             m |= (__fadd_rn(q.z, __fadd_rn((g + 2 == lb) ? ob : ot, e.z)) > thr) ? (4u << g) : 0u;
             m |= (__fadd_rn(q.w, __fadd_rn((g + 3 == lb) ? ob : ot, e.w)) > thr) ? (8u << g) : 0u;
           }
-          return m & valid_mask & ~ri.w;
+          return m & valid_mask & ~Rec::Mask(ri);
         }
         // prefix length = number of sorted scores above thr (the predicate is monotone): first the
         // heads of the 8 groups of 4, then the group itself. -inf padding never passes.
-        const float4 ha = *reinterpret_cast<const float4*>(s_plH), hb = *reinterpret_cast<const float4*>(s_plH + 4);
-        int g = 0;
-        g += (__fadd_rn(ha.x, ot) > thr) ? 1 : 0;
-        g += (__fadd_rn(ha.y, ot) > thr) ? 1 : 0;
-        g += (__fadd_rn(ha.z, ot) > thr) ? 1 : 0;
-        g += (__fadd_rn(ha.w, ot) > thr) ? 1 : 0;
-        g += (__fadd_rn(hb.x, ot) > thr) ? 1 : 0;
-        g += (__fadd_rn(hb.y, ot) > thr) ? 1 : 0;
-        g += (__fadd_rn(hb.z, ot) > thr) ? 1 : 0;
-        g += (__fadd_rn(hb.w, ot) > thr) ? 1 : 0;
-        int pos = 0;
-        if (g > 0) {  // group g-1 is the last one whose head passes
-          const float4 q = *reinterpret_cast<const float4*>(s_plS + 4 * (g - 1));
-          pos = 4 * (g - 1) + 1;
-          pos += (__fadd_rn(q.y, ot) > thr) ? 1 : 0;
-          pos += (__fadd_rn(q.z, ot) > thr) ? 1 : 0;
-          pos += (__fadd_rn(q.w, ot) > thr) ? 1 : 0;
+        int g = 0, pos = 0;
+        if constexpr (kF64) {
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const double2 h = *reinterpret_cast<const double2*>(s_plH + i);
+            g += (Ops::Add(h.x, ot) > thr) ? 1 : 0;
+            g += (Ops::Add(h.y, ot) > thr) ? 1 : 0;
+          }
+          if (g > 0) {  // group g-1 is the last one whose head passes
+            const double2 qa = *reinterpret_cast<const double2*>(s_plS + 4 * (g - 1));
+            const double2 qb = *reinterpret_cast<const double2*>(s_plS + 4 * (g - 1) + 2);
+            pos = 4 * (g - 1) + 1;
+            pos += (Ops::Add(qa.y, ot) > thr) ? 1 : 0;
+            pos += (Ops::Add(qb.x, ot) > thr) ? 1 : 0;
+            pos += (Ops::Add(qb.y, ot) > thr) ? 1 : 0;
+          }
+        } else {
+          const float4 ha = *reinterpret_cast<const float4*>(s_plH), hb = *reinterpret_cast<const float4*>(s_plH + 4);
+          g += (__fadd_rn(ha.x, ot) > thr) ? 1 : 0;
+          g += (__fadd_rn(ha.y, ot) > thr) ? 1 : 0;
+          g += (__fadd_rn(ha.z, ot) > thr) ? 1 : 0;
+          g += (__fadd_rn(ha.w, ot) > thr) ? 1 : 0;
+          g += (__fadd_rn(hb.x, ot) > thr) ? 1 : 0;
+          g += (__fadd_rn(hb.y, ot) > thr) ? 1 : 0;
+          g += (__fadd_rn(hb.z, ot) > thr) ? 1 : 0;
+          g += (__fadd_rn(hb.w, ot) > thr) ? 1 : 0;
+          if (g > 0) {  // group g-1 is the last one whose head passes
+            const float4 q = *reinterpret_cast<const float4*>(s_plS + 4 * (g - 1));
+            pos = 4 * (g - 1) + 1;
+            pos += (__fadd_rn(q.y, ot) > thr) ? 1 : 0;
+            pos += (__fadd_rn(q.z, ot) > thr) ? 1 : 0;
+            pos += (__fadd_rn(q.w, ot) > thr) ? 1 : 0;
+          }
         }
-        unsigned m = s_pref[pos] & ~ri.w;
-        const int lb = (int)ri.z;
-        if (lb >= 0 && ((m >> lb) & 1u) && !(__fadd_rn(s_pl[lb], __uint_as_float(ri.y)) > thr)) m &= ~(1u << lb);
+        unsigned m = s_pref[pos] & ~Rec::Mask(ri);
+        const int lb = Rec::Label(ri);
+        if (lb >= 0 && ((m >> lb) & 1u) && !(Ops::Add(s_pl[lb], Rec::Ob(ri)) > thr)) m &= ~(1u << lb);
         return m;
       };
 
@@ -558,11 +717,11 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
             const int pslot = m_pslot[m];
             int verdict = 0;
             if (!s_wiped[pslot]) {
-              const unsigned vkey = m_key[m];
-              const float v = m_nt[m];
+              const Key vkey = m_key[m];
+              const R v = m_nt[m];
               int cnt = 0;
               for (int j = lane; j < n; j += 32) {  // members ranking before m
-                const unsigned kj = m_key[j];
+                const Key kj = m_key[j];
                 cnt += (kj > vkey || (kj == vkey && j < m)) ? 1 : 0;
               }
               // children visited before the parent reaches label(m), from rows that are not wiped
@@ -612,24 +771,24 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
       }
 
       // ---- PB / PD: list + histogram of the items in the score range, boundary bin ----
-      const unsigned minkey_m = scu[kV2MinKey];
-      const float lp_max = s_fsc[cur * 4 + 1];
-      unsigned lo_true;  // no item lies below this key
+      const Key minkey_m = s_keys[kV4KMin];
+      const R lp_max = s_fsc[cur * 4 + 1];
+      Key lo_true;  // no item lies below this key
       if (n == W) {
         lo_true = minkey_m;  // decoder.h:151-155: nothing at or below the W-th member total is admitted
       } else {
-        const unsigned kb = scu[kV2MinBase];
-        unsigned lo_c = minkey_m;
-        if (kb != 0xffffffffu) lo_c = KeyOf(__fadd_rn(UnKey(kb), s_fsc[cur * 4 + 2]));
-        lo_true = max(min(minkey_m, lo_c), kKeyNegInf);
+        const Key kb = s_keys[kV4KMinBase];
+        Key lo_c = minkey_m;
+        if (kb != Ops::kKeyMax) lo_c = Ops::KeyOf(Ops::Add(Ops::UnKey(kb), s_fsc[cur * 4 + 2]));
+        lo_true = max(min(minkey_m, lo_c), Ops::kKeyNegInf);
       }
       // every item is <= max(best member, best possible child); old totals are sorted, slot 0 is the max
-      const unsigned hi_key = max(scu[kV2MaxKey], KeyOf(__fadd_rn(lp_max, o_total[0])));
-      unsigned lo_key = lo_true;
+      const Key hi_key = max(s_keys[kV4KMax], Ops::KeyOf(Ops::Add(lp_max, o_total[0])));
+      Key lo_key = lo_true;
       int shift = 0;
       bool clamped = false;
       int n_cand = 0;
-      auto bucket_of = [&](unsigned key) -> int { return (key > lo_key) ? (int)((key - lo_key) >> shift) : 0; };
+      auto bucket_of = [&](Key key) -> int { return (key > lo_key) ? (int)((key - lo_key) >> shift) : 0; };
       for (int attempt = 0; attempt < 2; ++attempt) {
         // Score range of the histogram. Survivors crowd near the top while the admissible range reaches
         // far below, so the first attempt only looks at [hi - 1.25*gap - 64, hi], gap = the previous
@@ -637,14 +796,14 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         // takes the whole admissible range. The prediction affects speed only.
         lo_key = lo_true;
         if (attempt == 0 && n == W) {
-          const unsigned gap = scu[kV2Gap];
-          const unsigned long long reach = (5ull * gap) / 4ull + 64ull;  // measured: 1.0-1.25 x gap is best, below 1.0 it always misses
-          if (gap != 0u && reach < (unsigned long long)(hi_key - lo_true)) lo_key = hi_key - (unsigned)reach;
+          const Key gap = s_keys[kV4KGap];
+          const unsigned long long reach = ReachOf(gap);  // 1.25 x gap + 64; measured: 1.0-1.25 x gap is best, below 1.0 it always misses
+          if (gap != (Key)0 && reach < (unsigned long long)(hi_key - lo_true)) lo_key = hi_key - (Key)reach;
         }
         clamped = (lo_key != lo_true);
-        const unsigned span = hi_key - lo_key;
-        shift = max(0, (32 - __clz(span | 1u)) - kBinsLog2V2);  // (key - lo) >> shift < kBinsV2
-        const float thr = (n == W) ? UnKey(lo_key) : NegInf();  // listed children: score > thr
+        const Key span = hi_key - lo_key;
+        shift = max(0, Ops::Bits(span | (Key)1) - kBinsLog2V2);  // (key - lo) >> shift < kBinsV2
+        const R thr = (n == W) ? Ops::UnKey(lo_key) : Ops::NegInf();  // listed children: score > thr
         const bool member_in = !clamped || my_key > lo_key;
         CTCX_TICK(16)  // PB: range
 
@@ -652,14 +811,14 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         // beyond the beam (the S warp at beam widths up to 112, for one) has nothing to list.
         const bool warp_has_rows = ((warp * 32) / PARTS) < n;
         unsigned mymask = 0u;
-        float r_ot = 0.0f, r_ob = 0.0f;
+        R r_ot = (R)0, r_ob = (R)0;
         int r_label = -1;
         if (prow < n && !s_wiped[prow]) {
-          const uint4 ri = s_row[prow];
-          r_ot = __uint_as_float(ri.x);
-          r_ob = __uint_as_float(ri.y);
-          r_label = (int)ri.z;
-          if (__fadd_rn(lp_max, r_ot) > thr) {
+          const Row ri = s_row[prow];
+          r_ot = Rec::Ot(ri);
+          r_ob = Rec::Ob(ri);
+          r_label = Rec::Label(ri);
+          if (Ops::Add(lp_max, r_ot) > thr) {
             const unsigned m = cand_mask(ri, thr, pbase, CP) >> pbase;
             mymask = (CP == 32) ? m : (m & ((1u << (CP & 31)) - 1u));
           }
@@ -689,10 +848,10 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
             const int k = __ffs(m) - 1;
             m &= m - 1u;
             const int l = pbase + k;
-            float cbase = (l == r_label) ? r_ob : r_ot;
-            if constexpr (LM) cbase = __fadd_rn(cbase, s_lm[(r_label + 1) * 32 + l]);
-            const unsigned key = KeyOf(__fadd_rn(s_pl[l], cbase));  // :172-182
-            c_list[pos++] = make_uint2(key, ((unsigned)prow << 16) | (unsigned)l);
+            R cbase = (l == r_label) ? r_ob : r_ot;
+            if constexpr (LM) cbase = Ops::Add(cbase, s_lm[(r_label + 1) * 32 + l]);
+            const Key key = Ops::KeyOf(Ops::Add(s_pl[l], cbase));  // :172-182
+            c_list[pos++] = Rec::MakeItem(key, ((unsigned)prow << 16) | (unsigned)l);
             atomicAdd(&s_hist[bucket_of(key)], 1u);
           }
           if (tid < n && member_in) atomicAdd(&s_hist[bucket_of(my_key)], 1u);
@@ -777,12 +936,12 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
       if (__builtin_expect(suspect, 0) && (!member_in || bucket_of(my_key) <= bstar)) sci[kV2Anomaly] = 1;
       const bool bnd_all = (e_b == k_rem);
       // next frame's range prediction: the measured top-to-threshold gap
-      const unsigned gap_next = (unsigned)(sc[kV2TopBin] - bstar + 1) << shift;
+      const Key gap_next = (Key)(unsigned)(sc[kV2TopBin] - bstar + 1) << shift;
 
       // ---- PE: scatter every item at or above the boundary bin into its score group ----
-      auto place = [&](unsigned key, unsigned okey) {
+      auto place = [&](Key key, unsigned okey) {
         const int bucket = bucket_of(key);
-        const unsigned long long comp = ((unsigned long long)key << 32) | (unsigned long long)(~okey);
+        const Comp comp = Ops::MakeComp(key, ~okey);
         if (bucket > bstar || (bucket == bstar && bnd_all)) {
           const unsigned pos = s_offs[bucket] + atomicAdd(&s_hist[bucket], 1u);
           if (pos < (unsigned)WMAX) s_sorted[pos] = comp;
@@ -793,15 +952,15 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
       };
       if (tid < n && member_in) place(my_key, (unsigned)tid);
       for (int c0 = tid; c0 < n_cand; c0 += 4 * NT) {  // four independent entries in flight
-        uint2 e[4];
+        Item e[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int c = c0 + u * NT;
-          e[u] = (c < n_cand) ? c_list[c] : make_uint2(0u, 0u);
+          e[u] = (c < n_cand) ? c_list[c] : Rec::NoItem();
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          if (e[u].x) place(e[u].x, 0x80000000u | e[u].y);
+          if (Rec::ItemKey(e[u])) place(Rec::ItemKey(e[u]), 0x80000000u | Rec::ItemId(e[u]));
       }
       __syncthreads();
       CTCX_TICK(4)  // PE
@@ -815,14 +974,9 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
       if (!bnd_all) {
         if (__builtin_expect(e_b <= kBndFast, 1)) {
           if (s_warp) {
-            const unsigned long long mine = (lane < e_b) ? s_bnd[lane] : 0ull;
-            const unsigned mlo = (unsigned)mine, mhi = (unsigned)(mine >> 32);
+            const Comp mine = (lane < e_b) ? s_bnd[lane] : Ops::MakeComp((Key)0, 0u);
             int rank = 0;
-            for (int j = 0; j < e_b; ++j) {
-              const unsigned olo = __shfl_sync(kFull, mlo, j), ohi = __shfl_sync(kFull, mhi, j);
-              const unsigned long long other = ((unsigned long long)ohi << 32) | olo;
-              rank += (other > mine) ? 1 : 0;
-            }
+            for (int j = 0; j < e_b; ++j) rank += Ops::Greater(ShflComp(mine, j), mine) ? 1 : 0;
             if (lane < e_b && rank < k_rem) s_fin[s_offs[bstar] + rank] = mine;
           }
         } else {
@@ -830,27 +984,24 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
           // ties such as constant logits): radix select of the k_rem largest (key, ~order) composites
           auto for_each_bnd = [&](auto&& f) {
             if (tid < n && member_in && bucket_of(my_key) == bstar)
-              f(((unsigned long long)my_key << 32) | (unsigned long long)(~(unsigned)tid), my_key, (unsigned)tid);
+              f(Ops::MakeComp(my_key, ~(unsigned)tid), my_key, (unsigned)tid);
             for (int c = tid; c < n_cand; c += NT) {
-              const uint2 e = c_list[c];
-              if (e.x && bucket_of(e.x) == bstar)
-                f(((unsigned long long)e.x << 32) | (unsigned long long)(~(0x80000000u | e.y)), e.x,
-                  0x80000000u | e.y);
+              const Item e = c_list[c];
+              const Key ek = Rec::ItemKey(e);
+              if (ek && bucket_of(ek) == bstar)
+                f(Ops::MakeComp(ek, ~(0x80000000u | Rec::ItemId(e))), ek, 0x80000000u | Rec::ItemId(e));
             }
           };
-          const int npass = 8;
-          if (tid == 0) { scu[kV2Prefix] = 0u; scu[kV2PrefixHi] = 0u; sci[kV2K] = k_rem; }
+          constexpr int npass = (int)sizeof(Key) + 4;  // bytes of a (key, ~order) composite
+          if (tid == 0) { *s_prefix = Ops::MakeComp((Key)0, 0u); sci[kV2K] = k_rem; }
           __syncthreads();
           for (int pass = npass - 1; pass >= 0; --pass) {
-            const int sh = pass * 8;
             unsigned* bins = s_bins2;
             for (int i = tid; i < 256; i += NT) bins[i] = 0u;
             __syncthreads();
-            const unsigned long long prefix =
-                ((unsigned long long)scu[kV2PrefixHi] << 32) | (unsigned long long)scu[kV2Prefix];
-            for_each_bnd([&](unsigned long long v, unsigned, unsigned) {
-              const unsigned long long hi = (sh + 8 >= 64) ? 0ull : (v >> (sh + 8));
-              if (hi == prefix) atomicAdd(&bins[(unsigned)(v >> sh) & 255u], 1u);
+            const Comp prefix = *s_prefix;  // the bytes above `pass` of the composite being selected
+            for_each_bnd([&](Comp v, Key, unsigned) {
+              if (CompEq(CompAbove(v, pass), prefix)) atomicAdd(&bins[CompByte(v, pass)], 1u);
             });
             __syncthreads();
             if (warp == 0) {
@@ -870,9 +1021,7 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
 #pragma unroll
                 for (int q = 7; q >= 0; --q) {
                   if ((int)(acc + h[q]) >= k && (int)acc < k) {
-                    const unsigned long long np = (prefix << 8) | (unsigned long long)(lane * 8 + q);
-                    scu[kV2Prefix] = (unsigned)np;
-                    scu[kV2PrefixHi] = (unsigned)(np >> 32);
+                    *s_prefix = CompWithByte(prefix, pass, (unsigned)(lane * 8 + q));
                     sci[kV2K] = k - (int)acc;
                   }
                   acc += h[q];
@@ -881,13 +1030,11 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
             }
             __syncthreads();
           }
-          const unsigned long long cut =
-              ((unsigned long long)scu[kV2PrefixHi] << 32) | (unsigned long long)scu[kV2Prefix];
-          for_each_bnd([&](unsigned long long v, unsigned key, unsigned okey) {
-            if (v >= cut) {
+          const Comp cut = *s_prefix;
+          for_each_bnd([&](Comp v, Key, unsigned) {
+            if (CompGe(v, cut)) {
               const unsigned pos = s_offs[bstar] + atomicAdd(&s_hist[bstar], 1u);
-              if (pos < (unsigned)WMAX)
-                s_sorted[pos] = ((unsigned long long)key << 32) | (unsigned long long)(~okey);
+              if (pos < (unsigned)WMAX) s_sorted[pos] = v;
             }
           });
           __syncthreads();
@@ -897,11 +1044,11 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
       CTCX_TICK(5)  // PF
       // ---- PG: rank inside the score group = new slot; write the next beam + back-pointers ----
       {
-        float* w_total = s_total + nxt * WMAX;
-        float* w_blk = s_blk + nxt * WMAX;
-        float* w_lab = s_lab + nxt * WMAX;
-        float* w_ab = s_ab + nxt * WMAX;
-        float* w_an = s_an + nxt * WMAX;
+        R* w_total = s_total + nxt * WMAX;
+        R* w_blk = s_blk + nxt * WMAX;
+        R* w_lab = s_lab + nxt * WMAX;
+        R* w_ab = s_ab + nxt * WMAX;
+        R* w_an = s_an + nxt * WMAX;
         int* w_label = s_label + nxt * WMAX;
         unsigned long long* w_hash = s_hash + nxt * WMAX;
         unsigned long long* w_phash = s_phash + nxt * WMAX;
@@ -911,8 +1058,8 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         // survivors above the boundary (and the radix-selected boundary items): scatter to the final slot
         const int n_grouped = min(n_new, bnd_start);
         if (tid < n_grouped) {
-          const unsigned long long comp = s_sorted[tid];
-          const int bucket = bucket_of((unsigned)(comp >> 32));
+          const Comp comp = s_sorted[tid];
+          const int bucket = bucket_of(Ops::CompKey(comp));
           const int g0 = (int)s_offs[bucket];
           const int g1 = (bucket == bstar && !bnd_all) ? n_new : g0 + (int)s_hist[bucket];
           // Groups usually hold 1-3 items; quantised logits (bfloat16 inputs) make exact ties, i.e. groups of
@@ -920,11 +1067,12 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
           int rank = 0, j = g0;
 #pragma unroll 1
           for (; j + 4 <= g1; j += 4) {
-            const unsigned long long a = s_sorted[j], b2 = s_sorted[j + 1], c2 = s_sorted[j + 2], d2 = s_sorted[j + 3];
-            rank += ((a > comp) ? 1 : 0) + ((b2 > comp) ? 1 : 0) + ((c2 > comp) ? 1 : 0) + ((d2 > comp) ? 1 : 0);
+            const Comp a = s_sorted[j], b2 = s_sorted[j + 1], c2 = s_sorted[j + 2], d2 = s_sorted[j + 3];
+            rank += (Ops::Greater(a, comp) ? 1 : 0) + (Ops::Greater(b2, comp) ? 1 : 0) + (Ops::Greater(c2, comp) ? 1 : 0) +
+                    (Ops::Greater(d2, comp) ? 1 : 0);
           }
 #pragma unroll 1
-          for (; j < g1; ++j) rank += (s_sorted[j] > comp) ? 1 : 0;
+          for (; j < g1; ++j) rank += Ops::Greater(s_sorted[j], comp) ? 1 : 0;
           s_fin[g0 + rank] = comp;
         }
         CTCX_TICK(13)  // PG: rank in group
@@ -934,22 +1082,22 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         if (tid == 0) {
           sci[kV2NCand] = 0;
           sci[kV2NRisk] = 0;
-              scu[kV2MinKey] = 0xffffffffu;
-          scu[kV2MaxKey] = 0u;
+          s_keys[kV4KMin] = Ops::kKeyMax;
+          s_keys[kV4KMax] = (Key)0;
           sci[kV2NBnd] = 0;
-          scu[kV2MinBase] = 0xffffffffu;
-          scu[kV2Gap] = gap_next;
+          s_keys[kV4KMinBase] = Ops::kKeyMax;
+          s_keys[kV4KGap] = gap_next;
           sci[kV3Found] = 0;
         }
         if (tid < n) s_wiped[tid] = 0u;
         if (pg_role < PGS && pg_slot < n_new) {
           const int r = pg_slot;
-          const unsigned long long comp = s_fin[r];
-          const unsigned okey = ~(unsigned)(comp & 0xffffffffull);
+          const Comp comp = s_fin[r];
+          const unsigned okey = ~Ops::CompNotOrder(comp);
           const bool fresh = (okey & 0x80000000u) != 0u;
           const int src = fresh ? (int)((okey & 0x7fffffffu) >> 16) : (int)okey;  // parent row / old slot
           const int lbl = fresh ? (int)(okey & 0xffffu) : o_label[src];
-          const float s = UnKey((unsigned)(comp >> 32));
+          const R s = Ops::UnKey(Ops::CompKey(comp));
           if (pg_role == 0) {  // state arrays + back-pointer record
             unsigned rec;
             if (!fresh) {  // surviving member
@@ -960,17 +1108,17 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
               w_an[r] = m_nan[src];
               rec = m_rec[src];
             } else {  // fresh child (decoder.h:170-187)
-              const float pl = __fsub_rn(x[lbl], off);
-              float v_an = __fadd_rn(o_ab[src], pl);
+              const R pl = Ops::Sub(x[lbl], off);
+              R v_an = Ops::Add(o_ab[src], pl);
               unsigned an_kind = kAnParAb;
               if (lbl != o_label[src]) {
-                const float c2 = __fadd_rn(o_an[src], pl);
+                const R c2 = Ops::Add(o_an[src], pl);
                 if (c2 > v_an) { v_an = c2; an_kind = kAnParAn; }
               }
               w_total[r] = s;
-              w_blk[r] = NegInf();
+              w_blk[r] = Ops::NegInf();
               w_lab[r] = s;
-              w_ab[r] = NegInf();
+              w_ab[r] = Ops::NegInf();
               w_an[r] = v_an;
               rec = PackRec32(0xffu, (unsigned)src, kAbFromAb, an_kind, (unsigned)lbl);
             }
@@ -980,7 +1128,7 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
           }
           if (PGS == 1 || pg_role == 1) {  // prefix hash, row info of the next frame, parent look-up table
             unsigned long long hsh;
-            float nt_, nb_;
+            R nt_, nb_;
             if (!fresh) {
               hsh = o_hash[src];
               w_phash[r] = o_phash[src];
@@ -990,10 +1138,10 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
               hsh = HashChild(o_hash[src], lbl);
               w_phash[r] = o_hash[src];
               nt_ = s;
-              nb_ = NegInf();
+              nb_ = Ops::NegInf();
             }
             w_hash[r] = hsh;
-            s_row[r] = make_uint4(__float_as_uint(nt_), __float_as_uint(nb_), (unsigned)lbl, 0u);
+            s_row[r] = Rec::MakeRow(nt_, nb_, lbl);
             unsigned h = (unsigned)hsh & (TS - 1);
             const unsigned entry = ((unsigned)(hsh >> 42) << 10) | (unsigned)r;
             while (atomicCAS(&s_htab[h], 0xffffffffu, entry) != 0xffffffffu) h = (h + 1) & (TS - 1);
@@ -1027,7 +1175,7 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
             p.fin_total[(size_t)b * p.P + q] = s_total[cur * WMAX + q];
             p.fin_kind[(size_t)b * p.P + q] = (s_ab[cur * WMAX + q] > s_an[cur * WMAX + q]) ? 1 : 0;
           } else {
-            p.fin_total[(size_t)b * p.P + q] = 0.0f;
+            p.fin_total[(size_t)b * p.P + q] = (R)0;
             p.fin_kind[(size_t)b * p.P + q] = 0;
           }
         }
@@ -1037,7 +1185,7 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         }
       }
       // ---- carry the beam (and the score-range prediction) to the next slice / the next call ----
-      if (p.state != nullptr && (!last_slice || p.t_done != nullptr)) {
+      if constexpr (!kF64) if (p.state != nullptr && (!last_slice || p.t_done != nullptr)) {
         StreamView sv(p.state + (size_t)b * StreamStateBytes(W), W);
         for (int i = tid; i < n; i += NT) {
           sv.total[i] = s_total[cur * WMAX + i]; sv.blk[i] = s_blk[cur * WMAX + i];
@@ -1047,7 +1195,7 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         }
         if (tid == 0) {
           sv.hdr->n = n;
-          sv.hdr->gap = scu[kV2Gap];
+          sv.hdr->gap = s_keys[kV4KGap];
           sv.hdr->flags = (sci[kV2Anomaly] ? 1 : 0) | overflow | lost | (carried & 4);
         }
       }

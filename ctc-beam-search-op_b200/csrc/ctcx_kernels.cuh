@@ -343,10 +343,6 @@ __global__ void __launch_bounds__(256, 3) NormTopClassesKernel(const IN* __restr
 
 #endif  // CTCX_WITH_NORM
 
-#ifdef CTCX_WITH_GENERIC
-// ---------------------------------------------------------------------------------------------
-// Kernel 2: the beam kernel.
-// ---------------------------------------------------------------------------------------------
 // Arithmetic of the score type R (float, or double for the reference's T = double registration,
 // kernels.cc:275): explicit round-to-nearest operations, the monotone score -> integer key map and
 // the (key, ~tie order) composite the survivors are ranked by.
@@ -397,6 +393,11 @@ struct RealOps<double> {
   __device__ static __forceinline__ Key CompKey(Comp c) { return c.x; }
   __device__ static __forceinline__ unsigned CompNotOrder(Comp c) { return (unsigned)c.y; }
 };
+
+#ifdef CTCX_WITH_GENERIC
+// ---------------------------------------------------------------------------------------------
+// Kernel 2: the beam kernel.
+// ---------------------------------------------------------------------------------------------
 
 
 // Shared-memory carve-up, computed identically on host and device.

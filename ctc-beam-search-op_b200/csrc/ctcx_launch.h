@@ -52,6 +52,7 @@ LaunchStatus LaunchUpcast(const void* in, int in_dtype, float* out, int T, int B
 
 // ---- kernel 2 ----
 LaunchStatus LaunchBeamNarrow(BeamParams& p, int in_dtype, cudaStream_t stream);
+LaunchStatus LaunchBeamNarrow(BeamParamsT<double>& p, cudaStream_t stream);  // float64 logits, double scores
 LaunchStatus LaunchBeamWide(BeamParams& p, int in_dtype, cudaStream_t stream);
 LaunchStatus LaunchBeamGeneric(BeamParamsT<float>& p, cudaStream_t stream);
 LaunchStatus LaunchBeamGeneric(BeamParamsT<double>& p, cudaStream_t stream);

@@ -30,7 +30,7 @@ constexpr int kMaxDevices = 64;
 constexpr int kMinSliceFrames = 32;  // shorter slices would not amortise the hand-over
 
 template <typename IN, int WMAX, bool TIMING, int MINB, bool LM = false>
-LaunchStatus LaunchOne(BeamParams& p, size_t smem, cudaStream_t stream) {
+LaunchStatus LaunchOne(BeamParamsT<typename ScoreOf<IN>::type>& p, size_t smem, cudaStream_t stream) {
   auto kern = BeamKernelV4<IN, WMAX, 256, TIMING, MINB, LM>;
   static LaunchCfg cfgs[kMaxDevices];
   int dev = 0;
@@ -100,8 +100,15 @@ LaunchStatus LaunchTyped(BeamParams& p, int wmax, size_t smem, cudaStream_t stre
   }
 }
 
-size_t SmemBytes(int wmax, int cand_cap, bool lm) {  // (the scorer table adds a constant)
+size_t SmemBytes(int wmax, int cand_cap, bool lm, bool f64 = false) {  // (the scorer table adds a constant)
   const size_t extra = lm ? (BeamSmemV4<32, true>::list - BeamSmemV4<32, false>::list) : 0;
+  if (f64) {
+    switch (wmax) {
+      case 32: return BeamSmemV4<32, false, 8>::Bytes(cand_cap);
+      case 128: return BeamSmemV4<128, false, 8>::Bytes(cand_cap);
+      default: return BeamSmemV4<256, false, 8>::Bytes(cand_cap);
+    }
+  }
   switch (wmax) {
     case 32: return BeamSmemV4<32>::Bytes(cand_cap) + extra;
     case 128: return BeamSmemV4<128>::Bytes(cand_cap) + extra;
@@ -112,7 +119,7 @@ size_t SmemBytes(int wmax, int cand_cap, bool lm) {  // (the scorer table adds a
 
 bool NarrowFastShape(int W, int C) {
   if (C > 32 || W > 256 || (long long)W * C > kListCapMax) return false;
-  return SmemBytes(TierOf(W), W * C, true) <= 220 * 1024;
+  return SmemBytes(TierOf(W), W * C, true) <= 220 * 1024 && SmemBytes(TierOf(W), W * C, false, true) <= 220 * 1024;
 }
 
 LaunchStatus LaunchBeamNarrow(BeamParams& p, int in_dtype, cudaStream_t stream) {
@@ -127,6 +134,28 @@ LaunchStatus LaunchBeamNarrow(BeamParams& p, int in_dtype, cudaStream_t stream) 
     case kInF16: return LaunchTyped<__half>(p, wmax, smem, stream);
     case kInBF16: return LaunchTyped<__nv_bfloat16>(p, wmax, smem, stream);
     default: return {kLaunchUnsupported, cudaSuccess, ""};
+  }
+}
+
+}  // namespace ctcx
+
+namespace ctcx {
+
+// float64 logits (the op's T = double registration): the same kernel computing in double, 64-bit keys
+LaunchStatus LaunchBeamNarrow(BeamParamsT<double>& p, cudaStream_t stream) {
+  if (!NarrowFastShape(p.W, p.C) || p.queue == nullptr || p.bp32 == nullptr || p.lm != nullptr)
+    return {kLaunchUnsupported, cudaSuccess, ""};
+  p.cand_cap = p.W * p.C;
+  p.kid_words = 1;
+  p.state = nullptr;  // no time slices: whole utterances from the queue
+  p.t_done = nullptr;
+  const int wmax = TierOf(p.W);
+  const size_t smem = SmemBytes(wmax, p.cand_cap, false, true);
+  // (~90 KB of shared memory at beam 100: two CTAs per SM in either regime, 128 registers)
+  switch (wmax) {
+    case 32: return LaunchOne<double, 32, false, 2>(p, smem, stream);
+    case 128: return LaunchOne<double, 128, false, 2>(p, smem, stream);
+    default: return LaunchOne<double, 256, false, 2>(p, smem, stream);
   }
 }
 

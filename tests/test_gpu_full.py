@@ -68,6 +68,28 @@ def test_every_utterance_of_the_baseline_shapes(op, name, kind):
     assert raw.flags == 0  # no utterance met the re-score anomaly
 
 
+@pytest.mark.parametrize("kind", ["gauss", "peaky", "quantised"])
+def test_float64_at_cfg2_size(op, kind):
+    """T = double (kernels.cc:275) at cfg2's full length and beam, 64 utterances against the float64
+    oracle: log-probabilities to the last bit of the double. "quantised" = float64 logits on a coarse
+    grid (exact ties between candidates: the tie order and the slow boundary cut in 64-bit keys)."""
+    T, B, C, W, P, merge, blank = FULL["cfg2"]
+    x32, sl = _inputs("cfg2", "peaky" if kind == "peaky" else "gauss")
+    rng = np.random.default_rng(9)
+    if kind == "quantised":
+        x = np.round(x32[:, :64].astype(np.float64) * 4.0) / 4.0
+    else:
+        x = x32[:, :64].astype(np.float64) + rng.standard_normal((T, 64, C)) * 1e-9  # genuine float64 values
+    x, sl = np.ascontiguousarray(x), sl[:64]
+    want = L.oracle_decode_threaded(x, sl, W, P, merge, blank, -1)
+    assert want.logp.dtype == np.float64
+    raw = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=W, top_paths=P, merge_repeated=merge,
+                                             blank_index=blank, blank_label=-1)
+    assert np.asarray(raw[6]).dtype == np.float64
+    bad = L.raw_mismatches(raw, want)
+    assert not bad, "float64 %s: %d of 64 utterances differ from the oracle, first %s" % (kind, len(bad), bad[:8])
+
+
 def test_scorer_table_at_cfg2_size(op):
     """The scorer extension point (ctcx_decode_scorer_f32, util/ctc_beam_scorer.h:31-65) at cfg2's
     full length and beam: 64 utterances, a random bigram table, against the oracle."""

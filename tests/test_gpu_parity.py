@@ -230,13 +230,19 @@ F64_CASES = [
     ("peaky", 20, 2, 300, 8, 2, False, 0),     # streaming candidate mode
     ("gauss", 12, 2, 12, 300, 3, False, 0),    # WMAX=1024 tier
     ("gauss", 25, 2, 40, 200, 2, True, 39),    # WMAX=256 tier
+    # the narrow fast kernel computing in double (num_classes <= 32): every beam tier
+    ("gauss", 50, 3, 32, 32, 2, False, 31),
+    ("peaky", 70, 3, 20, 128, 3, True, 4),
+    ("gauss", 40, 2, 12, 256, 2, False, 0),
+    ("gauss", 33, 700, 9, 6, 1, True, 8),      # more utterances than resident CTAs: the work queue
 ]
 
 
 @pytest.mark.parametrize("case", F64_CASES, ids=lambda c: "%s-T%d-C%d-W%d" % (c[0], c[1], c[3], c[4]))
 def test_float64_decode_is_bit_exact(op, case):
     """T = double (kernels.cc:275; the reference's own test feeds float64): decoded in float64 by the
-    double instantiation of the generic kernel, identical to the float64 oracle down to the bits."""
+    double instantiations of the narrow fast kernel (num_classes <= 32) and of the generic kernel,
+    identical to the float64 oracle down to the bits."""
     kind, T, B, C, W, P, merge, blank = case
     rng = np.random.default_rng(41)
     x = rng.standard_normal((T, B, C))  # genuine float64 values
