@@ -16,6 +16,9 @@
 //   * the histogram scan (PD) is one bin per thread over all eight warps instead of one warp
 //   * PG: survivors are scattered to their final slot first, then slot r is written by thread r
 //     (state) and thread WMAX + r (hash, row info, parent table) -- linear stores, half the chain
+//   * instantiated on the score type: float for f32 / f16 / bf16 logits, double for f64 logits (the
+//     reference's T = double registration) -- RealOps<R> supplies the arithmetic, the key and the
+//     (key, ~order) composite, V4Rec<R> the row record and the list item; and on LM, the scorer table
 //
 // Per frame:
 //   S   (last warp, for frame t+1) raw row -> x, off, per-class log-probs, classes ranked by log-prob,
