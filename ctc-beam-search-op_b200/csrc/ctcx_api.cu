@@ -293,6 +293,7 @@ int DecodeImpl(const void* logits_dev, int T, int B, int C, const int32_t* seq_l
       }
     } else if (PathOf(W, C, false) == kPathNarrow) {
       // float64 logits, narrow vocabulary: the fast kernel computing in double (normaliser inside)
+      bp.ready = opt.ready;
       ProfRecord(1, stream);
       CTCX_LAUNCH(ctcx::LaunchBeamNarrow(bp, stream));
     } else {
@@ -604,7 +605,7 @@ int ctcx_decode_hostin(const void* logits_host, int dtype, int64_t host_time_str
 
   // overlap needs a truly asynchronous copy (page-locked source) and the stream-ordered flag store;
   // pageable sources are staged by the driver, which may wait for the kernel that waits for them
-  const bool overlap = (B > 0) && dtype != CTCX_F64 && PathOf(W, C, false) == kPathNarrow && P <= W &&
+  const bool overlap = (B > 0) && PathOf(W, C, false) == kPathNarrow && P <= W &&
                        IsPinned(logits_host) && StreamWriteValue32() != nullptr;
   Feed feed = {(const unsigned char*)logits_host, (unsigned char*)staging_dev, (size_t)B * C * es,
                (size_t)hstride * es, T, d_ctrl + 1, overlap, copy_stream};

@@ -780,7 +780,7 @@ def test_side_stream_and_non_contiguous_inputs(op):
 
 # ------------------------------------------------------------------------------------------------
 # Round 2: host-input decode with the copy overlapped, views decoded in place, flags in the result
-@pytest.mark.parametrize("dt", ["float32", "float16", "bfloat16"])
+@pytest.mark.parametrize("dt", ["float32", "float16", "bfloat16", "float64"])
 def test_pinned_host_logits_are_fed_while_the_kernel_runs(op, dt):
     """ctcx_decode_hostin: page-locked host logits are copied in time slabs on a side stream while the
     beam kernel already consumes the frames that have landed (char-CTC shapes). The result must be
@@ -789,7 +789,7 @@ def test_pinned_host_logits_are_fed_while_the_kernel_runs(op, dt):
     T, B, C, W, P = 300, 48, 29, 100, 1
     x32 = L.make_logits("gauss", T, B, C, 28, 51)
     xh = torch.from_numpy(x32).to(getattr(torch, dt)).pin_memory()
-    up = xh.to(torch.float32).numpy()
+    up = xh.numpy() if dt == "float64" else xh.to(torch.float32).numpy()  # float64 is decoded in double
     sl = L.ragged_lengths(T, B, 51)
     want = L.oracle_decode_threaded(up, sl, W, P, True, 28, -1)
     for _ in range(3):  # repeated calls reuse the side stream and the staging memory
