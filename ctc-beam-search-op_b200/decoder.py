@@ -181,8 +181,8 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
     """The raw op: returns a 7-field namedtuple of (lists of) tensors, exactly the op's outputs.
 
     inputs            [max_time, batch, num_classes] float32 or float64 (the reference registers both,
-                      kernels.cc:269-275; float64 is computed in float64 by the double instantiation
-                      of the generic kernel and log_probability is float64); float16 / bfloat16 are
+                      kernels.cc:269-275; float64 is computed in float64 by the double instantiations
+                      of the kernels and log_probability is float64); float16 / bfloat16 are
                       read by the kernels as they are (widened exactly in registers); numpy array or
                       torch tensor on any device. A batch shard `x[:, b0:b1, :]` of a contiguous
                       tensor is decoded in place (device) / copied with a pitched copy (host) -- no

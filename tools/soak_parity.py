@@ -1,5 +1,5 @@
 """Full-batch parity soak: every utterance of the BASELINE shapes (cfg1-cfg4, Gaussian and peaky
-logits, float32; cfg2 also in float64 and with a random scorer table) decoded on the GPU and by the
+logits, float32; cfg2 / cfg3 also in float64, cfg2 with a random scorer table) decoded on the GPU and by the
 CPU oracle (oracle/, sharded over host threads), compared bit for bit -- labels, alignments, the
 IEEE bits of log_probability.   python tools/soak_parity.py [threads] [n_seeds] > profiles/<round>_soak.txt
 The oracle is the checker here, never the thing measured."""
@@ -51,6 +51,8 @@ print("threads for the oracle: %d" % NT)
 for seed, kind in [(21 + 100 * k, kd) for k in range(NSEEDS) for kd in ("gauss", "peaky")]:
     for name, T, B, C, W, P, merge, blank in CFGS:
         variants = [("f32", np.float32, None)]
+        if name == "cfg3":
+            variants += [("f64", np.float64, None)]
         if name == "cfg2":
             variants += [("f64", np.float64, None),
                          ("f32+scorer", np.float32,
