@@ -78,7 +78,7 @@ struct Workspace {
     int real_bytes;  // 4: float32 decode, 8: float64 decode
   };
   size_t header, result, ctrl, dec_len, ali_len, dec_off, ali_off, ptrs, fin_total, fin_kind, dec, ali,
-      seq, fin_n, flags, t_done, state, off, bp, srt_pl, srt_cls, scratch, bytes;
+      seq, chunk_len, fin_n, flags, t_done, state, off, bp, srt_pl, srt_cls, scratch, bytes;
   int Cs;         // row stride of the sorted-class arrays (0 when the wide fast path does not apply)
   int rec_bytes;  // back-pointer record size
   size_t InitPack(int T, int B, int P) {
@@ -102,6 +102,7 @@ struct Workspace {
     size_t o = InitPack(T, B, P);
     const size_t b = (size_t)B, t = (size_t)T, w = (size_t)W;
     seq = o; o += Align256(b * 4);                               // sequence_length of host-input decodes
+    chunk_len = o; o += Align256(b * 4);                         // frames per utterance of the time chunk being decoded
     fin_n = o; o += Align256(b * 4);
     flags = o; o += Align256(b * 4);
     t_done = o; o += Align256(b * 4);                            // streaming: frames consumed so far
@@ -143,6 +144,11 @@ struct DecodeOpts {
   long long tstride = 0;           // elements between frames; 0 = batch * num_classes
   const int* ready = nullptr;      // device word "frames landed" (narrow path only), or null
   const void* lm = nullptr;        // scorer table (float32 decodes)
+  // wide path, host feed: the logits arrive in n_slabs time slabs, slab k = frames [slab_end[k-1], slab_end[k]),
+  // complete once slab_event[k] has fired; the decode then runs slab by slab behind the copies
+  int n_slabs = 0;
+  const int* slab_end = nullptr;
+  const cudaEvent_t* slab_event = nullptr;
 };
 
 int ReportSizes(const long long* h_sizes, const int* h_stats, int B, int T, int P, ctcx_sizes* sizes,
@@ -277,7 +283,7 @@ int DecodeImpl(const void* logits_dev, int T, int B, int C, const int32_t* seq_l
         CTCX_CUDA(cudaMemsetAsync(bp.progress, 0, (size_t)B * 4, stream));
         ProfRecord(1, stream);
         CTCX_LAUNCH(ctcx::LaunchBeamNarrow(bp, in_dtype, stream));
-      } else if (path == kPathWide) {
+      } else if (path == kPathWide && opt.n_slabs == 0) {
         // wide vocabulary: normaliser and candidate classes in one pass over the logits
         bp.srt_pl = (const float*)(base + ws.srt_pl);
         bp.srt_cls = (const unsigned short*)(base + ws.srt_cls);
@@ -286,6 +292,36 @@ int DecodeImpl(const void* logits_dev, int T, int B, int C, const int32_t* seq_l
                                                (unsigned short*)(base + ws.srt_cls), B, tstride, stream));
         ProfRecord(1, stream);
         CTCX_LAUNCH(ctcx::LaunchBeamWide(bp, in_dtype, stream));
+      } else if (path == kPathWide && opt.n_slabs > 0) {
+        // Host feed of a wide-vocabulary batch: the copy (hundreds of MB) takes longer than the decode, so
+        // the decode runs time chunk by time chunk behind it -- plain stream order, one event per slab. The
+        // beam crosses chunks through the per-utterance state block, exactly as in a streamed decode
+        // (ctcx_stream_step_f32); the class-selection arrays are chunk-relative and stay in L2.
+        const size_t es = (in_dtype == ctcx::kInF32) ? 4 : 2;
+        int* d_chunk_len = (int*)(base + ws.chunk_len);
+        bp.srt_pl = (const float*)(base + ws.srt_pl);
+        bp.srt_cls = (const unsigned short*)(base + ws.srt_cls);
+        bp.seq_len = d_chunk_len;
+        bp.t_done = (int*)(base + ws.t_done);
+        bp.state = base + ws.state;
+        CTCX_CUDA(cudaMemsetAsync(bp.t_done, 0, (size_t)B * 4, stream));
+        ProfRecord(1, stream);
+        int t0 = 0;
+        for (int k = 0; k < opt.n_slabs; ++k) {
+          const int len = opt.slab_end[k] - t0;
+          const unsigned char* chunk = (const unsigned char*)logits_dev + (size_t)t0 * (size_t)tstride * es;
+          CTCX_CUDA(cudaStreamWaitEvent(stream, opt.slab_event[k], 0));
+          CTCX_LAUNCH(ctcx::LaunchChunkLen(seq_len_dev, B, T, t0, len, d_chunk_len, stream));
+          CTCX_LAUNCH(ctcx::LaunchNormTopClasses(chunk, in_dtype, (float*)(base + ws.off), (long long)len * B, C,
+                                                 blank_index, W, (float*)(base + ws.srt_pl),
+                                                 (unsigned short*)(base + ws.srt_cls), B, tstride, stream));
+          bp.logits = (const float*)chunk;
+          bp.T = len;
+          bp.slice_frames = len;
+          CTCX_LAUNCH(ctcx::LaunchBeamWide(bp, in_dtype, stream));
+          t0 = opt.slab_end[k];
+        }
+        bp.seq_len = seq_len_dev;
       } else {
         CTCX_LAUNCH(ctcx::LaunchLogNorm(bp.logits, (float*)(base + ws.off), (long long)T * B, C, B, bp.tstride, stream));
         ProfRecord(1, stream);
@@ -414,14 +450,18 @@ struct Feed {
   int* d_ready;               // device word: frames landed
   bool flags;                 // publish progress per slab (the narrow kernel consumes it)
   cudaStream_t copy_stream;
+  // explicit slab schedule (wide path): n_slabs slabs ending at frame slab_end[k], an event after each
+  int n_slabs = 0;
+  const int* slab_end = nullptr;
+  const cudaEvent_t* slab_event = nullptr;
 };
 int RunFeed(void* arg) {
   Feed& f = *(Feed*)arg;
   // Slabs grow geometrically (6, 12, 24, ... 192 frames): the first frames land after a few microseconds so
   // the beam kernel can start, the bulk moves in large copies.
-  int t0 = 0, n = f.flags ? 6 : f.T;
+  int t0 = 0, n = f.flags ? 6 : f.T, k = 0;
   while (t0 < f.T) {
-    const int t1 = std::min(f.T, t0 + n);
+    const int t1 = (f.n_slabs > 0) ? f.slab_end[k] : std::min(f.T, t0 + n);
     cudaError_t e;
     if (f.src_pitch == f.row_bytes)
       e = cudaMemcpyAsync(f.dst + (size_t)t0 * f.row_bytes, f.src + (size_t)t0 * f.src_pitch,
@@ -434,12 +474,14 @@ int RunFeed(void* arg) {
       std::snprintf(g_cuda_err, sizeof(g_cuda_err), "cuStreamWriteValue32 failed");
       ok = false;
     }
+    if (ok && f.n_slabs > 0) ok = Check(cudaEventRecord(f.slab_event[k], f.copy_stream), "cudaEventRecord");
     if (!ok) {
       // release the kernel: it must not wait for frames that will never come
       if (f.flags) StreamWriteValue32()(f.copy_stream, (unsigned long long)(uintptr_t)f.d_ready, (unsigned)INT_MAX, 0);
       return CTCX_ERR_CUDA;
     }
     t0 = t1;
+    ++k;
     n = std::min(192, n * 2);  // doubling: a slab lands before the previous one is consumed at any copy rate >= 2x the kernel's
   }
   return CTCX_OK;
@@ -613,6 +655,26 @@ int ctcx_decode_hostin(const void* logits_host, int dtype, int64_t host_time_str
   int rc = CTCX_OK;
   DecodeOpts opt;
   opt.in_dtype = InDtypeOf(dtype);
+  // wide vocabularies: the copy is the longer leg; the decode follows it slab by slab (events, no polling)
+  constexpr int kMaxSlabs = 8, kMinSlabFrames = 16;
+  int slab_end[kMaxSlabs];
+  cudaEvent_t slab_event[kMaxSlabs] = {};
+  int n_slabs = 0;
+  if (B > 0 && dtype != CTCX_F64 && PathOf(W, C, false) == kPathWide && P <= W && IsPinned(logits_host) &&
+      T >= 2 * kMinSlabFrames) {
+    n_slabs = std::min(kMaxSlabs, T / kMinSlabFrames);
+    for (int k = 0; k < n_slabs; ++k) slab_end[k] = (int)(((long long)T * (k + 1)) / n_slabs);
+    for (int k = 0; k < n_slabs && rc == CTCX_OK; ++k)
+      if (!Check(cudaEventCreateWithFlags(&slab_event[k], cudaEventDisableTiming), "cudaEventCreate")) rc = CTCX_ERR_CUDA;
+    if (rc != CTCX_OK) {
+      for (int k = 0; k < n_slabs; ++k)
+        if (slab_event[k]) cudaEventDestroy(slab_event[k]);
+      return rc;
+    }
+    feed.n_slabs = opt.n_slabs = n_slabs;
+    feed.slab_end = opt.slab_end = slab_end;
+    feed.slab_event = opt.slab_event = slab_event;
+  }
   if (B > 0) {
     CTCX_CUDA(cudaMemcpyAsync(d_seq, seq_len_host, (size_t)B * 4, cudaMemcpyHostToDevice, stream));
     CTCX_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -629,10 +691,11 @@ int ctcx_decode_hostin(const void* logits_host, int dtype, int64_t host_time_str
       rc = RunFeed(&feed);
     } else {
       // copy first (on the copy stream, so that it can still overlap other work of the caller), then decode
+      // (wide path: slab by slab -- the decode waits for each slab's own event as well)
       CTCX_CUDA(cudaEventRecord(ev, stream));
       CTCX_CUDA(cudaStreamWaitEvent(copy_stream, ev, 0));
       rc = RunFeed(&feed);
-      if (rc == CTCX_OK) {
+      if (rc == CTCX_OK && n_slabs == 0) {
         if (!Check(cudaEventRecord(ev, copy_stream), "cudaEventRecord") ||
             !Check(cudaStreamWaitEvent(stream, ev, 0), "cudaStreamWaitEvent"))
           rc = CTCX_ERR_CUDA;
@@ -651,6 +714,7 @@ int ctcx_decode_hostin(const void* logits_host, int dtype, int64_t host_time_str
     if (rc != CTCX_OK) cudaStreamSynchronize(copy_stream);  // nothing of this call stays in flight after an error
     cudaEventDestroy(ev);
   }
+  for (int k = 0; k < n_slabs; ++k) cudaEventDestroy(slab_event[k]);  // (deferred by the runtime until they have fired)
   return rc;
 }
 

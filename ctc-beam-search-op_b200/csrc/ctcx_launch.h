@@ -65,6 +65,8 @@ LaunchStatus LaunchTraceScanFlags(const TraceParams& tp, int rec_bytes, const Sc
 LaunchStatus LaunchFlagsOnly(const int* seq_len, int B, int T, int* stats, cudaStream_t stream);
 LaunchStatus LaunchPack(const PackParams& pp, cudaStream_t stream);
 LaunchStatus LaunchPositive(const float* v, long long n, int* flag, cudaStream_t stream);
+// out[b] = frames of utterance b inside the time chunk [t0, t0 + len) (lengths clamped to [0, T])
+LaunchStatus LaunchChunkLen(const int* seq_len, int B, int T, int t0, int len, int* out, cudaStream_t stream);
 LaunchStatus LaunchMathTest(int op, const float* x, float* y, int n, cudaStream_t stream);
 LaunchStatus LaunchMathTest(int op, const double* x, double* y, int n, cudaStream_t stream);
 

@@ -31,6 +31,12 @@ __global__ void PositiveKernel(const float* v, long long n, int* flag) {
     if (!(v[i] <= 0.0f)) *flag = 1;
 }
 
+// frames of utterance b inside the time chunk [t0, t0 + len) of a decode that is run chunk by chunk
+__global__ void ChunkLenKernel(const int* seq_len, int B, int T, int t0, int len, int* out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) out[b] = min(max(min(max(seq_len[b], 0), T) - t0, 0), len);
+}
+
 template <typename REC>
 LaunchStatus LaunchTrace(const TraceParams& tp, cudaStream_t stream) {
   const int W = tp.W;
@@ -78,6 +84,11 @@ LaunchStatus LaunchPack(const PackParams& pp, cudaStream_t stream) {
   dim3 grid((unsigned)pp.B, (unsigned)pp.P);
   PackKernel<<<grid, 128, 0, stream>>>(pp);
   return LaunchFrom(cudaGetLastError(), "PackKernel launch");
+}
+
+LaunchStatus LaunchChunkLen(const int* seq_len, int B, int T, int t0, int len, int* out, cudaStream_t stream) {
+  ChunkLenKernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(seq_len, B, T, t0, len, out);
+  return LaunchFrom(cudaGetLastError(), "ChunkLenKernel launch");
 }
 
 LaunchStatus LaunchPositive(const float* v, long long n, int* flag, cudaStream_t stream) {

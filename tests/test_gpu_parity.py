@@ -780,6 +780,40 @@ def test_side_stream_and_non_contiguous_inputs(op):
 
 # ------------------------------------------------------------------------------------------------
 # Round 2: host-input decode with the copy overlapped, views decoded in place, flags in the result
+@pytest.mark.parametrize("dt", ["float32", "bfloat16"])
+def test_pinned_host_logits_of_a_wide_vocabulary_are_decoded_slab_by_slab(op, dt):
+    """Wide vocabularies from page-locked host memory: the copy is cut into time slabs and the decode
+    follows it chunk by chunk (one event per slab; the beam crosses chunks through the state block).
+    Ragged lengths -- utterances that end inside the first slab, at a slab boundary, empty ones -- and
+    top_paths > 1 must give the oracle's result, as the one-shot decode of the device copy does."""
+    import torch
+    T, B, C, W, P, blank = 130, 9, 300, 16, 3, 299
+    x32 = L.make_logits("peaky", T, B, C, blank, 61)
+    xh = torch.from_numpy(x32).to(getattr(torch, dt)).pin_memory()
+    up = xh.to(torch.float32).numpy()
+    sl = np.array([130, 1, 5, 16, 17, 65, 129, 32, 100], np.int32)
+    want = L.oracle_decode(up, sl, W, P, False, blank, -1)
+    for _ in range(2):
+        raw = op.ctc_ext_beam_search_decoder_raw(xh, sl, beam_width=W, top_paths=P, blank_index=blank)
+        assert not raw[6].is_cuda
+        assert not L.raw_mismatches(raw, want)
+    # empty utterances (one leaf: top_paths 1), merge_repeated
+    sl0 = np.array([0, 130, 0, 48, 49, 0, 2, 97, 0], np.int32)
+    raw0 = op.ctc_ext_beam_search_decoder_raw(xh, sl0, beam_width=W, top_paths=1, merge_repeated=True, blank_index=blank)
+    assert not L.raw_mismatches(raw0, L.oracle_decode(up, sl0, W, 1, True, blank, -1))
+    dev = op.ctc_ext_beam_search_decoder_raw(xh.cuda(), torch.from_numpy(sl).cuda(), beam_width=W, top_paths=P,
+                                             blank_index=blank)
+    assert not L.raw_mismatches(dev, want)
+    # a batch shard of the pinned tensor (pitched slab copies)
+    part = op.ctc_ext_beam_search_decoder_raw(xh[:, 2:8, :], sl[2:8], beam_width=W, top_paths=P, blank_index=blank)
+    assert not L.raw_mismatches(part, L.oracle_decode(np.ascontiguousarray(up[:, 2:8]), sl[2:8], W, P, False, blank, -1))
+    # an out-of-range length is still reported as the reference reports it
+    bad = sl.copy()
+    bad[4] = T + 1
+    with pytest.raises(op.CtcxError, match=r"sequence_length\(4\) <= %d" % T):
+        op.ctc_ext_beam_search_decoder_raw(xh, bad, beam_width=W, top_paths=P, blank_index=blank)
+
+
 @pytest.mark.parametrize("dt", ["float32", "float16", "bfloat16", "float64"])
 def test_pinned_host_logits_are_fed_while_the_kernel_runs(op, dt):
     """ctcx_decode_hostin: page-locked host logits are copied in time slabs on a side stream while the
