@@ -112,8 +112,9 @@ int ctcx_decode_view(const void* logits_dev, int dtype, int64_t time_stride, int
  * contiguous; pinned memory copies asynchronously, pageable memory works too), seq_len_host [batch]
  * int32 in host memory. The logits are copied into staging_dev (device memory, at least
  * ctcx_hostin_staging_bytes(...) bytes) in time slabs on `copy_stream` while, for the char-CTC shapes
- * (num_classes <= 32), the beam kernel on `stream` already consumes the frames that have landed; other
- * shapes start after the copy. copy_stream must be a different stream from `stream`. The decode result
+ * (num_classes <= 32), the beam kernel on `stream` already consumes the frames that have landed; for
+ * wide vocabularies (the wide fast path) the decode follows the copy slab by slab in stream order; other
+ * shapes, and pageable sources, start after the copy. copy_stream must be a different stream from `stream`. The decode result
  * is left in the workspace exactly as by ctcx_decode_f32 (follow with ctcx_pack_f32 / _f64).
  * Synchronises `stream` once. */
 size_t ctcx_hostin_staging_bytes(int dtype, int max_time, int batch, int num_classes);
