@@ -7,7 +7,7 @@ best alignment of every returned path). See DESIGN.md / INTEGRATION.md at the re
         inputs, sequence_length, beam_width=100, top_paths=1, merge_repeated=True,
         blank_index=28, blank_label=-1)
 """
-from .decoder import (CTCExtBeamSearchDecoder, CTCExtBeamSearchDecoderStream, CtcxError, DecodeResult,  # noqa: F401
+from .decoder import (PendingDecode, CTCExtBeamSearchDecoder, CTCExtBeamSearchDecoderStream, CtcxError, DecodeResult,  # noqa: F401
                       FailedPreconditionError, FLAG_ROUNDING_ANOMALY, set_beam_impl,
                       InvalidArgumentError, SparseTensor, UnsupportedError,
                       ctc_ext_beam_search_decoder, ctc_ext_beam_search_decoder_raw,
@@ -16,6 +16,6 @@ from .decoder import (CTCExtBeamSearchDecoder, CTCExtBeamSearchDecoderStream, Ct
 from . import torch_op  # noqa: F401,E402  (registers torch.ops.ctcx.ctc_ext_beam_search_decoder)
 from .sharding import bind_host_to_device, decode_distributed, decode_multi_device, merge_raw, shard_bounds  # noqa: F401,E402
 
-__all__ = ["CTCExtBeamSearchDecoderStream", "DecodeResult", "FLAG_ROUNDING_ANOMALY", "set_beam_impl", "decode_multi_device", "decode_distributed", "bind_host_to_device", "shard_bounds", "merge_raw","ctc_ext_beam_search_decoder", "ctc_ext_beam_search_decoder_raw", "decode_host_cabi",
+__all__ = ["PendingDecode", "CTCExtBeamSearchDecoderStream", "DecodeResult", "FLAG_ROUNDING_ANOMALY", "set_beam_impl", "decode_multi_device", "decode_distributed", "bind_host_to_device", "shard_bounds", "merge_raw","ctc_ext_beam_search_decoder", "ctc_ext_beam_search_decoder_raw", "decode_host_cabi",
            "SparseTensor", "CTCExtBeamSearchDecoder", "CtcxError", "InvalidArgumentError",
            "FailedPreconditionError", "UnsupportedError"]

@@ -32,7 +32,7 @@ class CtcxHostResult(ctypes.Structure):
 EXPORTS = ("ctcx_strerror", "ctcx_last_cuda_error", "ctcx_error_batch_index", "ctcx_get_limits",
            "ctcx_workspace_bytes", "ctcx_decode_f32", "ctcx_decode_f64", "ctcx_decode_scorer_f32",
            "ctcx_decode_half", "ctcx_decode_view", "ctcx_hostin_staging_bytes", "ctcx_decode_hostin",
-           "ctcx_pack_f32", "ctcx_pack_f64", "ctcx_decode_host_f32", "ctcx_decode_host_f64", "ctcx_free_host",
+           "ctcx_pack_f32", "ctcx_pack_f64", "ctcx_pack_compact", "ctcx_finish", "ctcx_result_bytes", "ctcx_result_copy_async", "ctcx_result_parse", "ctcx_decode_host_f32", "ctcx_decode_host_f64", "ctcx_free_host",
            "ctcx_stream_workspace_bytes", "ctcx_stream_reset", "ctcx_stream_step_f32", "ctcx_stream_top_paths",
            # measurement and test hooks
            "ctcx_workspace_views", "ctcx_profile_enable", "ctcx_profile_get", "ctcx_debug_set_cycles_buffer",
@@ -91,6 +91,12 @@ def load():
     lib.ctcx_debug_set_beam_impl.restype = None
     lib.ctcx_pack_f32.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [_vp] * 6 + [_vp, _vp]
     lib.ctcx_pack_f64.argtypes = lib.ctcx_pack_f32.argtypes
+    lib.ctcx_pack_compact.argtypes = [_vp, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]
+    lib.ctcx_finish.argtypes = [_vp, _i, _i, _i, _vp, ctypes.POINTER(CtcxSizes), ctypes.POINTER(ctypes.c_int32)]
+    lib.ctcx_result_bytes.restype = ctypes.c_size_t
+    lib.ctcx_result_bytes.argtypes = [_i]
+    lib.ctcx_result_copy_async.argtypes = [_vp, _i, _i, _i, _vp, ctypes.c_size_t, _vp]
+    lib.ctcx_result_parse.argtypes = [_vp, _i, _i, _i, ctypes.POINTER(CtcxSizes), ctypes.POINTER(ctypes.c_int32)]
     lib.ctcx_decode_host_f32.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_int,

@@ -91,7 +91,7 @@ struct Workspace {
     ali_len = o; o += Align256(b * pp * 4);
     dec_off = o; o += Align256(pp * b * 8);
     ali_off = o; o += Align256(pp * b * 8);
-    ptrs = o; o += Align256(6 * pp * 8);
+    ptrs = o; o += Align256((6 * pp + 1) * 8);                  // output pointer table (+ log_probability for the compact pack)
     fin_total = o; o += Align256(b * pp * 8);                    // float or double
     fin_kind = o; o += Align256(b * pp * 4);
     dec = o; o += Align256(b * pp * t * 4);
@@ -191,6 +191,32 @@ struct InitBlock {
   }
 };
 
+size_t ResultBytes(int P) { return 4 * (size_t)P * 8 + kNStats * 4; }
+
+// per-kernel times of the LAST decode this thread enqueued (ctcx_profile_enable), once it has completed
+void CollectProfile(int B) {
+  if (!g_profile || B <= 0 || !g_ev_ready || cudaEventQuery(g_ev[4]) != cudaSuccess) return;
+  for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&g_ms[k], g_ev[k], g_ev[k + 1]);
+  cudaEventElapsedTime(&g_ms[4], g_ev[0], g_ev[4]);
+}
+
+// the result block (sizes [4,P] + status words) as it arrived on the host -> sizes, flags, return code
+int ParseResult(const unsigned char* h_res, int T, int B, int P, ctcx_sizes* sizes, int32_t* flags_out) {
+  const int* h_stats = (const int*)(h_res + 4 * (size_t)P * 8);
+  if (h_stats[6] != 0) return CTCX_ERR_WORKSPACE;  // ctcx_pack_compact: the caller's buffer was too small
+  return ReportSizes((const long long*)h_res, h_stats, B, T, P, sizes, flags_out);
+}
+
+// ONE copy brings the sparse sizes and the status words to the host; the only synchronisation of a decode
+int FinishImpl(const unsigned char* d_result, int T, int B, int P, cudaStream_t stream, ctcx_sizes* sizes,
+               int32_t* flags_out) {
+  std::vector<unsigned char> h_res(ResultBytes(P));
+  CTCX_CUDA(cudaMemcpyAsync(h_res.data(), d_result, h_res.size(), cudaMemcpyDeviceToHost, stream));
+  CTCX_CUDA(cudaStreamSynchronize(stream));
+  CollectProfile(B);
+  return ParseResult(h_res.data(), T, B, P, sizes, flags_out);
+}
+
 template <typename R>
 int DecodeImpl(const void* logits_dev, int T, int B, int C, const int32_t* seq_len_dev, int W,
                int P, int merge_repeated, int blank_index, int blank_label, void* workspace,
@@ -203,7 +229,7 @@ int DecodeImpl(const void* logits_dev, int T, int B, int C, const int32_t* seq_l
   if (T < 0 || B < 0 || C <= 0 || W < 1 || P < 1 || blank_index < 0 || blank_index >= C)
     return CTCX_ERR_BAD_ARGUMENT;
   if (W > kMaxBeamWidth || C > kMaxClasses) return CTCX_ERR_UNSUPPORTED;
-  if (sizes == nullptr) return CTCX_ERR_BAD_ARGUMENT;
+  const bool defer = (sizes == nullptr);  // enqueue only: ctcx_finish() brings the sizes and the status later
   const long long tstride = opt.tstride ? opt.tstride : (long long)B * C;
   if (tstride < (long long)B * C) return CTCX_ERR_BAD_ARGUMENT;
   Workspace ws;
@@ -355,16 +381,8 @@ int DecodeImpl(const void* logits_dev, int T, int B, int C, const int32_t* seq_l
     ProfRecord(4, stream);
   }
 
-  // ONE copy brings the sparse sizes and the status words to the host
-  std::vector<unsigned char> h_res(4 * (size_t)P * 8 + kNStats * 4);
-  CTCX_CUDA(cudaMemcpyAsync(h_res.data(), base + ws.result, h_res.size(), cudaMemcpyDeviceToHost, stream));
-  CTCX_CUDA(cudaStreamSynchronize(stream));
-  if (g_profile && B > 0) {
-    for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&g_ms[k], g_ev[k], g_ev[k + 1]);
-    cudaEventElapsedTime(&g_ms[4], g_ev[0], g_ev[4]);
-  }
-  return ReportSizes((const long long*)h_res.data(), (const int*)(h_res.data() + 4 * (size_t)P * 8), B, T, P, sizes,
-                     flags_out);
+  if (defer) return CTCX_OK;
+  return FinishImpl(base + ws.result, T, B, P, stream, sizes, flags_out);
 }
 
 int PackImpl(const void* workspace, int T, int B, int P, int64_t* const* decoded_indices,
@@ -399,6 +417,7 @@ int PackImpl(const void* workspace, int T, int B, int P, int64_t* const* decoded
     pp.fin_total = (const void*)(base + ws.fin_total);
     pp.ptrs = (long long* const*)(base + ws.ptrs);
     pp.log_prob = log_probability;
+    pp.skip = nullptr;
     pp.real_bytes = real_bytes;
     pp.T = T; pp.B = B; pp.P = P;
     CTCX_LAUNCH(ctcx::LaunchPack(pp, stream));
@@ -724,6 +743,66 @@ int ctcx_pack_f32(const void* workspace, int T, int B, int P, int64_t* const* de
                   int64_t* const* alignment_shape, float* log_probability, void* stream_v) {
   return PackImpl(workspace, T, B, P, decoded_indices, decoded_values, decoded_shape, alignment_indices,
                   alignment_values, alignment_shape, log_probability, 4, stream_v);
+}
+
+/* Compact pack: every output of the decode into ONE caller buffer, laid out on the device (see
+ * PackTableKernel), enqueued without knowing the sizes on the host. */
+int ctcx_pack_compact(void* workspace, int T, int B, int P, int real_bytes, int64_t* packed_dev,
+                      size_t packed_elems, void* stream_v) {
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  if (workspace == nullptr || T <= 0 || B < 1 || P < 1 || ((uintptr_t)workspace & 255u)) return CTCX_ERR_WORKSPACE;
+  if (packed_dev == nullptr || (real_bytes != 4 && real_bytes != 8)) return CTCX_ERR_BAD_ARGUMENT;
+  unsigned char* base = (unsigned char*)workspace;
+  Workspace ws;
+  ws.InitPack(T, B, P);
+  int* d_stats = (int*)(base + ws.result + 4 * (size_t)P * 8);
+  CTCX_LAUNCH(ctcx::LaunchPackTable((const long long*)(base + ws.result), B, P, real_bytes, (long long*)packed_dev,
+                                    (unsigned long long)packed_elems, (long long**)(base + ws.ptrs), d_stats + 6, stream));
+  ctcx::PackParams pp;
+  pp.dec_len = (const int*)(base + ws.dec_len); pp.dec = (const int*)(base + ws.dec);
+  pp.ali_len = (const int*)(base + ws.ali_len); pp.ali = (const int*)(base + ws.ali);
+  pp.dec_off = (const long long*)(base + ws.dec_off); pp.ali_off = (const long long*)(base + ws.ali_off);
+  pp.sizes = (const long long*)(base + ws.result);
+  pp.fin_total = (const void*)(base + ws.fin_total);
+  pp.ptrs = (long long* const*)(base + ws.ptrs);
+  pp.log_prob = nullptr;
+  pp.skip = d_stats + 6;
+  pp.real_bytes = real_bytes;
+  pp.T = T; pp.B = B; pp.P = P;
+  CTCX_LAUNCH(ctcx::LaunchPack(pp, stream));
+  return CTCX_OK;
+}
+
+/* Completes a decode that was enqueued with sizes == NULL: one device->host copy of the sizes and the
+ * status words, one synchronisation of `stream`, the reference's error checks. */
+int ctcx_finish(const void* workspace, int T, int B, int P, void* stream_v, ctcx_sizes* sizes, int32_t* flags_out) {
+  if (workspace == nullptr || sizes == nullptr || T <= 0 || B < 0 || P < 1 || ((uintptr_t)workspace & 255u))
+    return CTCX_ERR_WORKSPACE;
+  Workspace ws;
+  ws.InitPack(T, B, P);
+  return FinishImpl((const unsigned char*)workspace + ws.result, T, B, P, (cudaStream_t)stream_v, sizes, flags_out);
+}
+
+/* The two halves of ctcx_finish for callers that keep several decodes in flight on one stream: enqueue the
+ * copy of the result block into (page-locked) host memory right behind the decode, wait for an event of
+ * their own recorded there, then parse the block on the host. */
+size_t ctcx_result_bytes(int top_paths) { return top_paths > 0 ? ResultBytes(top_paths) : 0; }
+
+int ctcx_result_copy_async(const void* workspace, int T, int B, int P, void* result_host, size_t result_bytes,
+                           void* stream_v) {
+  if (workspace == nullptr || T <= 0 || B < 0 || P < 1 || ((uintptr_t)workspace & 255u)) return CTCX_ERR_WORKSPACE;
+  if (result_host == nullptr || result_bytes < ResultBytes(P)) return CTCX_ERR_BAD_ARGUMENT;
+  Workspace ws;
+  ws.InitPack(T, B, P);
+  CTCX_CUDA(cudaMemcpyAsync(result_host, (const unsigned char*)workspace + ws.result, ResultBytes(P),
+                            cudaMemcpyDeviceToHost, (cudaStream_t)stream_v));
+  return CTCX_OK;
+}
+
+int ctcx_result_parse(const void* result_host, int T, int B, int P, ctcx_sizes* sizes, int32_t* flags_out) {
+  if (result_host == nullptr || sizes == nullptr || T <= 0 || B < 0 || P < 1) return CTCX_ERR_BAD_ARGUMENT;
+  CollectProfile(B);
+  return ParseResult((const unsigned char*)result_host, T, B, P, sizes, flags_out);
 }
 
 int ctcx_pack_f64(const void* workspace, int T, int B, int P, int64_t* const* decoded_indices,

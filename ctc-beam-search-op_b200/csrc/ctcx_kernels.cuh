@@ -1346,7 +1346,30 @@ static __global__ void __launch_bounds__(1024) ScanKernel(ScanParams p) {
 }
 
 
+// Pointer table of the COMPACT output layout: all outputs of a decode as consecutive slices of one
+// int64 buffer -- per path: decoded indices [n,2], values [n], shape [2], alignment indices, values,
+// shape; then log_probability [B,P] (float32 pairs or float64 in int64 slots) -- computed on the device
+// from the sizes the scan left there, so that the pack can be enqueued before the host knows them.
+static __global__ void PackTableKernel(const long long* sizes, int B, int P, int real_bytes, long long* buf,
+                                       unsigned long long buf_elems, long long** ptrs, int* overflow) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  unsigned long long o = 0;
+  for (int p = 0; p < P; ++p) {
+    const unsigned long long nd = (unsigned long long)sizes[0 * P + p], na = (unsigned long long)sizes[2 * P + p];
+    ptrs[0 * P + p] = buf + o; o += 2 * nd;
+    ptrs[1 * P + p] = buf + o; o += nd;
+    ptrs[2 * P + p] = buf + o; o += 2;
+    ptrs[3 * P + p] = buf + o; o += 2 * na;
+    ptrs[4 * P + p] = buf + o; o += na;
+    ptrs[5 * P + p] = buf + o; o += 2;
+  }
+  ptrs[6 * P] = buf + o;
+  o += (real_bytes == 8) ? (unsigned long long)B * P : ((unsigned long long)B * P + 1) / 2;
+  if (o > buf_elems) *overflow = 1;
+}
+
 static __global__ void __launch_bounds__(128) PackKernel(PackParams p) {
+  if (p.skip != nullptr && *p.skip != 0) return;
   const int b = blockIdx.x, path = blockIdx.y;
   const size_t row = (size_t)b * p.P + path;
   {
@@ -1374,10 +1397,11 @@ static __global__ void __launch_bounds__(128) PackKernel(PackParams p) {
     }
   }
   if (threadIdx.x == 0) {
+    void* lp = (p.log_prob != nullptr) ? p.log_prob : (void*)p.ptrs[6 * p.P];
     if (p.real_bytes == 8)  // kernels.cc:87-89
-      ((double*)p.log_prob)[row] = ((const double*)p.fin_total)[row];
+      ((double*)lp)[row] = ((const double*)p.fin_total)[row];
     else
-      ((float*)p.log_prob)[row] = ((const float*)p.fin_total)[row];
+      ((float*)lp)[row] = ((const float*)p.fin_total)[row];
     if (b == 0) {
       long long* ds = p.ptrs[2 * p.P + path];
       long long* as = p.ptrs[5 * p.P + path];

@@ -64,6 +64,9 @@ LaunchStatus LaunchTraceScanFlags(const TraceParams& tp, int rec_bytes, const Sc
                                   int* stats, cudaStream_t stream, cudaEvent_t after_trace);
 LaunchStatus LaunchFlagsOnly(const int* seq_len, int B, int T, int* stats, cudaStream_t stream);
 LaunchStatus LaunchPack(const PackParams& pp, cudaStream_t stream);
+// pointer table of the compact one-buffer output layout, from the sizes on the device (PackTableKernel)
+LaunchStatus LaunchPackTable(const long long* sizes, int B, int P, int real_bytes, long long* buf,
+                             unsigned long long buf_elems, long long** ptrs, int* overflow, cudaStream_t stream);
 LaunchStatus LaunchPositive(const float* v, long long n, int* flag, cudaStream_t stream);
 // out[b] = frames of utterance b inside the time chunk [t0, t0 + len) (lengths clamped to [0, T])
 LaunchStatus LaunchChunkLen(const int* seq_len, int B, int T, int t0, int len, int* out, cudaStream_t stream);

@@ -110,7 +110,9 @@ struct PackParams {
   const long long* sizes;                                                   // [4,P]
   const void* fin_total;                                                    // [B,P] float or double
   long long* const* ptrs;  // device table [6,P]: dec_idx, dec_val, dec_shape, ali_idx, ali_val, ali_shape
+                           // (+ entry 6*P: log_probability, used when log_prob is null -- compact pack)
   void* log_prob;          // [B,P] float or double
+  const int* skip;         // optional device word: non-zero = the table is invalid, write nothing
   int real_bytes;          // 4 or 8
   int T, B, P;
 };

@@ -86,6 +86,12 @@ LaunchStatus LaunchPack(const PackParams& pp, cudaStream_t stream) {
   return LaunchFrom(cudaGetLastError(), "PackKernel launch");
 }
 
+LaunchStatus LaunchPackTable(const long long* sizes, int B, int P, int real_bytes, long long* buf,
+                             unsigned long long buf_elems, long long** ptrs, int* overflow, cudaStream_t stream) {
+  PackTableKernel<<<1, 32, 0, stream>>>(sizes, B, P, real_bytes, buf, buf_elems, ptrs, overflow);
+  return LaunchFrom(cudaGetLastError(), "PackTableKernel launch");
+}
+
 LaunchStatus LaunchChunkLen(const int* seq_len, int B, int T, int t0, int len, int* out, cudaStream_t stream) {
   ChunkLenKernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(seq_len, B, T, t0, len, out);
   return LaunchFrom(cudaGetLastError(), "ChunkLenKernel launch");

@@ -33,6 +33,7 @@ class CTCExtBeamSearchDecoder(_RawBase):
     """The raw op's 7 output groups (indexable [0..6] like the generated TF wrapper). `.flags` carries
     this decode's diagnostic bits (FLAG_ROUNDING_ANOMALY) -- an attribute, not an eighth output."""
     flags = 0
+    d2h_bytes = 0
 
 
 class DecodeResult(tuple):
@@ -166,6 +167,24 @@ def _pack(lib, ws, T, B, P, counts, device, stream, f64=False, host_out=False):
     return groups, logp, buf
 
 
+# Results up to this size take the deferred route (decode and pack enqueued back to back into a buffer
+# sized from an upper bound, ONE synchronisation at the end); larger ones the two-phase route (sizes
+# first, then exactly sized outputs), whose extra host round trip no longer matters at that scale and
+# which never holds or copies more than the exact result.
+DEFER_MAX_BYTES_DEVICE = 64 << 20
+DEFER_MAX_BYTES_HOST = 8 << 20
+
+
+def _bound_elems(T, B, P, seq, f64):
+    """Upper bound on the int64 slots of the compact output layout: a path's decoded sequence is never
+    longer than its alignment, an alignment has exactly sequence_length entries."""
+    if seq.is_cuda:
+        frames = B * T
+    else:
+        frames = int(seq.to(torch.int64).clamp(0, T).sum())
+    return P * (6 * frames + 4) + (B * P if f64 else (B * P + 1) // 2)
+
+
 def _frame_strided(x):
     """True if x[t, b, c] sits at t * stride + b * C + c, i.e. x is a contiguous tensor or a batch
     shard [:, b0:b1, :] of one -- what the kernels decode in place (ctcx_decode_view)."""
@@ -177,7 +196,7 @@ def _frame_strided(x):
 def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_paths,
                                     merge_repeated=False, blank_index=0, blank_label=-1,
                                     name=None, device=None, expansion_scores=None, batch_offset=0,
-                                    outputs="auto"):
+                                    outputs="auto", wait=True):
     """The raw op: returns a 7-field namedtuple of (lists of) tensors, exactly the op's outputs.
 
     inputs            [max_time, batch, num_classes] float32 or float64 (the reference registers both,
@@ -198,6 +217,8 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
     batch_offset      index of utterance 0 in the caller's whole batch (error messages of a shard)
     outputs           "auto": outputs live where the inputs live (numpy in -> numpy out); "device" /
                       "host" force the placement (torch tensors)
+    wait              False: return a PendingDecode right after the work has been enqueued on the
+                      current stream; its .result() synchronises and returns the outputs
     `.flags` = diagnostic bits; `.packed` = the one int64 buffer all outputs are views of.
     """
     del name
@@ -258,6 +279,12 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
         n_dec, max_dec, n_ali, max_ali = arr(), arr(), arr(), arr()
         sizes = _lib.CtcxSizes(n_dec, max_dec, n_ali, max_ali)
         flags = ctypes.c_int32(0)
+        host_out = host_in if outputs == "auto" else (outputs == "host")
+        n_bound = _bound_elems(T, B, P, seq, f64) if (B > 0 and expansion_scores is None and P <= W) else 0
+        deferred = 0 < 8 * n_bound <= (DEFER_MAX_BYTES_HOST if host_out else DEFER_MAX_BYTES_DEVICE)
+        sizes_arg = None if deferred else ctypes.byref(sizes)
+        flags_arg = None if deferred else ctypes.byref(flags)
+        xd = sd = sh = staging = esd = None  # device / staging copies made below (kept alive while in flight)
         if host_in and expansion_scores is None:
             # host logits: copied in time slabs on a side stream while the beam kernel already runs
             sh = seq.to(dtype=torch.int32).contiguous()
@@ -266,14 +293,14 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
             side = _copy_stream(device)
             rc = lib.ctcx_decode_hostin(x.data_ptr(), _DTYPE_CODE[x.dtype], tstride, T, B, C, sh.data_ptr(),
                                         *attrs, staging.data_ptr(), n_stage, ws.data_ptr(), ws_bytes, stream,
-                                        side.cuda_stream, ctypes.byref(sizes), ctypes.byref(flags))
+                                        side.cuda_stream, sizes_arg, flags_arg)
             if rc == 9 and x.dtype in (torch.float16, torch.bfloat16):  # (test hook only, see below)
                 x = x.float().contiguous()
                 n_stage = lib.ctcx_hostin_staging_bytes(_lib.F32, T, B, C)
                 staging = torch.empty(max(n_stage, 16), dtype=torch.uint8, device=device)
                 rc = lib.ctcx_decode_hostin(x.data_ptr(), _lib.F32, 0, T, B, C, sh.data_ptr(), *attrs,
                                             staging.data_ptr(), n_stage, ws.data_ptr(), ws_bytes, stream,
-                                            side.cuda_stream, ctypes.byref(sizes), ctypes.byref(flags))
+                                            side.cuda_stream, sizes_arg, flags_arg)
             staging.record_stream(side)
         else:
             xd = x.to(device=device, non_blocking=True)
@@ -289,27 +316,89 @@ def ctc_ext_beam_search_decoder_raw(inputs, sequence_length, beam_width, top_pat
                                                 ctypes.byref(flags))
             else:
                 rc = lib.ctcx_decode_view(xd.data_ptr(), _DTYPE_CODE[xd.dtype], tstride, T, B, C, sd.data_ptr(),
-                                          *attrs, ws.data_ptr(), ws_bytes, stream, ctypes.byref(sizes),
-                                          ctypes.byref(flags))
+                                          *attrs, ws.data_ptr(), ws_bytes, stream, sizes_arg, flags_arg)
                 if rc == 9 and xd.dtype in (torch.float16, torch.bfloat16):
                     # (test hook only: the generic kernel forced onto a fast-path shape has no room to widen
                     # half-precision logits in the workspace)
                     xd = xd.float().contiguous()
                     rc = lib.ctcx_decode_view(xd.data_ptr(), _lib.F32, 0, T, B, C, sd.data_ptr(), *attrs,
-                                              ws.data_ptr(), ws_bytes, stream, ctypes.byref(sizes),
-                                              ctypes.byref(flags))
+                                              ws.data_ptr(), ws_bytes, stream, sizes_arg, flags_arg)
         if rc != 0:
             _raise(lib, rc, int(batch_offset))
-        host_out = host_in if outputs == "auto" else (outputs == "host")
-        groups, logp, packed = _pack(lib, ws, T, B, P, (n_dec, n_ali), device, stream, f64, host_out)
+        hbuf = None
+        if deferred:  # the pack (and the copy of the result to the host) follow the decode without a round trip
+            buf = torch.empty((n_bound,), dtype=torch.int64, device=device)
+            rc = lib.ctcx_pack_compact(ws.data_ptr(), T, B, P, 8 if f64 else 4, buf.data_ptr(), n_bound, stream)
+            if rc != 0:
+                _raise(lib, rc)
+            if host_out:  # the whole bound crosses the bus (at most DEFER_MAX_BYTES_HOST)
+                hbuf = torch.empty((n_bound,), dtype=torch.int64, pin_memory=True)
+                hbuf.copy_(buf, non_blocking=True)
+            # sizes + status words follow into page-locked memory; an event of this decode's own marks the end,
+            # so that reading this result never waits for decodes enqueued after it
+            n_res = lib.ctcx_result_bytes(P)
+            hres = torch.empty((n_res,), dtype=torch.uint8, pin_memory=True)
+            rc = lib.ctcx_result_copy_async(ws.data_ptr(), T, B, P, hres.data_ptr(), n_res, stream)
+            if rc != 0:
+                _raise(lib, rc)
+            done = torch.cuda.Event()
+            done.record(cur)
+    # what the enqueued work reads stays alive until complete() has synchronised
+    keep = [x, seq, ws, xd, sd, sh, staging, esd]
+
+    def complete(_keep=keep):
+        with torch.cuda.device(device):
+            if deferred:
+                done.synchronize()
+                rc = lib.ctcx_result_parse(hres.data_ptr(), T, B, P, ctypes.byref(sizes), ctypes.byref(flags))
+                if rc != 0:
+                    _raise(lib, rc, int(batch_offset))
+                packed = (hbuf if host_out else buf)[:_pack_elems(B, P, (n_dec, n_ali), f64)]
+                groups, logp = _carve(packed, B, P, (n_dec, n_ali), f64)
+            else:
+                groups, logp, packed = _pack(lib, ws, T, B, P, (n_dec, n_ali), device, stream, f64, host_out)
         if host_out and x_np and outputs == "auto":
             groups = [[t.numpy() for t in g] for g in groups]
             logp = logp.numpy()
-    res = CTCExtBeamSearchDecoder(*groups, logp)
-    res.flags = int(flags.value)
-    res.packed = packed
-    res.max_lengths = ([int(v) for v in max_dec], [int(v) for v in max_ali])  # dense_shape[1] per path, on the host
-    return res
+        res = CTCExtBeamSearchDecoder(*groups, logp)
+        res.flags = int(flags.value)
+        res.packed = packed
+        res.max_lengths = ([int(v) for v in max_dec], [int(v) for v in max_ali])  # dense_shape[1] per path, on the host
+        # bytes copied device -> host by this call: sizes + status words, and for host outputs the result buffer
+        res.d2h_bytes = 4 * P * 8 + 64 + (8 * (n_bound if deferred else int(packed.numel())) if host_out else 0)
+        _keep.clear()
+        return res
+
+    if wait:
+        return complete()
+    return PendingDecode(complete, eager=not deferred)
+
+
+class PendingDecode:
+    """Handle of a decode that was enqueued with `wait=False`: the kernels, the pack and (for host
+    outputs) the copy of the result are in flight on the caller's CUDA stream; `.result()` synchronises
+    once and returns what the blocking call would have returned (or raises what it would have raised).
+    Lets a caller enqueue the next batch before reading this one -- the GPU then runs decode after
+    decode without waiting for the host. Results too large for the single-synchronisation route
+    (DEFER_MAX_BYTES_*) are computed before the handle is returned."""
+
+    def __init__(self, complete, eager=False):
+        self._complete = complete
+        self._res = None
+        self._exc = None
+        if eager:
+            self.result()
+
+    def result(self):
+        if self._complete is not None:
+            complete, self._complete = self._complete, None
+            try:
+                self._res = complete()
+            except Exception as e:  # re-raised on every call
+                self._exc = e
+        if self._exc is not None:
+            raise self._exc
+        return self._res
 
 
 def ctc_ext_beam_search_decoder(inputs, sequence_length, beam_width, top_paths,

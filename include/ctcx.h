@@ -81,7 +81,10 @@ typedef struct {
  *   workspace    DEVICE memory of at least ctcx_workspace_bytes(...) bytes, 256-byte aligned; it holds
  *                the decode result until ctcx_pack_f32 has run
  *   stream       cudaStream_t (as void*), may be NULL for the default stream
- *   sizes        host output, see ctcx_sizes
+ *   sizes        host output, see ctcx_sizes. NULL = DEFERRED: the decode is only enqueued, nothing is
+ *                synchronised and only argument errors are returned; ctcx_finish() later brings the
+ *                sizes, the flags and the reference's run-time errors. Every ctcx_decode_* entry on
+ *                device or page-locked inputs accepts it.
  *   flags_out    optional host int32: bit0 = some utterance hit the documented rounding anomaly
  * Synchronises `stream` once (sizes must reach the host). */
 int ctcx_decode_f32(const float* logits_dev, int max_time, int batch, int num_classes,
@@ -139,6 +142,34 @@ int ctcx_pack_f32(const void* workspace, int max_time, int batch, int top_paths,
                   int64_t* const* decoded_shape, int64_t* const* alignment_indices,
                   int64_t* const* alignment_values, int64_t* const* alignment_shape,
                   float* log_probability, void* stream);
+
+/* Compact pack for a host that does not know the sizes yet (a deferred decode): ALL outputs go into one
+ * int64 DEVICE buffer of packed_elems elements -- per path p: decoded_indices [n_decoded[p], 2],
+ * decoded_values [n_decoded[p]], decoded_shape [2], alignment_indices [n_alignment[p], 2],
+ * alignment_values [n_alignment[p]], alignment_shape [2]; after the last path log_probability [batch,
+ * top_paths] (real_bytes = 4: float32, two per slot, or 8: float64) -- laid out ON THE DEVICE from the
+ * sizes the decode left in the workspace. A sufficient size is top_paths * (6 * A + 4) + batch *
+ * top_paths slots, A = sum of the (clamped) sequence lengths <= batch * max_time. Only enqueues; a
+ * buffer that turns out too small writes nothing and makes ctcx_finish return CTCX_ERR_WORKSPACE. */
+int ctcx_pack_compact(void* workspace, int max_time, int batch, int top_paths, int real_bytes,
+                      int64_t* packed_dev, size_t packed_elems, void* stream);
+
+/* Completes a deferred decode (sizes == NULL above): one device->host copy of the sizes and status
+ * words, one synchronisation of `stream`, then the reference's checks exactly as the synchronous entry
+ * would have returned them. */
+int ctcx_finish(const void* workspace, int max_time, int batch, int top_paths, void* stream,
+                ctcx_sizes* sizes, int32_t* flags_out);
+
+/* ctcx_finish in two halves, for callers that keep SEVERAL decodes in flight on one stream (ctcx_finish
+ * would wait for all of them): ctcx_result_copy_async enqueues the copy of the sizes / status block
+ * (ctcx_result_bytes(top_paths) bytes) into result_host -- page-locked memory, or the call blocks --
+ * right behind the decode; the caller records an event of its own there, waits for it when it wants
+ * the result, and ctcx_result_parse (host only) turns the block into sizes, flags and the return code. */
+size_t ctcx_result_bytes(int top_paths);
+int ctcx_result_copy_async(const void* workspace, int max_time, int batch, int top_paths, void* result_host,
+                           size_t result_bytes, void* stream);
+int ctcx_result_parse(const void* result_host, int max_time, int batch, int top_paths, ctcx_sizes* sizes,
+                      int32_t* flags_out);
 
 /* Host-buffer entry point: what a TensorFlow CPU OpKernel::Compute (the reference's only
  * registration, kernels.cc:269-275) would call with its host tensors. Copies the inputs to the

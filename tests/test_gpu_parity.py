@@ -993,3 +993,85 @@ def test_host_input_and_view_entries_reject_bad_arguments(op):
     assert not L.raw_mismatches(raw, L.oracle_decode(x.numpy(), sl0.numpy(), W, 1, False, 7, -1))
     with pytest.raises(op.InvalidArgumentError, match="Less leaves"):
         op.ctc_ext_beam_search_decoder_raw(x, sl0, beam_width=W, top_paths=2, blank_index=7)
+
+
+def test_single_synchronisation_route_equals_the_two_phase_route(op):
+    """Small results are decoded and packed back to back into a buffer sized from an upper bound, with
+    one synchronisation (sizes == NULL, ctcx_pack_compact, ctcx_finish); large ones get their sizes
+    first and exactly sized outputs. Both routes must return identical tensors, the same `.packed`
+    layout and the same errors."""
+    import torch
+    from ctc_beam_search_op_b200 import decoder as D
+    cases = [("gauss", 60, 7, 29, 100, 1, True, 28, np.float32), ("peaky", 40, 5, 32, 16, 3, False, 31, np.float32),
+             ("peaky", 50, 4, 300, 16, 2, False, 299, np.float32), ("gauss", 30, 3, 12, 40, 2, True, 0, np.float64),
+             ("gauss", 20, 3, 40, 300, 2, False, 7, np.float32)]
+    saved = (D.DEFER_MAX_BYTES_DEVICE, D.DEFER_MAX_BYTES_HOST)
+    try:
+        for kind, T, B, C, W, P, merge, blank, dt in cases:
+            x = L.make_logits(kind, T, B, C, blank, 71).astype(dt)
+            sl = L.ragged_lengths(T, B, 71)
+            kw = dict(beam_width=W, top_paths=P, merge_repeated=merge, blank_index=blank)
+            got = {}
+            for route, limit in (("deferred", 1 << 30), ("two-phase", 0)):
+                D.DEFER_MAX_BYTES_DEVICE = D.DEFER_MAX_BYTES_HOST = limit
+                got[route] = [op.ctc_ext_beam_search_decoder_raw(x, sl, **kw),                       # host in, host out
+                              op.ctc_ext_beam_search_decoder_raw(torch.from_numpy(x).cuda(),         # device in / out
+                                                                 torch.from_numpy(sl).cuda(), **kw),
+                              op.ctc_ext_beam_search_decoder_raw(torch.from_numpy(x).pin_memory(), sl, **kw)]
+            for a, b in zip(got["deferred"], got["two-phase"]):
+                for g in range(6):
+                    for p in range(P):
+                        np.testing.assert_array_equal(np.asarray(torch.as_tensor(a[g][p]).cpu()), np.asarray(torch.as_tensor(b[g][p]).cpu()))
+                np.testing.assert_array_equal(np.asarray(torch.as_tensor(a[6]).cpu()), np.asarray(torch.as_tensor(b[6]).cpu()))
+                pa, pb = a.packed.cpu().numpy(), b.packed.cpu().numpy()
+                assert pa.shape == pb.shape
+                n_cmp = len(pa) - (1 if (dt == np.float32 and (B * P) % 2) else 0)  # (half of the last slot is padding)
+                np.testing.assert_array_equal(pa[:n_cmp], pb[:n_cmp])
+                assert a.flags == b.flags and a.max_lengths == b.max_lengths
+            want = L.oracle_decode(x, sl, W, P, merge, blank, -1)
+            assert not L.raw_mismatches(got["deferred"][0], want)
+        # errors surface identically (at ctcx_finish on the deferred route)
+        x = L.make_logits("gauss", 12, 3, 29, 28, 5)
+        for limit in (1 << 30, 0):
+            D.DEFER_MAX_BYTES_DEVICE = D.DEFER_MAX_BYTES_HOST = limit
+            with pytest.raises(op.FailedPreconditionError, match=r"sequence_length\(1\) <= 12") as e:
+                op.ctc_ext_beam_search_decoder_raw(x, [12, 13, 3], beam_width=8, top_paths=1, blank_index=28)
+            assert e.value.batch_index == 1
+            with pytest.raises(op.InvalidArgumentError, match="Less leaves"):
+                op.ctc_ext_beam_search_decoder_raw(x, [12, 0, 3], beam_width=8, top_paths=2, blank_index=28)
+            with pytest.raises(op.InvalidArgumentError, match="requested more paths"):
+                op.ctc_ext_beam_search_decoder_raw(x, [12, 5, 3], beam_width=2, top_paths=3, blank_index=28)
+            with pytest.raises(op.InvalidArgumentError):
+                op.ctc_ext_beam_search_decoder_raw(x, [12, -1, 3], beam_width=8, top_paths=1, blank_index=28)
+            empty = op.ctc_ext_beam_search_decoder_raw(np.zeros((4, 0, 5), np.float32), np.zeros((0,), np.int32),
+                                                       beam_width=3, top_paths=1, blank_index=4)
+            assert tuple(np.asarray(empty[2][0])) == (0, 0)
+    finally:
+        D.DEFER_MAX_BYTES_DEVICE, D.DEFER_MAX_BYTES_HOST = saved
+
+
+def test_pending_decodes_in_flight(op):
+    """wait=False: several decodes enqueued before any result is read (device and pinned-host inputs,
+    different shapes), resolved out of order; each equals its blocking twin, errors are raised by
+    .result() -- every time it is called."""
+    import torch
+    jobs = []
+    for k, (T, B, C, W, P, blank) in enumerate([(80, 6, 29, 100, 1, 28), (50, 4, 300, 16, 2, 299), (60, 5, 32, 20, 3, 31),
+                                               (80, 6, 29, 100, 1, 28)]):
+        x = L.make_logits("gauss" if k % 2 else "peaky", T, B, C, blank, 80 + k)
+        sl = L.ragged_lengths(T, B, 80 + k)
+        kw = dict(beam_width=W, top_paths=P, merge_repeated=bool(k % 2), blank_index=blank)
+        xin = torch.from_numpy(x).pin_memory() if k % 2 else torch.from_numpy(x).cuda()
+        sin = sl if k % 2 else torch.from_numpy(sl).cuda()
+        jobs.append((x, sl, kw, op.ctc_ext_beam_search_decoder_raw(xin, sin, wait=False, **kw)))
+    bad = op.ctc_ext_beam_search_decoder_raw(torch.from_numpy(jobs[0][0]).cuda(), [81, 3, 3, 3, 3, 3], beam_width=4,
+                                             top_paths=1, blank_index=28, wait=False)
+    assert all(isinstance(j[3], op.PendingDecode) for j in jobs)
+    for x, sl, kw, pending in reversed(jobs):
+        got = pending.result()
+        assert pending.result() is got
+        want = L.oracle_decode(x, sl, kw["beam_width"], kw["top_paths"], kw["merge_repeated"], kw["blank_index"], -1)
+        assert not L.raw_mismatches(got, want)
+    for _ in range(2):
+        with pytest.raises(op.FailedPreconditionError, match=r"sequence_length\(0\) <= 80"):
+            bad.result()
