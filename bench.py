@@ -363,8 +363,9 @@ def run_own_arm(args, rank, world, local_rank, out_fd=1):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": bytes_per_batch + B * 4,
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
-        # per step: [normaliser + class selection pre-pass (wide vocabularies only)], beam, trace, scan, flags, pack
-        "gpu_launches": ((6 if C <= 32 else 7) if args.scorer else 6 if C > 32 else 5) * args.steps,
+        # per step: [normaliser + class selection pre-pass (wide vocabularies only)], beam, trace, scan, flags,
+        # [output pointer table (single-synchronisation route) | scorer-table check], pack
+        "gpu_launches": (5 + (1 if C > 32 else 0) + (1 if args.scorer else 0) + (0 if args.scorer else 1)) * args.steps,
         "kernel_ms": {"lognorm": float(kern_ms[:, 0].mean()), "beam": beam_ms,
                       "trace": float(kern_ms[:, 2].mean()), "scan": float(kern_ms[:, 3].mean()),
                       "wall_ms_per_step": 1e3 * wall_dev / args.steps},
