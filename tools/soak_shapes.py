@@ -1,6 +1,7 @@
 """Random-shape parity soak: many small decodes with random (T, B, C, beam_width, top_paths, blank,
 merge) -- narrow, wide and very wide vocabularies, all beam-width tiers, Gaussian / peaky / quantised
-(tie-heavy) / micro-spaced / masked logits, float32 and float64, with and without a scorer table --
+(tie-heavy) / micro-spaced / masked logits, float32 and float64, with and without a scorer table,
+inputs as numpy arrays, page-locked host tensors (overlapped / slab-wise host feed) or CUDA tensors --
 each compared bit for bit with the CPU oracle.   python tools/soak_shapes.py [n_cases] [seed]"""
 import os
 import sys
@@ -52,31 +53,42 @@ for case in range(N):
             x = x + r2.standard_normal(x.shape) * 1e-9
     sl = r2.integers(0 if P == 1 else 1, T + 1, B).astype(np.int32)
     lm = (-np.abs(r2.standard_normal((C + 1, C))).astype(np.float32)) if scorer else None
-    tag = "case %d: %s T=%d B=%d C=%d W=%d P=%d blank=%d merge=%d f64=%d scorer=%d seed=%d" % (
-        case, kind, T, B, C, W, P, blank, merge, f64, scorer, seed)
+    place = ["numpy", "pinned", "cuda"][int(rng.integers(0, 3))]
+    tag = "case %d: %s T=%d B=%d C=%d W=%d P=%d blank=%d merge=%d f64=%d scorer=%d %s seed=%d" % (
+        case, kind, T, B, C, W, P, blank, merge, f64, scorer, place, seed)
+    if place == "numpy":
+        xin, sin = x, sl
+    else:
+        import torch
+        xin = torch.from_numpy(x).pin_memory() if place == "pinned" else torch.from_numpy(x).cuda()
+        sin = sl if place == "pinned" else torch.from_numpy(sl).cuda()
     try:
         want = L.oracle_decode(x, sl, W, P, merge, blank, -1, lm=lm)
     except L.OracleError as e:
         try:
-            op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=W, top_paths=P, merge_repeated=merge,
+            op.ctc_ext_beam_search_decoder_raw(xin, sin, beam_width=W, top_paths=P, merge_repeated=merge,
                                                blank_index=blank, expansion_scores=lm)
             bad_cases.append(tag + " -> oracle error '%s' but the GPU path succeeded" % e)
         except op.CtcxError:
             n_err += 1
         continue
     try:
-        raw = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=W, top_paths=P, merge_repeated=merge,
+        raw = op.ctc_ext_beam_search_decoder_raw(xin, sin, beam_width=W, top_paths=P, merge_repeated=merge,
                                                  blank_index=blank, blank_label=-1, expansion_scores=lm)
     except op.CtcxError as e:
         bad_cases.append(tag + " -> GPU error %s" % e)
         continue
     packed = L.pack_sparse(want)
     view = np.uint64 if f64 else np.uint32
-    ok = all(np.array_equal(np.asarray(raw[g][p]), packed[g][p]) for g in range(6) for p in range(P))
-    ok = ok and np.array_equal(np.asarray(raw[6]).view(view), np.asarray(packed[6]).view(view))
+    def npy(a):
+        return a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
+    ok = all(np.array_equal(npy(raw[g][p]), packed[g][p]) for g in range(6) for p in range(P))
+    ok = ok and np.array_equal(npy(raw[6]).view(view), np.asarray(packed[6]).view(view))
     frames += int(sl.sum())
     if not ok:
         bad_cases.append(tag + " -> MISMATCH")
+    if (case + 1) % 100 == 0:  # progress survives a time limit
+        print("... %d cases, %d frames, %d failures so far" % (case + 1, frames, len(bad_cases)), flush=True)
 print("%d cases, %d frames, %d expected errors (both sides), %d failures" % (N, frames, n_err, len(bad_cases)))
 for b in bad_cases[:20]:
     print(b)
