@@ -35,7 +35,7 @@ struct BeamParamsT {
   int Cs;                        // row stride of the two arrays (a multiple of 8)
   int Kc;                        // sorted classes per frame the kernel may use (entry Kc, if < C-1
                                  // classes are listed, is a sentinel: the best class left out)
-  // scorer extension point (util/ctc_beam_scorer.h:31-65), generic kernel only: null = the default
+  // scorer extension point (util/ctc_beam_scorer.h:31-65), generic kernel and the narrow kernel's LM variant: null = the default
   // scorer; otherwise a [C+1, C] table of expansion scores (<= 0), row = label of the expanded
   // entry + 1 (row 0: the root), column = new label: GetStateExpansionScore(state, s) = s + entry
   const R* lm;
