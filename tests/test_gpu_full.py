@@ -169,11 +169,11 @@ def test_cfg5_size_batch_on_one_gpu(op, B):
 @pytest.mark.skipif(not L.have_ref(), reason="oracle/_ref not present on this box")
 def test_gpu_against_the_compiled_reference_directly(op):
     """No restatement in between: the CUDA path against the reference's own code (oracle/_ref,
-    compiled from the unmodified headers) at the full cfg2 / cfg3 lengths. The reference orders exact
+    compiled from the unmodified headers) at the full cfg2 / cfg3 / cfg4 lengths. The reference orders exact
     ties by libstdc++ heap mechanics, so utterances in which an order-deciding
     comparison ties exactly are excused -- they are identified by the oracle's decision margins --
     and must stay a small minority on peaky logits."""
-    for name, kind, n_utt in (("cfg2", "peaky", 32), ("cfg2", "gauss", 16), ("cfg3", "peaky", 8)):
+    for name, kind, n_utt in (("cfg2", "peaky", 32), ("cfg2", "gauss", 16), ("cfg3", "peaky", 8), ("cfg4", "peaky", 16)):
         T, B, C, W, P, merge, blank = FULL[name]
         x, sl = _inputs(name, kind)
         x, sl = np.ascontiguousarray(x[:, :n_utt]), sl[:n_utt]
