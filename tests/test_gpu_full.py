@@ -190,3 +190,27 @@ def test_gpu_against_the_compiled_reference_directly(op):
         # (on Gaussian logits at T=500 every utterance has SOME exact tie; ~1 in 16 has one that matters)
         assert len(differ) <= max(1, n_utt // 8), (name, kind, differ, int(tie_free.sum()))
         assert kind != "peaky" or tie_free.sum() >= n_utt // 4
+
+
+@pytest.mark.skipif(not L.have_ref(), reason="oracle/_ref not present on this box")
+def test_float64_gpu_against_the_compiled_reference_directly(op):
+    """T = double (kernels.cc:275): the double kernels against the reference's own float64 code at the
+    full cfg2 / cfg3 lengths, log-probabilities to the last bit of the double. Genuine float64 values
+    (float32 logits plus 1e-9 noise) make exact ties rare; tied utterances are excused as above."""
+    for name, kind, n_utt in (("cfg2", "peaky", 16), ("cfg2", "gauss", 8), ("cfg3", "peaky", 6)):
+        T, B, C, W, P, merge, blank = FULL[name]
+        x32, sl = _inputs(name, kind)
+        x = np.ascontiguousarray(x32[:, :n_utt].astype(np.float64) +
+                                 np.random.default_rng(17).standard_normal((T, n_utt, C)) * 1e-9)
+        sl = sl[:n_utt]
+        ref = L.ref_decode_threaded(x, sl, W, P, merge, blank, -1, threads=min(L.host_threads(), 16))
+        assert ref.logp.dtype == np.float64
+        _, margins = L.oracle_decode(x, sl, W, P, merge, blank, -1, want_margin=True)
+        tie_free = margins[:, [1, 2, 4]].min(axis=1) > 0
+        raw = op.ctc_ext_beam_search_decoder_raw(x, sl, beam_width=W, top_paths=P, merge_repeated=merge,
+                                                 blank_index=blank, blank_label=-1)
+        assert np.asarray(raw[6]).dtype == np.float64
+        differ = [b for b in L.raw_mismatches(raw, ref) if b >= 0]
+        bad = [b for b in differ if tie_free[b]]
+        assert not bad, "float64 %s %s: utterances %s differ from the compiled reference" % (name, kind, bad)
+        assert len(differ) <= max(1, n_utt // 8), (name, kind, differ, int(tie_free.sum()))
