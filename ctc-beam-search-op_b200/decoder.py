@@ -389,6 +389,15 @@ class PendingDecode:
         if eager:
             self.result()
 
+    def __del__(self):
+        # a handle dropped unread still has copies into its page-locked buffers in flight: wait for them
+        # before the buffers go back to the allocator
+        if getattr(self, "_complete", None) is not None:
+            try:
+                self.result()
+            except Exception:
+                pass
+
     def result(self):
         if self._complete is not None:
             complete, self._complete = self._complete, None
