@@ -288,9 +288,11 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
   }
 
   // thread -> (row, class slice) mapping of the candidate pass
-  // (latency regime: all threads share the rows, two per row at the 128-slot tier; throughput regime:
-  // one thread per row -- the candidate search runs on half as many warps, fewer instructions in total)
-  constexpr int PARTS = (MINB >= 4 && !TIMING) ? 1 : NT / WMAX;  // threads per row
+  // (latency regime: the threads share the rows -- two per row at the 128-slot tier, at most four (the
+  // 32-slot tier: every thread of a row computes the row's whole mask, and more warps in the list scan
+  // mean more atomics; eight per row cost 10 % at beam 32); throughput regime: one thread per row -- the
+  // candidate search runs on half as many warps, fewer instructions in total)
+  constexpr int PARTS = (MINB >= 4 && !TIMING) ? 1 : (NT / WMAX > 4 ? 4 : NT / WMAX);  // threads per row
   constexpr int CP = 32 / PARTS;    // classes per thread
   static_assert(NT % WMAX == 0 && 32 % PARTS == 0, "row/class tiling");
   const int prow = tid / PARTS, pbase = (tid % PARTS) * CP;
