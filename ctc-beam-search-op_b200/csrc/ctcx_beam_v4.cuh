@@ -47,6 +47,12 @@ namespace ctcx {
 // "base + immediate" and spends no registers on array pointers.
 // RB = bytes of the score type R (4: float, 8: double). Keys are as wide as scores; a (key, ~order)
 // composite, a row-info record and a list item are 2 / 4 / 2 scores wide.
+// Row stride of the scorer table in shared memory, in floats. Lanes read rows of DIFFERENT previous
+// labels at the same column: a stride of 32 would put them all on the same banks (a 29-way conflict on
+// every 16-byte load of the candidate test); 36 spreads consecutive rows over the banks and keeps
+// 16-byte alignment.
+constexpr int kLmStride = 36;
+
 template <int WMAX, bool LM = false, int RB = 4>
 struct BeamSmemV4 {
   static constexpr size_t w = (size_t)WMAX;
@@ -93,7 +99,7 @@ struct BeamSmemV4 {
   static constexpr size_t keys = scal + 32 * 4;           // Key [8]      min / max member key, min base, range prediction
   static constexpr size_t prefix = keys + 8 * rb;         // Comp [1] (+ pad) radix-select prefix of the slow boundary cut
   static constexpr size_t lm = (prefix + 32 + 15) / 16 * 16;      // f32 [33][32]  scorer table (LM kernels only), row = previous label + 1
-  static constexpr size_t list = lm + (LM ? 33 * 32 * 4 : 0);     // Item [cand_cap] {score key, (row<<16)|label}
+  static constexpr size_t list = lm + (LM ? 33 * kLmStride * 4 : 0);  // Item [cand_cap] {score key, (row<<16)|label}
   static constexpr size_t Bytes(int cand_cap) { return (list + (size_t)cand_cap * 2 * rb + 15) / 16 * 16; }
 };
 
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
     float* w_lm = (float*)(smem + lay::lm);
     for (int i = tid; i < 33 * 32; i += NT) {
       const int r = i >> 5, l = i & 31;
-      w_lm[i] = (r <= C && l < C) ? p.lm[(size_t)r * C + l] : 0.0f;
+      w_lm[r * kLmStride + l] = (r <= C && l < C) ? p.lm[(size_t)r * C + l] : 0.0f;
     }
     valid_mask = ((C >= 32) ? 0xffffffffu : ((1u << C) - 1u)) & ~(1u << blank);
   }
@@ -579,7 +585,7 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
           if (pslot >= 0) {
             const bool same = (lbl == o_label[pslot]);
             R base = same ? o_blk[pslot] : o_total[pslot];
-            if constexpr (LM) base = Ops::Add(base, s_lm[(o_label[pslot] + 1) * 32 + lbl]);  // decoder.h:103,114
+            if constexpr (LM) base = Ops::Add(base, s_lm[(o_label[pslot] + 1) * kLmStride + lbl]);  // decoder.h:103,114
             v_nl = Ops::Sub(Ops::Add(LogSumExp(o_lab[i], base, s_exptab), xl), off);
             rescore = Ops::Add(pl, base);
             v_an = Ops::Add(o_ab[pslot], pl);
@@ -659,7 +665,7 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
         if constexpr (LM) {  // every class of [c_lo, c_lo + c_n) on its own: score = pl + (base + lm)  (decoder.h:171-182)
           const float ob = Rec::Ob(ri);
           const int lb = Rec::Label(ri);
-          const float* lmrow = s_lm + (lb + 1) * 32;
+          const float* lmrow = s_lm + (lb + 1) * kLmStride;
           unsigned m = 0u;
 #pragma unroll 2
           for (int g = c_lo; g < c_lo + c_n; g += 4) {
@@ -854,7 +860,7 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
             m &= m - 1u;
             const int l = pbase + k;
             R cbase = (l == r_label) ? r_ob : r_ot;
-            if constexpr (LM) cbase = Ops::Add(cbase, s_lm[(r_label + 1) * 32 + l]);
+            if constexpr (LM) cbase = Ops::Add(cbase, s_lm[(r_label + 1) * kLmStride + l]);
             const Key key = Ops::KeyOf(Ops::Add(s_pl[l], cbase));  // :172-182
             c_list[pos++] = Rec::MakeItem(key, ((unsigned)prow << 16) | (unsigned)l);
             atomicAdd(&s_hist[bucket_of(key)], 1u);
