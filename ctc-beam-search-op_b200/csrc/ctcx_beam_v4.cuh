@@ -82,7 +82,9 @@ struct BeamSmemV4 {
   static constexpr size_t risk = m_pslot + w * 4;         // i32 [WMAX]
   static constexpr size_t risk_new = risk + w * 4;        // i32 [WMAX]
   static constexpr size_t wiped = risk_new + w * 4;       // u32 [WMAX]
-  static constexpr size_t htab = wiped + w * 4;           // u32 [8*WMAX]  (hash tag << 10 | slot), 0xffffffff = empty
+  static constexpr size_t qcnt = wiped + w * 4;           // i32 [WMAX]   revisit-wipe queries: items ranking before the member
+  static constexpr size_t qchg = qcnt + w * 4;            // u32 [WMAX]   rows whose wiped state changed in this round: (row << 1) | new state
+  static constexpr size_t htab = qchg + w * 4;            // u32 [8*WMAX]  (hash tag << 10 | slot), 0xffffffff = empty
   static constexpr size_t hist = htab + 8 * w * 4;        // u32 [kBinsV2]
   static constexpr size_t offs = hist + kBinsV2 * 4;      // u32 [kBinsV2]
   static constexpr size_t bins2 = offs + kBinsV2 * 4;     // u32 [256]
@@ -205,7 +207,7 @@ __device__ __forceinline__ unsigned long long ReachOf(unsigned long long gap) {
   return (gap > (1ull << 62)) ? ~0ull : gap + gap / 4ull + 64ull;
 }
 
-enum { kV4Utt = 23, kV4Abort = 24 };  // scalar slots in addition to the kV2* / kV3* ones
+enum { kV4Utt = 23, kV4Abort = 24, kV4NChg = 25 };  // scalar slots in addition to the kV2* / kV3* ones
 
 // MINB = resident CTAs per SM the register allocation is tuned for: 4 (64 registers) for batches that
 // fill the machine, 2 (128 registers: more loads in flight, no re-materialisation) for the latency
@@ -260,6 +262,8 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
   int* s_risk = (int*)(smem + lay::risk);
   int* s_risk_new = (int*)(smem + lay::risk_new);
   unsigned* s_wiped = (unsigned*)(smem + lay::wiped);
+  int* s_qcnt = (int*)(smem + lay::qcnt);
+  unsigned* s_qchg = (unsigned*)(smem + lay::qchg);
   unsigned* s_htab = (unsigned*)(smem + lay::htab);
   unsigned* s_hist = (unsigned*)(smem + lay::hist);
   unsigned* s_offs = (unsigned*)(smem + lay::offs);
@@ -721,36 +725,39 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
       };
 
       // ---- PC: revisit-wipe fixed point ----
+      // Round 1 counts, for every at-risk member, the items the parent's sweep meets before it (one warp
+      // per member). When verdicts wipe rows, the counts are not recomputed: a later round only adds or
+      // removes the contribution of the rows whose state CHANGED -- one thread per (member, changed row)
+      // pair -- and re-derives the verdicts; a handful of candidate tests instead of a full sweep each.
       if (__builtin_expect(n_risk > 0, 0)) {
-        for (;;) {
-          for (int q = warp; q < n_risk; q += NWARP) {  // one warp per at-risk member
-            const int m = s_risk[q];
-            const int pslot = m_pslot[m];
-            int verdict = 0;
-            if (!s_wiped[pslot]) {
-              const Key vkey = m_key[m];
-              const R v = m_nt[m];
-              int cnt = 0;
-              for (int j = lane; j < n; j += 32) {  // members ranking before m
-                const Key kj = m_key[j];
-                cnt += (kj > vkey || (kj == vkey && j < m)) ? 1 : 0;
-              }
-              // children visited before the parent reaches label(m), from rows that are not wiped
-              const unsigned below = (1u << o_label[m]) - 1u;
-#pragma unroll 1
-              for (int r0 = 0; r0 <= pslot; r0 += 32) {
-                const int r = r0 + lane;
-                if (r <= pslot && !s_wiped[r]) {
-                  unsigned mk = cand_mask(s_row[r], v);
-                  if (r == pslot) mk &= below;
-                  cnt += __popc(mk);
-                }
-              }
-              cnt = __reduce_add_sync(kFull, cnt);
-              verdict = (cnt >= W) ? 1 : 0;
-            }
-            if (lane == 0) s_risk_new[q] = verdict;
+        for (int q = warp; q < n_risk; q += NWARP) {  // round 1: one warp per at-risk member (nothing is wiped yet)
+          const int m = s_risk[q];
+          const int pslot = m_pslot[m];
+          const Key vkey = m_key[m];
+          const R v = m_nt[m];
+          int cnt = 0;
+          for (int j = lane; j < n; j += 32) {  // members ranking before m
+            const Key kj = m_key[j];
+            cnt += (kj > vkey || (kj == vkey && j < m)) ? 1 : 0;
           }
+          // children visited before the parent reaches label(m)
+          const unsigned below = (1u << o_label[m]) - 1u;
+#pragma unroll 1
+          for (int r0 = 0; r0 <= pslot; r0 += 32) {
+            const int r = r0 + lane;
+            if (r <= pslot) {
+              unsigned mk = cand_mask(s_row[r], v);
+              if (r == pslot) mk &= below;
+              cnt += __popc(mk);
+            }
+          }
+          cnt = __reduce_add_sync(kFull, cnt);
+          if (lane == 0) {
+            s_qcnt[q] = cnt;
+            s_risk_new[q] = (cnt >= W) ? 1 : 0;
+          }
+        }
+        for (;;) {
           __syncthreads();
           // every thread inspects the (few) verdicts itself: no flag, no extra barrier when nothing
           // changes -- the common case
@@ -765,11 +772,39 @@ __global__ void __launch_bounds__(NT, (TIMING ? 1 : MINB)) BeamKernelV4(BeamPara
           }
           if (!changed) break;
           __syncthreads();  // all reads of s_wiped are done
-          for (int q = tid; q < n_risk; q += NT) s_wiped[s_risk[q]] = (unsigned)s_risk_new[q];
+          if (tid == 0) sci[kV4NChg] = 0;
+          __syncthreads();
+          for (int q = tid; q < n_risk; q += NT) {  // apply the verdicts, list the rows that changed
+            const int m = s_risk[q];
+            const unsigned nv = (unsigned)s_risk_new[q];
+            if (s_wiped[m] != nv) {
+              s_wiped[m] = nv;
+              s_qchg[atomicAdd(&sci[kV4NChg], 1)] = ((unsigned)m << 1) | nv;
+            }
+          }
           __syncthreads();
           // a query only counts rows up to its parent's: if every wiped row lies beyond every parent
           // row, no count (and no parent) is affected and the verdicts are final
           if (min_wiped > max_parent) break;
+          const int n_chg = sci[kV4NChg];
+          for (int pr = tid; pr < n_risk * n_chg; pr += NT) {  // one (member, changed row) pair per thread
+            const int q = pr / n_chg, c = pr - q * n_chg;
+            const unsigned e = s_qchg[c];
+            const int r = (int)(e >> 1);
+            const int m = s_risk[q];
+            const int pslot = m_pslot[m];
+            if (r <= pslot) {
+              unsigned mk = cand_mask(s_row[r], m_nt[m]);
+              if (r == pslot) mk &= (1u << o_label[m]) - 1u;
+              const int d = __popc(mk);
+              if (d) atomicAdd(&s_qcnt[q], (e & 1u) ? -d : d);  // wiped rows stop counting, restored ones count again
+            }
+          }
+          __syncthreads();
+          for (int q = tid; q < n_risk; q += NT) {  // a wiped parent never sweeps (decoder.h:167)
+            const int pslot = m_pslot[s_risk[q]];
+            s_risk_new[q] = (!s_wiped[pslot] && s_qcnt[q] >= W) ? 1 : 0;
+          }
         }
       }
       CTCX_TICK(2)  // PC
