@@ -26,7 +26,8 @@
 //   PA  member update, one thread per member                          decoder.h:95-143
 //   PC  revisit-wipe fixed point. A row's candidates above ANY threshold v are a
 //       bitmask: pref[L(v)] & ~member-children, L found by an exact search over the sorted class
-//       scores (fp add is monotone); a wipe query is a sum of popcounts -- no list.
+//       scores (fp add is monotone); a wipe query is a sum of popcounts -- no list. Rounds after
+//       the first correct the counts by the rows whose state changed instead of recounting.
 //   PB  only candidates inside the predicted score range (previous top-to-threshold gap x1.25) are
 //       listed and histogrammed (256 bins); wiped rows are skipped                 decoder.h:146-187
 //   PD  suffix scan -> boundary bin of the W-th item; if the prediction missed (fewer than
